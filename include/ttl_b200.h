@@ -1,0 +1,181 @@
+/* libttl_b200.so -- C ABI of the B200-native TTL per-sample test-time-adaptation path.
+ *
+ * The reference (Razaimam45/TTL-Test-Time-Low-Rank-Adaptation) has NO FFI for this path: it sits behind a Python
+ * module API (clip/custom_clip.py + ttl.py).  This header is the boundary a reference maintainer would bind with
+ * ctypes; each entry cites the reference interface it stands in for.  Plain pointers and
+ * sizes only; no torch types.  Every function returns 0 on success or a negative TTL_E_* code and never throws;
+ * the message is available from ttl_last_error().  No CPU fallback and no non-sm_100 fallback: ttl_create fails
+ * with TTL_E_ARCH on any device whose compute capability is not 10.x.
+ *
+ * Threading: one context per (process, device); calls are not thread-safe.  All work is enqueued on the
+ * caller's stream (a cudaStream_t passed as void*; NULL = legacy default stream) and nothing synchronises unless
+ * stated ("host" variants and getters do).
+ *
+ * Ownership: the library owns weights, activations, workspaces, LoRA factors/gradients/AdamW moments and the
+ * reset snapshot.  Callers own the image / logits buffers they pass and keep them alive until the stream has
+ * consumed them.
+ */
+#ifndef TTL_B200_H_
+#define TTL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTL_OK 0
+#define TTL_E_INVALID (-1)
+#define TTL_E_SHAPE (-2)
+#define TTL_E_ARCH (-3)
+#define TTL_E_CUDA (-4)
+#define TTL_E_NOMEM (-5)
+#define TTL_E_STATE (-6)
+
+typedef struct ttl_ctx ttl_ctx;
+
+/* Architecture + adapter geometry.  Stands in for the arguments of get_coop()/ClipTestTimeTuning.__init__
+ * (clip/custom_clip.py:706-723, 571-624) and LoraConfig (clip/custom_clip.py:583-591). */
+typedef struct ttl_config {
+  int32_t image_size;    /* 224 */
+  int32_t patch;         /* 16 (ViT-B/16), 14 (ViT-L/14) */
+  int32_t width;         /* 768 / 1024; multiple of 128, head_dim must be 64 */
+  int32_t layers;        /* 12 / 24 */
+  int32_t heads;         /* 12 / 16 */
+  int32_t mlp_dim;       /* 3072 / 4096 */
+  int32_t proj_dim;      /* 512 / 768 */
+  int32_t max_views;     /* views per forward call (--batch-size, ttl.py:389) */
+  int32_t max_classes;   /* upper bound on C for buffer sizing */
+  int32_t lora_rank;     /* 16 (or 32) */
+  float lora_alpha;      /* 32 */
+  int32_t lora_layer_lo; /* --layer_range, inclusive (ttl.py:402) */
+  int32_t lora_layer_hi;
+  float ln_eps;          /* 1e-5 */
+  int32_t device;        /* CUDA ordinal (--gpu) */
+} ttl_config;
+
+/* Frozen-weight slots; names follow the HF CLIP vision tower state_dict that
+ * CLIPModel.from_pretrained (clip/custom_clip.py:581) yields. */
+enum ttl_weight_kind {
+  TTL_W_CLASS_EMB = 0, /* vision_model.embeddings.class_embedding           [d]           */
+  TTL_W_PATCH_EMB = 1, /* vision_model.embeddings.patch_embedding.weight    [d,3,p,p]     */
+  TTL_W_POS_EMB = 2,   /* vision_model.embeddings.position_embedding.weight [tokens,d]    */
+  TTL_W_PRE_LN_G = 3, TTL_W_PRE_LN_B = 4,   /* vision_model.pre_layrnorm                  */
+  TTL_W_POST_LN_G = 5, TTL_W_POST_LN_B = 6, /* vision_model.post_layernorm                */
+  TTL_W_VIS_PROJ = 7,  /* visual_projection.weight [P,d]                                  */
+  /* per encoder layer (layer index argument) */
+  TTL_W_LN1_G = 16, TTL_W_LN1_B = 17,
+  TTL_W_Q_W = 18, TTL_W_Q_B = 19, TTL_W_K_W = 20, TTL_W_K_B = 21, TTL_W_V_W = 22, TTL_W_V_B = 23,
+  TTL_W_O_W = 24, TTL_W_O_B = 25,
+  TTL_W_LN2_G = 26, TTL_W_LN2_B = 27,
+  TTL_W_FC1_W = 28, TTL_W_FC1_B = 29, TTL_W_FC2_W = 30, TTL_W_FC2_B = 31
+};
+
+/* LoRA tensor slots of one layer, in the tuple order of LoRA_AB.init_weights (clip/custom_clip.py:193-200). */
+enum ttl_lora_which { TTL_LORA_A_Q = 0, TTL_LORA_B_Q = 1, TTL_LORA_A_V = 2, TTL_LORA_B_V = 3 };
+enum ttl_lora_what { TTL_LORA_PARAM = 0, TTL_LORA_GRAD = 1, TTL_LORA_INIT = 2 };
+
+/* Loss heads of test_time_tuning (ttl.py:70-110). */
+enum ttl_head {
+  TTL_HEAD_TPT = 0,  /* top-p confidence selection + marginal entropy: ttl.py:50-61, 86-110 (deyo_selection falsy) */
+  TTL_HEAD_DEYO = 1  /* weighted entropy over all views: deyo.py:93-196 with default flags (deyo_selection truthy) */
+};
+
+/* Optimiser / loop hyper-parameters (argparse defaults ttl.py:367-424; AdamW defaults ttl.py:218). */
+typedef struct ttl_hparams {
+  int32_t head;        /* enum ttl_head */
+  int32_t tta_steps;   /* --tta_steps; the DeYO head performs tta_steps^2 optimiser steps like the reference */
+  float selection_p;   /* --selection_p 0.1  -> K = (int)(V * p) */
+  float lr;            /* 5e-3 */
+  float beta1, beta2;  /* 0.9, 0.999 */
+  float eps;           /* 1e-8 */
+  float weight_decay;  /* 1e-2 */
+  float deyo_margin_e0;/* 0.4 */
+} ttl_hparams;
+
+/* Optional outputs of ttl_adapt_predict*: any pointer may be NULL. */
+typedef struct ttl_outputs {
+  float* logits0;      /* [V,C] first-forward logits                                  */
+  float* entropy;      /* [V]   per-view entropies                                    */
+  int32_t* idx;        /* [K]   selected views in argsort order (TPT head)            */
+  float* loss;         /* [1]   loss of the last optimiser step                       */
+  float* pred_logits;  /* [C]   adapted prediction on view 0 (ttl.py:350-352)         */
+} ttl_outputs;
+
+/* ---- lifetime ----------------------------------------------------------------------------------------- */
+int ttl_create(ttl_ctx** out, const ttl_config* cfg);               /* get_coop(), clip/custom_clip.py:706 */
+void ttl_destroy(ttl_ctx* ctx);
+const char* ttl_last_error(const ttl_ctx* ctx);                     /* ctx may be NULL: last create error  */
+int ttl_version(void);
+
+/* ---- frozen state ------------------------------------------------------------------------------------- */
+/* CLIPModel.from_pretrained(...) weights, fp32 host pointers, copied/converted once (clip/custom_clip.py:581). */
+int ttl_set_weight(ttl_ctx* ctx, int32_t layer, int32_t kind, const float* host, int64_t numel);
+/* Cached, L2-normalised text features [C,P] and logit_scale (log domain): get_text_features(),
+ * clip/custom_clip.py:651-663 and :619 -- computed once per class-name set instead of twice per sample. */
+int ttl_set_text_features(ttl_ctx* ctx, const float* host_text, int32_t n_classes, int32_t proj_dim, float logit_scale);
+
+/* ---- adapter ------------------------------------------------------------------------------------------ */
+/* LoRA_AB.initialize_layer_weights snapshot (clip/custom_clip.py:176-200): sets both the live factor and p0. */
+int ttl_lora_set_init(ttl_ctx* ctx, int32_t layer, int32_t which, const float* host, int64_t numel);
+/* ClipTestTimeTuning.LoRA_reset() + optimizer.load_state_dict(optim_state)  (ttl.py:338-344). */
+int ttl_lora_reset(ttl_ctx* ctx, void* stream);
+/* Synchronising getter: what = param | grad | init. */
+int ttl_lora_get(ttl_ctx* ctx, int32_t layer, int32_t which, int32_t what, float* host_out, int64_t numel);
+/* Device aliases of one tensor so a host framework can wrap them as parameters/gradients
+ * (the names ttl.py:159-160,197-201 walk).  After writing through them call ttl_lora_touch(). */
+int ttl_lora_device_ptr(ttl_ctx* ctx, int32_t layer, int32_t which, int32_t what, float** dev_ptr, int64_t* numel);
+int ttl_lora_touch(ttl_ctx* ctx, void* stream);
+/* torch.optim.AdamW.step() on the 4*n_layers LoRA tensors (ttl.py:105-108 via GradScaler, disabled in bf16). */
+int ttl_adamw_step(ttl_ctx* ctx, const ttl_hparams* hp, void* stream);
+
+/* ---- model calls -------------------------------------------------------------------------------------- */
+/* ClipTestTimeTuning.forward/inference (clip/custom_clip.py:665-703): images fp32 [n_views,3,S,S] on device ->
+ * logits fp32 [n_views,C] on device.  train != 0 keeps what ttl_backward needs (autograd-enabled forward). */
+int ttl_forward(ttl_ctx* ctx, const float* images_dev, int32_t n_views, int32_t train, float* logits_dev, void* stream);
+/* loss.backward() restricted to the LoRA factors (ttl.py:106): dlogits fp32 [n_views,C] of the last train forward. */
+int ttl_backward(ttl_ctx* ctx, const float* dlogits_dev, void* stream);
+/* The whole per-sample body of test_time_adapt_eval (ttl.py:338-352): reset -> test_time_tuning -> predict.
+ * forced_idx_dev (nullable, TPT head) teacher-forces the selected views (selected_idx reuse, ttl.py:97-98). */
+int ttl_adapt_predict(ttl_ctx* ctx, const float* images_dev, int32_t n_views, const ttl_hparams* hp,
+                      const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream);
+/* Same with HOST buffers (pinned recommended): H2D of the views, D2H of the requested outputs, stream sync. */
+int ttl_adapt_predict_host(ttl_ctx* ctx, const float* images_host, int32_t n_views, const ttl_hparams* hp,
+                           const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream);
+/* Toggle CUDA-graph replay of ttl_adapt_predict (default on). */
+int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
+/* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */
+int64_t ttl_last_launch_count(const ttl_ctx* ctx);
+
+/* ---- head pieces (select_confident_samples ttl.py:50-54, avg_entropy ttl.py:56-61, deyo.py:85-181) ---------- */
+int ttl_op_logits_entropy(const float* feats_dev, const float* text_dev, float scale, float* logits_dev,
+                          float* entropy_dev, int32_t V, int32_t C, int32_t P, void* stream);
+int ttl_op_select(const float* entropy_dev, int32_t V, int32_t K, int32_t* idx_dev, void* stream);
+int ttl_op_tpt_loss(const float* logits_dev, const int32_t* idx_dev, int32_t K, int32_t C, float* loss_dev,
+                    float* dlogits_dev, void* stream);
+int ttl_op_deyo_loss(const float* logits_dev, int32_t V, int32_t C, float margin_e0, float* loss_dev,
+                     float* dlogits_dev, void* stream);
+
+/* ---- single kernels, exposed for parity tests --------------------------------------------------------- */
+/* C[M,N] = epi(A[M,K] B[N,K]^T (+ A2[M,K2] B2[N,K2]^T)); bf16 operands (uint16 storage), see csrc/gemm.cuh. */
+int ttl_op_gemm(const void* a, const void* b, const void* a2, const void* b2, int32_t M, int32_t N, int32_t K,
+                int32_t K2, int32_t epi, const float* bias, void* out, void* out2, const float* resid,
+                const void* aux, const float* pos, int32_t tokens_per_view, int32_t block_n, void* stream);
+int ttl_op_layernorm(const float* x, void* y_bf16, const float* gamma, const float* beta, int32_t rows, int32_t d,
+                     float eps, void* stream);
+int ttl_op_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
+                         void* dx_bf16, int32_t rows, int32_t d, float eps, void* stream);
+int ttl_op_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int32_t V, int32_t tokens, int32_t heads,
+                         float scale, void* stream);
+int ttl_op_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                         void* dqkv_bf16, int32_t V, int32_t tokens, int32_t heads, float scale, void* stream);
+int ttl_op_im2col(const float* images, void* patches_bf16, int32_t V, int32_t S, int32_t p, void* stream);
+int ttl_op_adamw(float* p, const float* g, float* m, float* v, int32_t n, int32_t step, float lr, float b1, float b2,
+                 float eps, float wd, void* stream);
+int ttl_op_skinny_reduce(const void* wide_bf16, int32_t ldw, int32_t nw, const void* narrow_bf16, int32_t ldn,
+                         int32_t nn, int32_t M, float scale, float* out, int32_t transpose_out, float* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTL_B200_H_ */

@@ -1,0 +1,166 @@
+"""End-to-end parity of the CUDA path (through the C ABI / Engine) against
+  * the golden fixtures produced by the UNMODIFIED reference (tests/golden/ref_b16_c10_*.npz), ViT-B/16, 64 views;
+  * the CPU oracle run live on a tiny geometry.
+Tolerances are the north-star ones (BASELINE.json): logits and LoRA gradients within 1e-2 relative (norm-wise) in
+bf16; selection indices bit-exact given identical entropies (tests/test_gpu_ops.py); post-step LoRA factors compared
+on the elements with |g| > 0.1*mean|g| (step-1 Adam turns g into ~sign(g)); adapted prediction
+within 1e-2."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ttl_oracle as O  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = ("A_q", "B_q", "A_v", "B_v")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def b16_engine(b16_weights):
+    from ttl_b200 import Engine
+    eng = Engine("ViT-B/16", max_views=64, max_classes=1000, layer_range=(9, 11))
+    eng.load_weights(b16_weights)
+    eng.set_lora_init(O.lora_init(O.ARCHS["ViT-B/16"], O.LoraSpec(), seed=0))
+    yield eng
+    eng.close()
+
+
+def test_forward_logits_vs_reference(b16_engine, b16_views):
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt.npz"))
+    eng = b16_engine
+    eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+    eng.lora_reset()
+    logits = eng.forward(b16_views.cuda(), train=False).cpu().numpy()
+    assert _rel(logits, g["logits0"]) < 1e-2
+    logits_t = eng.forward(b16_views.cuda(), train=True).cpu().numpy()      # autograd-enabled flavour, same numbers
+    assert _rel(logits_t, g["logits0"]) < 1e-2
+    assert _rel(logits_t, logits) < 2e-3
+
+
+@pytest.mark.parametrize("case,graphs", [("tpt", False), ("tpt", True), ("deyo", False), ("deyo", True)])
+def test_adapt_predict_vs_reference(b16_engine, b16_views, case, graphs):
+    from ttl_b200 import Hparams
+    from ttl_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, f"ref_b16_c10_{case}.npz"))
+    eng = b16_engine
+    eng.set_graphs(graphs)
+    eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+    hp = Hparams(head=str(g["head"]), tta_steps=int(g["tta_steps"]))
+    forced = torch.from_numpy(g["idx_sorted"].astype(np.int32)) if case == "tpt" else None
+    imgs = b16_views.cuda()
+    for rep in range(3 if graphs else 1):     # rep 0 eager, rep 1 captures, rep 2 replays
+        out = eng.adapt_predict(imgs, hp, forced_idx=forced, want=("logits0", "entropy", "idx", "loss", "pred_logits"))
+    torch.cuda.synchronize()
+    assert _rel(out["logits0"].cpu().numpy(), g["logits0"]) < 1e-2
+    assert float(np.abs(out["entropy"].cpu().numpy() - g["entropies"]).max()) < 2e-2
+    assert _rel(out["pred_logits"].cpu().numpy(), g["pred_logits"][0]) < 1e-2
+    if case == "tpt":
+        assert sorted(out["idx"].cpu().tolist()) == g["idx_sorted"].tolist()
+    worst = 0.0
+    for i in (9, 10, 11):
+        for j, nm in enumerate(NAMES):
+            ref_g = g[f"grad_{i}_{nm}"]
+            got_g = eng.lora_get(i, j, L.LORA_GRAD)
+            if nm.startswith("A"):
+                assert np.abs(got_g).max() == 0.0 and np.abs(ref_g).max() == 0.0      # dA == 0 exactly at step 1
+                # A only sees weight decay
+                np.testing.assert_allclose(eng.lora_get(i, j), g[f"lora_{i}_{nm}"], atol=1e-7)
+                continue
+            e = _rel(got_g, ref_g)
+            worst = max(worst, e)
+            got_p, ref_p = eng.lora_get(i, j), g[f"lora_{i}_{nm}"]
+            mask = np.abs(ref_g) > 0.1 * np.abs(ref_g).mean()
+            assert mask.mean() > 0.5
+            assert _rel(got_p[mask], ref_p[mask]) < 1e-2, (i, nm)
+            flips = float((np.sign(got_p) != np.sign(ref_p)).mean())
+            assert flips < 0.05, (i, nm, flips)
+    print(f"[{case} graphs={graphs}] worst LoRA-gradient rel err {worst:.3e}")
+    assert worst < 1e-2
+
+
+def test_two_steps_vs_reference(b16_engine, b16_views):
+    """tta_steps=2 (dA != 0, LoRA active in the second forward, selected_idx reuse)."""
+    from ttl_b200 import Hparams
+    from ttl_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt2.npz"))
+    eng = b16_engine
+    eng.set_graphs(False)
+    eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+    hp = Hparams(head="tpt", tta_steps=2)
+    forced = torch.from_numpy(g["idx_sorted"].astype(np.int32))
+    out = eng.adapt_predict(b16_views.cuda(), hp, forced_idx=forced, want=("pred_logits", "loss"))
+    assert _rel(out["pred_logits"].cpu().numpy(), g["pred_logits"][0]) < 1e-2
+    for i in (9, 10, 11):
+        for j, nm in enumerate(NAMES):
+            ref_g, got_g = g[f"grad_{i}_{nm}"], eng.lora_get(i, j, L.LORA_GRAD)
+            # second-step gradients depend on first-step sign-like updates (0.2-0.6 % of which flip in bf16):
+            # the tolerance is therefore looser than the single-step 1e-2 (documented in DESIGN.md)
+            assert _rel(got_g, ref_g) < 1e-1, (i, nm, _rel(got_g, ref_g))
+            assert np.abs(got_g).max() > 0
+
+
+def test_free_running_selection_overlap(b16_engine, b16_views):
+    from ttl_b200 import Hparams
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt.npz"))
+    eng = b16_engine
+    eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+    out = eng.adapt_predict(b16_views.cuda(), Hparams(head="tpt"), want=("idx", "entropy"))
+    got = set(out["idx"].cpu().tolist())
+    ref = set(g["idx_sorted"].tolist())
+    ent = out["entropy"].cpu()
+    # the kernel's own selection must be the stable argsort of the kernel's own entropies (bit-exact)
+    assert out["idx"].cpu().tolist() == torch.argsort(ent, stable=True)[:6].tolist()
+    print("free-running selection overlap with fp32 reference:", len(got & ref), "of 6")
+
+
+def test_host_buffer_path(b16_engine, b16_views):
+    from ttl_b200 import Hparams
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt.npz"))
+    eng = b16_engine
+    eng.set_graphs(True)
+    eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+    forced = torch.from_numpy(g["idx_sorted"].astype(np.int32))
+    host = b16_views.pin_memory()
+    for _ in range(3):
+        out = eng.adapt_predict(host, Hparams(head="tpt"), forced_idx=forced, want=("pred_logits",))
+    assert not out["pred_logits"].is_cuda
+    assert _rel(out["pred_logits"].numpy(), g["pred_logits"][0]) < 1e-2
+
+
+@pytest.mark.parametrize("head,steps", [("tpt", 1), ("deyo", 1), ("tpt", 2)])
+def test_tiny_geometry_vs_live_oracle(head, steps):
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200 import _lib as L
+    arch = O.ARCHS["ViT-tiny"]
+    spec = O.LoraSpec(rank=16, alpha=32.0, layer_lo=1, layer_hi=2)      # layer 3 is frozen but back-propagated through
+    w = O.make_synthetic_weights(arch, 5)
+    lora0 = O.lora_init(arch, spec, 1)
+    imgs = O.make_synthetic_views(16, arch.image_size, 9)
+    text = O.make_text_features(7, arch.proj, seed=2)
+    ref = O.adapt_and_predict(arch, w, imgs, text, math.log(100.0), lora0, spec, head=head, tta_steps=steps,
+                              selection_p=0.25)
+    eng = Engine("ViT-tiny", max_views=16, max_classes=16, layer_range=(1, 2))
+    eng.load_weights(w)
+    eng.set_text_features(text, math.log(100.0))
+    eng.set_lora_init(lora0)
+    eng.set_graphs(False)
+    out = eng.adapt_predict(imgs.cuda(), Hparams(head=head, tta_steps=steps, selection_p=0.25),
+                            forced_idx=ref.idx if head == "tpt" else None, want=("logits0", "pred_logits", "loss"))
+    assert _rel(out["logits0"].cpu().numpy(), ref.logits0.numpy()) < 1e-2
+    assert _rel(out["pred_logits"].cpu().numpy(), ref.pred_logits[0].numpy()) < 2e-2
+    if steps == 1:
+        assert abs(float(out["loss"]) - ref.loss) < 2e-2 * max(1.0, abs(ref.loss))
+        for i in spec.layers():
+            for j in (1, 3):
+                assert _rel(eng.lora_get(i, j, L.LORA_GRAD), ref.grads[i][j].numpy()) < 2e-2, (i, j)
+    eng.close()

@@ -1,0 +1,929 @@
+// Context, buffers and orchestration of the TTL path + the extern "C" surface declared in include/ttl_b200.h.
+//
+// Data layout in HBM (ViT-B/16, V views, N = 197 tokens, M = V*N rows, d = 768, F = 3072):
+//   residual stream      fp32 [M, d]      XK (input of the first LoRA layer, preserved per sample), XA, XB
+//   GEMM operands        bf16 row-major, K contiguous: H [M,d], QKV [M,3d], AO [M,d], G [M,F]; weights [N,K]
+//   train-mode tape      per layer lo..L-1: h1, T=h1 A^T, qkv, ao, lse, x_mid, h2, z, g, x_out (rows of the views
+//                        that carry gradient: the K selected views for the TPT head, all views for DeYO / autograd)
+//   LoRA state           fp32 [n_lora_layers][A_q | B_q | A_v | B_v] x {param, grad, init, m, v}; bf16 packs per layer
+// Exact shortcuts: LoRA GEMM extension skipped while B == 0; layers below lo run once per sample
+// and XK is reused by the train-mode recompute, later steps and the view-0 prediction.
+#include "../../include/ttl_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ttl;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+inline uint16_t f2bf(float f) {  // round-to-nearest-even, matches __float2bfloat16 for finite values
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+struct LayerW {
+  bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;       // [3d,d] [d,d] [F,d] [d,F]
+  bf16 *wqkvT = nullptr, *woT = nullptr, *w1T = nullptr, *w2T = nullptr;   // transposes (train layers only)
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+};
+
+struct Tape {  // one train-mode layer
+  bf16 *h1 = nullptr, *T = nullptr, *qkv = nullptr, *ao = nullptr, *h2 = nullptr, *z = nullptr, *g = nullptr;
+  float *lse = nullptr, *x_mid = nullptr, *x_out = nullptr;
+};
+
+struct GraphKey {
+  int n_views, forced;
+  ttl_hparams hp;
+  bool operator==(const GraphKey& o) const {
+    return n_views == o.n_views && forced == o.forced && std::memcmp(&hp, &o.hp, sizeof(hp)) == 0;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  int uses = 0;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  // host-side state the body leaves behind (replayed graphs do not run the host code)
+  bool b_zero_after = false;
+  int opt_step_after = 0, train_views_after = 0;
+  const float* train_in_after = nullptr;
+};
+
+}  // namespace
+
+struct ttl_ctx {
+  ttl_config cfg{};
+  int tokens = 0, T = 0, Kp = 0, d = 0, F = 0, P = 0, L = 0, H = 0, r = 0, lo = 0, hi = 0, n_train = 0, n_lora = 0;
+  int Vm = 0, Mm = 0, Cm = 0;
+  float s = 2.f;
+  int num_sms = 148;
+  std::string err;
+  std::vector<void*> allocs;
+
+  // frozen weights
+  float *cls = nullptr, *pos = nullptr, *preg = nullptr, *preb = nullptr, *postg = nullptr, *postb = nullptr, *Wp = nullptr;
+  bf16* wpatch = nullptr;  // [d, Kp]
+  std::vector<LayerW> lw;
+  float* text = nullptr;
+  int C = 0;
+  float logit_scale_exp = 1.f;
+
+  // activations
+  bf16 *patches = nullptr, *Hb = nullptr, *QKV = nullptr, *AO = nullptr, *Gb = nullptr, *Tm = nullptr;
+  float *XK = nullptr, *XA = nullptr, *XB = nullptr, *TIN = nullptr;
+  float *feats = nullptr, *feats_c = nullptr, *logits = nullptr, *logits_c = nullptr, *entropy = nullptr,
+        *entropy_c = nullptr, *loss = nullptr, *dlogits = nullptr, *pred = nullptr, *pred_feats = nullptr,
+        *pred_entropy = nullptr;
+  int* idx = nullptr;
+  std::vector<Tape> tape;
+  // backward temporaries
+  float *DX = nullptr, *DX2 = nullptr, *DH = nullptr, *ws = nullptr;
+  bf16 *DXB = nullptr, *DZ = nullptr, *DAO = nullptr, *DQKV = nullptr, *U = nullptr;
+
+  // LoRA
+  float *lp = nullptr, *lg = nullptr, *l0 = nullptr, *lm = nullptr, *lv = nullptr;
+  int64_t lora_per_layer = 0, lora_total = 0;
+  std::vector<LoraPacked> pk;
+  int opt_step = 0;
+  bool b_zero = true, init_b_zero = true;
+  std::vector<float> host_init;  // mirror of l0 to know whether B0 == 0
+
+  // train-forward bookkeeping
+  int last_train_views = 0;
+  const float* last_train_in = nullptr;
+
+  // graphs
+  bool graphs = true;
+  std::vector<GraphEntry> gcache;
+  int64_t launches = 0, last_launches = 0;
+};
+
+namespace {
+
+#define CK(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      c->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                            \
+      return TTL_E_CUDA;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+#define RET_IF(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != TTL_OK) return _r;\
+  } while (0)
+
+template <typename Tp>
+int dalloc(ttl_ctx* c, Tp** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(Tp) + 256);
+  if (e != cudaSuccess) {
+    c->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+    return TTL_E_NOMEM;
+  }
+  cudaMemset(q, 0, n * sizeof(Tp) + 256);
+  c->allocs.push_back(q);
+  *p = reinterpret_cast<Tp*>(q);
+  return TTL_OK;
+}
+
+int check_launch(ttl_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return TTL_E_CUDA;
+  }
+  return TTL_OK;
+}
+
+int gemm(ttl_ctx* c, GemmArgs& g, cudaStream_t st) {
+  cudaError_t e = gemm_launch(g, st, c->num_sms);
+  c->launches++;
+  if (e != cudaSuccess) {
+    c->err = std::string("gemm: ") + gemm_last_error() + " / " + cudaGetErrorString(e);
+    return e == cudaErrorInvalidValue ? TTL_E_SHAPE : TTL_E_CUDA;
+  }
+  return TTL_OK;
+}
+
+GemmOperand opnd(const bf16* p, int rows, int k, int ld) {
+  GemmOperand o;
+  o.ptr = p; o.rows = rows; o.k = k; o.ld = ld;
+  return o;
+}
+
+bool has_lora(const ttl_ctx* c, int layer) { return layer >= c->lo && layer <= c->hi; }
+
+// ---------------------------------------------------------------------------------------------- forward pieces
+int embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
+  if (images != nullptr) {  // nullptr: graph capture, im2col is issued by the caller outside the graph
+    launch_im2col(images, c->patches, V, c->cfg.image_size, c->cfg.patch, st);
+  }
+  c->launches++;
+  GemmArgs g;
+  g.a1 = opnd(c->patches, V * c->T, c->Kp, c->Kp);
+  g.b1 = opnd(c->wpatch, c->d, c->Kp, c->Kp);
+  g.M = V * c->T; g.N = c->d; g.epi = EPI_PATCH_F32; g.out = x; g.ldo = c->d; g.pos = c->pos; g.tokens_per_view = c->T;
+  RET_IF(gemm(c, g, st));
+  launch_embed_preln(x, c->cls, c->pos, c->preg, c->preb, V, c->tokens, c->d, c->cfg.ln_eps, st);
+  c->launches++;
+  return check_launch(c, "embed");
+}
+
+// One encoder layer.  tp == nullptr: inference buffers; else train mode (tape kept for the backward).
+int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_out, int V, bool lora_on, Tape* tp,
+              cudaStream_t st) {
+  const LayerW& w = c->lw[layer];
+  const int M = V * c->tokens, d = c->d, F = c->F;
+  bf16* h1 = tp ? tp->h1 : c->Hb;
+  bf16* qkv = tp ? tp->qkv : c->QKV;
+  bf16* ao = tp ? tp->ao : c->AO;
+  bf16* h2 = tp ? tp->h2 : c->Hb;
+  bf16* gb = tp ? tp->g : c->Gb;
+  bf16* Tb = tp ? tp->T : c->Tm;
+  const bool lora = has_lora(c, layer);
+  launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+  c->launches++;
+  if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T  (needed by dB even while B == 0)
+    GemmArgs g;
+    g.a1 = opnd(h1, M, d, d);
+    g.b1 = opnd(c->pk[layer - c->lo].a_ext, 64, d, d);
+    g.M = M; g.N = 64; g.epi = EPI_BF16; g.out = Tb; g.ldo = 64;
+    RET_IF(gemm(c, g, st));
+  }
+  {
+    GemmArgs g;
+    g.a1 = opnd(h1, M, d, d);
+    g.b1 = opnd(w.wqkv, 3 * d, d, d);
+    if (lora && lora_on) {
+      g.a2 = opnd(Tb, M, 64, 64);
+      g.b2 = opnd(c->pk[layer - c->lo].b_ext, 3 * d, 64, 64);
+    }
+    g.M = M; g.N = 3 * d; g.epi = EPI_BF16; g.bias = w.bqkv; g.out = qkv; g.ldo = 3 * d;
+    RET_IF(gemm(c, g, st));
+  }
+  launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
+  c->launches++;
+  {
+    GemmArgs g;
+    g.a1 = opnd(ao, M, d, d);
+    g.b1 = opnd(w.wo, d, d, d);
+    g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.bo; g.out = x_mid; g.ldo = d; g.resid = x_in; g.ldr = d;
+    RET_IF(gemm(c, g, st));
+  }
+  launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
+  c->launches++;
+  {
+    GemmArgs g;
+    g.a1 = opnd(h2, M, d, d);
+    g.b1 = opnd(w.w1, F, d, d);
+    g.M = M; g.N = F; g.epi = EPI_GELU; g.bias = w.b1; g.out = gb; g.ldo = F; g.out2 = tp ? tp->z : nullptr;
+    RET_IF(gemm(c, g, st));
+  }
+  {
+    GemmArgs g;
+    g.a1 = opnd(gb, M, F, F);
+    g.b1 = opnd(w.w2, d, F, F);
+    g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.b2; g.out = x_out; g.ldo = d; g.resid = x_mid; g.ldr = d;
+    RET_IF(gemm(c, g, st));
+  }
+  return check_launch(c, "run_layer");
+}
+
+// layers [0, lo) on all views: images -> XK
+int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
+  RET_IF(embed(c, images, V, c->XK, st));
+  for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, c->XK, c->XB, c->XK, V, false, nullptr, st));
+  return TTL_OK;
+}
+
+// layers [lo, L) in inference mode from x_in (V views) -> feats/logits/entropy written to the given buffers
+int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float* logits, float* entropy,
+                       cudaStream_t st) {
+  const float* cur = x_in;
+  for (int l = c->lo; l < c->L; ++l) {
+    RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, !c->b_zero, nullptr, st));
+    cur = c->XA;
+  }
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
+  c->launches += 2;
+  return check_launch(c, "forward_tail_infer");
+}
+
+// layers [lo, L) in train mode from x_in (G views): tape + feats_c
+int forward_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
+  const float* cur = x_in;
+  for (int l = c->lo; l < c->L; ++l) {
+    Tape& tp = c->tape[l - c->lo];
+    RET_IF(run_layer(c, l, cur, tp.x_mid, tp.x_out, G, !c->b_zero, &tp, st));
+    cur = tp.x_out;
+  }
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  c->launches++;
+  c->last_train_views = G;
+  c->last_train_in = x_in;
+  return check_launch(c, "forward_tail_train");
+}
+
+// dlogits_c [G,C] -> LoRA gradients (overwrites c->lg)
+int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
+  if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
+  const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
+  const float* x_last = c->tape[c->n_train - 1].x_out;
+  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->DX, c->DXB, G, c->C,
+                  c->P, c->tokens, d, c->cfg.ln_eps, st);
+  c->launches += 1;
+  float* dx = c->DX;
+  float* dx2 = c->DX2;
+  for (int l = c->L - 1; l >= c->lo; --l) {
+    const LayerW& w = c->lw[l];
+    Tape& tp = c->tape[l - c->lo];
+    const float* x_in = (l == c->lo) ? c->last_train_in : c->tape[l - c->lo - 1].x_out;
+    {  // dz = (dx_out W2) * gelu'(z)
+      GemmArgs g;
+      g.a1 = opnd(c->DXB, Mg, d, d);
+      g.b1 = opnd(w.w2T, F, d, d);
+      g.M = Mg; g.N = F; g.epi = EPI_GELU_BWD; g.out = c->DZ; g.ldo = F; g.aux = tp.z;
+      RET_IF(gemm(c, g, st));
+    }
+    {  // dh2 = dz W1
+      GemmArgs g;
+      g.a1 = opnd(c->DZ, Mg, F, F);
+      g.b1 = opnd(w.w1T, d, F, F);
+      g.M = Mg; g.N = d; g.epi = EPI_F32; g.out = c->DH; g.ldo = d;
+      RET_IF(gemm(c, g, st));
+    }
+    launch_layernorm_bwd(c->DH, tp.x_mid, w.ln2g, dx, dx2, c->DXB, Mg, d, c->cfg.ln_eps, st);   // dx_mid
+    c->launches++;
+    {  // d attn_out = dx_mid Wo
+      GemmArgs g;
+      g.a1 = opnd(c->DXB, Mg, d, d);
+      g.b1 = opnd(w.woT, d, d, d);
+      g.M = Mg; g.N = d; g.epi = EPI_BF16; g.out = c->DAO; g.ldo = d;
+      RET_IF(gemm(c, g, st));
+    }
+    launch_attention_bwd(tp.qkv, tp.ao, c->DAO, tp.lse, c->DQKV, G, c->tokens, c->H, 0.125f, st);
+    c->launches++;
+    const bool lora = has_lora(c, l);
+    if (lora) {
+      float* gl = c->lg + static_cast<int64_t>(l - c->lo) * c->lora_per_layer;
+      float* gAq = gl;
+      float* gBq = gl + r * d;
+      float* gAv = gl + 2 * r * d;
+      float* gBv = gl + 3 * r * d;
+      // dB = s * dY^T (X A^T)
+      launch_skinny_reduce(c->DQKV, 3 * d, d, tp.T, 64, r, Mg, c->s, gBq, 0, c->ws, st);
+      launch_skinny_reduce(c->DQKV + 2 * d, 3 * d, d, tp.T + r, 64, r, Mg, c->s, gBv, 0, c->ws, st);
+      c->launches += 4;
+      if (!c->b_zero) {  // U = dqkv (s B)  ;  dA = U^T X
+        GemmArgs g;
+        g.a1 = opnd(c->DQKV, Mg, 3 * d, 3 * d);
+        g.b1 = opnd(c->pk[l - c->lo].b_ext_t, 64, 3 * d, 3 * d);
+        g.M = Mg; g.N = 64; g.epi = EPI_BF16; g.out = c->U; g.ldo = 64;
+        RET_IF(gemm(c, g, st));
+        launch_skinny_reduce(tp.h1, d, d, c->U, 64, r, Mg, 1.f, gAq, 1, c->ws, st);
+        launch_skinny_reduce(tp.h1, d, d, c->U + r, 64, r, Mg, 1.f, gAv, 1, c->ws, st);
+        c->launches += 4;
+      } else {  // dA == 0 exactly while B == 0
+        cudaMemsetAsync(gAq, 0, sizeof(float) * r * d, st);
+        cudaMemsetAsync(gAv, 0, sizeof(float) * r * d, st);
+      }
+    }
+    if (l > c->lo) {
+      GemmArgs g;  // dh1 = dqkv Wqkv (+ U [A_q;A_v])
+      g.a1 = opnd(c->DQKV, Mg, 3 * d, 3 * d);
+      g.b1 = opnd(w.wqkvT, d, 3 * d, 3 * d);
+      if (lora && !c->b_zero) {
+        g.a2 = opnd(c->U, Mg, 64, 64);
+        g.b2 = opnd(c->pk[l - c->lo].a_ext_t, d, 64, 64);
+      }
+      g.M = Mg; g.N = d; g.epi = EPI_F32; g.out = c->DH; g.ldo = d;
+      RET_IF(gemm(c, g, st));
+      launch_layernorm_bwd(c->DH, x_in, w.ln1g, dx2, dx, c->DXB, Mg, d, c->cfg.ln_eps, st);  // dx_in -> next dx_out
+      c->launches++;
+    }
+  }
+  return check_launch(c, "backward");
+}
+
+int repack(ttl_ctx* c, cudaStream_t st) {
+  for (int i = 0; i < c->n_lora; ++i) {
+    launch_lora_pack(c->lp + i * c->lora_per_layer, c->pk[i], c->d, c->r, c->s, st);
+    c->launches++;
+  }
+  return check_launch(c, "lora_pack");
+}
+
+int lora_reset(ttl_ctx* c, cudaStream_t st) {
+  launch_lora_reset(c->lp, c->l0, c->lm, c->lv, static_cast<int>(c->lora_total), st);
+  c->launches++;
+  c->opt_step = 0;
+  c->b_zero = c->init_b_zero;
+  return repack(c, st);
+}
+
+int adamw(ttl_ctx* c, const ttl_hparams& hp, cudaStream_t st) {
+  c->opt_step++;
+  launch_adamw(c->lp, c->lg, c->lm, c->lv, static_cast<int>(c->lora_total), c->opt_step, hp.lr, hp.beta1, hp.beta2,
+               hp.eps, hp.weight_decay, st);
+  c->launches++;
+  c->b_zero = false;
+  return repack(c, st);
+}
+
+// The per-sample body (everything after im2col-able input is in place).  Recorded into a CUDA graph when enabled.
+int adapt_body(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
+  RET_IF(lora_reset(c, st));
+  RET_IF(forward_frozen(c, images, V, st));
+  const int K = static_cast<int>(V * hp.selection_p);
+  if (hp.head == TTL_HEAD_TPT) {
+    RET_IF(forward_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    if (hp.tta_steps > 0 && K > 0) {
+      launch_select(c->entropy, V, K, forced ? c->idx : nullptr, c->idx, st);
+      launch_gather_views(c->XK, c->TIN, c->idx, K, c->tokens, c->d, st);
+      c->launches += 2;
+      for (int step = 0; step < hp.tta_steps; ++step) {
+        RET_IF(forward_tail_train(c, c->TIN, K, st));
+        if (step == 0) {
+          launch_tpt_loss(c->logits, c->idx, K, c->C, c->loss, c->dlogits, st);
+        } else {
+          launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, K, c->C, c->P, st);
+          launch_tpt_loss(c->logits_c, nullptr, K, c->C, c->loss, c->dlogits, st);
+          c->launches++;
+        }
+        c->launches++;
+        RET_IF(backward(c, c->dlogits, K, st));
+        RET_IF(adamw(c, hp, st));
+      }
+    }
+  } else {
+    const int nsteps = hp.tta_steps * hp.tta_steps;  // deyo.DeYO loops `steps` times inside the tta_steps loop
+    if (nsteps == 0) RET_IF(forward_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    for (int step = 0; step < nsteps; ++step) {
+      RET_IF(forward_tail_train(c, c->XK, V, st));
+      float* lg = step == 0 ? c->logits : c->logits_c;
+      float* en = step == 0 ? c->entropy : c->entropy_c;
+      launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, V, c->C, c->P, st);
+      launch_deyo_loss(lg, V, c->C, hp.deyo_margin_e0, c->loss, c->dlogits, st);
+      c->launches += 2;
+      RET_IF(backward(c, c->dlogits, V, st));
+      RET_IF(adamw(c, hp, st));
+    }
+  }
+  // predict on view 0 with the adapted factors (ttl.py:350-352); XK rows [0, tokens) are view 0
+  RET_IF(forward_tail_infer(c, c->XK, 1, c->pred_feats, c->pred, c->pred_entropy, st));
+  return TTL_OK;
+}
+
+int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
+  if (!o) return TTL_OK;
+  const int K = static_cast<int>(V * hp.selection_p);
+  if (o->logits0) CK(cudaMemcpyAsync(o->logits0, c->logits, sizeof(float) * V * c->C, kind, st));
+  if (o->entropy) CK(cudaMemcpyAsync(o->entropy, c->entropy, sizeof(float) * V, kind, st));
+  if (o->idx && K > 0) CK(cudaMemcpyAsync(o->idx, c->idx, sizeof(int) * K, kind, st));
+  if (o->loss) CK(cudaMemcpyAsync(o->loss, c->loss, sizeof(float), kind, st));
+  if (o->pred_logits) CK(cudaMemcpyAsync(o->pred_logits, c->pred, sizeof(float) * c->C, kind, st));
+  return TTL_OK;
+}
+
+int validate_run(ttl_ctx* c, int V, const ttl_hparams* hp) {
+  if (!c || !hp) return TTL_E_INVALID;
+  if (V <= 0 || V > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
+  if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
+  if (hp->head != TTL_HEAD_TPT && hp->head != TTL_HEAD_DEYO) { c->err = "unknown head"; return TTL_E_INVALID; }
+  if (hp->tta_steps < 0 || hp->tta_steps > 64) { c->err = "tta_steps out of range"; return TTL_E_INVALID; }
+  if (hp->selection_p < 0.f || hp->selection_p > 1.f) { c->err = "selection_p out of range"; return TTL_E_INVALID; }
+  return TTL_OK;
+}
+
+int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
+  const int64_t before = c->launches;
+  if (!c->graphs || st == nullptr) {  // the legacy default stream cannot be captured
+    int r = adapt_body(c, images_dev, V, *hp, forced, st);
+    c->last_launches = c->launches - before;
+    return r;
+  }
+  GraphKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.n_views = V; key.forced = forced ? 1 : 0; key.hp = *hp;
+  GraphEntry* ge = nullptr;
+  for (auto& e : c->gcache) if (e.key == key) ge = &e;
+  if (!ge) {
+    GraphEntry e;
+    e.key = key;
+    c->gcache.push_back(e);
+    ge = &c->gcache.back();
+  }
+  // The graph reads the views from the library-owned staging buffer (patches are produced from `images_dev` by the
+  // first kernel), so im2col is launched outside the graph with the caller's pointer and the graph starts after it.
+  if (ge->uses == 0) {  // first use: eager (also sets kernel attributes outside capture)
+    int r = adapt_body(c, images_dev, V, *hp, forced, st);
+    ge->uses = 1;
+    ge->launches = c->launches - before;
+    ge->b_zero_after = c->b_zero; ge->opt_step_after = c->opt_step;
+    ge->train_views_after = c->last_train_views; ge->train_in_after = c->last_train_in;
+    c->last_launches = ge->launches;
+    return r;
+  }
+  if (!ge->exec) {
+    // capture with the *same* image pointer semantics: the body consumes `images_dev` only in im2col; to keep the
+    // graph pointer-independent we capture the body on a fixed internal image pointer = c->img_stage (see below).
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int r = adapt_body(c, nullptr, V, *hp, forced, st);  // nullptr -> embed() skips im2col (done by caller below)
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (r != TTL_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(e); return TTL_E_CUDA; }
+    e = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return TTL_E_CUDA; }
+  }
+  launch_im2col(images_dev, c->patches, V, c->cfg.image_size, c->cfg.patch, st);
+  CK(cudaGraphLaunch(ge->exec, st));
+  c->launches = before + ge->launches;
+  c->last_launches = ge->launches;
+  c->b_zero = ge->b_zero_after; c->opt_step = ge->opt_step_after;
+  c->last_train_views = ge->train_views_after; c->last_train_in = ge->train_in_after;
+  ge->uses++;
+  return TTL_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int ttl_version(void) { return 100; }
+
+const char* ttl_last_error(const ttl_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
+  if (!out || !cfg) { g_create_err = "null argument"; return TTL_E_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_err = "no CUDA device (no CPU fallback exists)"; return TTL_E_ARCH; }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return TTL_E_INVALID; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) {
+    g_create_err = "device is not compute capability 10.x (sm_100a only; no fallback)";
+    return TTL_E_ARCH;
+  }
+  if (cfg->width % 128 != 0 || cfg->width > 1024 || cfg->width != cfg->heads * 64 || cfg->image_size % cfg->patch != 0 ||
+      cfg->mlp_dim % 64 != 0 || (cfg->lora_rank != 16 && cfg->lora_rank != 32) || cfg->lora_layer_lo < 0 ||
+      cfg->lora_layer_hi >= cfg->layers || cfg->lora_layer_lo > cfg->lora_layer_hi || cfg->max_views <= 0 ||
+      cfg->max_classes <= 0 || cfg->proj_dim <= 0 || (cfg->patch & 1)) {
+    g_create_err = "unsupported geometry (width%128, head_dim 64, rank 16/32, layer range, even patch)";
+    return TTL_E_SHAPE;
+  }
+  cudaSetDevice(cfg->device);
+  ttl_ctx* c = new ttl_ctx();
+  c->cfg = *cfg;
+  c->num_sms = prop.multiProcessorCount;
+  c->d = cfg->width; c->F = cfg->mlp_dim; c->P = cfg->proj_dim; c->L = cfg->layers; c->H = cfg->heads;
+  c->r = cfg->lora_rank; c->lo = cfg->lora_layer_lo; c->hi = cfg->lora_layer_hi;
+  c->s = cfg->lora_alpha / cfg->lora_rank;
+  c->T = (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch);
+  c->tokens = c->T + 1;
+  c->Kp = (3 * cfg->patch * cfg->patch + 63) / 64 * 64;
+  c->Vm = cfg->max_views; c->Mm = c->Vm * c->tokens; c->Cm = cfg->max_classes;
+  c->n_train = c->L - c->lo; c->n_lora = c->hi - c->lo + 1;
+  const int d = c->d, F = c->F, M = c->Mm;
+  int rc = TTL_OK;
+#define A(p, n) if (rc == TTL_OK) rc = dalloc(c, &(p), static_cast<size_t>(n))
+  A(c->cls, d); A(c->pos, c->tokens * d); A(c->preg, d); A(c->preb, d); A(c->postg, d); A(c->postb, d);
+  A(c->Wp, c->P * d); A(c->wpatch, d * c->Kp); A(c->text, c->Cm * c->P);
+  c->lw.resize(c->L);
+  for (int l = 0; l < c->L && rc == TTL_OK; ++l) {
+    LayerW& w = c->lw[l];
+    A(w.wqkv, 3 * d * d); A(w.wo, d * d); A(w.w1, F * d); A(w.w2, d * F);
+    A(w.bqkv, 3 * d); A(w.bo, d); A(w.b1, F); A(w.b2, d);
+    A(w.ln1g, d); A(w.ln1b, d); A(w.ln2g, d); A(w.ln2b, d);
+    if (l >= c->lo) { A(w.wqkvT, 3 * d * d); A(w.woT, d * d); A(w.w1T, F * d); A(w.w2T, d * F); }
+  }
+  A(c->patches, static_cast<size_t>(c->Vm) * c->T * c->Kp);
+  A(c->Hb, static_cast<size_t>(M) * d); A(c->QKV, static_cast<size_t>(M) * 3 * d); A(c->AO, static_cast<size_t>(M) * d);
+  A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64);
+  A(c->XK, static_cast<size_t>(M) * d); A(c->XA, static_cast<size_t>(M) * d); A(c->XB, static_cast<size_t>(M) * d);
+  A(c->TIN, static_cast<size_t>(M) * d);
+  A(c->feats, c->Vm * c->P); A(c->feats_c, c->Vm * c->P); A(c->logits, c->Vm * c->Cm); A(c->logits_c, c->Vm * c->Cm);
+  A(c->entropy, c->Vm); A(c->entropy_c, c->Vm); A(c->loss, 4); A(c->dlogits, c->Vm * c->Cm); A(c->pred, c->Cm);
+  A(c->pred_feats, c->P); A(c->pred_entropy, 4); A(c->idx, c->Vm);
+  c->tape.resize(c->n_train);
+  for (int t = 0; t < c->n_train && rc == TTL_OK; ++t) {
+    Tape& tp = c->tape[t];
+    A(tp.h1, static_cast<size_t>(M) * d); A(tp.T, static_cast<size_t>(M) * 64); A(tp.qkv, static_cast<size_t>(M) * 3 * d);
+    A(tp.ao, static_cast<size_t>(M) * d); A(tp.h2, static_cast<size_t>(M) * d); A(tp.z, static_cast<size_t>(M) * F);
+    A(tp.g, static_cast<size_t>(M) * F); A(tp.lse, static_cast<size_t>(c->Vm) * c->H * c->tokens);
+    A(tp.x_mid, static_cast<size_t>(M) * d); A(tp.x_out, static_cast<size_t>(M) * d);
+  }
+  A(c->DX, static_cast<size_t>(M) * d); A(c->DX2, static_cast<size_t>(M) * d); A(c->DH, static_cast<size_t>(M) * d);
+  A(c->DXB, static_cast<size_t>(M) * d); A(c->DZ, static_cast<size_t>(M) * F); A(c->DAO, static_cast<size_t>(M) * d);
+  A(c->DQKV, static_cast<size_t>(M) * 3 * d); A(c->U, static_cast<size_t>(M) * 64);
+  A(c->ws, static_cast<size_t>((M + 127) / 128) * d * 32);
+  c->lora_per_layer = 4LL * c->r * d;
+  c->lora_total = c->lora_per_layer * c->n_lora;
+  A(c->lp, c->lora_total); A(c->lg, c->lora_total); A(c->l0, c->lora_total); A(c->lm, c->lora_total); A(c->lv, c->lora_total);
+  c->pk.resize(c->n_lora);
+  for (int i = 0; i < c->n_lora && rc == TTL_OK; ++i) {
+    A(c->pk[i].a_ext, 64 * d); A(c->pk[i].a_ext_t, d * 64); A(c->pk[i].b_ext, 3 * d * 64); A(c->pk[i].b_ext_t, 64 * 3 * d);
+  }
+#undef A
+  c->host_init.assign(c->lora_total, 0.f);
+  if (rc != TTL_OK) {
+    g_create_err = c->err;
+    ttl_destroy(c);
+    return rc;
+  }
+  cudaDeviceSynchronize();
+  *out = c;
+  return TTL_OK;
+}
+
+void ttl_destroy(ttl_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& e : c->gcache) if (e.exec) cudaGraphExecDestroy(e.exec);
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+}
+
+static int upload_f32(ttl_ctx* c, float* dst, const float* host, int64_t n) {
+  CK(cudaMemcpy(dst, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+  return TTL_OK;
+}
+// host [rows, cols] fp32 -> device bf16 at dst (ld_dst), optionally also the transpose at dstT ([cols, rows], ld = ldT)
+static int upload_bf16(ttl_ctx* c, bf16* dst, int ld_dst, bf16* dstT, int ldT, int rowT0, const float* host, int rows,
+                       int cols) {
+  std::vector<uint16_t> tmp(static_cast<size_t>(rows) * cols);
+  for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = f2bf(host[i]);
+  CK(cudaMemcpy2D(dst, sizeof(uint16_t) * ld_dst, tmp.data(), sizeof(uint16_t) * cols, sizeof(uint16_t) * cols, rows,
+                  cudaMemcpyHostToDevice));
+  if (dstT) {
+    std::vector<uint16_t> tt(static_cast<size_t>(rows) * cols);
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < cols; ++j) tt[static_cast<size_t>(j) * rows + i] = tmp[static_cast<size_t>(i) * cols + j];
+    // transpose is [cols, rows]; placed at column offset rowT0 of a [cols, ldT] matrix
+    CK(cudaMemcpy2D(dstT + rowT0, sizeof(uint16_t) * ldT, tt.data(), sizeof(uint16_t) * rows, sizeof(uint16_t) * rows,
+                    cols, cudaMemcpyHostToDevice));
+  }
+  return TTL_OK;
+}
+
+int ttl_set_weight(ttl_ctx* c, int32_t layer, int32_t kind, const float* host, int64_t numel) {
+  if (!c || !host) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  const int d = c->d, F = c->F;
+  auto need = [&](int64_t n) { if (numel != n) { c->err = "ttl_set_weight: wrong numel"; return false; } return true; };
+  if (kind < 16) {
+    switch (kind) {
+      case TTL_W_CLASS_EMB: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->cls, host, numel);
+      case TTL_W_POS_EMB: if (!need(static_cast<int64_t>(c->tokens) * d)) return TTL_E_SHAPE; return upload_f32(c, c->pos, host, numel);
+      case TTL_W_PRE_LN_G: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->preg, host, numel);
+      case TTL_W_PRE_LN_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->preb, host, numel);
+      case TTL_W_POST_LN_G: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->postg, host, numel);
+      case TTL_W_POST_LN_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->postb, host, numel);
+      case TTL_W_VIS_PROJ: if (!need(static_cast<int64_t>(c->P) * d)) return TTL_E_SHAPE; return upload_f32(c, c->Wp, host, numel);
+      case TTL_W_PATCH_EMB: {
+        const int K = 3 * c->cfg.patch * c->cfg.patch;
+        if (!need(static_cast<int64_t>(d) * K)) return TTL_E_SHAPE;
+        return upload_bf16(c, c->wpatch, c->Kp, nullptr, 0, 0, host, d, K);   // padding columns stay zero
+      }
+      default: c->err = "ttl_set_weight: unknown kind"; return TTL_E_INVALID;
+    }
+  }
+  if (layer < 0 || layer >= c->L) { c->err = "ttl_set_weight: bad layer"; return TTL_E_INVALID; }
+  LayerW& w = c->lw[layer];
+  const bool tr = layer >= c->lo;
+  switch (kind) {
+    case TTL_W_LN1_G: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.ln1g, host, numel);
+    case TTL_W_LN1_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.ln1b, host, numel);
+    case TTL_W_LN2_G: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.ln2g, host, numel);
+    case TTL_W_LN2_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.ln2b, host, numel);
+    case TTL_W_Q_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.bqkv, host, numel);
+    case TTL_W_K_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.bqkv + d, host, numel);
+    case TTL_W_V_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.bqkv + 2 * d, host, numel);
+    case TTL_W_O_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.bo, host, numel);
+    case TTL_W_FC1_B: if (!need(F)) return TTL_E_SHAPE; return upload_f32(c, w.b1, host, numel);
+    case TTL_W_FC2_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, w.b2, host, numel);
+    case TTL_W_Q_W: case TTL_W_K_W: case TTL_W_V_W: {
+      if (!need(static_cast<int64_t>(d) * d)) return TTL_E_SHAPE;
+      const int blk = kind == TTL_W_Q_W ? 0 : (kind == TTL_W_K_W ? 1 : 2);
+      // wqkv rows [blk*d, (blk+1)*d); transpose wqkvT [d, 3d] columns [blk*d, ...)
+      return upload_bf16(c, w.wqkv + static_cast<size_t>(blk) * d * d, d, tr ? w.wqkvT : nullptr, 3 * d, blk * d, host, d, d);
+    }
+    case TTL_W_O_W: if (!need(static_cast<int64_t>(d) * d)) return TTL_E_SHAPE;
+      return upload_bf16(c, w.wo, d, tr ? w.woT : nullptr, d, 0, host, d, d);
+    case TTL_W_FC1_W: if (!need(static_cast<int64_t>(F) * d)) return TTL_E_SHAPE;
+      return upload_bf16(c, w.w1, d, tr ? w.w1T : nullptr, F, 0, host, F, d);     // w1T [d, F]
+    case TTL_W_FC2_W: if (!need(static_cast<int64_t>(d) * F)) return TTL_E_SHAPE;
+      return upload_bf16(c, w.w2, F, tr ? w.w2T : nullptr, d, 0, host, d, F);     // w2T [F, d]
+    default: c->err = "ttl_set_weight: unknown kind"; return TTL_E_INVALID;
+  }
+}
+
+int ttl_set_text_features(ttl_ctx* c, const float* host_text, int32_t n_classes, int32_t proj_dim, float logit_scale) {
+  if (!c || !host_text) return TTL_E_INVALID;
+  if (proj_dim != c->P || n_classes <= 0 || n_classes > c->Cm) { c->err = "text features: bad shape"; return TTL_E_SHAPE; }
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  RET_IF(upload_f32(c, c->text, host_text, static_cast<int64_t>(n_classes) * proj_dim));
+  if (n_classes != c->C) {   // C is baked into captured graphs
+    for (auto& e : c->gcache) if (e.exec) cudaGraphExecDestroy(e.exec);
+    c->gcache.clear();
+  }
+  c->C = n_classes;
+  c->logit_scale_exp = std::exp(logit_scale);
+  return TTL_OK;
+}
+
+static int lora_slot(ttl_ctx* c, int layer, int which, int64_t* off, int64_t* n) {
+  if (layer < c->lo || layer > c->hi || which < 0 || which > 3) { c->err = "lora: bad layer/which"; return TTL_E_INVALID; }
+  const int64_t rd = static_cast<int64_t>(c->r) * c->d;
+  *off = static_cast<int64_t>(layer - c->lo) * c->lora_per_layer + which * rd;
+  *n = rd;
+  return TTL_OK;
+}
+
+int ttl_lora_set_init(ttl_ctx* c, int32_t layer, int32_t which, const float* host, int64_t numel) {
+  if (!c || !host) return TTL_E_INVALID;
+  int64_t off, n;
+  RET_IF(lora_slot(c, layer, which, &off, &n));
+  if (numel != n) { c->err = "lora_set_init: wrong numel"; return TTL_E_SHAPE; }
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  RET_IF(upload_f32(c, c->l0 + off, host, n));
+  RET_IF(upload_f32(c, c->lp + off, host, n));
+  std::memcpy(c->host_init.data() + off, host, sizeof(float) * n);
+  bool bz = true;
+  const int64_t rd = static_cast<int64_t>(c->r) * c->d;
+  for (int i = 0; i < c->n_lora && bz; ++i)
+    for (int wch = 1; wch < 4 && bz; wch += 2) {
+      const float* p = c->host_init.data() + i * c->lora_per_layer + wch * rd;
+      for (int64_t k = 0; k < rd; ++k) if (p[k] != 0.f) { bz = false; break; }
+    }
+  c->init_b_zero = bz;
+  c->b_zero = false;  // until the next reset/touch
+  return TTL_OK;
+}
+
+int ttl_lora_reset(ttl_ctx* c, void* stream) {
+  if (!c) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  return lora_reset(c, static_cast<cudaStream_t>(stream));
+}
+
+int ttl_lora_get(ttl_ctx* c, int32_t layer, int32_t which, int32_t what, float* host_out, int64_t numel) {
+  if (!c || !host_out) return TTL_E_INVALID;
+  int64_t off, n;
+  RET_IF(lora_slot(c, layer, which, &off, &n));
+  if (numel != n) { c->err = "lora_get: wrong numel"; return TTL_E_SHAPE; }
+  const float* src = what == TTL_LORA_PARAM ? c->lp : (what == TTL_LORA_GRAD ? c->lg : c->l0);
+  cudaSetDevice(c->cfg.device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host_out, src + off, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return TTL_OK;
+}
+
+int ttl_lora_device_ptr(ttl_ctx* c, int32_t layer, int32_t which, int32_t what, float** dev_ptr, int64_t* numel) {
+  if (!c || !dev_ptr) return TTL_E_INVALID;
+  int64_t off, n;
+  RET_IF(lora_slot(c, layer, which, &off, &n));
+  float* src = what == TTL_LORA_PARAM ? c->lp : (what == TTL_LORA_GRAD ? c->lg : c->l0);
+  *dev_ptr = src + off;
+  if (numel) *numel = n;
+  return TTL_OK;
+}
+
+int ttl_lora_touch(ttl_ctx* c, void* stream) {
+  if (!c) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  c->b_zero = false;  // factors were written from outside: assume B != 0
+  return repack(c, static_cast<cudaStream_t>(stream));
+}
+
+int ttl_adamw_step(ttl_ctx* c, const ttl_hparams* hp, void* stream) {
+  if (!c || !hp) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  return adamw(c, *hp, static_cast<cudaStream_t>(stream));
+}
+
+int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t train, float* logits_dev, void* stream) {
+  if (!c || !images_dev) return TTL_E_INVALID;
+  if (n_views <= 0 || n_views > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
+  if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET_IF(forward_frozen(c, images_dev, n_views, st));
+  if (train) {
+    RET_IF(forward_tail_train(c, c->XK, n_views, st));
+    launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits, c->entropy, n_views, c->C, c->P, st);
+    c->launches++;
+  } else {
+    RET_IF(forward_tail_infer(c, c->XK, n_views, c->feats, c->logits, c->entropy, st));
+  }
+  if (logits_dev) CK(cudaMemcpyAsync(logits_dev, c->logits, sizeof(float) * n_views * c->C, cudaMemcpyDeviceToDevice, st));
+  return check_launch(c, "ttl_forward");
+}
+
+int ttl_backward(ttl_ctx* c, const float* dlogits_dev, void* stream) {
+  if (!c || !dlogits_dev) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  return backward(c, dlogits_dev, c->last_train_views, static_cast<cudaStream_t>(stream));
+}
+
+int ttl_adapt_predict(ttl_ctx* c, const float* images_dev, int32_t n_views, const ttl_hparams* hp,
+                      const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream) {
+  RET_IF(validate_run(c, n_views, hp));
+  if (!images_dev) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = static_cast<int>(n_views * hp->selection_p);
+  const bool forced = forced_idx_dev != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
+  RET_IF(adapt_predict_impl(c, images_dev, n_views, hp, forced, st));
+  return copy_outputs(c, out_dev, n_views, *hp, cudaMemcpyDeviceToDevice, st);
+}
+
+int ttl_adapt_predict_host(ttl_ctx* c, const float* images_host, int32_t n_views, const ttl_hparams* hp,
+                           const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream) {
+  RET_IF(validate_run(c, n_views, hp));
+  if (!images_host) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // stage the views in TIN's tail?  No: a dedicated staging area is the (otherwise idle at this point) DZ buffer,
+  // which is >= V*3*S*S*4 bytes for every supported geometry (checked).
+  const size_t img_bytes = static_cast<size_t>(n_views) * 3 * c->cfg.image_size * c->cfg.image_size * sizeof(float);
+  const size_t dz_bytes = static_cast<size_t>(c->Mm) * c->F * sizeof(bf16);
+  if (img_bytes > dz_bytes) { c->err = "host staging buffer too small"; return TTL_E_SHAPE; }
+  float* stage = reinterpret_cast<float*>(c->DZ);
+  CK(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  const int K = static_cast<int>(n_views * hp->selection_p);
+  const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K, cudaMemcpyHostToDevice, st));
+  RET_IF(adapt_predict_impl(c, stage, n_views, hp, forced, st));
+  RET_IF(copy_outputs(c, out_host, n_views, *hp, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TTL_OK;
+}
+
+int ttl_set_graphs(ttl_ctx* c, int32_t enabled) {
+  if (!c) return TTL_E_INVALID;
+  c->graphs = enabled != 0;
+  return TTL_OK;
+}
+
+int64_t ttl_last_launch_count(const ttl_ctx* c) { return c ? c->last_launches : 0; }
+
+// ---------------------------------------------------------------------------------- single-kernel entries
+static int op_done(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return TTL_E_CUDA;
+  }
+  return TTL_OK;
+}
+
+int ttl_op_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int32_t V,
+                          int32_t C, int32_t P, void* stream) {
+  launch_logits_entropy(feats, text, scale, logits, entropy, V, C, P, static_cast<cudaStream_t>(stream));
+  return op_done("logits_entropy");
+}
+int ttl_op_select(const float* entropy, int32_t V, int32_t K, int32_t* idx, void* stream) {
+  launch_select(entropy, V, K, nullptr, idx, static_cast<cudaStream_t>(stream));
+  return op_done("select");
+}
+int ttl_op_tpt_loss(const float* logits, const int32_t* idx, int32_t K, int32_t C, float* loss, float* dlogits,
+                    void* stream) {
+  launch_tpt_loss(logits, idx, K, C, loss, dlogits, static_cast<cudaStream_t>(stream));
+  return op_done("tpt_loss");
+}
+int ttl_op_deyo_loss(const float* logits, int32_t V, int32_t C, float e0, float* loss, float* dlogits, void* stream) {
+  launch_deyo_loss(logits, V, C, e0, loss, dlogits, static_cast<cudaStream_t>(stream));
+  return op_done("deyo_loss");
+}
+int ttl_op_gemm(const void* a, const void* b, const void* a2, const void* b2, int32_t M, int32_t N, int32_t K,
+                int32_t K2, int32_t epi, const float* bias, void* out, void* out2, const float* resid, const void* aux,
+                const float* pos, int32_t tokens_per_view, int32_t block_n, void* stream) {
+  GemmArgs g;
+  g.a1 = opnd(static_cast<const bf16*>(a), M, K, K);
+  g.b1 = opnd(static_cast<const bf16*>(b), N, K, K);
+  if (a2 && K2 > 0) {
+    g.a2 = opnd(static_cast<const bf16*>(a2), M, K2, K2);
+    g.b2 = opnd(static_cast<const bf16*>(b2), N, K2, K2);
+  }
+  g.M = M; g.N = N; g.epi = epi; g.bias = bias; g.out = out; g.ldo = N; g.out2 = out2; g.resid = resid; g.ldr = N;
+  g.aux = static_cast<const bf16*>(aux); g.pos = pos; g.tokens_per_view = tokens_per_view; g.force_block_n = block_n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = gemm_launch(g, static_cast<cudaStream_t>(stream), sms);
+  if (e != cudaSuccess) {
+    g_create_err = std::string("gemm: ") + gemm_last_error() + " / " + cudaGetErrorString(e);
+    return e == cudaErrorInvalidValue ? TTL_E_SHAPE : TTL_E_CUDA;
+  }
+  return TTL_OK;
+}
+int ttl_op_layernorm(const float* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t d, float eps,
+                     void* stream) {
+  if (d % 128 != 0 || d > 1024) { g_create_err = "layernorm: d must be a multiple of 128 <= 1024"; return TTL_E_SHAPE; }
+  launch_layernorm(x, static_cast<bf16*>(y), gamma, beta, rows, d, eps, static_cast<cudaStream_t>(stream));
+  return op_done("layernorm");
+}
+int ttl_op_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx, void* dxb,
+                         int32_t rows, int32_t d, float eps, void* stream) {
+  if (d % 128 != 0 || d > 1024) { g_create_err = "layernorm_bwd: d must be a multiple of 128 <= 1024"; return TTL_E_SHAPE; }
+  launch_layernorm_bwd(dy, x, gamma, dres, dx, static_cast<bf16*>(dxb), rows, d, eps, static_cast<cudaStream_t>(stream));
+  return op_done("layernorm_bwd");
+}
+int ttl_op_attention_fwd(const void* qkv, void* out, float* lse, int32_t V, int32_t tokens, int32_t heads, float scale,
+                         void* stream) {
+  if (attention_fwd_smem(tokens) > 227 * 1024) { g_create_err = "attention: too many tokens"; return TTL_E_SHAPE; }
+  launch_attention_fwd(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, V, tokens, heads, scale,
+                       static_cast<cudaStream_t>(stream));
+  return op_done("attention_fwd");
+}
+int ttl_op_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t V,
+                         int32_t tokens, int32_t heads, float scale, void* stream) {
+  if (attention_bwd_smem(tokens) > 227 * 1024) { g_create_err = "attention_bwd: too many tokens"; return TTL_E_SHAPE; }
+  launch_attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,
+                       static_cast<bf16*>(dqkv), V, tokens, heads, scale, static_cast<cudaStream_t>(stream));
+  return op_done("attention_bwd");
+}
+int ttl_op_im2col(const float* images, void* patches, int32_t V, int32_t S, int32_t p, void* stream) {
+  launch_im2col(images, static_cast<bf16*>(patches), V, S, p, static_cast<cudaStream_t>(stream));
+  return op_done("im2col");
+}
+int ttl_op_adamw(float* p, const float* g, float* m, float* v, int32_t n, int32_t step, float lr, float b1, float b2,
+                 float eps, float wd, void* stream) {
+  launch_adamw(p, g, m, v, n, step, lr, b1, b2, eps, wd, static_cast<cudaStream_t>(stream));
+  return op_done("adamw");
+}
+int ttl_op_skinny_reduce(const void* wide, int32_t ldw, int32_t nw, const void* narrow, int32_t ldn, int32_t nn,
+                         int32_t M, float scale, float* out, int32_t transpose_out, float* ws, void* stream) {
+  if (nw % 64 != 0 || (nn != 16 && nn != 32)) { g_create_err = "skinny_reduce: nw%64, nn in {16,32}"; return TTL_E_SHAPE; }
+  launch_skinny_reduce(static_cast<const bf16*>(wide), ldw, nw, static_cast<const bf16*>(narrow), ldn, nn, M, scale, out,
+                       transpose_out, ws, static_cast<cudaStream_t>(stream));
+  return op_done("skinny_reduce");
+}
+
+}  // extern "C"

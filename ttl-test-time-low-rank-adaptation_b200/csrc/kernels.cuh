@@ -1,0 +1,75 @@
+// Launchers of the non-GEMM kernels (rowops.cu, attention.cu, head.cu, lora.cu).  All enqueue on the given
+// stream and never synchronise.  Shapes use the reference's vocabulary: a "view" is one augmented crop of the
+// test image (ttl.py:324-336), a view has `tokens` rows (CLS + patches) of width d.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ttl {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- rowops.cu
+// images fp32 [V,3,S,S] -> patches bf16 [V*T, 3*p*p] in conv-weight order (c, i, j)  (HF CLIPVisionEmbeddings conv k=p s=p)
+void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cudaStream_t st);
+// x[V*tokens, d] holds patch rows = conv + pos (GEMM epilogue); writes CLS rows = cls + pos[0], then pre-LN in place.
+void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
+                        int tokens, int d, float eps, cudaStream_t st);
+// y(bf16) = LN(x) * gamma + beta, one warp per row, fp32 statistics.
+void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
+                      cudaStream_t st);
+// dx = dres + LN'(x)^T (dy * gamma); statistics recomputed from x.  dres nullable.  dx_bf16 nullable.
+void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
+                          bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st);
+// dst[g*tokens + t, :] = src[view_idx[g]*tokens + t, :]   (view_idx on device)
+void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int tokens, int d,
+                         cudaStream_t st);
+
+// ---- attention.cu   qkv bf16 [V*tokens, 3d] (q | k | v, heads concatenated, 64 per head)
+// out bf16 [V*tokens, d]; lse (nullable) fp32 [V, heads, tokens] natural-log softmax normaliser of scale*q.k
+void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                          cudaStream_t st);
+// dqkv bf16 [V*tokens, 3d]  from dout bf16 [V*tokens, d], qkv, out, lse
+void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
+                          int tokens, int heads, float scale, cudaStream_t st);
+size_t attention_fwd_smem(int tokens);
+size_t attention_bwd_smem(int tokens);
+
+// ---- head.cu
+// pooled = LN(x[v*tokens + 0, :]) ; feats[v,:] = Wp[P,d] @ pooled  (HF post_layernorm + visual_projection)
+void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* feats, int V,
+                         int tokens, int d, int P, float eps, cudaStream_t st);
+// logits[v,c] = scale * <feats[v]/|feats[v]|, T[c]> ; entropy[v] = H(softmax(logits[v]))   (custom_clip.py:680-687, ttl.py:51)
+void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
+                           int C, int P, cudaStream_t st);
+// idx[0..K) = argsort(entropy, stable)[:K]  (ttl.py:52; ties -> lowest index).  forced_idx (nullable) overrides.
+void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st);
+// marginal-entropy loss of the K rows logits[idx[k]] (ttl.py:56-61) and its gradient, compact: dlogits[K,C]
+void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st);
+// weighted-entropy (DeYO, default flags) loss over all V rows and gradient dlogits[V,C]  (deyo.py:97-181)
+void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st);
+// head backward for G compact views: dlogits[G,C] -> dx[G*tokens, d] (fp32, zero except CLS rows) + bf16 copy.
+void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
+                     const float* x, const float* gamma, float* dx, bf16* dx_bf16, int G, int C, int P, int tokens,
+                     int d, float eps, cudaStream_t st);
+
+// ---- lora.cu   per-layer fp32 master tensors in the reference's tuple order (A_q[r,d], B_q[d,r], A_v[r,d], B_v[d,r])
+struct LoraPacked {       // bf16 operands consumed by the GEMM's second operand pair (64 = padded 2r)
+  bf16* a_ext;            // [64, d]   rows 0..r-1 = A_q, r..2r-1 = A_v, rest 0          (T = h1 @ a_ext^T)
+  bf16* a_ext_t;          // [d, 64]   transpose of a_ext                                  (dh1 += U @ a_ext_t^T)
+  bf16* b_ext;            // [3d, 64]  rows of q: s*B_q in cols 0..r-1; rows of v: s*B_v in cols r..2r-1   (qkv += T @ b_ext^T)
+  bf16* b_ext_t;          // [64, 3d]  transpose of b_ext                                  (U = dqkv @ b_ext_t^T)
+};
+void launch_lora_pack(const float* params, LoraPacked pk, int d, int r, float s, cudaStream_t st);
+// out[w, j] (or out[j, w] if transpose_out) = scale * sum_m Wd[m, w] * Nr[m, j];  w < nw (multiple of 64), j < 16 * nj16
+// Deterministic two-pass reduction (partials in workspace `ws`, >= ceil(M/256)*nw*nn floats).
+void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
+                          float* out, int transpose_out, float* ws, cudaStream_t st);
+// Fused AdamW (torch.optim.AdamW rule, ttl.py:218 defaults) over n contiguous fp32 elements.
+void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step, float lr, float b1, float b2,
+                  float eps, float wd, cudaStream_t st);
+// p <- p0, m <- 0, v <- 0   (LoRA_AB.reset + optimizer.load_state_dict(optim_state), ttl.py:338-344)
+void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, cudaStream_t st);
+
+}  // namespace ttl

@@ -1,0 +1,139 @@
+// LoRA-side kernels: packing the fp32 master factors into the bf16 operands of the GEMM's second operand pair,
+// the tall-skinny weight-gradient reductions (dB = s dY^T (X A^T), dA = s (dY B)^T X; peft LoRA Linear backward),
+// and the fused AdamW step / adapter+optimiser reset (torch.optim.AdamW at ttl.py:218; LoRA_AB.reset at
+// clip/custom_clip.py:202-215 + optimizer.load_state_dict at ttl.py:344).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ttl {
+
+namespace {
+
+// params layout per layer: A_q[r,d] | B_q[d,r] | A_v[r,d] | B_v[d,r]   (fp32, contiguous)
+__global__ void lora_pack_kernel(const float* __restrict__ prm, LoraPacked pk, int d, int r, float s) {
+  const int n_a = 64 * d;          // a_ext / a_ext_t elements
+  const int n_b = 3 * d * 64;      // b_ext / b_ext_t elements
+  const float* A_q = prm;
+  const float* B_q = prm + r * d;
+  const float* A_v = prm + 2 * r * d;
+  const float* B_v = prm + 3 * r * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_a + n_b; i += gridDim.x * blockDim.x) {
+    if (i < n_a) {
+      const int j = i / d, k = i - j * d;   // a_ext[j, k]
+      float v = 0.f;
+      if (j < r) v = A_q[j * d + k];
+      else if (j < 2 * r) v = A_v[(j - r) * d + k];
+      const bf16 b = __float2bfloat16(v);
+      pk.a_ext[i] = b;
+      pk.a_ext_t[k * 64 + j] = b;
+    } else {
+      const int e = i - n_a;
+      const int n = e / 64, j = e - n * 64;  // b_ext[n, j], n in [0, 3d)
+      float v = 0.f;
+      if (n < d) { if (j < r) v = s * B_q[n * r + j]; }
+      else if (n >= 2 * d) { if (j >= r && j < 2 * r) v = s * B_v[(n - 2 * d) * r + (j - r)]; }
+      const bf16 b = __float2bfloat16(v);
+      pk.b_ext[e] = b;
+      pk.b_ext_t[static_cast<size_t>(j) * 3 * d + n] = b;
+    }
+  }
+}
+
+// partial[mc, w, j] = sum_{m in chunk mc} wide[m, w] * narrow[m, j]     (w in a 64-wide block, j < 16*?)
+constexpr int SR_MC = 128;  // rows per CTA
+template <int NN>           // narrow width (16 or 32)
+__global__ void __launch_bounds__(256)
+skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __restrict__ narrow, int ldn, int M, int nw,
+                      float* __restrict__ ws) {
+  __shared__ __align__(16) bf16 sW[SR_MC][64 + 8];
+  __shared__ __align__(16) bf16 sN[SR_MC][NN + 8];
+  const int w0 = blockIdx.x * 64, m0 = blockIdx.y * SR_MC;
+  for (int i = threadIdx.x; i < SR_MC * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m0 + r < M) v = *reinterpret_cast<const uint4*>(wide + static_cast<size_t>(m0 + r) * ldw + w0 + c);
+    *reinterpret_cast<uint4*>(&sW[r][c]) = v;
+  }
+  for (int i = threadIdx.x; i < SR_MC * (NN / 8); i += blockDim.x) {
+    const int r = i / (NN / 8), c = (i % (NN / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m0 + r < M) v = *reinterpret_cast<const uint4*>(narrow + static_cast<size_t>(m0 + r) * ldn + c);
+    *reinterpret_cast<uint4*>(&sN[r][c]) = v;
+  }
+  __syncthreads();
+  constexpr int JPT = NN / 4;              // outputs per thread along j
+  const int w = threadIdx.x & 63, jg = threadIdx.x >> 6;  // 4 groups of JPT
+  float acc[JPT];
+#pragma unroll
+  for (int j = 0; j < JPT; ++j) acc[j] = 0.f;
+  for (int m = 0; m < SR_MC; ++m) {
+    const float a = __bfloat162float(sW[m][w]);
+#pragma unroll
+    for (int j = 0; j < JPT; ++j) acc[j] += a * __bfloat162float(sN[m][jg * JPT + j]);
+  }
+  float* o = ws + (static_cast<size_t>(blockIdx.y) * nw + w0 + w) * NN + jg * JPT;
+#pragma unroll
+  for (int j = 0; j < JPT; ++j) o[j] = acc[j];
+}
+
+__global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, int nw, int nn, float scale,
+                                    float* __restrict__ out, int transpose_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw * nn) return;
+  float a = 0.f;
+  for (int c = 0; c < chunks; ++c) a += ws[static_cast<size_t>(c) * nw * nn + i];
+  const int w = i / nn, j = i - w * nn;
+  if (transpose_out) out[static_cast<size_t>(j) * nw + w] = a * scale;
+  else out[i] = a * scale;
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float wd,
+                             float step_size, float bc2_sqrt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  float pi = p[i] * (1.0f - lr * wd);
+  const float mi = m[i] + (gi - m[i]) * (1.0f - b1);            // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;           // (sqrt(v) / sqrt(bc2)).add_(eps)
+  pi -= step_size * (mi / denom);                               // addcdiv_(m, denom, -lr / bc1)
+  p[i] = pi; m[i] = mi; v[i] = vi;
+}
+
+__global__ void lora_reset_kernel(float* __restrict__ p, const float* __restrict__ p0, float* __restrict__ m,
+                                  float* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = p0[i]; m[i] = 0.f; v[i] = 0.f;
+}
+
+}  // namespace
+
+void launch_lora_pack(const float* params, LoraPacked pk, int d, int r, float s, cudaStream_t st) {
+  const int total = 64 * d + 3 * d * 64;
+  lora_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(params, pk, d, r, s);
+}
+
+void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
+                          float* out, int transpose_out, float* ws, cudaStream_t st) {
+  const int chunks = (M + SR_MC - 1) / SR_MC;
+  dim3 grid(nw / 64, chunks);
+  if (nn == 16) skinny_partial_kernel<16><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws);
+  else skinny_partial_kernel<32><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws);
+  skinny_final_kernel<<<(nw * nn + 255) / 256, 256, 0, st>>>(ws, chunks, nw, nn, scale, out, transpose_out);
+}
+
+void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step, float lr, float b1, float b2,
+                  float eps, float wd, cudaStream_t st) {
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+  adamw_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, static_cast<float>(lr / bc1),
+                                                static_cast<float>(sqrt(bc2)));
+}
+
+void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, cudaStream_t st) {
+  lora_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, p0, m, v, n);
+}
+
+}  // namespace ttl

@@ -1,0 +1,205 @@
+// Row-wise HBM-bound kernels: im2col for the patch embedding, CLS/pos + pre-LN, LayerNorm forward/backward,
+// view gather.  One warp per row, 128-bit loads/stores, warp-shuffle reductions, fp32 statistics.
+// Replaces ATen layer_norm / elementwise launches behind HF CLIPVisionEmbeddings, CLIPEncoderLayer
+// (layer_norm1/2, pre_layrnorm) on the path clip/custom_clip.py:69-71 -> CLIPModel.get_image_features.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ttl {
+
+namespace {
+
+constexpr int MAXV = 8;            // d <= 1024, d % 128 == 0
+constexpr int ROWS_PER_BLOCK = 8;  // 8 warps per CTA
+
+__global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int V, int S, int p, int Kp) {
+  const int gp = S / p, T = gp * gp, K = 3 * p * p;
+  const size_t total = static_cast<size_t>(V) * T * (Kp / 2);
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(e % (Kp / 2)) * 2;
+    const size_t row = e / (Kp / 2);
+    float2 v = make_float2(0.f, 0.f);
+    if (col < K) {
+      const int view = static_cast<int>(row / T), patch = static_cast<int>(row % T);
+      const int py = patch / gp, px = patch % gp;
+      const int c = col / (p * p), rem = col % (p * p), i = rem / p, j = rem % p;
+      const size_t src = ((static_cast<size_t>(view) * 3 + c) * S + (py * p + i)) * S + px * p + j;
+      v = *reinterpret_cast<const float2*>(img + src);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + row * Kp + col) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+__device__ __forceinline__ void row_stats(const float4 (&v)[MAXV], int nv, int d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += a * a + b * b + c * c + e * e;
+    }
+  rstd = rsqrtf(warp_sum(q) / d + eps);
+}
+
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int tokens, int d,
+                   float eps) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nv = d / 128;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * d);
+  const bool is_cls = (row % tokens) == 0;
+  float4 v[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c4 = i * 32 + lane;
+      if (is_cls) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(cls) + c4), b = __ldg(reinterpret_cast<const float4*>(pos) + c4);
+        v[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      } else {
+        v[i] = xr[c4];
+      }
+    }
+  float mean, rstd;
+  row_stats(v, nv, d, eps, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c4 = i * 32 + lane;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      xr[c4] = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                           (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    }
+}
+
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+layernorm_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int rows, int d, float eps) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nv = d / 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+  float4 v[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) v[i] = xr[i * 32 + lane];
+  float mean, rstd;
+  row_stats(v, nv, d, eps, mean, rstd);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * d);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c4 = i * 32 + lane;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      uint2 o;
+      o.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      o.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      yr[c4] = o;
+    }
+}
+
+// dx = dres + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dxb, int rows, int d,
+                     float eps) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31, nv = d / 128;
+  const size_t base = static_cast<size_t>(row) * d;
+  const float4* xr = reinterpret_cast<const float4*>(x + base);
+  const float4* dyr = reinterpret_cast<const float4*>(dy + base);
+  float4 v[MAXV], gy[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) v[i] = xr[i * 32 + lane];
+  float mean, rstd;
+  row_stats(v, nv, d, eps, mean, rstd);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c4 = i * 32 + lane;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), t = dyr[c4];
+      gy[i] = make_float4(g.x * t.x, g.y * t.y, g.z * t.z, g.w * t.w);
+      v[i] = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
+      s2 += gy[i].x * v[i].x + gy[i].y * v[i].y + gy[i].z * v[i].z + gy[i].w * v[i].w;
+    }
+  s1 = warp_sum(s1) / d;
+  s2 = warp_sum(s2) / d;
+  float4* dxr = reinterpret_cast<float4*>(dx + base);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      const int c4 = i * 32 + lane;
+      float4 o = make_float4(rstd * (gy[i].x - s1 - v[i].x * s2), rstd * (gy[i].y - s1 - v[i].y * s2),
+                             rstd * (gy[i].z - s1 - v[i].z * s2), rstd * (gy[i].w - s1 - v[i].w * s2));
+      if (dres != nullptr) {
+        float4 r = reinterpret_cast<const float4*>(dres + base)[c4];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      dxr[c4] = o;
+      if (dxb != nullptr) {
+        uint2 u;
+        u.x = pack_bf16(o.x, o.y);
+        u.y = pack_bf16(o.z, o.w);
+        reinterpret_cast<uint2*>(dxb + base)[c4] = u;
+      }
+    }
+}
+
+__global__ void gather_views_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                    const int* __restrict__ idx, int n_sel, int per_view4) {
+  const int g = blockIdx.y;
+  const float4* s = src + static_cast<size_t>(idx[g]) * per_view4;
+  float4* o = dst + static_cast<size_t>(g) * per_view4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_view4; i += gridDim.x * blockDim.x) o[i] = s[i];
+}
+
+}  // namespace
+
+void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cudaStream_t st) {
+  const int K = 3 * p * p, Kp = (K + 63) / 64 * 64;
+  const size_t total = static_cast<size_t>(V) * (S / p) * (S / p) * (Kp / 2);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col_kernel<<<blocks, 256, 0, st>>>(images, patches, V, S, p, Kp);
+}
+
+void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
+                        int tokens, int d, float eps, cudaStream_t st) {
+  const int rows = V * tokens;
+  embed_preln_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(
+      x, cls, pos, gamma, beta, rows, tokens, d, eps);
+}
+
+void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
+                      cudaStream_t st) {
+  layernorm_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(x, y, gamma, beta,
+                                                                                                rows, d, eps);
+}
+
+void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
+                          bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st) {
+  layernorm_bwd_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(
+      dy, x, gamma, dres, dx, dx_bf16, rows, d, eps);
+}
+
+void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int tokens, int d,
+                         cudaStream_t st) {
+  const int per_view4 = tokens * d / 4;
+  dim3 grid((per_view4 + 255) / 256 < 32 ? (per_view4 + 255) / 256 : 32, n_sel);
+  gather_views_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
+                                            view_idx, n_sel, per_view4);
+}
+
+}  // namespace ttl

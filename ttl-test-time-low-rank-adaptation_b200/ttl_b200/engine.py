@@ -1,0 +1,228 @@
+"""Host-side handle on one libttl_b200 context (one per process and GPU).
+
+PyTorch is used for device memory and streams only; all arithmetic of the path runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# geometry per --arch (ttl.py:386); head_dim is 64 for both
+ARCH_GEOMETRY = {
+    "ViT-B/16": dict(image_size=224, patch=16, width=768, layers=12, heads=12, mlp_dim=3072, proj_dim=512),
+    "ViT-L/14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, mlp_dim=4096, proj_dim=768),
+    "ViT-tiny": dict(image_size=64, patch=16, width=128, layers=4, heads=2, mlp_dim=512, proj_dim=64),
+}
+
+
+@dataclass
+class Hparams:
+    """ttl.py argparse defaults (:367-424) + torch.optim.AdamW defaults (ttl.py:218)."""
+    head: str = "tpt"            # "tpt" (deyo_selection falsy) | "deyo" (deyo_selection truthy)
+    tta_steps: int = 1
+    selection_p: float = 0.1
+    lr: float = 5e-3
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    weight_decay: float = 1e-2
+    deyo_margin_e0: float = 0.4
+
+    def to_c(self) -> L.TtlHparams:
+        return L.TtlHparams(L.HEAD_DEYO if self.head == "deyo" else L.HEAD_TPT, self.tta_steps, self.selection_p,
+                            self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.deyo_margin_e0)
+
+
+def _f32(a) -> np.ndarray:
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class _DevAlias:
+    """Expose library-owned device memory through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class Engine:
+    def __init__(self, arch: str = "ViT-B/16", max_views: int = 64, max_classes: int = 1000, lora_rank: int = 16,
+                 lora_alpha: float = 32.0, layer_range: Sequence[int] = (9, 11), device: int = 0,
+                 geometry: Optional[dict] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ttl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        g = dict(geometry or ARCH_GEOMETRY[arch])
+        self.arch, self.geom = arch, g
+        self.device = torch.device("cuda", device)
+        self.max_views, self.max_classes = max_views, max_classes
+        self.rank, self.alpha = lora_rank, lora_alpha
+        self.layer_lo, self.layer_hi = int(layer_range[0]), int(layer_range[1])
+        self.tokens = (g["image_size"] // g["patch"]) ** 2 + 1
+        self.n_classes = 0
+        cfg = L.TtlConfig(g["image_size"], g["patch"], g["width"], g["layers"], g["heads"], g["mlp_dim"], g["proj_dim"],
+                          max_views, max_classes, lora_rank, lora_alpha, self.layer_lo, self.layer_hi, 1e-5, device)
+        ctx = C.c_void_p()
+        L.check(self.lib.ttl_create(C.byref(ctx), C.byref(cfg)))
+        self.ctx = ctx
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream()   # a capturable (non-legacy) stream for the CUDA-graph replay
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.lib.ttl_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ frozen state
+    def _set(self, layer: int, kind: int, arr) -> None:
+        a = _f32(arr)
+        L.check(self.lib.ttl_set_weight(self.ctx, layer, kind, a.ctypes.data_as(C.c_void_p), a.size), self.ctx)
+
+    def load_weights(self, sd: Dict[str, "torch.Tensor"]) -> None:
+        """`sd`: HF CLIP state-dict names of the vision tower + visual_projection (clip/custom_clip.py:581)."""
+        p = "vision_model."
+        self._set(-1, L.W_CLASS_EMB, sd[p + "embeddings.class_embedding"])
+        self._set(-1, L.W_PATCH_EMB, sd[p + "embeddings.patch_embedding.weight"])
+        self._set(-1, L.W_POS_EMB, sd[p + "embeddings.position_embedding.weight"])
+        self._set(-1, L.W_PRE_LN_G, sd[p + "pre_layrnorm.weight"])
+        self._set(-1, L.W_PRE_LN_B, sd[p + "pre_layrnorm.bias"])
+        self._set(-1, L.W_POST_LN_G, sd[p + "post_layernorm.weight"])
+        self._set(-1, L.W_POST_LN_B, sd[p + "post_layernorm.bias"])
+        self._set(-1, L.W_VIS_PROJ, sd["visual_projection.weight"])
+        for i in range(self.geom["layers"]):
+            q = f"{p}encoder.layers.{i}."
+            for kind, name in ((L.W_LN1_G, "layer_norm1.weight"), (L.W_LN1_B, "layer_norm1.bias"),
+                               (L.W_Q_W, "self_attn.q_proj.weight"), (L.W_Q_B, "self_attn.q_proj.bias"),
+                               (L.W_K_W, "self_attn.k_proj.weight"), (L.W_K_B, "self_attn.k_proj.bias"),
+                               (L.W_V_W, "self_attn.v_proj.weight"), (L.W_V_B, "self_attn.v_proj.bias"),
+                               (L.W_O_W, "self_attn.out_proj.weight"), (L.W_O_B, "self_attn.out_proj.bias"),
+                               (L.W_LN2_G, "layer_norm2.weight"), (L.W_LN2_B, "layer_norm2.bias"),
+                               (L.W_FC1_W, "mlp.fc1.weight"), (L.W_FC1_B, "mlp.fc1.bias"),
+                               (L.W_FC2_W, "mlp.fc2.weight"), (L.W_FC2_B, "mlp.fc2.bias")):
+                self._set(i, kind, sd[q + name])
+
+    def set_text_features(self, text, logit_scale: float) -> None:
+        t = _f32(text)
+        self.n_classes = int(t.shape[0])
+        L.check(self.lib.ttl_set_text_features(self.ctx, t.ctypes.data_as(C.c_void_p), t.shape[0], t.shape[1],
+                                               float(logit_scale)), self.ctx)
+
+    # ------------------------------------------------------------------ adapter
+    def set_lora_init(self, lora: Dict[int, Sequence]) -> None:
+        for layer, tensors in lora.items():
+            for which, t in enumerate(tensors):
+                a = _f32(t)
+                L.check(self.lib.ttl_lora_set_init(self.ctx, layer, which, a.ctypes.data_as(C.c_void_p), a.size),
+                        self.ctx)
+        self.lora_reset()
+
+    def lora_reset(self) -> None:
+        L.check(self.lib.ttl_lora_reset(self.ctx, self._st()), self.ctx)
+
+    def lora_get(self, layer: int, which: int, what: int = L.LORA_PARAM) -> np.ndarray:
+        d, r = self.geom["width"], self.rank
+        shape = (r, d) if which in (L.LORA_A_Q, L.LORA_A_V) else (d, r)
+        out = np.empty(shape, dtype=np.float32)
+        L.check(self.lib.ttl_lora_get(self.ctx, layer, which, what, out.ctypes.data_as(C.c_void_p), out.size), self.ctx)
+        return out
+
+    def lora_alias(self, layer: int, which: int, what: int = L.LORA_PARAM) -> torch.Tensor:
+        """torch tensor aliasing the library's device buffer (call lora_touch() after writing through it)."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        L.check(self.lib.ttl_lora_device_ptr(self.ctx, layer, which, what, C.byref(ptr), C.byref(n)), self.ctx)
+        d, r = self.geom["width"], self.rank
+        shape = (r, d) if which in (L.LORA_A_Q, L.LORA_A_V) else (d, r)
+        return torch.as_tensor(_DevAlias(ptr.value, shape), device=self.device)
+
+    def lora_touch(self) -> None:
+        L.check(self.lib.ttl_lora_touch(self.ctx, self._st()), self.ctx)
+
+    def adamw_step(self, hp: Hparams) -> None:
+        h = hp.to_c()
+        L.check(self.lib.ttl_adamw_step(self.ctx, C.byref(h), self._st()), self.ctx)
+
+    # ------------------------------------------------------------------ model calls
+    def _st(self) -> C.c_void_p:
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def _sync_in(self) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
+    def _sync_out(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def forward(self, images: torch.Tensor, train: bool = False) -> torch.Tensor:
+        """ClipTestTimeTuning.forward: images fp32 [B,3,S,S] on device -> logits fp32 [B,C]."""
+        images = images.to(self.device, torch.float32).contiguous()
+        logits = torch.empty(images.shape[0], self.n_classes, device=self.device, dtype=torch.float32)
+        self._sync_in()
+        L.check(self.lib.ttl_forward(self.ctx, images.data_ptr(), images.shape[0], int(train), logits.data_ptr(),
+                                     self._st()), self.ctx)
+        self._sync_out()
+        images.record_stream(self.stream)
+        return logits
+
+    def backward(self, dlogits: torch.Tensor) -> None:
+        dlogits = dlogits.to(self.device, torch.float32).contiguous()
+        self._sync_in()
+        L.check(self.lib.ttl_backward(self.ctx, dlogits.data_ptr(), self._st()), self.ctx)
+        self._sync_out()
+        dlogits.record_stream(self.stream)
+
+    def adapt_predict(self, images: torch.Tensor, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
+                      want: Sequence[str] = ("pred_logits",)) -> Dict[str, torch.Tensor]:
+        """One test sample: reset -> adapt -> predict (ttl.py:338-352).  `images` may live on the device (fast path)
+        or in (pinned) host memory, in which case the library does the H2D/D2H itself and synchronises."""
+        V = int(images.shape[0])
+        K = int(V * hp.selection_p)
+        host = not images.is_cuda
+        dev = torch.device("cpu") if host else self.device
+        images = images.to(torch.float32).contiguous()
+        outs: Dict[str, torch.Tensor] = {}
+        o = L.TtlOutputs()
+        shapes = {"logits0": ((V, self.n_classes), torch.float32), "entropy": ((V,), torch.float32),
+                  "idx": ((max(K, 1),), torch.int32), "loss": ((1,), torch.float32),
+                  "pred_logits": ((self.n_classes,), torch.float32)}
+        for name in want:
+            shp, dt = shapes[name]
+            t = torch.empty(shp, dtype=dt, device=dev, pin_memory=host)
+            outs[name] = t
+            setattr(o, name, t.data_ptr())
+        fidx = None
+        if forced_idx is not None:
+            fidx = forced_idx.to(dev, torch.int32).contiguous()
+        h = hp.to_c()
+        if host:
+            L.check(self.lib.ttl_adapt_predict_host(self.ctx, images.data_ptr(), V, C.byref(h),
+                                                    fidx.data_ptr() if fidx is not None else None, C.byref(o),
+                                                    self._st()), self.ctx)
+        else:
+            self._sync_in()
+            L.check(self.lib.ttl_adapt_predict(self.ctx, images.data_ptr(), V, C.byref(h),
+                                               fidx.data_ptr() if fidx is not None else None, C.byref(o), self._st()),
+                    self.ctx)
+            self._sync_out()
+            images.record_stream(self.stream)
+        if "idx" in outs:
+            outs["idx"] = outs["idx"][:K]
+        return outs
+
+    def set_graphs(self, enabled: bool) -> None:
+        L.check(self.lib.ttl_set_graphs(self.ctx, int(enabled)), self.ctx)
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.ttl_last_launch_count(self.ctx))
