@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- adapted samples/s of the TTL per-sample loop (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one pass of the hot path over one test sample: reset -> 64-view forward with rank-16 LoRA -> confidence
+selection -> marginal-entropy loss -> backward into the LoRA factors -> AdamW -> predict on view 0 (ttl.py:338-352).
+Workload = BASELINE.json configs[1]: ViT-B/16, 1000 classes, 64 views, r=16, 1 TTA step, bf16, synthetic data,
+random-init weights.  Test samples are independent, so ranks shard them with no data-path collective (weak scaling);
+the only collective is the final all-reduce of the accuracy counters.
+
+    python bench.py                                   # N=1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference                  # the reference algorithm on this box's host cores (oracle port)
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "ttl-test-time-low-rank-adaptation_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "adapted samples/s, ViT-B/16 64-view TTL"
+UNIT = "samples/s"
+F_ALG_TFLOP = 2.342   # algorithmic TFLOP per adapted sample, north-star head (SURVEY.md §8d / BASELINE.md §3)
+F_ALG_TFLOP_DEYO = 2.876
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--head", default="tpt", choices=["tpt", "deyo"])
+    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--views", type=int, default=64)
+    ap.add_argument("--ring", type=int, default=8, help="distinct pre-staged samples (ring * 38.5 MB > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-baseline-samples", type=int, default=2)
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return dict(hbm=pk.get("hbm_gbs", 6650.0), tf_burst=pk.get("bf16_tflops", 1590.0),
+                    tf_sus=pk.get("bf16_tflops_sustained", 1400.0), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synth_sample_gpu(torch, gen, views: int, size: int = 224):
+    """One smooth base image -> view 0 = centre crop, views 1.. = random-resized-crop + flip (data/datautils.py:98-157)."""
+    import torch.nn.functional as F
+    big = int(size * 1.25)
+    lo = F.interpolate(torch.randn(1, 3, 7, 7, device="cuda", generator=gen), size=(big, big), mode="bicubic")
+    hi = F.interpolate(torch.randn(1, 3, 56, 56, device="cuda", generator=gen), size=(big, big), mode="bilinear")
+    base = lo + 0.5 * hi
+    off = (big - size) // 2
+    out = [base[:, :, off:off + size, off:off + size]]
+    r = torch.rand(views - 1, 5, device="cuda", generator=gen).cpu()
+    for i in range(views - 1):
+        s = (0.08 + 0.92 * float(r[i, 0])) * big * big
+        ar = math.exp(math.log(3 / 4) + float(r[i, 1]) * (math.log(4 / 3) - math.log(3 / 4)))
+        cw, ch = min(big, max(8, int(round(math.sqrt(s * ar))))), min(big, max(8, int(round(math.sqrt(s / ar)))))
+        top, left = int(float(r[i, 2]) * (big - ch)), int(float(r[i, 3]) * (big - cw))
+        v = F.interpolate(base[:, :, top:top + ch, left:left + cw], size=(size, size), mode="bilinear")
+        out.append(v.flip(-1) if float(r[i, 4]) < 0.5 else v)
+    return torch.cat(out).contiguous()
+
+
+def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, threads: int):
+    """The reference algorithm (oracle port, fp32, autograd) on the host cores; returns (seconds_per_sample list)."""
+    import torch
+    from oracle import ttl_oracle as O
+    torch.set_num_threads(threads)
+    arch, spec = O.ARCHS["ViT-B/16"], O.LoraSpec()
+    w = O.make_synthetic_weights(arch, 1234)
+    lora0 = O.lora_init(arch, spec, 0)
+    text = O.make_text_features(classes, arch.proj)
+    times = []
+    for i in range(n_samples):
+        imgs = O.make_synthetic_views(views, arch.image_size, seed=100 + i)
+        t0 = time.perf_counter()
+        O.adapt_and_predict(arch, w, imgs, text, math.log(100.0), lora0, spec, head=head)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port -- the reference itself needs
+    peft/ftfy/network and is not installable on the box), all host threads, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    views = args.views
+    bounded = total > 24
+    if bounded:   # keep the run within a few minutes: fewer views per step, scaled back to 64-view samples
+        views = max(10, min(args.views, int(1500 / total)))
+    times = cpu_reference_pass(total, args.classes, views, args.head, cores)
+    timed = times[args.warmup:]
+    per_step = sum(timed) / len(timed)
+    value = (views / args.views) / per_step
+    sample = (f"{len(timed)} timed steps of {views}-view adapt+predict, fp32, oracle port of ttl.py:338-352"
+              + (f"; bounded: scaled by {views}/{args.views} views" if bounded else ""))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step * 1e3 * (args.views / views), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head)",
+                       "device": "host CPU"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called plainly with --gpus N
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
+        sys.exit(subprocess.call(cmd + sys.argv[1:]))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    import torch.distributed as dist
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200 import dist as tdist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+
+    # ---- model: random-init ViT-B/16 (seed 1234), synthetic unit text features, Xavier LoRA A / zero B
+    from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features
+    eng = Engine("ViT-B/16", max_views=args.views, max_classes=max(args.classes, 16), device=local_rank)
+    eng.load_weights(synthetic_vit_weights("ViT-B/16", seed=1234))
+    eng.set_text_features(synthetic_text_features(args.classes, 512, seed=11), math.log(100.0))
+    eng.set_lora_init(synthetic_lora_init("ViT-B/16", rank=16, layers=(9, 11), seed=0))
+    hp = Hparams(head=args.head)
+
+    # ---- data: this rank's shard of a seeded synthetic evaluation set, pre-staged in HBM (ring > L2)
+    gen = torch.Generator(device="cuda").manual_seed(7 + 1000 * rank)
+    ring = [synth_sample_gpu(torch, gen, args.views) for _ in range(args.ring)]
+    # labels = zero-shot prediction of the un-adapted model, so "accuracy" is well-defined on random weights
+    labels = []
+    eng.lora_reset()
+    for s in ring:
+        labels.append(int(eng.forward(s[:1]).argmax()))
+    correct = torch.zeros(3, dtype=torch.int64, device="cuda")   # top1, top5, n
+
+    def step(i, images):
+        out = eng.adapt_predict(images, hp, want=("pred_logits",))["pred_logits"]
+        top5 = out.topk(5).indices
+        lab = labels[i % args.ring]
+        correct[0] += (top5[0] == lab)
+        correct[1] += (top5 == lab).any()
+        correct[2] += 1
+
+    for i in range(args.warmup):
+        step(i, ring[i % args.ring])
+    torch.cuda.synchronize()
+    correct.zero_()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i, ring[i % args.ring])
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.last_launch_count() * args.steps
+    t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_max_ms = float(t)
+    counts = tdist.reduce_counts(correct, world)          # the path's only collective (24 bytes)
+    value = world * args.steps / (t_max_ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (H2D of the views + D2H of the prediction in the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host = [s.cpu().pin_memory() for s in ring[:4]]
+        for i in range(3):
+            eng.adapt_predict(host[i % 4], hp, want=("pred_logits",))
+        n_e2e = max(10, args.steps // 4)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            o = eng.adapt_predict(host[i % 4], hp, want=("pred_logits",))["pred_logits"]
+            _ = int(o.argmax())
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n_e2e / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": int(args.classes * 4),
+               "steps": n_e2e, "api": "ttl_b200.Engine.adapt_predict(host tensor) -> ttl_adapt_predict_host"}
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch, instrumented eager pass
+    roof = None
+    if not args.no_roofline and rank == 0:
+        from ttl_b200 import profile as tprof
+        roof = tprof.gemm_roofline(eng, hp, ring, peaks, samples=4)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        times = cpu_reference_pass(args.cpu_baseline_samples, args.classes, args.views, args.head, cores)
+        per = sum(times) / len(times)
+        cpu_base = {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{len(times)} samples of the same workload, oracle port (fp32 PyTorch CPU, autograd) of "
+                              f"ttl.py:338-352, {per:.2f} s/sample"}
+
+    if rank == 0:
+        f_alg = F_ALG_TFLOP if args.head == "tpt" else F_ALG_TFLOP_DEYO
+        per_gpu_tflops = value / world * f_alg
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head), "
+                                       f"random-init weights", "samples_per_rank": args.steps,
+                           "l2": f"inputs larger than L2: ring of {args.ring} pre-staged samples x {ring[0].numel() * 4 / 1e6:.1f} MB",
+                           "parallelism": f"sample-sharded x{world}"},
+                "tflops_per_gpu_alg": per_gpu_tflops,
+                "frac_of_bf16_peak": {"sustained_measured": per_gpu_tflops / peaks["tf_sus"],
+                                      "burst_measured": per_gpu_tflops / peaks["tf_burst"], "spec_2250": per_gpu_tflops / 2250.0,
+                                      "peaks": peaks["src"]},
+                "accuracy": {"top1": 100.0 * counts[0] / max(counts[2], 1), "top5": 100.0 * counts[1] / max(counts[2], 1),
+                             "n": counts[2], "note": "labels = zero-shot prediction of the un-adapted random-init model"},
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,12 @@ int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
 /* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */
 int64_t ttl_last_launch_count(const ttl_ctx* ctx);
 
+/* Per-launch timing of the dominant kernel (the tcgen05 GEMM) with CUDA events on the launching stream; while enabled
+ * ttl_adapt_predict runs eagerly (no graph replay).  ttl_profile_read synchronises, returns and clears the records. */
+typedef struct ttl_gemm_record { int32_t M, N, K, epi; float ms; } ttl_gemm_record;
+int ttl_profile_gemm(ttl_ctx* ctx, int32_t enable);
+int ttl_profile_read(ttl_ctx* ctx, ttl_gemm_record* out, int32_t max_records, int32_t* n_records);
+
 /* ---- head pieces (select_confident_samples ttl.py:50-54, avg_entropy ttl.py:56-61, deyo.py:85-181) ---------- */
 int ttl_op_logits_entropy(const float* feats_dev, const float* text_dev, float scale, float* logits_dev,
                           float* entropy_dev, int32_t V, int32_t C, int32_t P, void* stream);

@@ -184,7 +184,7 @@ def test_selection_bit_exact_given_entropies(G):
         V = 64
         ent = torch.rand(V, generator=g)
         if trial % 2:                                   # engineered ties
-            ent[torch.randint(0, V, (24,), generator=g)] = ent[5]
+            ent[torch.randint(0, V, (24,), generator=g)] = float(ent[5])
         K = int(V * 0.1)
         idx = torch.empty(K, dtype=torch.int32, device="cuda")
         e = ent.cuda()

@@ -106,6 +106,11 @@ struct ttl_ctx {
   int last_train_views = 0;
   const float* last_train_in = nullptr;
 
+  // per-launch GEMM timing (bench.py roofline): CUDA events around every gemm launch while enabled
+  bool prof = false;
+  struct ProfRec { cudaEvent_t e0, e1; int M, N, K, epi; };
+  std::vector<ProfRec> prof_recs;
+
   // graphs
   bool graphs = true;
   std::vector<GraphEntry> gcache;
@@ -153,7 +158,18 @@ int check_launch(ttl_ctx* c, const char* what) {
 }
 
 int gemm(ttl_ctx* c, GemmArgs& g, cudaStream_t st) {
+  ttl_ctx::ProfRec rec{};
+  if (c->prof) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    rec.M = g.M; rec.N = g.N; rec.K = g.a1.k + (g.a2.ptr ? g.a2.k : 0); rec.epi = g.epi;
+    cudaEventRecord(rec.e0, st);
+  }
   cudaError_t e = gemm_launch(g, st, c->num_sms);
+  if (c->prof) {
+    cudaEventRecord(rec.e1, st);
+    c->prof_recs.push_back(rec);
+  }
   c->launches++;
   if (e != cudaSuccess) {
     c->err = std::string("gemm: ") + gemm_last_error() + " / " + cudaGetErrorString(e);
@@ -455,7 +471,7 @@ int validate_run(ttl_ctx* c, int V, const ttl_hparams* hp) {
 
 int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
   const int64_t before = c->launches;
-  if (!c->graphs || st == nullptr) {  // the legacy default stream cannot be captured
+  if (!c->graphs || c->prof || st == nullptr) {  // the legacy default stream cannot be captured
     int r = adapt_body(c, images_dev, V, *hp, forced, st);
     c->last_launches = c->launches - before;
     return r;
@@ -832,6 +848,32 @@ int ttl_set_graphs(ttl_ctx* c, int32_t enabled) {
 }
 
 int64_t ttl_last_launch_count(const ttl_ctx* c) { return c ? c->last_launches : 0; }
+
+int ttl_profile_gemm(ttl_ctx* c, int32_t enable) {
+  if (!c) return TTL_E_INVALID;
+  c->prof = enable != 0;
+  return TTL_OK;
+}
+
+int ttl_profile_read(ttl_ctx* c, ttl_gemm_record* out, int32_t max_records, int32_t* n_records) {
+  if (!c || !n_records) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  CK(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : c->prof_recs) {
+    if (out && n < max_records) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      out[n].M = r.M; out[n].N = r.N; out[n].K = r.K; out[n].epi = r.epi; out[n].ms = ms;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof_recs.clear();
+  *n_records = n;
+  return TTL_OK;
+}
 
 // ---------------------------------------------------------------------------------- single-kernel entries
 static int op_done(const char* what) {

@@ -125,7 +125,7 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   float* red = sh + 2 * K;    // [32]
   float* a = red + 32;        // [C]
   for (int k = 0; k < K; ++k) {
-    const float* x = logits + static_cast<size_t>(idx[k]) * C;
+    const float* x = logits + static_cast<size_t>(idx ? idx[k] : k) * C;
     float mx = -INFINITY;
     for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, x[c]);
     mx = block_max(mx, red);
@@ -139,9 +139,9 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   float part = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, logits[static_cast<size_t>(idx[k]) * C + c] - lse[k]);
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, logits[static_cast<size_t>(idx ? idx[k] : k) * C + c] - lse[k]);
     float se = 0.f;
-    for (int k = 0; k < K; ++k) se += expf(logits[static_cast<size_t>(idx[k]) * C + c] - lse[k] - mx);
+    for (int k = 0; k < K; ++k) se += expf(logits[static_cast<size_t>(idx ? idx[k] : k) * C + c] - lse[k] - mx);
     float ac = mx + logf(se) - lnK;
     ac = fmaxf(ac, -FLT_MAX);
     a[c] = ac;
@@ -150,7 +150,7 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   part = block_sum(part, red);
   if (threadIdx.x == 0) *loss = part;
   for (int k = 0; k < K; ++k) {
-    const float* x = logits + static_cast<size_t>(idx[k]) * C;
+    const float* x = logits + static_cast<size_t>(idx ? idx[k] : k) * C;
     float s = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(x[c] - lse[k]) * a[c];
     s = block_sum(s, red);
@@ -160,7 +160,7 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   const float invK = 1.f / K;
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
     const int k = i / C, c = i - k * C;
-    const float p = expf(logits[static_cast<size_t>(idx[k]) * C + c] - lse[k]);
+    const float p = expf(logits[static_cast<size_t>(idx ? idx[k] : k) * C + c] - lse[k]);
     dlogits[i] = -invK * p * (a[c] - sk[k]);
   }
 }

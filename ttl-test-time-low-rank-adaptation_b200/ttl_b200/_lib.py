@@ -30,6 +30,10 @@ class TtlHparams(C.Structure):
                 ("deyo_margin_e0", C.c_float)]
 
 
+class TtlGemmRecord(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("epi", C.c_int32), ("ms", C.c_float)]
+
+
 class TtlOutputs(C.Structure):
     _fields_ = [("logits0", vp), ("entropy", vp), ("idx", vp), ("loss", vp), ("pred_logits", vp)]
 
@@ -62,6 +66,8 @@ _SIGS = {
     "ttl_adapt_predict_host": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_set_graphs": (C.c_int, [vp, C.c_int32]),
     "ttl_last_launch_count": (C.c_int64, [vp]),
+    "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),
+    "ttl_profile_read": (C.c_int, [vp, C.POINTER(TtlGemmRecord), C.c_int32, C.POINTER(C.c_int32)]),
     "ttl_op_logits_entropy": (C.c_int, [vp, vp, C.c_float, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
     "ttl_op_select": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
     "ttl_op_tpt_loss": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
