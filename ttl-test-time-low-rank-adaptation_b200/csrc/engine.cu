@@ -87,7 +87,7 @@ struct ttl_ctx {
   float *XK = nullptr, *XA = nullptr, *XB = nullptr, *TIN = nullptr;
   float *feats = nullptr, *feats_c = nullptr, *logits = nullptr, *logits_c = nullptr, *entropy = nullptr,
         *entropy_c = nullptr, *loss = nullptr, *dlogits = nullptr, *pred = nullptr, *pred_feats = nullptr,
-        *pred_entropy = nullptr;
+        *pred_entropy = nullptr, *pooled = nullptr, *dfh = nullptr, *dpool = nullptr;
   int* idx = nullptr;
   std::vector<Tape> tape;
   // backward temporaries
@@ -277,9 +277,9 @@ int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float
     RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, !c->b_zero, nullptr, st));
     cur = c->XA;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
   launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
-  c->launches += 2;
+  c->launches += 4;
   return check_launch(c, "forward_tail_infer");
 }
 
@@ -291,8 +291,8 @@ int forward_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
     RET_IF(run_layer(c, l, cur, tp.x_mid, tp.x_out, G, !c->b_zero, &tp, st));
     cur = tp.x_out;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
-  c->launches++;
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  c->launches += 2;
   c->last_train_views = G;
   c->last_train_in = x_in;
   return check_launch(c, "forward_tail_train");
@@ -303,9 +303,9 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
   const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
   const float* x_last = c->tape[c->n_train - 1].x_out;
-  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->DX, c->DXB, G, c->C,
-                  c->P, c->tokens, d, c->cfg.ln_eps, st);
-  c->launches += 1;
+  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX,
+                  c->DXB, G, c->C, c->P, c->tokens, d, c->cfg.ln_eps, st);
+  c->launches += 4;
   float* dx = c->DX;
   float* dx2 = c->DX2;
   for (int l = c->L - 1; l >= c->lo; --l) {
@@ -422,7 +422,7 @@ int adapt_body(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bo
         } else {
           launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, K, c->C, c->P, st);
           launch_tpt_loss(c->logits_c, nullptr, K, c->C, c->loss, c->dlogits, st);
-          c->launches++;
+          c->launches += 2;
         }
         c->launches++;
         RET_IF(backward(c, c->dlogits, K, st));
@@ -438,7 +438,7 @@ int adapt_body(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bo
       float* en = step == 0 ? c->entropy : c->entropy_c;
       launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, V, c->C, c->P, st);
       launch_deyo_loss(lg, V, c->C, hp.deyo_margin_e0, c->loss, c->dlogits, st);
-      c->launches += 2;
+      c->launches += 3;
       RET_IF(backward(c, c->dlogits, V, st));
       RET_IF(adamw(c, hp, st));
     }
@@ -582,6 +582,7 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   A(c->feats, c->Vm * c->P); A(c->feats_c, c->Vm * c->P); A(c->logits, c->Vm * c->Cm); A(c->logits_c, c->Vm * c->Cm);
   A(c->entropy, c->Vm); A(c->entropy_c, c->Vm); A(c->loss, 4); A(c->dlogits, c->Vm * c->Cm); A(c->pred, c->Cm);
   A(c->pred_feats, c->P); A(c->pred_entropy, 4); A(c->idx, c->Vm);
+  A(c->pooled, c->Vm * d); A(c->dfh, c->Vm * c->P); A(c->dpool, c->Vm * d);
   c->tape.resize(c->n_train);
   for (int t = 0; t < c->n_train && rc == TTL_OK; ++t) {
     Tape& tp = c->tape[t];
@@ -792,7 +793,7 @@ int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t tr
   if (train) {
     RET_IF(forward_tail_train(c, c->XK, n_views, st));
     launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits, c->entropy, n_views, c->C, c->P, st);
-    c->launches++;
+    c->launches += 2;
   } else {
     RET_IF(forward_tail_infer(c, c->XK, n_views, c->feats, c->logits, c->entropy, st));
   }

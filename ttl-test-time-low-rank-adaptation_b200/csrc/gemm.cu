@@ -34,7 +34,8 @@ struct Cfg {
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096;   // one 32x32 fp32 block per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAGING_BYTES + 1024;  // +1024: alignment slack
 };
 
 struct EpiParams {
@@ -53,83 +54,96 @@ struct EpiParams {
 
 __device__ __forceinline__ float quick_gelu_sig(float z) { return __fdividef(1.0f, 1.0f + __expf(-1.702f * z)); }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-    d[i] = u;
-  }
+__device__ __forceinline__ uint2 pack4(const float4& a) {
+  uint2 u;
+  u.x = pack_bf16(a.x, a.y);
+  u.y = pack_bf16(a.z, a.w);
+  return u;
 }
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
-  float4* d = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
+// One 32-row x 32-column block of the accumulator, owned by one warp.
+//   phase 1: every lane holds ONE ROW (32 fp32 straight from tcgen05.ld) -> 16-byte chunks into the warp's smem block,
+//            XOR-swizzled so both phases are bank-conflict free;
+//   phase 2: lane l handles columns 4*(l&7)..+3 of rows (l>>3)+4j: global accesses are 128 B (fp32) / 64 B (bf16)
+//            contiguous per row, 4 rows per instruction -> fully coalesced residual reads and output writes.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, int row, int col, const uint32_t (&r)[32]) {
-  float v[32];
+__device__ __forceinline__ void epilogue_block(const EpiParams& p, float* stag, int row0, int col0, int lane,
+                                               const uint32_t (&r)[32]) {
+  float4* s4 = reinterpret_cast<float4*>(stag);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (EPI != EPI_PATCH_F32 && EPI != EPI_GELU_BWD && p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+  for (int i = 0; i < 8; ++i)
+    s4[lane * 8 + (i ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+  __syncwarp();
+  const int ci = lane & 7, col = col0 + ci * 4;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI != EPI_PATCH_F32 && EPI != EPI_GELU_BWD && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  // Issue every global read of this block before any use (8 independent 16-byte loads in flight per lane).
+  float4 ext[8];
+  uint2 zext[8];
+  if (EPI == EPI_RESID_F32 || EPI == EPI_PATCH_F32 || EPI == EPI_GELU_BWD) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
-  }
-  const size_t o = static_cast<size_t>(row) * p.ldo + col;
-  if (EPI == EPI_BF16) {
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, v);
-  } else if (EPI == EPI_GELU) {
-    if (p.out2 != nullptr) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out2) + o, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] * quick_gelu_sig(v[j]);
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, v);
-  } else if (EPI == EPI_RESID_F32) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldr + col);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = r4[i];
-      v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-    }
-    store_f32x32(reinterpret_cast<float*>(p.out) + o, v);
-    if (p.out2 != nullptr) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out2) + o, v);
-  } else if (EPI == EPI_PATCH_F32) {
-    const int view = row / p.tpv, patch = row - view * p.tpv;
-    const float4* p4 = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + patch) * p.N + col);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = __ldg(p4 + i);
-      v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
-    }
-    const size_t orow = static_cast<size_t>(view) * (p.tpv + 1) + 1 + patch;
-    store_f32x32(reinterpret_cast<float*>(p.out) + orow * p.ldo + col, v);
-  } else if (EPI == EPI_F32) {
-    store_f32x32(reinterpret_cast<float*>(p.out) + o, v);
-    if (p.out2 != nullptr) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out2) + o, v);
-  } else if (EPI == EPI_GELU_BWD) {
-    const uint4* z4 = reinterpret_cast<const uint4*>(p.aux + o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u = z4[i];
-      const __nv_bfloat162* zz = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 z = __bfloat1622float2(zz[q]);
-        float s0 = quick_gelu_sig(z.x), s1 = quick_gelu_sig(z.y);
-        v[8 * i + 2 * q] *= s0 * (1.0f + 1.702f * z.x * (1.0f - s0));
-        v[8 * i + 2 * q + 1] *= s1 * (1.0f + 1.702f * z.y * (1.0f - s1));
+    for (int j = 0; j < 8; ++j) {
+      int row = row0 + (lane >> 3) + 4 * j;
+      row = row < p.M ? row : p.M - 1;   // clamp instead of branching; out-of-range rows are not stored
+      if (EPI == EPI_RESID_F32) {
+        ext[j] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldr + col);
+      } else if (EPI == EPI_PATCH_F32) {
+        const int patch = row % p.tpv;
+        ext[j] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(1 + patch) * p.N + col));
+      } else {
+        zext[j] = *reinterpret_cast<const uint2*>(p.aux + static_cast<size_t>(row) * p.ldo + col);
       }
     }
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + o, v);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rr = (lane >> 3) + 4 * j;
+    const int row = row0 + rr;
+    float4 a = add4(s4[rr * 8 + (ci ^ (rr & 7))], bias4);
+    const size_t o = static_cast<size_t>(row) * p.ldo + col;
+    if (EPI == EPI_BF16) {
+      if (row < p.M) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack4(a);
+    } else if (EPI == EPI_GELU) {
+      const uint2 zp = pack4(a);
+      a.x *= quick_gelu_sig(a.x); a.y *= quick_gelu_sig(a.y); a.z *= quick_gelu_sig(a.z); a.w *= quick_gelu_sig(a.w);
+      if (row < p.M) {
+        if (p.out2 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o) = zp;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack4(a);
+      }
+    } else if (EPI == EPI_RESID_F32) {
+      a = add4(a, ext[j]);
+      if (row < p.M) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = a;
+        if (p.out2 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o) = pack4(a);
+      }
+    } else if (EPI == EPI_PATCH_F32) {
+      a = add4(a, ext[j]);
+      if (row < p.M) {
+        const int view = row / p.tpv, patch = row - view * p.tpv;
+        const size_t orow = static_cast<size_t>(view) * (p.tpv + 1) + 1 + patch;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = a;
+      }
+    } else if (EPI == EPI_F32) {
+      if (row < p.M) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = a;
+        if (p.out2 != nullptr) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + o) = pack4(a);
+      }
+    } else if (EPI == EPI_GELU_BWD) {
+      const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zext[j].x));
+      const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zext[j].y));
+      const float s0 = quick_gelu_sig(z01.x), s1 = quick_gelu_sig(z01.y), s2 = quick_gelu_sig(z23.x), s3 = quick_gelu_sig(z23.y);
+      a.x *= s0 * (1.0f + 1.702f * z01.x * (1.0f - s0));
+      a.y *= s1 * (1.0f + 1.702f * z01.y * (1.0f - s1));
+      a.z *= s2 * (1.0f + 1.702f * z23.x * (1.0f - s2));
+      a.w *= s3 * (1.0f + 1.702f * z23.y * (1.0f - s3));
+      if (row < p.M) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack4(a);
+    }
+  }
+  __syncwarp();   // the block is rewritten by the next chunk
 }
 
 template <int BLOCK_N, int EPI>
@@ -147,6 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,13 +264,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + quad * 32;
+      float* stag = staging + ew * 1024;
 #pragma unroll 1
       for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + c, r);
         tmem_ld_wait();
-        if (row < p.M) epilogue_chunk<EPI>(p, row, n_blk * BLOCK_N + c, r);
+        if (row0 < p.M) epilogue_block<EPI>(p, stag, row0, n_blk * BLOCK_N + c, lane, r);
       }
       tc_fence_before();
       __syncwarp();

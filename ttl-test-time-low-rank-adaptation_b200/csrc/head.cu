@@ -34,13 +34,11 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
-// one CTA per view: pooled = LN(x_cls); feats = Wp @ pooled  (one warp per output feature, coalesced over d)
+// pooled[v,:] = LN(x[v*tokens + 0, :])   (HF post_layernorm on the CLS token); one CTA per view
 __global__ void __launch_bounds__(HT)
-pool_project_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ Wp, float* __restrict__ feats, int tokens, int d, int P, float eps) {
-  extern __shared__ float sh[];
-  float* pooled = sh;       // [d]
-  float* red = sh + d;      // [32]
+cls_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ pooled, int tokens, int d, float eps) {
+  __shared__ float red[32];
   const int v = blockIdx.x;
   const float* xr = x + static_cast<size_t>(v) * tokens * d;
   float s = 0.f;
@@ -49,44 +47,93 @@ pool_project_kernel(const float* __restrict__ x, const float* __restrict__ gamma
   float q = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) { const float t = xr[i] - mean; q += t * t; }
   const float rstd = rsqrtf(block_sum(q, red) / d + eps);
-  for (int i = threadIdx.x; i < d; i += blockDim.x) pooled[i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = warp; p < P; p += nw) {
-    const float* w = Wp + static_cast<size_t>(p) * d;
-    float a = 0.f;
-    for (int i = lane; i < d; i += 32) a += w[i] * pooled[i];
-    a = warp_sum(a);
-    if (lane == 0) feats[static_cast<size_t>(v) * P + p] = a;
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    pooled[static_cast<size_t>(v) * d + i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+}
+
+// out[m, n] = sum_k A[m, k] * B[n, k]      fp32, tile 16 x 64, K chunks of 64 staged in smem (padded, conflict-free)
+constexpr int SG_TM = 16, SG_TN = 64, SG_KC = 64;
+__global__ void __launch_bounds__(256)
+small_gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int M, int N,
+                     int K) {
+  __shared__ float As[SG_TM][SG_KC + 1];
+  __shared__ float Bs[SG_TN][SG_KC + 1];
+  const int n0 = blockIdx.x * SG_TN, m0 = blockIdx.y * SG_TM;
+  const int tn = threadIdx.x & 63, tg = threadIdx.x >> 6;   // 4 groups x 4 rows
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += SG_KC) {
+    for (int i = threadIdx.x; i < SG_TM * SG_KC; i += 256) {
+      const int r = i / SG_KC, c = i % SG_KC;
+      As[r][c] = (m0 + r < M && k0 + c < K) ? A[static_cast<size_t>(m0 + r) * K + k0 + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < SG_TN * SG_KC; i += 256) {
+      const int r = i / SG_KC, c = i % SG_KC;
+      Bs[r][c] = (n0 + r < N && k0 + c < K) ? B[static_cast<size_t>(n0 + r) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < SG_KC; ++kk) {
+      const float b = Bs[tn][kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += As[tg * 4 + i][kk] * b;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tg * 4 + i;
+    if (m < M && n0 + tn < N) out[static_cast<size_t>(m) * N + n0 + tn] = acc[i];
   }
 }
 
-// one CTA per view: logits over all classes + entropy
-__global__ void __launch_bounds__(HT)
-logits_entropy_kernel(const float* __restrict__ feats, const float* __restrict__ text, float scale,
-                      float* __restrict__ logits, float* __restrict__ entropy, int C, int P) {
+// out[m, n] = alpha * sum_k A[m, k] * B[k, n]     fp32; 8 rows of A per CTA, 64 columns, K split over 4 thread groups
+__global__ void __launch_bounds__(256)
+small_gemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int M, int N,
+                     int K, float alpha) {
   extern __shared__ float sh[];
-  float* f = sh;        // [P] normalised feature * scale
-  float* red = sh + P;  // [32]
+  float* As = sh;                    // [8][K]
+  float* part = sh + 8 * K;          // [4][8][64]
+  const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    const int r = i / K, c = i - r * K;
+    As[i] = (m0 + r < M) ? A[static_cast<size_t>(m0 + r) * K + c] : 0.f;
+  }
+  __syncthreads();
+  const int tn = threadIdx.x & 63, ks = threadIdx.x >> 6;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (n0 + tn < N) {
+#pragma unroll 4
+    for (int k = ks; k < K; k += 4) {
+      const float b = B[static_cast<size_t>(k) * N + n0 + tn];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += As[i * K + k] * b;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[(ks * 8 + i) * 64 + tn] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    if (m0 + r < M && n0 + c < N)
+      out[static_cast<size_t>(m0 + r) * N + n0 + c] =
+          alpha * (part[(0 * 8 + r) * 64 + c] + part[(1 * 8 + r) * 64 + c] + part[(2 * 8 + r) * 64 + c] + part[(3 * 8 + r) * 64 + c]);
+  }
+}
+
+// logits[v, :] = raw[v, :] * scale / |feats[v]| (in place) ; entropy[v] = H(softmax(logits[v]));  one CTA per view
+__global__ void __launch_bounds__(HT)
+scale_entropy_kernel(const float* __restrict__ feats, float scale, float* __restrict__ logits,
+                     float* __restrict__ entropy, int C, int P) {
+  __shared__ float red[32];
   const int v = blockIdx.x;
   float s = 0.f;
   for (int i = threadIdx.x; i < P; i += blockDim.x) { const float t = feats[static_cast<size_t>(v) * P + i]; s += t * t; }
-  const float inv = rsqrtf(block_sum(s, red));
-  for (int i = threadIdx.x; i < P; i += blockDim.x) f[i] = feats[static_cast<size_t>(v) * P + i] * inv * scale;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float mul = rsqrtf(block_sum(s, red)) * scale;
   float* lg = logits + static_cast<size_t>(v) * C;
-  for (int c = warp; c < C; c += nw) {
-    const float* t = text + static_cast<size_t>(c) * P;
-    float a = 0.f;
-    for (int i = lane; i < P; i += 32) a += t[i] * f[i];
-    a = warp_sum(a);
-    if (lane == 0) lg[c] = a;
-  }
-  __syncthreads();
-  // entropy = -sum p log p  with log p = x - lse
   float mx = -INFINITY;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lg[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { const float t = lg[c] * mul; lg[c] = t; mx = fmaxf(mx, t); }
   mx = block_max(mx, red);
   float se = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(lg[c] - mx);
@@ -211,43 +258,30 @@ deyo_loss_kernel(const float* __restrict__ logits, int V, int C, float e0, float
   }
 }
 
-// one CTA per compact view g: dlogits[g,:] -> dx[g*tokens + 0, :]
+// d/d f from d/d fhat:  df = (dfh - fhat <fhat, dfh>) / |f|     (in place on dfh); one CTA per compact view
 __global__ void __launch_bounds__(HT)
-head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ text, float scale,
-                const float* __restrict__ feats, const float* __restrict__ Wp, const float* __restrict__ x,
-                const float* __restrict__ gamma, float* __restrict__ dx, bf16* __restrict__ dxb, int C, int P,
-                int tokens, int d, float eps) {
-  extern __shared__ float sh[];
-  float* dfh = sh;           // [P] d/d fhat, then d/d f
-  float* dpool = sh + P;     // [d]
-  float* red = dpool + d;    // [32]
+l2norm_bwd_kernel(const float* __restrict__ feats, float* __restrict__ dfh, int P) {
+  __shared__ float red[32];
   const int g = blockIdx.x;
-  const float* dl = dlogits + static_cast<size_t>(g) * C;
   const float* f = feats + static_cast<size_t>(g) * P;
-  // dfhat[p] = scale * sum_c dl[c] T[c,p]
-  for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < C; ++c) a += dl[c] * text[static_cast<size_t>(c) * P + p];
-    dfh[p] = a * scale;
-  }
+  float* dd = dfh + static_cast<size_t>(g) * P;
   float s = 0.f;
   for (int p = threadIdx.x; p < P; p += blockDim.x) s += f[p] * f[p];
-  const float nrm2 = block_sum(s, red);
-  const float inv = rsqrtf(nrm2);
+  const float inv = rsqrtf(block_sum(s, red));
   float dt = 0.f;
-  for (int p = threadIdx.x; p < P; p += blockDim.x) dt += f[p] * inv * dfh[p];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) dt += f[p] * inv * dd[p];
   dt = block_sum(dt, red);
-  for (int p = threadIdx.x; p < P; p += blockDim.x) dfh[p] = (dfh[p] - f[p] * inv * dt) * inv;   // d/d f
-  __syncthreads();
-  // dpooled[k] = sum_p df[p] Wp[p,k]
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
-    float a = 0.f;
-    for (int p = 0; p < P; ++p) a += dfh[p] * Wp[static_cast<size_t>(p) * d + k];
-    dpool[k] = a;
-  }
-  __syncthreads();
-  // LayerNorm backward on the CLS row
+  for (int p = threadIdx.x; p < P; p += blockDim.x) dd[p] = (dd[p] - f[p] * inv * dt) * inv;
+}
+
+// LayerNorm backward on the CLS row of compact view g: dpool[g,:] -> dx[g*tokens + 0, :] (+ bf16 copy)
+__global__ void __launch_bounds__(HT)
+cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, const float* __restrict__ gamma,
+                  float* __restrict__ dx, bf16* __restrict__ dxb, int tokens, int d, float eps) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
   const float* xr = x + static_cast<size_t>(g) * tokens * d;
+  const float* dp = dpool + static_cast<size_t>(g) * d;
   float sm = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) sm += xr[i];
   const float mean = block_sum(sm, red) / d;
@@ -256,7 +290,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ tex
   const float rstd = rsqrtf(block_sum(q, red) / d + eps);
   float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    const float gy = gamma[i] * dpool[i], xh = (xr[i] - mean) * rstd;
+    const float gy = gamma[i] * dp[i], xh = (xr[i] - mean) * rstd;
     s1 += gy; s2 += gy * xh;
   }
   s1 = block_sum(s1, red) / d;
@@ -264,7 +298,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ tex
   float* dxr = dx + static_cast<size_t>(g) * tokens * d;
   bf16* dbr = dxb + static_cast<size_t>(g) * tokens * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    const float gy = gamma[i] * dpool[i], xh = (xr[i] - mean) * rstd;
+    const float gy = gamma[i] * dp[i], xh = (xr[i] - mean) * rstd;
     const float o = rstd * (gy - s1 - xh * s2);
     dxr[i] = o;
     dbr[i] = __float2bfloat16(o);
@@ -273,13 +307,15 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ tex
 
 }  // namespace
 
-void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* feats, int V,
-                         int tokens, int d, int P, float eps, cudaStream_t st) {
-  pool_project_kernel<<<V, HT, (d + 32) * sizeof(float), st>>>(x, gamma, beta, Wp, feats, tokens, d, P, eps);
+void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
+                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st) {
+  cls_ln_kernel<<<V, HT, 0, st>>>(x, gamma, beta, pooled, tokens, d, eps);
+  small_gemm_nt_kernel<<<dim3((P + SG_TN - 1) / SG_TN, (V + SG_TM - 1) / SG_TM), 256, 0, st>>>(pooled, Wp, feats, V, P, d);
 }
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st) {
-  logits_entropy_kernel<<<V, HT, (P + 32) * sizeof(float), st>>>(feats, text, scale, logits, entropy, C, P);
+  small_gemm_nt_kernel<<<dim3((C + SG_TN - 1) / SG_TN, (V + SG_TM - 1) / SG_TM), 256, 0, st>>>(feats, text, logits, V, C, P);
+  scale_entropy_kernel<<<V, HT, 0, st>>>(feats, scale, logits, entropy, C, P);
 }
 void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st) {
   select_kernel<<<1, 256, 0, st>>>(entropy, V, K, forced_idx, idx);
@@ -291,12 +327,17 @@ void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float*
   deyo_loss_kernel<<<1, 1024, 3 * V * sizeof(float), st>>>(logits, V, C, margin_e0, loss, dlogits);
 }
 void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
-                     const float* x, const float* gamma, float* dx, bf16* dx_bf16, int G, int C, int P, int tokens,
-                     int d, float eps, cudaStream_t st) {
+                     const float* x, const float* gamma, float* dfh, float* dpool, float* dx, bf16* dx_bf16, int G, int C,
+                     int P, int tokens, int d, float eps, cudaStream_t st) {
   cudaMemsetAsync(dx, 0, static_cast<size_t>(G) * tokens * d * sizeof(float), st);
   cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(G) * tokens * d * sizeof(bf16), st);
-  head_bwd_kernel<<<G, HT, (P + d + 32) * sizeof(float), st>>>(dlogits, text, scale, feats, Wp, x, gamma, dx, dx_bf16,
-                                                               C, P, tokens, d, eps);
+  // d fhat = scale * dlogits @ T ; d f ; d pooled = d f @ Wp ; LN backward on the CLS rows
+  small_gemm_nn_kernel<<<dim3((P + 63) / 64, (G + 7) / 8), 256, (8 * C + 4 * 8 * 64) * sizeof(float), st>>>(
+      dlogits, text, dfh, G, P, C, scale);
+  l2norm_bwd_kernel<<<G, HT, 0, st>>>(feats, dfh, P);
+  small_gemm_nn_kernel<<<dim3((d + 63) / 64, (G + 7) / 8), 256, (8 * P + 4 * 8 * 64) * sizeof(float), st>>>(
+      dfh, Wp, dpool, G, d, P, 1.0f);
+  cls_ln_bwd_kernel<<<G, HT, 0, st>>>(dpool, x, gamma, dx, dx_bf16, tokens, d, eps);
 }
 
 }  // namespace ttl

@@ -38,8 +38,8 @@ size_t attention_bwd_smem(int tokens);
 
 // ---- head.cu
 // pooled = LN(x[v*tokens + 0, :]) ; feats[v,:] = Wp[P,d] @ pooled  (HF post_layernorm + visual_projection)
-void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* feats, int V,
-                         int tokens, int d, int P, float eps, cudaStream_t st);
+void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
+                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st);
 // logits[v,c] = scale * <feats[v]/|feats[v]|, T[c]> ; entropy[v] = H(softmax(logits[v]))   (custom_clip.py:680-687, ttl.py:51)
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st);
@@ -51,8 +51,8 @@ void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* l
 void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st);
 // head backward for G compact views: dlogits[G,C] -> dx[G*tokens, d] (fp32, zero except CLS rows) + bf16 copy.
 void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
-                     const float* x, const float* gamma, float* dx, bf16* dx_bf16, int G, int C, int P, int tokens,
-                     int d, float eps, cudaStream_t st);
+                     const float* x, const float* gamma, float* dfh, float* dpool, float* dx, bf16* dx_bf16, int G, int C,
+                     int P, int tokens, int d, float eps, cudaStream_t st);
 
 // ---- lora.cu   per-layer fp32 master tensors in the reference's tuple order (A_q[r,d], B_q[d,r], A_v[r,d], B_v[d,r])
 struct LoraPacked {       // bf16 operands consumed by the GEMM's second operand pair (64 = padded 2r)
