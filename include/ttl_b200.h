@@ -156,6 +156,8 @@ int ttl_profile_read(ttl_ctx* ctx, ttl_gemm_record* out, int32_t max_records, in
 /* ---- head pieces (select_confident_samples ttl.py:50-54, avg_entropy ttl.py:56-61, deyo.py:85-181) ---------- */
 int ttl_op_logits_entropy(const float* feats_dev, const float* text_dev, float scale, float* logits_dev,
                           float* entropy_dev, int32_t V, int32_t C, int32_t P, void* stream);
+/* batch_entropy of select_confident_samples (ttl.py:51) / softmax_entropy (deyo.py:85-90) */
+int ttl_op_entropy(const float* logits_dev, float* entropy_dev, int32_t V, int32_t C, void* stream);
 int ttl_op_select(const float* entropy_dev, int32_t V, int32_t K, int32_t* idx_dev, void* stream);
 int ttl_op_tpt_loss(const float* logits_dev, const int32_t* idx_dev, int32_t K, int32_t C, float* loss_dev,
                     float* dlogits_dev, void* stream);

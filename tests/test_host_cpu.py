@@ -1,0 +1,134 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, the product path
+refuses to run without its CUDA device (no fallback), the CLI keeps the reference's flags, the multi-rank plumbing
+works under gloo with world_size 2, and the bench-side synthetic generators equal the oracle's."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "ttl-test-time-low-rank-adaptation_b200")
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from ttl_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "ttl_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ttl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared      # the ctypes table binds exactly the header
+    assert lib.ttl_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    import ctypes as C
+    from ttl_b200 import Engine, _lib
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine("ViT-B/16")
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    cfg = _lib.TtlConfig(224, 16, 768, 12, 12, 3072, 512, 64, 1000, 16, 32.0, 9, 11, 1e-5, 0)
+    assert lib.ttl_create(C.byref(ctx), C.byref(cfg)) == -3          # TTL_E_ARCH
+    assert b"no CPU fallback" in lib.ttl_last_error(None)
+    from ttl_b200 import functional as F
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F.avg_entropy(torch.zeros(6, 10))
+
+
+def test_cli_keeps_reference_flags():
+    import ttl
+    p = ttl.build_parser()
+    d = vars(p.parse_args([]))
+    expect = dict(test_sets='A', dataset_mode='test', arch='ViT-B/16', resolution=224, workers=4, batch_size=64, lr=5e-3,
+                  print_freq=10, gpu=1, tpt=True, selection_p=0.1, tta_steps=1, n_ctx=4, ctx_init='a_photo_of_a',
+                  cocoop=False, load=None, seed=0, images_per_class=None, layer_range=(9, 11), init_method='xavier',
+                  lora_encoder='image', rank=16, deyo_selection=True, aug_type='patch', occlusion_size=112, patch_len=6,
+                  row_start=56, column_start=56, deyo_margin=0.5, deyo_margin_e0=0.4, plpd_threshold=0.2, fishers=0,
+                  filter_ent=0, filter_plpd=0, reweight_ent=1, reweight_plpd=0)
+    for k, v in expect.items():
+        assert d[k] == v, k
+    # the launcher's abbreviations (scripts/test_ttl.sh:22,26) and the untyped --deyo_selection quirk
+    a = p.parse_args(['--data', 'x', '--b', '32', '--deyo_selection', 'False', '--layer_range', '9,11'])
+    assert a.dataset_mode == 'x' and a.batch_size == 32 and bool(a.deyo_selection) and a.layer_range == [9, 11]
+    assert not bool(p.parse_args(['--deyo_selection', '']).deyo_selection)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/ttl.py"), reason="reference tree not present")
+def test_cli_matches_reference_parser():
+    """Every option string and default of the reference's parser (ttl.py:382-424) exists unchanged in ours."""
+    src = open("/root/reference/ttl.py").read()
+    block = src[src.index("    default_data_root"):src.index("    args = parser.parse_args()\n\n    main()")]
+    ns = {"argparse": __import__("argparse"), "list_of_ints": lambda s: list(map(int, s.split(',')))}
+    exec("\n".join(l[4:] for l in block.splitlines()), ns)
+    ref = {tuple(a.option_strings) or (a.dest,): a for a in ns["parser"]._actions}
+    import ttl
+    ours = {tuple(a.option_strings) or (a.dest,): a for a in ttl.build_parser()._actions}
+    for k, a in ref.items():
+        assert k in ours, k
+        assert ours[k].default == a.default and ours[k].dest == a.dest and ours[k].choices == a.choices, k
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ttl_b200 import dist as tdist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 11
+    mine = list(tdist.shard_indices(n, rank, world))
+    # each rank "evaluates" its shard: correct iff sample index is even; top5 always
+    counts = torch.tensor([sum(1 for i in mine if i % 2 == 0), len(mine), len(mine)], dtype=torch.int64)
+    tot = tdist.reduce_counts(counts, world)
+    preds = torch.tensor([i * 10 for i in mine] + [-1] * (6 - len(mine)), dtype=torch.int32)
+    allp = tdist.gather_predictions(preds, world)
+    q.put((rank, mine, tot, allp.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_count_reduction_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    (r0, m0, t0, a0), (r1, m1, t1, a1) = res
+    assert m0 == [0, 2, 4, 6, 8, 10] and m1 == [1, 3, 5, 7, 9]
+    assert t0 == t1 == [6, 11, 11]                      # single all-reduce(sum) of {top1, top5, n}
+    from ttl_b200 import dist as tdist
+    assert tdist.merge_sharded([m0, m1]) == list(range(11))
+    assert a0 == a1 and a0[:4] == [0, 10, 20, 30]       # interleaved back into sample order
+
+
+def test_synthetic_generators_equal_oracle():
+    from oracle import ttl_oracle as O
+    from ttl_b200.synthetic import synthetic_lora_init, synthetic_text_features, synthetic_vit_weights
+    a, b = synthetic_vit_weights("ViT-tiny", 3), O.make_synthetic_weights(O.ARCHS["ViT-tiny"], 3)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    l1, l2 = synthetic_lora_init("ViT-B/16"), O.lora_init(O.ARCHS["ViT-B/16"], O.LoraSpec(), 0)
+    assert all(torch.equal(x, y) for i in l2 for x, y in zip(l1[i], l2[i]))
+    assert torch.equal(synthetic_text_features(10, 64, 2), O.make_text_features(10, 64, 2))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the agreed keys (tiny step count; CPU only)."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--views", "10", "--classes", "10"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

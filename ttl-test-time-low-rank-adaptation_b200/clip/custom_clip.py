@@ -1,0 +1,351 @@
+"""Drop-in for the reference's `clip/custom_clip.py` test-time-tuning module API (get_coop, ClipTestTimeTuning, LoRA_AB),
+for `--lora_encoder image`, executed by libttl_b200 (hand-written sm_100a CUDA) instead of HF transformers + peft.
+
+What is kept from the reference interface (clip/custom_clip.py:139-217, 570-723):
+  * `get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls, layer_range, init_method, lora_encoder, rank)`
+  * `ClipTestTimeTuning(...)` with `.forward(input) -> logits[B,C]`, `.inference`, `.LoRA_reset()`, `.reset()`,
+    `.reset_classnames(classnames, arch)`, `.get_text_features()`, `.logit_scale`, `.image_encoder`, `.text_encoder`,
+    `.prompt_learner.tokenized_prompts`, `.LoRA_AB`
+  * parameter names `image_encoder.vision_model.encoder.layers.{i}.self_attn.{q_proj|v_proj}.lora_{A|B}.default.weight`
+    (ttl.py:159-160 string-matches them, ttl.py:197-201 walks them), A [r,d], B [d,r]
+  * `LoRA_AB(model, layer_range, init_method, lora_encoder)` with `.init_weights` (one 4-tuple per layer) and `.reset()`
+
+Two execution modes behind that surface:
+  * compat: `model(images)` returns logits carrying a grad_fn (one autograd.Function around ttl_forward/ttl_backward), so
+    unmodified reference-style code (test_time_tuning, torch.optim.AdamW, GradScaler) can drive it;
+  * fast:   `model.adapt_and_predict(images, args)` = one fused C-ABI call / CUDA-graph replay per test sample.
+
+Differences, all documented in DESIGN.md: text features are computed once per class-name set and cached (the reference
+re-runs the text tower on every forward); `--rank`/`--arch` are honoured; LoRA in layers outside `layer_range` is exactly
+zero in the reference (B=0, never trained) and is exposed as plain tensors that take no part in the computation.
+"""
+from __future__ import annotations
+
+import math
+import os
+import zlib
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from ttl_b200 import ARCH_GEOMETRY, Engine, Hparams
+from ttl_b200 import _lib as L
+from ttl_b200.synthetic import synthetic_vit_weights
+
+_HF_NAME = {"ViT-B/16": "openai/clip-vit-base-patch16", "ViT-L/14": "openai/clip-vit-large-patch14"}
+
+
+# ----------------------------------------------------------------------------- module tree (names only; math is in CUDA)
+class _Weight(nn.Module):
+    def __init__(self, t: torch.Tensor, trainable: bool):
+        super().__init__()
+        self.weight = nn.Parameter(t, requires_grad=trainable)
+
+
+class _LoraProj(nn.Module):
+    """Stands where peft's LoRA Linear sits: `.lora_A.default.weight` [r,d], `.lora_B.default.weight` [d,r]."""
+
+    def __init__(self, a: torch.Tensor, b: torch.Tensor, trainable: bool):
+        super().__init__()
+        self.lora_A = nn.ModuleDict({"default": _Weight(a, trainable)})
+        self.lora_B = nn.ModuleDict({"default": _Weight(b, trainable)})
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, q: _LoraProj, v: _LoraProj):
+        super().__init__()
+        self.q_proj, self.v_proj = q, v
+
+
+class _Layer(nn.Module):
+    def __init__(self, sa: _SelfAttn):
+        super().__init__()
+        self.self_attn = sa
+
+
+class _Encoder(nn.Module):
+    def __init__(self, layers: Sequence[_Layer]):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+
+class _VisionModel(nn.Module):
+    def __init__(self, enc: _Encoder):
+        super().__init__()
+        self.encoder = enc
+
+
+class VisionEncoder(nn.Module):
+    """Name-compatible stand-in of the reference's VisionEncoder (clip/custom_clip.py:62-71)."""
+
+    def __init__(self, vm: _VisionModel):
+        super().__init__()
+        self.vision_model = vm
+        self.dtype = torch.float32
+
+
+class PromptEncoder(nn.Module):
+    """Frozen text side (clip/custom_clip.py:73-82): holds the cached, L2-normalised class features."""
+
+    def __init__(self):
+        super().__init__()
+        self.dtype = torch.float32
+
+
+class _PromptState:
+    """The part of PromptLearner the image-LoRA path reads (clip/custom_clip.py:655): class names / tokenised prompts."""
+
+    def __init__(self, owner, classnames, ctx_init):
+        self.owner = owner
+        self.training = False
+        self.ctx_init = (ctx_init or "a_photo_of_a").replace("_", " ")
+        self.set(classnames)
+
+    def set(self, classnames):
+        self.classnames = [c.replace("_", " ") for c in classnames]
+        self.prompts = [f"{self.ctx_init} {c}." for c in self.classnames]
+        self.tokenized_prompts = None      # tokeniser + text tower are the "next" row N2
+
+    def reset_classnames(self, classnames, arch):
+        self.set(classnames)
+        self.owner._refresh_text_features()
+
+    def reset(self):
+        pass
+
+
+# ----------------------------------------------------------------------------- LoRA_AB
+class LoRA_AB:
+    """clip/custom_clip.py:139-217: initialise A (B stays 0), snapshot, restore the snapshot for layers in range."""
+
+    def __init__(self, model, layer_range, init_method="xavier", lora_encoder="text"):
+        self.model = model
+        self.layer_range = layer_range
+        self.init_method = init_method
+        self.lora_encoder = lora_encoder
+        self.init_weights = []
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        if self.init_method in ("xavier", None):
+            fn = init.xavier_normal_
+        elif self.init_method == "gaussian":
+            fn = init.normal_
+        elif self.init_method == "kaiming":
+            fn = init.kaiming_normal_
+        elif self.init_method == "pretrained":
+            fn = None
+        else:
+            raise ValueError(f"Unsupported init_method: {self.init_method}")
+        if self.lora_encoder != "image":
+            raise NotImplementedError("only --lora_encoder image is on the B200 path")
+        for layer in self.model.vision_model.encoder.layers:
+            self.initialize_layer_weights(layer, fn)
+
+    def initialize_layer_weights(self, layer, fn):
+        ws = [layer.self_attn.q_proj.lora_A.default.weight, layer.self_attn.q_proj.lora_B.default.weight,
+              layer.self_attn.v_proj.lora_A.default.weight, layer.self_attn.v_proj.lora_B.default.weight]
+        if fn is not None:
+            with torch.no_grad():
+                fn(ws[0])
+                fn(ws[2])
+        self.init_weights.append(tuple(w.detach().clone() for w in ws))
+
+    def reset(self):
+        layers = self.model.vision_model.encoder.layers
+        with torch.no_grad():
+            for i, layer in enumerate(layers):
+                if i in range(self.layer_range[0], self.layer_range[1] + 1):
+                    a_q, b_q, a_v, b_v = self.init_weights[i]
+                    layer.self_attn.q_proj.lora_A.default.weight.data.copy_(a_q)
+                    layer.self_attn.q_proj.lora_B.default.weight.data.copy_(b_q)
+                    layer.self_attn.v_proj.lora_A.default.weight.data.copy_(a_v)
+                    layer.self_attn.v_proj.lora_B.default.weight.data.copy_(b_v)
+
+
+# ----------------------------------------------------------------------------- autograd bridge (compat mode)
+class _TtlLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, owner, *params):
+        eng: Engine = owner.engine
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        eng.lora_touch()                       # factors may have been written through the aliases (optimizer / reset)
+        logits = eng.forward(images, train=train)
+        ctx.owner = owner
+        ctx.n_params = len(params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        owner = ctx.owner
+        owner.engine.backward(dlogits)
+        grads = [g.clone() for g in owner._grad_aliases]
+        return (None, None, *grads)
+
+
+# ----------------------------------------------------------------------------- the module
+class ClipTestTimeTuning(nn.Module):
+    def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-B/16", n_ctx=16, ctx_init=None,
+                 ctx_position="end", learned_cls=False, layer_range=[9, 11], init_method=None, lora_encoder="text",
+                 rank=16, max_views: int = 64, weights: Optional[dict] = None, text_features: Optional[torch.Tensor] = None,
+                 logit_scale: float = math.log(100.0)):
+        super().__init__()
+        if lora_encoder != "image":
+            raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
+                                      "'text' and 'prompt' are out of scope (SURVEY.md §8f N4)")
+        dev_index = device if isinstance(device, int) else (torch.device(device).index or 0)
+        self.device = torch.device("cuda", dev_index)
+        self.lora_encoder = lora_encoder
+        self.arch = arch
+        self.criterion = criterion
+        geo = ARCH_GEOMETRY[arch]
+        d, n_layers = geo["width"], geo["layers"]
+        self.layer_range = [int(layer_range[0]), int(layer_range[1])]
+        self.engine = Engine(arch, max_views=max_views, max_classes=max(1000, len(classnames)), lora_rank=rank,
+                             lora_alpha=32.0, layer_range=self.layer_range, device=dev_index)
+        self.engine.load_weights(weights if weights is not None else self._load_vision_weights(arch))
+
+        # LoRA module tree.  Trainable-range tensors alias the library's device buffers.
+        layers: List[_Layer] = []
+        self._param_aliases, self._grad_aliases = [], []
+        for i in range(n_layers):
+            in_range = self.layer_range[0] <= i <= self.layer_range[1]
+            ts = []
+            for which in range(4):
+                if in_range:
+                    t = self.engine.lora_alias(i, which, L.LORA_PARAM)
+                    self._param_aliases.append(t)
+                    self._grad_aliases.append(self.engine.lora_alias(i, which, L.LORA_GRAD))
+                else:
+                    shape = (rank, d) if which in (0, 2) else (d, rank)
+                    t = torch.zeros(shape, device=self.device)
+                ts.append(t)
+            layers.append(_Layer(_SelfAttn(_LoraProj(ts[0], ts[1], in_range), _LoraProj(ts[2], ts[3], in_range))))
+        self.image_encoder = VisionEncoder(_VisionModel(_Encoder(layers)))
+        self.text_encoder = PromptEncoder()
+        self.LoRA_AB = LoRA_AB(self.image_encoder, layer_range=self.layer_range, init_method=init_method,
+                               lora_encoder=lora_encoder)
+        # snapshot -> library (p0 for the fused reset) ; the live factors already hold it through the aliases
+        for i in range(self.layer_range[0], self.layer_range[1] + 1):
+            self.engine.set_lora_init({i: [t.cpu() for t in self.LoRA_AB.init_weights[i]]})
+        self.logit_scale = torch.tensor(float(logit_scale), device=self.device)
+        self._given_text = text_features
+        self.prompt_learner = _PromptState(self, classnames, ctx_init)
+        self.tokenized_prompts = self.prompt_learner.tokenized_prompts
+        self._refresh_text_features()
+
+    # ---- frozen inputs ------------------------------------------------------------------------------
+    @staticmethod
+    def _load_vision_weights(arch):
+        """HF checkpoint from the local cache when present (clip/custom_clip.py:581), else seeded random init
+        (set TTL_SYNTHETIC_WEIGHTS=0 to forbid the fallback to random weights)."""
+        try:
+            from transformers import CLIPModel
+            m = CLIPModel.from_pretrained(_HF_NAME[arch], local_files_only=True)
+            sd = {k: v for k, v in m.state_dict().items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
+            ClipTestTimeTuning._hf_logit_scale = float(m.logit_scale)
+            return sd
+        except Exception:
+            if os.environ.get("TTL_SYNTHETIC_WEIGHTS", "1") == "0":
+                raise
+            print("ttl_b200: no local CLIP checkpoint; using seeded random-init ViT weights (synthetic mode)")
+            return synthetic_vit_weights(arch, seed=1234)
+
+    def _refresh_text_features(self):
+        """Once per class-name set (the reference recomputes the text tower in every forward, custom_clip.py:667-671)."""
+        names = self.prompt_learner.classnames
+        P = ARCH_GEOMETRY[self.arch]["proj_dim"]
+        if self._given_text is not None and self._given_text.shape[0] == len(names):
+            t = self._given_text.detach().float().cpu()
+        else:
+            # No tokenizer/text tower offline: deterministic unit vectors keyed by the prompt text.
+            rows = []
+            for p in self.prompt_learner.prompts:
+                g = torch.Generator().manual_seed(zlib.crc32(p.encode()))
+                rows.append(torch.randn(P, generator=g))
+            t = torch.stack(rows)
+        t = t / t.norm(dim=-1, keepdim=True)
+        self.text_features = t.to(self.device)
+        self.engine.set_text_features(t, float(self.logit_scale))
+
+    def set_text_features(self, text_features: torch.Tensor, logit_scale: Optional[float] = None):
+        """Install externally computed class features [C,P] (e.g. from a real CLIP text tower)."""
+        if logit_scale is not None:
+            self.logit_scale = torch.tensor(float(logit_scale), device=self.device)
+        self._given_text = text_features
+        self._refresh_text_features()
+
+    # ---- reference surface -----------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def LoRA_reset(self):
+        self.LoRA_AB.reset()
+
+    def reset(self):
+        self.prompt_learner.reset()
+
+    def reset_classnames(self, classnames, arch):
+        self.prompt_learner.reset_classnames(classnames, arch)
+
+    def get_text_features(self):
+        return self.text_features
+
+    def _trainable(self):
+        return [p for n, p in self.named_parameters() if "lora_" in n and
+                any(f"layers.{i}." in n for i in range(self.layer_range[0], self.layer_range[1] + 1))]
+
+    def inference(self, image, label=None, coeff=None):
+        if coeff is not None:
+            raise NotImplementedError("coeff-weighted feature averaging is not on the TTL path")
+        image = image.to(self.device, torch.float32)
+        return _TtlLogits.apply(image, self, *self._trainable())
+
+    def forward(self, input, label=None, coeff=None):
+        if isinstance(input, tuple) or input.dim() == 2:
+            raise NotImplementedError("contrastive / directional prompt tuning are not on the TTL path")
+        return self.inference(input, label, coeff)
+
+    # ---- fast path -------------------------------------------------------------------------------------
+    def hparams_from_args(self, args) -> Hparams:
+        deyo = bool(getattr(args, "deyo_selection", True)) and getattr(args, "lora_encoder", "image") != "prompt"
+        return Hparams(head="deyo" if deyo else "tpt", tta_steps=int(args.tta_steps), selection_p=float(args.selection_p),
+                       lr=float(args.lr), deyo_margin_e0=float(getattr(args, "deyo_margin_e0", 0.4)))
+
+    def fast_path_ok(self, args) -> bool:
+        """The fused call covers the default flag set; anything else goes through compat mode."""
+        return (not getattr(args, "cocoop", False) and getattr(args, "filter_ent", 0) == 0
+                and getattr(args, "filter_plpd", 0) == 0 and getattr(args, "reweight_ent", 1) == 1
+                and getattr(args, "reweight_plpd", 0) == 0)
+
+    def adapt_and_predict(self, images: torch.Tensor, args=None, hparams: Optional[Hparams] = None,
+                          want=("pred_logits",)):
+        """reset -> test_time_tuning -> model(image)  (ttl.py:338-352) as ONE library call.  `images` [V,3,S,S], on the
+        device or in pinned host memory.  Returns a dict with `pred_logits` [C] (+ anything else in `want`)."""
+        hp = hparams or self.hparams_from_args(args)
+        return self.engine.adapt_predict(images, hp, want=want)
+
+
+def get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls=False, layer_range=[0, 11], init_method=None,
+             lora_encoder="text", rank=16, classnames: Optional[Sequence[str]] = None, **kw):
+    """clip/custom_clip.py:706-723.  Class names come from the reference's `data` package when importable."""
+    if classnames is None:
+        classnames = _default_classnames(test_set)
+    return ClipTestTimeTuning(device, classnames, None, arch=clip_arch, n_ctx=n_ctx, ctx_init=ctx_init,
+                              learned_cls=learned_cls, layer_range=layer_range, init_method=init_method,
+                              lora_encoder=lora_encoder, rank=rank, **kw)
+
+
+def _default_classnames(test_set):
+    try:   # the reference's data/ package (class lists are data, out of the hot path; not vendored here)
+        from data.imagnet_prompts import imagenet_classes
+        from data.fewshot_datasets import fewshot_datasets
+        if test_set in fewshot_datasets:
+            import data.cls_to_names as c2n
+            return getattr(c2n, f"{test_set.lower()}_classes")
+        return imagenet_classes
+    except Exception:
+        return [f"class {i}" for i in range(1000)]

@@ -891,6 +891,10 @@ int ttl_op_logits_entropy(const float* feats, const float* text, float scale, fl
   launch_logits_entropy(feats, text, scale, logits, entropy, V, C, P, static_cast<cudaStream_t>(stream));
   return op_done("logits_entropy");
 }
+int ttl_op_entropy(const float* logits, float* entropy, int32_t V, int32_t C, void* stream) {
+  launch_entropy(const_cast<float*>(logits), entropy, V, C, static_cast<cudaStream_t>(stream));
+  return op_done("entropy");
+}
 int ttl_op_select(const float* entropy, int32_t V, int32_t K, int32_t* idx, void* stream) {
   launch_select(entropy, V, K, nullptr, idx, static_cast<cudaStream_t>(stream));
   return op_done("select");

@@ -128,9 +128,12 @@ scale_entropy_kernel(const float* __restrict__ feats, float scale, float* __rest
                      float* __restrict__ entropy, int C, int P) {
   __shared__ float red[32];
   const int v = blockIdx.x;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) { const float t = feats[static_cast<size_t>(v) * P + i]; s += t * t; }
-  const float mul = rsqrtf(block_sum(s, red)) * scale;
+  float mul = 1.f;   // feats == nullptr: logits are final, only the entropy is wanted
+  if (feats != nullptr) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) { const float t = feats[static_cast<size_t>(v) * P + i]; s += t * t; }
+    mul = rsqrtf(block_sum(s, red)) * scale;
+  }
   float* lg = logits + static_cast<size_t>(v) * C;
   float mx = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) { const float t = lg[c] * mul; lg[c] = t; mx = fmaxf(mx, t); }
@@ -316,6 +319,9 @@ void launch_logits_entropy(const float* feats, const float* text, float scale, f
                            int C, int P, cudaStream_t st) {
   small_gemm_nt_kernel<<<dim3((C + SG_TN - 1) / SG_TN, (V + SG_TM - 1) / SG_TM), 256, 0, st>>>(feats, text, logits, V, C, P);
   scale_entropy_kernel<<<V, HT, 0, st>>>(feats, scale, logits, entropy, C, P);
+}
+void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st) {
+  scale_entropy_kernel<<<V, HT, 0, st>>>(nullptr, 1.f, logits, entropy, C, 0);
 }
 void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st) {
   select_kernel<<<1, 256, 0, st>>>(entropy, V, K, forced_idx, idx);

@@ -43,6 +43,8 @@ void launch_pool_project(const float* x, const float* gamma, const float* beta, 
 // logits[v,c] = scale * <feats[v]/|feats[v]|, T[c]> ; entropy[v] = H(softmax(logits[v]))   (custom_clip.py:680-687, ttl.py:51)
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st);
+// entropy[v] = H(softmax(logits[v]))  (ttl.py:51 / deyo.py:85-90); logits are read-only in effect (scaled by 1)
+void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st);
 // idx[0..K) = argsort(entropy, stable)[:K]  (ttl.py:52; ties -> lowest index).  forced_idx (nullable) overrides.
 void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st);
 // marginal-entropy loss of the K rows logits[idx[k]] (ttl.py:56-61) and its gradient, compact: dlogits[K,C]

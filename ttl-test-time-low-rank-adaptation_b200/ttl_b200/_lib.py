@@ -69,6 +69,7 @@ _SIGS = {
     "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),
     "ttl_profile_read": (C.c_int, [vp, C.POINTER(TtlGemmRecord), C.c_int32, C.POINTER(C.c_int32)]),
     "ttl_op_logits_entropy": (C.c_int, [vp, vp, C.c_float, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "ttl_op_entropy": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp]),
     "ttl_op_select": (C.c_int, [vp, C.c_int32, C.c_int32, vp, vp]),
     "ttl_op_tpt_loss": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
     "ttl_op_deyo_loss": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_float, vp, vp, vp]),
