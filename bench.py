@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-baseline-samples", type=int, default=2)
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -235,11 +237,15 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_region:
+        torch.cuda.profiler.start()
     ev0.record()
     for i in range(args.steps):
         step(i, ring[i % args.ring])
     ev1.record()
     torch.cuda.synchronize()
+    if args.profile_region:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()

@@ -168,9 +168,8 @@ class LoRA_AB:
 # ----------------------------------------------------------------------------- autograd bridge (compat mode)
 class _TtlLogits(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, images, owner, *params):
-        eng: Engine = owner.engine
-        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, images, owner, train, *params):
+        eng: Engine = owner.engine        # grad mode is off inside Function.forward, so `train` is decided by the caller
         eng.lora_touch()                       # factors may have been written through the aliases (optimizer / reset)
         logits = eng.forward(images, train=train)
         ctx.owner = owner
@@ -182,7 +181,7 @@ class _TtlLogits(torch.autograd.Function):
         owner = ctx.owner
         owner.engine.backward(dlogits)
         grads = [g.clone() for g in owner._grad_aliases]
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 # ----------------------------------------------------------------------------- the module
@@ -302,7 +301,9 @@ class ClipTestTimeTuning(nn.Module):
         if coeff is not None:
             raise NotImplementedError("coeff-weighted feature averaging is not on the TTL path")
         image = image.to(self.device, torch.float32)
-        return _TtlLogits.apply(image, self, *self._trainable())
+        params = self._trainable()
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _TtlLogits.apply(image, self, train, *params)
 
     def forward(self, input, label=None, coeff=None):
         if isinstance(input, tuple) or input.dim() == 2:

@@ -131,7 +131,9 @@ class Engine:
         self.lora_reset()
 
     def lora_reset(self) -> None:
+        self._sync_in()
         L.check(self.lib.ttl_lora_reset(self.ctx, self._st()), self.ctx)
+        self._sync_out()
 
     def lora_get(self, layer: int, which: int, what: int = L.LORA_PARAM) -> np.ndarray:
         d, r = self.geom["width"], self.rank
@@ -149,11 +151,16 @@ class Engine:
         return torch.as_tensor(_DevAlias(ptr.value, shape), device=self.device)
 
     def lora_touch(self) -> None:
+        # the aliases are written on torch's current stream (optimizer.step / LoRA_AB.reset): order the repack after it
+        self._sync_in()
         L.check(self.lib.ttl_lora_touch(self.ctx, self._st()), self.ctx)
+        self._sync_out()
 
     def adamw_step(self, hp: Hparams) -> None:
         h = hp.to_c()
+        self._sync_in()
         L.check(self.lib.ttl_adamw_step(self.ctx, C.byref(h), self._st()), self.ctx)
+        self._sync_out()
 
     # ------------------------------------------------------------------ model calls
     def _st(self) -> C.c_void_p:
