@@ -40,6 +40,37 @@ def test_gemm_bias_bf16(G, M, N, K, bn):
     assert torch.isfinite(out.float()).all()
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(12608, 768, 768, 192), (12608, 2304, 768, 256), (1182, 768, 3072, 128),
+                                      (12608, 3072, 768, 192), (2100, 768, 256, 256), (300, 384, 128, 128)])
+def test_gemm_cta_pair_kernel(G, M, N, K, bn):
+    """The cta_group::2 kernel (block_n = 1000 + BLOCK_N): TMA-store epilogues, ragged last 256-row tile."""
+    gu, L = G
+    a, b = _bf(M, K, seed=11), _bf(N, K, scale=K ** -0.5, seed=12)
+    bias = torch.randn(N, device="cuda") * 0.2
+    acc = a.float() @ b.float().t()
+    out, _ = gu.gemm(a, b, L.EPI_BF16, bias=bias, block_n=1000 + bn)
+    assert gu.rel_err(out, acc + bias) < 4e-3 and torch.isfinite(out.float()).all()
+    out, _ = gu.gemm(a, b, L.EPI_GELU, bias=bias, block_n=1000 + bn)
+    z = acc + bias
+    assert gu.rel_err(out, z * torch.sigmoid(1.702 * z)) < 6e-3
+    resid = torch.randn(M, N, device="cuda")
+    out, _ = gu.gemm(a, b, L.EPI_RESID_F32, bias=bias, resid=resid, block_n=1000 + bn)
+    assert gu.rel_err(out, resid + acc + bias) < 1e-5
+    out, _ = gu.gemm(a, b, L.EPI_F32, block_n=1000 + bn)
+    assert gu.rel_err(out, acc) < 1e-5
+
+
+def test_gemm_cta_pair_lora_pair_and_guard_rows(G):
+    gu, L = G
+    M, N, K = 2500, 2304, 768
+    a, b = _bf(M, K, seed=1), _bf(N, K, scale=K ** -0.5, seed=2)
+    a2, b2 = _bf(M, 64, seed=3), _bf(N, 64, scale=0.1, seed=4)
+    out, _ = gu.gemm(a, b, L.EPI_BF16, a2=a2, b2=b2, block_n=1256, out_rows=M + 40)
+    ref = a.float() @ b.float().t() + a2.float() @ b2.float().t()
+    assert gu.rel_err(out[:M], ref) < 4e-3
+    assert float(out[M:].float().abs().max()) == 0.0          # TMA clips rows >= M
+
+
 def test_gemm_lora_second_pair(G):
     gu, L = G
     M, N, K = 1182, 2304, 768

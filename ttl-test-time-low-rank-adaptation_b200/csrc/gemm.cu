@@ -13,6 +13,7 @@
 
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -289,6 +290,280 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   }
 }
 
+
+// =============================================================================================== CTA-pair kernel
+// Same contract as above for the big-M GEMMs of the 64-view forward, built around tcgen05 cta_group::2:
+//   * a cluster of two CTAs (one SM each) owns a 256 x BLOCK_N output tile; each CTA stages its own 128 rows of A and
+//     HALF of the B tile (BLOCK_N/2 rows) per k-block, so the pair reads (256 + BLOCK_N) x 64 bf16 from L2 per
+//     256 x BLOCK_N x 64 MMA block instead of 2 x (128 + BLOCK_N) x 64 -- the 1-CTA kernel is L2->SM bandwidth bound;
+//   * the leader CTA's single MMA thread issues 256 x BLOCK_N x 16 MMAs for both; completion is multicast to both
+//     CTAs' mbarriers (tcgen05.commit ... multicast::cluster);
+//   * epilogue: 8 warps per CTA, tcgen05.ld -> registers -> (bias / QuickGELU / + residual tile that TMA prefetched
+//     into smem) -> 128B/64B-swizzled smem -> TMA store.  No per-thread global addressing, rows >= M are clipped by TMA.
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_THREADS = 64 + G2_EPI_WARPS * 32;
+constexpr int G2_SMEM_MAX = 232448;   // 227 KB
+
+template <int BLOCK_N, int EPI>
+struct Cfg2 {
+  static constexpr bool OUT_F32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EBUF_BYTES = OUT_F32 ? 4096 : 2048;          // 32 rows x 32 columns
+  static constexpr int EPI_BYTES = G2_EPI_WARPS * 2 * EBUF_BYTES;   // two buffers per epilogue warp
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int STAGES_RAW = (G2_SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+  static constexpr int CHUNKS = BLOCK_N / 64;                       // 32-column chunks per epilogue warp
+  static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024 B alignment");
+};
+
+struct Epi2Params {
+  int M, N;
+  int kb1, kb2;
+  const float* bias;
+  int dbg;   // TTL_GEMM_DBG bits (development only): 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const Epi2Params p) {
+  using C = Cfg2<BLOCK_N, EPI>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint8_t* sE = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + C::EPI_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* lbar = tempty + 2;                       // [G2_EPI_WARPS][2] residual-tile arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 2 * G2_EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmOut);
+    if (EPI == EPI_RESID_F32) tma_prefetch_desc(&tmRes);
+    if (p.kb2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 2);    // one arrival per CTA's producer (used in the leader only)
+      mbar_init(&empty[s], 1);   // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);                      // multicast tcgen05.commit
+      mbar_init(&tempty[a], 2 * G2_EPI_WARPS);      // every epilogue warp of both CTAs (leader's copy is used)
+    }
+    for (int i = 0; i < 2 * G2_EPI_WARPS; ++i) mbar_init(&lbar[i], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int m_pairs = (p.M + 255) / 256;
+  const int n_tiles = p.N / BLOCK_N;
+  const int num_tiles = m_pairs * n_tiles;
+  const int num_kb = p.kb1 + p.kb2;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (one thread per CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);   // the LEADER's full barriers
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+        const int a_row = m_pair * 256 + static_cast<int>(rank) * 128;
+        const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t fb = full0 + stage * 8;
+          if (leader) mbar_expect_tx(&full[stage], (p.dbg & 4) ? 0 : 2 * C::STAGE_BYTES);
+          else mbar_arrive_cluster(fb);
+          uint8_t* a_dst = sA + stage * C::A_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          if (p.dbg & 4) {
+          } else if (kb < p.kb1) {
+            tma_load_2d_cg2(&tmA1, fb, a_dst, kb * BLOCK_K, a_row);
+            tma_load_2d_cg2(&tmB1, fb, b_dst, kb * BLOCK_K, b_row);
+          } else {
+            tma_load_2d_cg2(&tmA2, fb, a_dst, (kb - p.kb1) * BLOCK_K, a_row);
+            tma_load_2d_cg2(&tmB2, fb, b_dst, (kb - p.kb1) * BLOCK_K, b_row);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer (one thread of the leader CTA)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            if (p.dbg & 2) break;
+            umma_bf16_cg2(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
+                          idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_mc2(&empty[stage], 3);   // frees the slot in BOTH CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_mc2(&tfull[as], 3);        // accumulator complete -> both CTAs' epilogues
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      // drain: the peer's epilogue arrives remotely on OUR tempty barriers; do not exit under them
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- epilogue warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;           // which half of the BLOCK_N columns
+    uint8_t* ebuf = sE + ew * 2 * C::EBUF_BYTES;
+    uint64_t* lb = lbar + ew * 2;
+    const uint32_t tempty0 = mapa_u32(smem_u32(&tempty[0]), 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int row0 = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
+      const bool live = row0 < p.M;     // warp-uniform
+      if (EPI == EPI_RESID_F32 && live && lane == 0 && !(p.dbg & 1)) {
+        bulk_wait_read<0>();            // both buffers are free of pending store reads
+#pragma unroll
+        for (int c = 0; c < 2 && c < C::CHUNKS; ++c) {
+          const uint32_t b = (g + c) & 1;
+          mbar_expect_tx(&lb[b], C::EBUF_BYTES);
+          tma_load_2d(&tmRes, &lb[b], ebuf + b * C::EBUF_BYTES, col_base + c * 32, row0);
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < C::CHUNKS; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + half * (BLOCK_N / 2) + c * 32, r);
+        tmem_ld_wait();
+        if (c == C::CHUNKS - 1) {       // accumulator fully read: hand the TMEM stage back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty0 + as * 8);
+        }
+        if (!live || (p.dbg & 1)) continue;
+        const uint32_t b = g & 1;
+        uint8_t* buf = ebuf + b * C::EBUF_BYTES;
+        const int col = col_base + c * 32;
+        if (EPI == EPI_RESID_F32) {
+          mbar_wait(&lb[b], (g >> 1) & 1);
+        } else {
+          if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer has finished reading it
+          __syncwarp();
+        }
+        if (C::OUT_F32) {
+          float4* row = reinterpret_cast<float4*>(buf + lane * 128);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                   __uint_as_float(r[4 * i + 3]));
+            if (p.bias != nullptr) v = add4(v, __ldg(reinterpret_cast<const float4*>(p.bias + col) + i));
+            float4* slot = row + (i ^ (lane & 7));
+            if (EPI == EPI_RESID_F32) v = add4(v, *slot);
+            *slot = v;
+          }
+        } else {
+          uint4* row = reinterpret_cast<uint4*>(buf + lane * 64);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * i + j]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 2 * i);
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 2 * i + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (EPI == EPI_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] * (0.5f + 0.5f * tanh_approx(0.851f * v[j]));   // z * sigmoid(1.702 z)
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            row[i ^ ((lane >> 1) & 3)] = o;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, buf, col, row0);
+          bulk_commit();
+          if (EPI == EPI_RESID_F32 && c + 2 < C::CHUNKS) {
+            bulk_wait_read<0>();        // the store just issued must be done with the buffer before it is refilled
+            mbar_expect_tx(&lb[b], C::EBUF_BYTES);
+            tma_load_2d(&tmRes, &lb[b], buf, col + 64, row0);
+          }
+        }
+        ++g;
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) bulk_wait<0>();      // all output tiles written before the CTA retires
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -297,6 +572,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 thread_local char g_err[256] = "";
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
+int g_pairs_hint = 0;   // co-resident CTA pairs reported by the occupancy API (0 until the first pair launch)
 
 void set_err(const char* msg) { std::snprintf(g_err, sizeof(g_err), "%s", msg); }
 
@@ -311,24 +587,124 @@ EncodeTiledFn get_encode() {
   return g_encode;
 }
 
-bool make_map(CUtensorMap* m, const GemmOperand& op, int box_rows) {
+bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* ptr, int inner, int rows, int ld,
+                int box_inner, int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_err("cuTensorMapEncodeTiled unavailable"); return false; }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(op.k), static_cast<cuuint64_t>(op.rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(op.ld) * 2};
-  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(op.ptr), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[200];
-    std::snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%d k=%d ld=%d box_rows=%d", int(r),
-                  (const void*)op.ptr, op.rows, op.k, op.ld, box_rows);
+    std::snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%d inner=%d ld=%d box=%dx%d", int(r), ptr,
+                  rows, inner, ld, box_inner, box_rows);
     set_err(b);
     return false;
   }
   return true;
+}
+
+bool make_map(CUtensorMap* m, const GemmOperand& op, int box_rows) {
+  return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, op.ptr, op.k, op.rows, op.ld, BLOCK_K, box_rows,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BLOCK_N, int EPI>
+cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
+  using C = Cfg2<BLOCK_N, EPI>;
+  CUtensorMap tA1, tB1, tA2, tB2, tOut, tRes;
+  if (!make_map(&tA1, g.a1, 128) || !make_map(&tB1, g.b1, BLOCK_N / 2)) return cudaErrorInvalidValue;
+  const bool two = g.a2.ptr != nullptr && g.a2.k > 0;
+  if (two) {
+    if (!make_map(&tA2, g.a2, 128) || !make_map(&tB2, g.b2, BLOCK_N / 2)) return cudaErrorInvalidValue;
+  } else {
+    tA2 = tA1;
+    tB2 = tB1;
+  }
+  if (C::OUT_F32) {
+    if (!encode_map(&tOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, g.N, g.M, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+      return cudaErrorInvalidValue;
+  } else {
+    if (!encode_map(&tOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.out, g.N, g.M, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+      return cudaErrorInvalidValue;
+  }
+  if (EPI == EPI_RESID_F32) {
+    if (!encode_map(&tRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.resid, g.N, g.M, g.ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+      return cudaErrorInvalidValue;
+  } else {
+    tRes = tOut;
+  }
+  Epi2Params p;
+  p.M = g.M; p.N = g.N;
+  p.kb1 = g.a1.k / BLOCK_K;
+  p.kb2 = two ? g.a2.k / BLOCK_K : 0;
+  p.bias = g.bias;
+  static const char* dbg_env = std::getenv("TTL_GEMM_DBG");
+  p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  auto kern = gemm2_kernel<BLOCK_N, EPI>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem) failed (gemm2)"); return e; }
+    attr_done = true;
+  }
+  // A persistent grid must be co-resident: not every TPC of a B200 has both SMs enabled, so the number of CTA pairs
+  // that fit at once can be below num_sms / 2 -- ask the occupancy API once per instantiation.
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~1);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
+    max_pairs = n < num_sms / 2 ? n : num_sms / 2;
+    g_pairs_hint = max_pairs;
+    if (std::getenv("TTL_DEBUG")) std::fprintf(stderr, "ttl: gemm2<%d,%d> co-resident CTA pairs: %d (SMs %d)\n", BLOCK_N, EPI, n, num_sms);
+  }
+  const int tiles = ((g.M + 255) / 256) * (g.N / BLOCK_N);
+  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  kern<<<grid, G2_THREADS, C::SMEM_BYTES, stream>>>(tA1, tB1, tA2, tB2, tOut, tRes, p);
+  return cudaGetLastError();
+}
+
+template <int BLOCK_N>
+cudaError_t launch2_n(const GemmArgs& g, cudaStream_t s, int sms) {
+  switch (g.epi) {
+    case EPI_BF16: return launch2_t<BLOCK_N, EPI_BF16>(g, s, sms);
+    case EPI_GELU: return launch2_t<BLOCK_N, EPI_GELU>(g, s, sms);
+    case EPI_RESID_F32: return launch2_t<BLOCK_N, EPI_RESID_F32>(g, s, sms);
+    case EPI_F32: return launch2_t<BLOCK_N, EPI_F32>(g, s, sms);
+    default: set_err("gemm2: epilogue not supported by the CTA-pair kernel"); return cudaErrorInvalidValue;
+  }
+}
+
+// The CTA-pair kernel covers the plain epilogues (no second output, no scatter); BLOCK_N by a per-k-block cost model:
+// rounds of the persistent schedule x bytes a pair pulls from L2 per k-block (the kernel is L2->SM bound).
+int pick_pair_block_n(const GemmArgs& g, int num_sms) {
+  if (g.out2 != nullptr || g.M < 1024) return 0;
+  if (g.epi != EPI_BF16 && g.epi != EPI_GELU && g.epi != EPI_RESID_F32 && g.epi != EPI_F32) return 0;
+  if (g.ldo % 4 != 0 || (g.epi == EPI_RESID_F32 && (g.resid == nullptr || g.ldr % 4 != 0))) return 0;
+  const int pairs = g_pairs_hint > 0 ? g_pairs_hint : num_sms / 2, m_pairs = (g.M + 255) / 256;
+  int best = 0;
+  double best_cost = 0;
+  const int cands[3] = {256, 192, 128};
+  for (int bn : cands) {
+    if (g.N % bn != 0) continue;
+    const int tiles = m_pairs * (g.N / bn);
+    const int rounds = (tiles + pairs - 1) / pairs;
+    const double cost = rounds * (256.0 + bn);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 template <int BLOCK_N, int EPI>
@@ -390,6 +766,25 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   }
   if (g.a1.rows < g.M || g.b1.rows < g.N) { set_err("gemm_launch: operand rows smaller than M/N"); return cudaErrorInvalidValue; }
   int bn = g.force_block_n;
+  {
+    // force_block_n: 0 = heuristic; 64/128/256 = 1-CTA kernel; 1000 + {128,192,256} = CTA-pair kernel
+    int bn2 = bn >= 1000 ? bn - 1000 : (bn == 0 ? pick_pair_block_n(g, num_sms) : 0);
+    static const char* env = std::getenv("TTL_GEMM_PAIR");
+    if (bn == 0 && env != nullptr) {
+      const int v = std::atoi(env);
+      if (v == 0) bn2 = 0;
+      else if (v > 1 && bn2 != 0 && g.N % v == 0) bn2 = v;
+    }
+    if (bn2 != 0) {
+      if (g.N % bn2 != 0 || g.out2 != nullptr) { set_err("gemm_launch: CTA-pair kernel: bad BLOCK_N / out2"); return cudaErrorInvalidValue; }
+      switch (bn2) {
+        case 256: return launch2_n<256>(g, stream, num_sms);
+        case 192: return launch2_n<192>(g, stream, num_sms);
+        case 128: return launch2_n<128>(g, stream, num_sms);
+        default: set_err("gemm_launch: CTA-pair BLOCK_N must be 128/192/256"); return cudaErrorInvalidValue;
+      }
+    }
+  }
   if (bn == 0) {
     const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
     if (g.N % 256 == 0 && m_tiles * (g.N / 256) >= num_sms) bn = 256;
