@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--head", default="tpt", choices=["tpt", "deyo"])
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--views", type=int, default=64)
-    ap.add_argument("--ring", type=int, default=8, help="distinct pre-staged samples (ring * 38.5 MB > L2)")
+    ap.add_argument("--ring", type=int, default=4, help="distinct pre-staged batches (ring * S * 38.5 MB > L2)")
+    ap.add_argument("--concurrent", type=int, default=3,
+                    help="test samples adapted concurrently per step (BASELINE config 5); 3 x 64 x 197 rows = 147.75 "
+                         "tiles of 256 rows, one full wave of the 74 CTA pairs per 256-column block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -53,6 +56,15 @@ def parse_args():
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "gemm2_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
 
 
 def load_peaks():
@@ -203,7 +215,8 @@ def main():
 
     # ---- model: random-init ViT-B/16 (seed 1234), synthetic unit text features, Xavier LoRA A / zero B
     from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features
-    eng = Engine("ViT-B/16", max_views=args.views, max_classes=max(args.classes, 16), device=local_rank)
+    S = args.concurrent
+    eng = Engine("ViT-B/16", max_views=args.views, max_classes=max(args.classes, 16), device=local_rank, max_samples=S)
     eng.load_weights(synthetic_vit_weights("ViT-B/16", seed=1234))
     eng.set_text_features(synthetic_text_features(args.classes, 512, seed=11), math.log(100.0))
     eng.set_lora_init(synthetic_lora_init("ViT-B/16", rank=16, layers=(9, 11), seed=0))
@@ -211,21 +224,21 @@ def main():
 
     # ---- data: this rank's shard of a seeded synthetic evaluation set, pre-staged in HBM (ring > L2)
     gen = torch.Generator(device="cuda").manual_seed(7 + 1000 * rank)
-    ring = [synth_sample_gpu(torch, gen, args.views) for _ in range(args.ring)]
+    ring = [torch.stack([synth_sample_gpu(torch, gen, args.views) for _ in range(S)]) for _ in range(args.ring)]
     # labels = zero-shot prediction of the un-adapted model, so "accuracy" is well-defined on random weights
     labels = []
     eng.lora_reset()
-    for s in ring:
-        labels.append(int(eng.forward(s[:1]).argmax()))
+    for b in ring:
+        labels.append(torch.stack([eng.forward(b[j, :1]).argmax() for j in range(S)]))
     correct = torch.zeros(3, dtype=torch.int64, device="cuda")   # top1, top5, n
 
-    def step(i, images):
-        out = eng.adapt_predict(images, hp, want=("pred_logits",))["pred_logits"]
-        top5 = out.topk(5).indices
+    def step(i, images):      # one step = one batch of S test samples: reset -> adapt -> predict for each of them
+        out = eng.adapt_predict_batch(images, hp, want=("pred_logits",))["pred_logits"]      # [S, C]
+        top5 = out.topk(5, dim=1).indices
         lab = labels[i % args.ring]
-        correct[0] += (top5[0] == lab)
-        correct[1] += (top5 == lab).any()
-        correct[2] += 1
+        correct[0] += (top5[:, 0] == lab).sum()
+        correct[1] += (top5 == lab[:, None]).any(dim=1).sum()
+        correct[2] += S
 
     for i in range(args.warmup):
         step(i, ring[i % args.ring])
@@ -250,41 +263,43 @@ def main():
         dist.barrier()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
-    launches = eng.last_launch_count() * args.steps
+    launches = eng.last_launch_count() * args.steps   # kernels per batch (graph replay + im2col) x steps
     t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_max_ms = float(t)
     counts = tdist.reduce_counts(correct, world)          # the path's only collective (24 bytes)
-    value = world * args.steps / (t_max_ms * 1e-3)
+    value = world * args.steps * S / (t_max_ms * 1e-3)
 
     # ---- end-to-end through the public API with HOST buffers (H2D of the views + D2H of the prediction in the timed region)
     e2e = None
     if not args.no_e2e:
-        host = [s.cpu().pin_memory() for s in ring[:4]]
+        host = [b.cpu().pin_memory() for b in ring[:4]]
+        nh = len(host)
         for i in range(3):
-            eng.adapt_predict(host[i % 4], hp, want=("pred_logits",))
+            eng.adapt_predict_batch(host[i % nh], hp, want=("pred_logits",))
         n_e2e = max(10, args.steps // 4)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            o = eng.adapt_predict(host[i % 4], hp, want=("pred_logits",))["pred_logits"]
-            _ = int(o.argmax())
+            o = eng.adapt_predict_batch(host[i % nh], hp, want=("pred_logits",))["pred_logits"]
+            _ = o.argmax(dim=1).tolist()
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_e2e / float(dt), "unit": UNIT,
-               "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": int(args.classes * 4),
-               "steps": n_e2e, "api": "ttl_b200.Engine.adapt_predict(host tensor) -> ttl_adapt_predict_host"}
+        e2e = {"value": world * n_e2e * S / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": int(S * args.classes * 4),
+               "steps": n_e2e, "samples_per_step": S,
+               "api": "ttl_b200.Engine.adapt_predict_batch(pinned host tensor [S,V,3,224,224]) -> ttl_adapt_predict_batch_host"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch, instrumented eager pass
     roof = None
     if not args.no_roofline and rank == 0:
         from ttl_b200 import profile as tprof
-        roof = tprof.gemm_roofline(eng, hp, ring, peaks, samples=4)
+        roof = tprof.gemm_roofline(eng, hp, ring, peaks, batches=3, traffic=load_traffic())
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,8 +317,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head), "
-                                       f"random-init weights", "samples_per_rank": args.steps,
-                           "l2": f"inputs larger than L2: ring of {args.ring} pre-staged samples x {ring[0].numel() * 4 / 1e6:.1f} MB",
+                                       f"random-init weights", "samples_per_rank": args.steps * S,
+                           "concurrent_samples_per_step": S,
+                           "l2": f"inputs larger than L2: ring of {args.ring} pre-staged batches x {ring[0].numel() * 4 / 1e6:.1f} MB",
                            "parallelism": f"sample-sharded x{world}"},
                 "tflops_per_gpu_alg": per_gpu_tflops,
                 "frac_of_bf16_peak": {"sustained_measured": per_gpu_tflops / peaks["tf_sus"],

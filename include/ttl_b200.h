@@ -52,6 +52,7 @@ typedef struct ttl_config {
   int32_t lora_layer_hi;
   float ln_eps;          /* 1e-5 */
   int32_t device;        /* CUDA ordinal (--gpu) */
+  int32_t max_samples;   /* test samples adapted concurrently per call (BASELINE config 5); 0 or 1 = one at a time */
 } ttl_config;
 
 /* Frozen-weight slots; names follow the HF CLIP vision tower state_dict that
@@ -93,13 +94,14 @@ typedef struct ttl_hparams {
   float deyo_margin_e0;/* 0.4 */
 } ttl_hparams;
 
-/* Optional outputs of ttl_adapt_predict*: any pointer may be NULL. */
+/* Optional outputs of ttl_adapt_predict*: any pointer may be NULL.  The batch entry points return one block per
+ * sample, sample-major (S = n_samples). */
 typedef struct ttl_outputs {
-  float* logits0;      /* [V,C] first-forward logits                                  */
-  float* entropy;      /* [V]   per-view entropies                                    */
-  int32_t* idx;        /* [K]   selected views in argsort order (TPT head)            */
-  float* loss;         /* [1]   loss of the last optimiser step                       */
-  float* pred_logits;  /* [C]   adapted prediction on view 0 (ttl.py:350-352)         */
+  float* logits0;      /* [S,V,C] first-forward logits                                            */
+  float* entropy;      /* [S,V]   per-view entropies                                              */
+  int32_t* idx;        /* [S,K]   selected views (index within the sample) in argsort order (TPT) */
+  float* loss;         /* [S]     loss of the last optimiser step                                 */
+  float* pred_logits;  /* [S,C]   adapted prediction on view 0 (ttl.py:350-352)                   */
 } ttl_outputs;
 
 /* ---- lifetime ----------------------------------------------------------------------------------------- */
@@ -142,6 +144,14 @@ int ttl_adapt_predict(ttl_ctx* ctx, const float* images_dev, int32_t n_views, co
 /* Same with HOST buffers (pinned recommended): H2D of the views, D2H of the requested outputs, stream sync. */
 int ttl_adapt_predict_host(ttl_ctx* ctx, const float* images_host, int32_t n_views, const ttl_hparams* hp,
                            const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream);
+/* n_samples independent test samples adapted concurrently (each: reset -> adapt -> predict with its own LoRA factors
+ * and AdamW state, exactly as n_samples consecutive ttl_adapt_predict calls): images [n_samples, n_views, 3, S, S].
+ * The frozen 64-view forward of all samples is one GEMM/attention pass; n_samples <= ttl_config.max_samples. */
+int ttl_adapt_predict_batch(ttl_ctx* ctx, const float* images_dev, int32_t n_samples, int32_t n_views,
+                            const ttl_hparams* hp, const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream);
+int ttl_adapt_predict_batch_host(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
+                                 const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
+                                 void* stream);
 /* Toggle CUDA-graph replay of ttl_adapt_predict (default on). */
 int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
 /* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */

@@ -167,3 +167,55 @@ def test_tiny_geometry_vs_live_oracle(head, steps):
             for j in (1, 3):
                 assert _rel(eng.lora_get(i, j, L.LORA_GRAD), ref.grads[i][j].numpy()) < 8e-2, (i, j)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ concurrent samples
+@pytest.mark.parametrize("head,steps", [("tpt", 1), ("tpt", 2), ("deyo", 1)])
+def test_concurrent_samples_equal_sequential(b16_weights, head, steps):
+    """S samples adapted in one call (shared frozen pass, K-concatenated per-sample adapters, segmented weight-gradient
+    reductions) must give what S consecutive single-sample calls give: same selected views, same loss and adapted
+    prediction (same kernels and accumulation order per sample; tolerance only covers tile-shape dependent rounding)."""
+    from ttl_b200 import Engine, Hparams
+    S, V = 3, 64
+    arch = O.ARCHS["ViT-B/16"]
+    eng = Engine("ViT-B/16", max_views=V, max_classes=64, layer_range=(9, 11), max_samples=S)
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(O.lora_init(arch, O.LoraSpec(), seed=0))
+        eng.set_text_features(O.make_text_features(37, arch.proj), math.log(100.0))
+        hp = Hparams(head=head, tta_steps=steps)
+        imgs = torch.stack([O.make_synthetic_views(V, arch.image_size, seed=21 + i) for i in range(S)]).cuda()
+        want = ("logits0", "entropy", "idx", "loss", "pred_logits")
+        for graphs in (False, True, True):     # eager, first graph use (eager + capture), replay
+            eng.set_graphs(graphs)
+            single = [eng.adapt_predict(imgs[i], hp, want=want) for i in range(S)]
+            single = {k: torch.stack([s[k] for s in single]).cpu() for k in want}
+            batch = {k: v.cpu() for k, v in eng.adapt_predict_batch(imgs, hp, want=want).items()}
+            assert _rel(batch["logits0"].numpy(), single["logits0"].numpy()) < 1e-5
+            if head == "tpt":
+                assert batch["idx"].tolist() == single["idx"].tolist()
+            assert _rel(batch["loss"].numpy(), single["loss"].numpy()) < 1e-4
+            assert _rel(batch["pred_logits"].numpy(), single["pred_logits"].numpy()) < 2e-3
+            # the samples really are different problems
+            assert _rel(batch["pred_logits"][0].numpy(), batch["pred_logits"][1].numpy()) > 1e-2
+    finally:
+        eng.close()
+
+
+def test_concurrent_samples_host_path_and_partial_batch(b16_weights):
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-B/16"]
+    eng = Engine("ViT-B/16", max_views=64, max_classes=16, layer_range=(9, 11), max_samples=3)
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(O.lora_init(arch, O.LoraSpec(), seed=0))
+        eng.set_text_features(O.make_text_features(10, arch.proj), math.log(100.0))
+        hp = Hparams(head="tpt")
+        imgs = torch.stack([O.make_synthetic_views(64, arch.image_size, seed=5 + i) for i in range(2)])
+        dev = eng.adapt_predict_batch(imgs.cuda(), hp)["pred_logits"].cpu()          # S=2 on a max_samples=3 engine
+        host = eng.adapt_predict_batch(imgs.pin_memory(), hp)["pred_logits"]
+        assert host.device.type == "cpu" and _rel(host.numpy(), dev.numpy()) < 1e-6
+        with pytest.raises(ValueError):
+            eng.adapt_predict_batch(torch.zeros(4, 64, 3, 224, 224), hp)
+    finally:
+        eng.close()

@@ -167,7 +167,7 @@ def _attn_ref(qkv, V, tokens, heads):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("V,tokens,heads", [(3, 197, 12), (2, 257, 16), (4, 17, 2), (1, 64, 1)])
+@pytest.mark.parametrize("V,tokens,heads", [(3, 197, 12), (2, 257, 16), (4, 17, 2), (1, 64, 1), (64, 197, 12), (5, 50, 3)])
 def test_attention_fwd_bwd(G, V, tokens, heads):
     gu, L = G
     d = heads * 64

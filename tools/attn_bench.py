@@ -1,0 +1,29 @@
+"""Micro-benchmark of the fused attention kernels through the C ABI.  Usage: python tools/attn_bench.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "ttl-test-time-low-rank-adaptation_b200"), os.path.join(ROOT, "tests")]
+import torch
+import gpu_util as gu
+
+lib = gu.lib()
+for (V, tokens, heads) in ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197, 12), (64, 257, 16)):
+    d = heads * 64
+    ring = 4
+    qkvs = [(torch.randn(V * tokens, 3 * d, device="cuda") * 1.5).bfloat16() for _ in range(ring)]
+    outs = [torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16) for _ in range(ring)]
+    def run(i):
+        gu.ok(lib.ttl_op_attention_fwd(gu.ptr(qkvs[i % ring]), gu.ptr(outs[i % ring]), None, V, tokens, heads, 0.125, gu.stream()))
+    for i in range(5):
+        run(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 40
+    e0.record()
+    for i in range(iters):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    fl = 4.0 * tokens * tokens * 64 * heads * V
+    by = V * tokens * d * 2 * 4
+    print(f"attention fwd V={V} tokens={tokens} heads={heads}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)

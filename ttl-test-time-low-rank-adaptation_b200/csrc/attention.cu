@@ -8,7 +8,11 @@
 //   backward: phase A per 16-query tile -> dQ ; phase B per 16-key tile (transposed problem) -> dK, dV.
 //             No atomics, deterministic.
 #include "kernels.cuh"
+#include "gemm.cuh"
 #include "ptx.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
 
 namespace ttl {
 
@@ -314,6 +318,215 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   }
 }
 
+
+// =============================================================================================== TMA-fed forward
+// Persistent forward kernel for the 64-view pass: one CTA per SM walks (view, head) units; Q/K/V of the NEXT unit are
+// fetched by three 3-D TMA loads (box 64 x rows x 1 of the [views][tokens][3d] tensor, 128-byte swizzle, tokens beyond
+// the view zero-filled by the TMA) into the other half of a double buffer while the current unit is computed.
+// Each warp owns 32 query rows (two m16 tiles share every K/V fragment read from smem) and walks the keys in chunks of
+// 64 + one exact 16-key tail (197 tokens -> 208 keys, not 256).  The normalised tile goes back through the warp's own
+// Q rows (swizzled) and one TMA store per warp; rows >= tokens are clipped by the TMA.
+constexpr int ATT_MAX_WARPS = 8;   // up to 256 tokens; longer sequences (ViT-L/14: 257) use the cp-style kernel above
+
+__device__ __forceinline__ uint32_t sw128(uint32_t base, int r, int c) {   // c: element column, multiple of 8
+  return base + r * 128 + ((((c >> 3) ^ r) & 7) << 4);
+}
+__device__ __forceinline__ void lda_sw(uint32_t base, int row0, int col0, int lane, uint32_t (&a)[4]) {
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int c = col0 + (lane >> 4) * 8;
+  ldsm_x4(sw128(base, r, c), a[0], a[1], a[2], a[3]);
+}
+__device__ __forceinline__ void ldb_nk_sw(uint32_t base, int n0, int k0, int lane, uint32_t (&b)[4]) {
+  const int mi = lane >> 3;
+  ldsm_x4(sw128(base, n0 + (mi >> 1) * 8 + (lane & 7), k0 + (mi & 1) * 8), b[0], b[1], b[2], b[3]);
+}
+__device__ __forceinline__ void ldb_kn_sw(uint32_t base, int k0, int n0, int lane, uint32_t (&b)[4]) {
+  const int mi = lane >> 3;
+  ldsm_x4_t(sw128(base, k0 + (mi & 1) * 8 + (lane & 7), n0 + (mi >> 1) * 8), b[0], b[1], b[2], b[3]);
+}
+
+// One chunk of NT*8 keys for NMT m16 query tiles of one warp (online softmax, exp2 domain).
+template <int NMT, int NT>
+__device__ __forceinline__ void att_chunk(float (&o)[2][8][4], float (&mrow)[2][2], float (&lrow)[2][2],
+                                          const uint32_t (&aq)[2][4][4], uint32_t sK, uint32_t sV, int kc, int tokens,
+                                          float scale_log2, int lane) {
+  float s[NMT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldb_nk_sw(sK, kc + np * 16, ks * 16, lane, b);
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt) {
+        mma_bf16_16816(s[mt][2 * np], aq[mt][ks], b[0], b[1]);
+        mma_bf16_16816(s[mt][2 * np + 1], aq[mt][ks], b[2], b[3]);
+      }
+    }
+  }
+  const bool tail = kc + NT * 8 > tokens;   // warp-uniform: some keys of this chunk are padding
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int key = kc + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = s[mt][nt][e] * scale_log2;
+        if (tail && key + (e & 1) >= tokens) v = -INFINITY;
+        s[mt][nt][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(mrow[mt][0], mx0), mn1 = fmaxf(mrow[mt][1], mx1);   // finite: every chunk holds a real key
+    const float c0 = exp2f(mrow[mt][0] - mn0), c1 = exp2f(mrow[mt][1] - mn1);
+    mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+    float l0 = lrow[mt][0] * c0, l1 = lrow[mt][1] * c1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[mt][nt][0] *= c0; o[mt][nt][1] *= c0; o[mt][nt][2] *= c1; o[mt][nt][3] *= c1; }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[mt][nt][0] = exp2f(s[mt][nt][0] - mn0); s[mt][nt][1] = exp2f(s[mt][nt][1] - mn0);
+      s[mt][nt][2] = exp2f(s[mt][nt][2] - mn1); s[mt][nt][3] = exp2f(s[mt][nt][3] - mn1);
+      l0 += s[mt][nt][0] + s[mt][nt][1];
+      l1 += s[mt][nt][2] + s[mt][nt][3];
+    }
+    lrow[mt][0] = l0; lrow[mt][1] = l1;
+  }
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t pf[NMT][4];
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+      pf[mt][0] = pack_bf16(s[mt][2 * kk][0], s[mt][2 * kk][1]);
+      pf[mt][1] = pack_bf16(s[mt][2 * kk][2], s[mt][2 * kk][3]);
+      pf[mt][2] = pack_bf16(s[mt][2 * kk + 1][0], s[mt][2 * kk + 1][1]);
+      pf[mt][3] = pack_bf16(s[mt][2 * kk + 1][2], s[mt][2 * kk + 1][3]);
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldb_kn_sw(sV, kc + kk * 16, np * 16, lane, b);
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt) {
+        mma_bf16_16816(o[mt][2 * np], pf[mt], b[0], b[1]);
+        mma_bf16_16816(o[mt][2 * np + 1], pf[mt], b[2], b[3]);
+      }
+    }
+  }
+}
+
+template <int NMT>
+__device__ __forceinline__ void att_warp_rows(uint32_t sQ, uint32_t sK, uint32_t sV, int m0, int tokens, int rows_pad,
+                                              float scale_log2, int lane, float* lse_unit) {
+  uint32_t aq[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) lda_sw(sQ, m0 + mt * 16, ks * 16, lane, aq[mt][ks]);
+  float o[2][8][4];
+  float mrow[2][2], lrow[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    mrow[mt][0] = mrow[mt][1] = -INFINITY;
+    lrow[mt][0] = lrow[mt][1] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+  }
+  int kc = 0;
+  for (; kc + 64 <= rows_pad; kc += 64) att_chunk<NMT, 8>(o, mrow, lrow, aq, sK, sV, kc, tokens, scale_log2, lane);
+  const int rem = rows_pad - kc;   // 0, 16, 32 or 48
+  if (rem == 16) att_chunk<NMT, 2>(o, mrow, lrow, aq, sK, sV, kc, tokens, scale_log2, lane);
+  else if (rem == 32) att_chunk<NMT, 4>(o, mrow, lrow, aq, sK, sV, kc, tokens, scale_log2, lane);
+  else if (rem == 48) att_chunk<NMT, 6>(o, mrow, lrow, aq, sK, sV, kc, tokens, scale_log2, lane);
+  __syncwarp();   // all lanes are done with this warp's Q rows (aq loaded long ago) -> reuse them as the output stage
+#pragma unroll
+  for (int mt = 0; mt < NMT; ++mt) {
+    float l0 = lrow[mt][0], l1 = lrow[mt][1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = m0 + mt * 16 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const uint32_t lo = pack_bf16(o[mt][nt][0] * i0, o[mt][nt][1] * i0), hi = pack_bf16(o[mt][nt][2] * i1, o[mt][nt][3] * i1);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128(sQ, r0, nt * 8) + (lane & 3) * 4), "r"(lo) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw128(sQ, r1, nt * 8) + (lane & 3) * 4), "r"(hi) : "memory");
+    }
+    if (lse_unit != nullptr && (lane & 3) == 0) {
+      if (r0 < tokens) lse_unit[r0] = (mrow[mt][0] + log2f(l0)) * LN2;
+      if (r1 < tokens) lse_unit[r1] = (mrow[mt][1] + log2f(l1)) * LN2;
+    }
+  }
+}
+
+__global__ void __maxnreg__(224)
+attention_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut,
+                         float* __restrict__ lse, int tokens, int heads, int units, float scale_log2, int rows_alloc,
+                         int rows_pad, int nbox, int box_rows) {
+  extern __shared__ uint8_t smem_att_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_att_raw) + 1023) & ~uintptr_t(1023));
+  const int RB = rows_alloc * 128;                      // bytes of one operand (rows_alloc x 64 bf16)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 6 * RB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = heads * DH;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  auto issue = [&](int unit, int buf) {   // thread 0 only
+    const int view = unit / heads, h = unit - view * heads;
+    uint8_t* dst = smem + buf * 3 * RB;
+    mbar_expect_tx(&full[buf], 3 * RB);
+    for (int j = 0; j < nbox; ++j)
+#pragma unroll
+      for (int mat = 0; mat < 3; ++mat)
+        tma_load_3d(&tmQKV, &full[buf], dst + mat * RB + j * box_rows * 128, mat * d + h * DH, j * box_rows, view);
+  };
+  if (tid == 0 && static_cast<int>(blockIdx.x) < units) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && unit + static_cast<int>(gridDim.x) < units) issue(unit + gridDim.x, buf ^ 1);
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const int view = unit / heads, h = unit - view * heads;
+    const uint32_t sQ = smem_u32(smem + buf * 3 * RB), sK = sQ + RB, sV = sK + RB;
+    const int m0 = warp * 32;
+    if (m0 < rows_pad) {
+      float* lse_unit = lse != nullptr ? lse + (static_cast<size_t>(view) * heads + h) * tokens : nullptr;
+      if (rows_pad - m0 >= 32) att_warp_rows<2>(sQ, sK, sV, m0, tokens, rows_pad, scale_log2, lane, lse_unit);
+      else att_warp_rows<1>(sQ, sK, sV, m0, tokens, rows_pad, scale_log2, lane, lse_unit);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && m0 < tokens) {
+        tma_store_3d(&tmOut, smem + buf * 3 * RB + m0 * 128, h * DH, m0, view);
+        bulk_commit();
+        bulk_wait_read<0>();   // the stage is refilled by the TMA load issued after the barrier below
+      }
+    }
+    __syncthreads();
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
 inline int pick_warps(int tiles) {
   const int rounds = (tiles + 7) / 8;
   return (tiles + rounds - 1) / rounds;
@@ -330,8 +543,54 @@ size_t attention_bwd_smem(int tokens) {
   return static_cast<size_t>(4 * nkp) * LDS * sizeof(bf16) + 2 * nkp * sizeof(float);
 }
 
+static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                                     cudaStream_t st) {
+  const int rows_pad = (tokens + 15) / 16 * 16, rows_alloc = (rows_pad + 31) / 32 * 32;
+  if (rows_alloc > ATT_MAX_WARPS * 32) return false;
+  const int nbox = (rows_alloc + 255) / 256;
+  if (rows_alloc % nbox != 0) return false;
+  const int box_rows = rows_alloc / nbox;
+  const size_t smem = static_cast<size_t>(6) * rows_alloc * 128 + 64 + 1024;
+  if (smem > 227 * 1024) return false;
+  const int d = heads * DH;
+  CUtensorMap tq, to;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+    if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, box, 128)) return false;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    if (!encode_tiled_map(&to, 0, out, 3, dims, strides, box, 128)) return false;
+  }
+  static size_t configured = 0;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attention_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem;
+  }
+  const int units = V * heads;
+  const int grid = units < num_sms ? units : num_sms;
+  attention_fwd_tma_kernel<<<grid, (rows_alloc / 32) * 32, smem, st>>>(tq, to, lse, tokens, heads, units, scale * LOG2E, rows_alloc,
+                                                                      rows_pad, nbox, box_rows);
+  return true;
+}
+
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                           cudaStream_t st) {
+  static const bool use_tma = std::getenv("TTL_ATTN_LEGACY") == nullptr;
+  if (use_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_fwd_smem(tokens);
   static size_t configured = 0;

@@ -5,7 +5,12 @@
 //   GEMM operands        bf16 row-major, K contiguous: H [M,d], QKV [M,3d], AO [M,d], G [M,F]; weights [N,K]
 //   train-mode tape      per layer lo..L-1: h1, T=h1 A^T, qkv, ao, lse, x_mid, h2, z, g, x_out (rows of the views
 //                        that carry gradient: the K selected views for the TPT head, all views for DeYO / autograd)
-//   LoRA state           fp32 [n_lora_layers][A_q | B_q | A_v | B_v] x {param, grad, init, m, v}; bf16 packs per layer
+//   LoRA state           fp32 [sample][n_lora_layers][A_q | B_q | A_v | B_v] x {param, grad, m, v}; one shared init
+//                        snapshot; bf16 packs per layer, K-concatenated over the samples of the call
+// Concurrent samples (BASELINE config 5): a call may carry S independent test samples (S x V views).  Everything frozen
+// is one big GEMM/attention over S*V views; the per-sample adapters ride as a K-concatenated second operand pair
+// (T[M, 64 S] with only the sample's own 64-column block non-zero, times [B_0 | B_1 | ...]), gradients are segment
+// reductions over each sample's rows, AdamW/reset are elementwise over all samples.
 // Exact shortcuts: LoRA GEMM extension skipped while B == 0; layers below lo run once per sample
 // and XK is reused by the train-mode recompute, later steps and the view-0 prediction.
 #include "../../include/ttl_b200.h"
@@ -46,10 +51,10 @@ struct Tape {  // one train-mode layer
 };
 
 struct GraphKey {
-  int n_views, forced;
+  int n_samples, n_views, forced;
   ttl_hparams hp;
   bool operator==(const GraphKey& o) const {
-    return n_views == o.n_views && forced == o.forced && std::memcmp(&hp, &o.hp, sizeof(hp)) == 0;
+    return n_samples == o.n_samples && n_views == o.n_views && forced == o.forced && std::memcmp(&hp, &o.hp, sizeof(hp)) == 0;
   }
 };
 struct GraphEntry {
@@ -59,7 +64,7 @@ struct GraphEntry {
   int64_t launches = 0;
   // host-side state the body leaves behind (replayed graphs do not run the host code)
   bool b_zero_after = false;
-  int opt_step_after = 0, train_views_after = 0;
+  int opt_step_after = 0, train_views_after = 0, train_samples_after = 1, pack_samples_after = 1;
   const float* train_in_after = nullptr;
 };
 
@@ -68,7 +73,7 @@ struct GraphEntry {
 struct ttl_ctx {
   ttl_config cfg{};
   int tokens = 0, T = 0, Kp = 0, d = 0, F = 0, P = 0, L = 0, H = 0, r = 0, lo = 0, hi = 0, n_train = 0, n_lora = 0;
-  int Vm = 0, Mm = 0, Cm = 0;
+  int Vm = 0, Sm = 1, VVm = 0, Mm = 0, Cm = 0;   // per-sample views, samples per call, total views, total rows, classes
   float s = 2.f;
   int num_sms = 148;
   std::string err;
@@ -84,7 +89,7 @@ struct ttl_ctx {
 
   // activations
   bf16 *patches = nullptr, *Hb = nullptr, *QKV = nullptr, *AO = nullptr, *Gb = nullptr, *Tm = nullptr;
-  float *XK = nullptr, *XA = nullptr, *XB = nullptr, *TIN = nullptr;
+  float *XK = nullptr, *XA = nullptr, *XB = nullptr, *TIN = nullptr, *PIN = nullptr;
   float *feats = nullptr, *feats_c = nullptr, *logits = nullptr, *logits_c = nullptr, *entropy = nullptr,
         *entropy_c = nullptr, *loss = nullptr, *dlogits = nullptr, *pred = nullptr, *pred_feats = nullptr,
         *pred_entropy = nullptr, *pooled = nullptr, *dfh = nullptr, *dpool = nullptr;
@@ -103,8 +108,9 @@ struct ttl_ctx {
   std::vector<float> host_init;  // mirror of l0 to know whether B0 == 0
 
   // train-forward bookkeeping
-  int last_train_views = 0;
+  int last_train_views = 0, last_train_samples = 1;   // total views / samples of the last train-mode forward
   const float* last_train_in = nullptr;
+  int pack_samples = 1;                                // K-concatenation width (in samples) of the current bf16 packs
 
   // per-launch GEMM timing (bench.py roofline): CUDA events around every gemm launch while enabled
   bool prof = false;
@@ -202,11 +208,13 @@ int embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
   return check_launch(c, "embed");
 }
 
-// One encoder layer.  tp == nullptr: inference buffers; else train mode (tape kept for the backward).
-int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_out, int V, bool lora_on, Tape* tp,
+// One encoder layer over V views belonging to S samples (V/S views each).  tp == nullptr: inference buffers; else
+// train mode (tape kept for the backward).
+int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_out, int V, int S, bool lora_on, Tape* tp,
               cudaStream_t st) {
   const LayerW& w = c->lw[layer];
   const int M = V * c->tokens, d = c->d, F = c->F;
+  const int kc = 64 * c->pack_samples;          // K-concatenated adapter width
   bf16* h1 = tp ? tp->h1 : c->Hb;
   bf16* qkv = tp ? tp->qkv : c->QKV;
   bf16* ao = tp ? tp->ao : c->AO;
@@ -216,20 +224,25 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   const bool lora = has_lora(c, layer);
   launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
   c->launches++;
-  if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T  (needed by dB even while B == 0)
+  if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T per sample (needed by dB even while B == 0)
+    if (S != c->pack_samples) { c->err = "run_layer: adapter packs were built for another sample count"; return TTL_E_STATE; }
     GemmArgs g;
     g.a1 = opnd(h1, M, d, d);
-    g.b1 = opnd(c->pk[layer - c->lo].a_ext, 64, d, d);
-    g.M = M; g.N = 64; g.epi = EPI_BF16; g.out = Tb; g.ldo = 64;
+    g.b1 = opnd(c->pk[layer - c->lo].a_ext, kc, d, d);
+    g.M = M; g.N = kc; g.epi = EPI_BF16; g.out = Tb; g.ldo = kc;
     RET_IF(gemm(c, g, st));
+    if (S > 1) {   // keep only each sample's own 64-column block
+      launch_block_mask(Tb, M, kc, M / S, st);
+      c->launches++;
+    }
   }
   {
     GemmArgs g;
     g.a1 = opnd(h1, M, d, d);
     g.b1 = opnd(w.wqkv, 3 * d, d, d);
     if (lora && lora_on) {
-      g.a2 = opnd(Tb, M, 64, 64);
-      g.b2 = opnd(c->pk[layer - c->lo].b_ext, 3 * d, 64, 64);
+      g.a2 = opnd(Tb, M, kc, kc);
+      g.b2 = opnd(c->pk[layer - c->lo].b_ext, 3 * d, kc, kc);
     }
     g.M = M; g.N = 3 * d; g.epi = EPI_BF16; g.bias = w.bqkv; g.out = qkv; g.ldo = 3 * d;
     RET_IF(gemm(c, g, st));
@@ -265,16 +278,16 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
 // layers [0, lo) on all views: images -> XK
 int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
   RET_IF(embed(c, images, V, c->XK, st));
-  for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, c->XK, c->XB, c->XK, V, false, nullptr, st));
+  for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, c->XK, c->XB, c->XK, V, 1, false, nullptr, st));
   return TTL_OK;
 }
 
-// layers [lo, L) in inference mode from x_in (V views) -> feats/logits/entropy written to the given buffers
-int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float* logits, float* entropy,
+// layers [lo, L) in inference mode from x_in (V views of S samples) -> feats/logits/entropy written to the given buffers
+int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats, float* logits, float* entropy,
                        cudaStream_t st) {
   const float* cur = x_in;
   for (int l = c->lo; l < c->L; ++l) {
-    RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, !c->b_zero, nullptr, st));
+    RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, S, !c->b_zero, nullptr, st));
     cur = c->XA;
   }
   launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
@@ -283,25 +296,29 @@ int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float
   return check_launch(c, "forward_tail_infer");
 }
 
-// layers [lo, L) in train mode from x_in (G views): tape + feats_c
-int forward_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
+// layers [lo, L) in train mode from x_in (G views of S samples): tape + feats_c
+int forward_tail_train(ttl_ctx* c, const float* x_in, int G, int S, cudaStream_t st) {
   const float* cur = x_in;
   for (int l = c->lo; l < c->L; ++l) {
     Tape& tp = c->tape[l - c->lo];
-    RET_IF(run_layer(c, l, cur, tp.x_mid, tp.x_out, G, !c->b_zero, &tp, st));
+    RET_IF(run_layer(c, l, cur, tp.x_mid, tp.x_out, G, S, !c->b_zero, &tp, st));
     cur = tp.x_out;
   }
   launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
   c->launches += 2;
   c->last_train_views = G;
+  c->last_train_samples = S;
   c->last_train_in = x_in;
   return check_launch(c, "forward_tail_train");
 }
 
-// dlogits_c [G,C] -> LoRA gradients (overwrites c->lg)
+// dlogits_c [G,C] (G views of S samples, sample-major) -> LoRA gradients of every sample (overwrites c->lg)
 int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
-  const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
+  const int S = c->last_train_samples;
+  const int Mg = G * c->tokens, Ms = Mg / S, d = c->d, F = c->F, r = c->r;
+  const int kc = 64 * c->pack_samples;
+  const int64_t lt = c->lora_total;
   const float* x_last = c->tape[c->n_train - 1].x_out;
   launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX,
                   c->DXB, G, c->C, c->P, c->tokens, d, c->cfg.ln_eps, st);
@@ -339,27 +356,33 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
     c->launches++;
     const bool lora = has_lora(c, l);
     if (lora) {
-      float* gl = c->lg + static_cast<int64_t>(l - c->lo) * c->lora_per_layer;
+      float* gl = c->lg + static_cast<int64_t>(l - c->lo) * c->lora_per_layer;   // sample 0; sample s at + s * lora_total
       float* gAq = gl;
       float* gBq = gl + r * d;
       float* gAv = gl + 2 * r * d;
       float* gBv = gl + 3 * r * d;
-      // dB = s * dY^T (X A^T)
-      launch_skinny_reduce(c->DQKV, 3 * d, d, tp.T, 64, r, Mg, c->s, gBq, 0, c->ws, st);
-      launch_skinny_reduce(c->DQKV + 2 * d, 3 * d, d, tp.T + r, 64, r, Mg, c->s, gBv, 0, c->ws, st);
+      // dB_s = scale * dY_s^T (X_s A_s^T): segment reduction over the rows of each sample
+      launch_skinny_reduce(c->DQKV, 3 * d, d, tp.T, kc, r, Ms, c->s, gBq, 0, c->ws, S, 64, lt, st);
+      launch_skinny_reduce(c->DQKV + 2 * d, 3 * d, d, tp.T + r, kc, r, Ms, c->s, gBv, 0, c->ws, S, 64, lt, st);
       c->launches += 4;
-      if (!c->b_zero) {  // U = dqkv (s B)  ;  dA = U^T X
+      if (!c->b_zero) {  // U = dqkv (s B_s)  ;  dA_s = U_s^T X_s
         GemmArgs g;
         g.a1 = opnd(c->DQKV, Mg, 3 * d, 3 * d);
-        g.b1 = opnd(c->pk[l - c->lo].b_ext_t, 64, 3 * d, 3 * d);
-        g.M = Mg; g.N = 64; g.epi = EPI_BF16; g.out = c->U; g.ldo = 64;
+        g.b1 = opnd(c->pk[l - c->lo].b_ext_t, kc, 3 * d, 3 * d);
+        g.M = Mg; g.N = kc; g.epi = EPI_BF16; g.out = c->U; g.ldo = kc;
         RET_IF(gemm(c, g, st));
-        launch_skinny_reduce(tp.h1, d, d, c->U, 64, r, Mg, 1.f, gAq, 1, c->ws, st);
-        launch_skinny_reduce(tp.h1, d, d, c->U + r, 64, r, Mg, 1.f, gAv, 1, c->ws, st);
+        if (S > 1) {
+          launch_block_mask(c->U, Mg, kc, Ms, st);
+          c->launches++;
+        }
+        launch_skinny_reduce(tp.h1, d, d, c->U, kc, r, Ms, 1.f, gAq, 1, c->ws, S, 64, lt, st);
+        launch_skinny_reduce(tp.h1, d, d, c->U + r, kc, r, Ms, 1.f, gAv, 1, c->ws, S, 64, lt, st);
         c->launches += 4;
       } else {  // dA == 0 exactly while B == 0
-        cudaMemsetAsync(gAq, 0, sizeof(float) * r * d, st);
-        cudaMemsetAsync(gAv, 0, sizeof(float) * r * d, st);
+        for (int sm = 0; sm < S; ++sm) {
+          cudaMemsetAsync(gAq + sm * lt, 0, sizeof(float) * r * d, st);
+          cudaMemsetAsync(gAv + sm * lt, 0, sizeof(float) * r * d, st);
+        }
       }
     }
     if (l > c->lo) {
@@ -367,8 +390,8 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
       g.a1 = opnd(c->DQKV, Mg, 3 * d, 3 * d);
       g.b1 = opnd(w.wqkvT, d, 3 * d, 3 * d);
       if (lora && !c->b_zero) {
-        g.a2 = opnd(c->U, Mg, 64, 64);
-        g.b2 = opnd(c->pk[l - c->lo].a_ext_t, d, 64, 64);
+        g.a2 = opnd(c->U, Mg, kc, kc);
+        g.b2 = opnd(c->pk[l - c->lo].a_ext_t, d, kc, kc);
       }
       g.M = Mg; g.N = d; g.epi = EPI_F32; g.out = c->DH; g.ldo = d;
       RET_IF(gemm(c, g, st));
@@ -379,88 +402,109 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   return check_launch(c, "backward");
 }
 
-int repack(ttl_ctx* c, cudaStream_t st) {
+// bf16 operand packs of the live factors of samples [0, S), K-concatenated
+int repack(ttl_ctx* c, int S, cudaStream_t st) {
   for (int i = 0; i < c->n_lora; ++i) {
-    launch_lora_pack(c->lp + i * c->lora_per_layer, c->pk[i], c->d, c->r, c->s, st);
+    launch_lora_pack(c->lp + i * c->lora_per_layer, c->lora_total, c->pk[i], c->d, c->r, c->s, S, st);
     c->launches++;
   }
+  c->pack_samples = S;
   return check_launch(c, "lora_pack");
 }
 
-int lora_reset(ttl_ctx* c, cudaStream_t st) {
-  launch_lora_reset(c->lp, c->l0, c->lm, c->lv, static_cast<int>(c->lora_total), st);
+int lora_reset(ttl_ctx* c, int S, cudaStream_t st) {
+  launch_lora_reset(c->lp, c->l0, c->lm, c->lv, static_cast<int>(c->lora_total) * S, static_cast<int>(c->lora_total), st);
   c->launches++;
   c->opt_step = 0;
   c->b_zero = c->init_b_zero;
-  return repack(c, st);
+  return repack(c, S, st);
 }
 
-int adamw(ttl_ctx* c, const ttl_hparams& hp, cudaStream_t st) {
+int adamw(ttl_ctx* c, const ttl_hparams& hp, int S, cudaStream_t st) {
   c->opt_step++;
-  launch_adamw(c->lp, c->lg, c->lm, c->lv, static_cast<int>(c->lora_total), c->opt_step, hp.lr, hp.beta1, hp.beta2,
+  launch_adamw(c->lp, c->lg, c->lm, c->lv, static_cast<int>(c->lora_total) * S, c->opt_step, hp.lr, hp.beta1, hp.beta2,
                hp.eps, hp.weight_decay, st);
   c->launches++;
   c->b_zero = false;
-  return repack(c, st);
+  return repack(c, S, st);
 }
 
-// The per-sample body (everything after im2col-able input is in place).  Recorded into a CUDA graph when enabled.
-int adapt_body(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
-  RET_IF(lora_reset(c, st));
-  RET_IF(forward_frozen(c, images, V, st));
+// The body for S concurrent samples of V views each (everything after im2col-able input is in place).  Recorded into a
+// CUDA graph when enabled.  Per-sample results live sample-major in the ctx buffers.
+int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
+  const int VV = S * V;
+  RET_IF(lora_reset(c, S, st));
+  RET_IF(forward_frozen(c, images, VV, st));
   const int K = static_cast<int>(V * hp.selection_p);
+  const size_t view_elems = static_cast<size_t>(c->tokens) * c->d;
   if (hp.head == TTL_HEAD_TPT) {
-    RET_IF(forward_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, c->logits, c->entropy, st));
     if (hp.tta_steps > 0 && K > 0) {
-      launch_select(c->entropy, V, K, forced ? c->idx : nullptr, c->idx, st);
-      launch_gather_views(c->XK, c->TIN, c->idx, K, c->tokens, c->d, st);
-      c->launches += 2;
+      for (int sm = 0; sm < S; ++sm) {
+        launch_select(c->entropy + sm * V, V, K, forced ? c->idx + sm * K : nullptr, c->idx + sm * K, st);
+        launch_gather_views(c->XK + sm * V * view_elems, c->TIN + sm * K * view_elems, c->idx + sm * K, K, 0, c->tokens, c->d, st);
+        c->launches += 2;
+      }
       for (int step = 0; step < hp.tta_steps; ++step) {
-        RET_IF(forward_tail_train(c, c->TIN, K, st));
-        if (step == 0) {
-          launch_tpt_loss(c->logits, c->idx, K, c->C, c->loss, c->dlogits, st);
-        } else {
-          launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, K, c->C, c->P, st);
-          launch_tpt_loss(c->logits_c, nullptr, K, c->C, c->loss, c->dlogits, st);
+        RET_IF(forward_tail_train(c, c->TIN, S * K, S, st));
+        if (step > 0) {
+          launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, S * K, c->C, c->P, st);
           c->launches += 2;
         }
-        c->launches++;
-        RET_IF(backward(c, c->dlogits, K, st));
-        RET_IF(adamw(c, hp, st));
+        for (int sm = 0; sm < S; ++sm) {
+          if (step == 0) launch_tpt_loss(c->logits + static_cast<size_t>(sm) * V * c->C, c->idx + sm * K, K, c->C, c->loss + sm,
+                                         c->dlogits + static_cast<size_t>(sm) * K * c->C, st);
+          else launch_tpt_loss(c->logits_c + static_cast<size_t>(sm) * K * c->C, nullptr, K, c->C, c->loss + sm,
+                               c->dlogits + static_cast<size_t>(sm) * K * c->C, st);
+          c->launches++;
+        }
+        RET_IF(backward(c, c->dlogits, S * K, st));
+        RET_IF(adamw(c, hp, S, st));
       }
     }
   } else {
     const int nsteps = hp.tta_steps * hp.tta_steps;  // deyo.DeYO loops `steps` times inside the tta_steps loop
-    if (nsteps == 0) RET_IF(forward_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    if (nsteps == 0) RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, c->logits, c->entropy, st));
     for (int step = 0; step < nsteps; ++step) {
-      RET_IF(forward_tail_train(c, c->XK, V, st));
+      RET_IF(forward_tail_train(c, c->XK, VV, S, st));
       float* lg = step == 0 ? c->logits : c->logits_c;
       float* en = step == 0 ? c->entropy : c->entropy_c;
-      launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, V, c->C, c->P, st);
-      launch_deyo_loss(lg, V, c->C, hp.deyo_margin_e0, c->loss, c->dlogits, st);
-      c->launches += 3;
-      RET_IF(backward(c, c->dlogits, V, st));
-      RET_IF(adamw(c, hp, st));
+      launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, VV, c->C, c->P, st);
+      c->launches += 2;
+      for (int sm = 0; sm < S; ++sm) {
+        launch_deyo_loss(lg + static_cast<size_t>(sm) * V * c->C, V, c->C, hp.deyo_margin_e0, c->loss + sm,
+                         c->dlogits + static_cast<size_t>(sm) * V * c->C, st);
+        c->launches++;
+      }
+      RET_IF(backward(c, c->dlogits, VV, st));
+      RET_IF(adamw(c, hp, S, st));
     }
   }
-  // predict on view 0 with the adapted factors (ttl.py:350-352); XK rows [0, tokens) are view 0
-  RET_IF(forward_tail_infer(c, c->XK, 1, c->pred_feats, c->pred, c->pred_entropy, st));
+  // predict on view 0 of every sample with its adapted factors (ttl.py:350-352); layers below lo are reused from XK
+  const float* pin = c->XK;
+  if (S > 1) {
+    launch_gather_views(c->XK, c->PIN, nullptr, S, V, c->tokens, c->d, st);
+    c->launches++;
+    pin = c->PIN;
+  }
+  RET_IF(forward_tail_infer(c, pin, S, S, c->pred_feats, c->pred, c->pred_entropy, st));
   return TTL_OK;
 }
 
-int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
+int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int S, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
   if (!o) return TTL_OK;
   const int K = static_cast<int>(V * hp.selection_p);
-  if (o->logits0) CK(cudaMemcpyAsync(o->logits0, c->logits, sizeof(float) * V * c->C, kind, st));
-  if (o->entropy) CK(cudaMemcpyAsync(o->entropy, c->entropy, sizeof(float) * V, kind, st));
-  if (o->idx && K > 0) CK(cudaMemcpyAsync(o->idx, c->idx, sizeof(int) * K, kind, st));
-  if (o->loss) CK(cudaMemcpyAsync(o->loss, c->loss, sizeof(float), kind, st));
-  if (o->pred_logits) CK(cudaMemcpyAsync(o->pred_logits, c->pred, sizeof(float) * c->C, kind, st));
+  if (o->logits0) CK(cudaMemcpyAsync(o->logits0, c->logits, sizeof(float) * S * V * c->C, kind, st));
+  if (o->entropy) CK(cudaMemcpyAsync(o->entropy, c->entropy, sizeof(float) * S * V, kind, st));
+  if (o->idx && K > 0) CK(cudaMemcpyAsync(o->idx, c->idx, sizeof(int) * S * K, kind, st));
+  if (o->loss) CK(cudaMemcpyAsync(o->loss, c->loss, sizeof(float) * S, kind, st));
+  if (o->pred_logits) CK(cudaMemcpyAsync(o->pred_logits, c->pred, sizeof(float) * S * c->C, kind, st));
   return TTL_OK;
 }
 
-int validate_run(ttl_ctx* c, int V, const ttl_hparams* hp) {
+int validate_run(ttl_ctx* c, int S, int V, const ttl_hparams* hp) {
   if (!c || !hp) return TTL_E_INVALID;
+  if (S <= 0 || S > c->Sm) { c->err = "n_samples out of range (ttl_config.max_samples)"; return TTL_E_SHAPE; }
   if (V <= 0 || V > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
   if (hp->head != TTL_HEAD_TPT && hp->head != TTL_HEAD_DEYO) { c->err = "unknown head"; return TTL_E_INVALID; }
@@ -469,16 +513,16 @@ int validate_run(ttl_ctx* c, int V, const ttl_hparams* hp) {
   return TTL_OK;
 }
 
-int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
+int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
   const int64_t before = c->launches;
   if (!c->graphs || c->prof || st == nullptr) {  // the legacy default stream cannot be captured
-    int r = adapt_body(c, images_dev, V, *hp, forced, st);
+    int r = adapt_body(c, images_dev, S, V, *hp, forced, st);
     c->last_launches = c->launches - before;
     return r;
   }
   GraphKey key;
   std::memset(&key, 0, sizeof(key));
-  key.n_views = V; key.forced = forced ? 1 : 0; key.hp = *hp;
+  key.n_samples = S; key.n_views = V; key.forced = forced ? 1 : 0; key.hp = *hp;
   GraphEntry* ge = nullptr;
   for (auto& e : c->gcache) if (e.key == key) ge = &e;
   if (!ge) {
@@ -487,23 +531,22 @@ int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int V, const ttl_hpa
     c->gcache.push_back(e);
     ge = &c->gcache.back();
   }
-  // The graph reads the views from the library-owned staging buffer (patches are produced from `images_dev` by the
-  // first kernel), so im2col is launched outside the graph with the caller's pointer and the graph starts after it.
+  // The graph reads the views from the library-owned patch buffer (patches are produced from `images_dev` by im2col),
+  // so im2col is launched outside the graph with the caller's pointer and the graph starts after it.
   if (ge->uses == 0) {  // first use: eager (also sets kernel attributes outside capture)
-    int r = adapt_body(c, images_dev, V, *hp, forced, st);
+    int r = adapt_body(c, images_dev, S, V, *hp, forced, st);
     ge->uses = 1;
     ge->launches = c->launches - before;
     ge->b_zero_after = c->b_zero; ge->opt_step_after = c->opt_step;
     ge->train_views_after = c->last_train_views; ge->train_in_after = c->last_train_in;
+    ge->train_samples_after = c->last_train_samples; ge->pack_samples_after = c->pack_samples;
     c->last_launches = ge->launches;
     return r;
   }
   if (!ge->exec) {
-    // capture with the *same* image pointer semantics: the body consumes `images_dev` only in im2col; to keep the
-    // graph pointer-independent we capture the body on a fixed internal image pointer = c->img_stage (see below).
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int r = adapt_body(c, nullptr, V, *hp, forced, st);  // nullptr -> embed() skips im2col (done by caller below)
+    int r = adapt_body(c, nullptr, S, V, *hp, forced, st);  // nullptr -> embed() skips im2col (done by caller below)
     cudaError_t e = cudaStreamEndCapture(st, &graph);
     if (r != TTL_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess) { c->err = std::string("graph capture: ") + cudaGetErrorString(e); return TTL_E_CUDA; }
@@ -511,12 +554,13 @@ int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int V, const ttl_hpa
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { c->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return TTL_E_CUDA; }
   }
-  launch_im2col(images_dev, c->patches, V, c->cfg.image_size, c->cfg.patch, st);
+  launch_im2col(images_dev, c->patches, S * V, c->cfg.image_size, c->cfg.patch, st);
   CK(cudaGraphLaunch(ge->exec, st));
   c->launches = before + ge->launches;
   c->last_launches = ge->launches;
   c->b_zero = ge->b_zero_after; c->opt_step = ge->opt_step_after;
   c->last_train_views = ge->train_views_after; c->last_train_in = ge->train_in_after;
+  c->last_train_samples = ge->train_samples_after; c->pack_samples = ge->pack_samples_after;
   ge->uses++;
   return TTL_OK;
 }
@@ -545,8 +589,8 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   if (cfg->width % 128 != 0 || cfg->width > 1024 || cfg->width != cfg->heads * 64 || cfg->image_size % cfg->patch != 0 ||
       cfg->mlp_dim % 64 != 0 || (cfg->lora_rank != 16 && cfg->lora_rank != 32) || cfg->lora_layer_lo < 0 ||
       cfg->lora_layer_hi >= cfg->layers || cfg->lora_layer_lo > cfg->lora_layer_hi || cfg->max_views <= 0 ||
-      cfg->max_classes <= 0 || cfg->proj_dim <= 0 || (cfg->patch & 1)) {
-    g_create_err = "unsupported geometry (width%128, head_dim 64, rank 16/32, layer range, even patch)";
+      cfg->max_classes <= 0 || cfg->proj_dim <= 0 || (cfg->patch & 1) || cfg->max_samples < 0 || cfg->max_samples > 16) {
+    g_create_err = "unsupported geometry (width%128, head_dim 64, rank 16/32, layer range, even patch, max_samples <= 16)";
     return TTL_E_SHAPE;
   }
   cudaSetDevice(cfg->device);
@@ -559,7 +603,8 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   c->T = (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch);
   c->tokens = c->T + 1;
   c->Kp = (3 * cfg->patch * cfg->patch + 63) / 64 * 64;
-  c->Vm = cfg->max_views; c->Mm = c->Vm * c->tokens; c->Cm = cfg->max_classes;
+  c->Vm = cfg->max_views; c->Sm = cfg->max_samples > 0 ? cfg->max_samples : 1;
+  c->VVm = c->Vm * c->Sm; c->Mm = c->VVm * c->tokens; c->Cm = cfg->max_classes;
   c->n_train = c->L - c->lo; c->n_lora = c->hi - c->lo + 1;
   const int d = c->d, F = c->F, M = c->Mm;
   int rc = TTL_OK;
@@ -574,33 +619,36 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     A(w.ln1g, d); A(w.ln1b, d); A(w.ln2g, d); A(w.ln2b, d);
     if (l >= c->lo) { A(w.wqkvT, 3 * d * d); A(w.woT, d * d); A(w.w1T, F * d); A(w.w2T, d * F); }
   }
-  A(c->patches, static_cast<size_t>(c->Vm) * c->T * c->Kp);
+  A(c->patches, static_cast<size_t>(c->VVm) * c->T * c->Kp);
   A(c->Hb, static_cast<size_t>(M) * d); A(c->QKV, static_cast<size_t>(M) * 3 * d); A(c->AO, static_cast<size_t>(M) * d);
-  A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64);
+  A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64 * c->Sm);
   A(c->XK, static_cast<size_t>(M) * d); A(c->XA, static_cast<size_t>(M) * d); A(c->XB, static_cast<size_t>(M) * d);
-  A(c->TIN, static_cast<size_t>(M) * d);
-  A(c->feats, c->Vm * c->P); A(c->feats_c, c->Vm * c->P); A(c->logits, c->Vm * c->Cm); A(c->logits_c, c->Vm * c->Cm);
-  A(c->entropy, c->Vm); A(c->entropy_c, c->Vm); A(c->loss, 4); A(c->dlogits, c->Vm * c->Cm); A(c->pred, c->Cm);
-  A(c->pred_feats, c->P); A(c->pred_entropy, 4); A(c->idx, c->Vm);
-  A(c->pooled, c->Vm * d); A(c->dfh, c->Vm * c->P); A(c->dpool, c->Vm * d);
+  A(c->TIN, static_cast<size_t>(M) * d); A(c->PIN, static_cast<size_t>(c->Sm) * c->tokens * d);
+  const size_t VV = c->VVm;
+  A(c->feats, VV * c->P); A(c->feats_c, VV * c->P); A(c->logits, VV * c->Cm); A(c->logits_c, VV * c->Cm);
+  A(c->entropy, VV); A(c->entropy_c, VV); A(c->loss, c->Sm + 4); A(c->dlogits, VV * c->Cm); A(c->pred, static_cast<size_t>(c->Sm) * c->Cm);
+  A(c->pred_feats, static_cast<size_t>(c->Sm) * c->P); A(c->pred_entropy, c->Sm + 4); A(c->idx, VV);
+  A(c->pooled, VV * d); A(c->dfh, VV * c->P); A(c->dpool, VV * d);
   c->tape.resize(c->n_train);
   for (int t = 0; t < c->n_train && rc == TTL_OK; ++t) {
     Tape& tp = c->tape[t];
-    A(tp.h1, static_cast<size_t>(M) * d); A(tp.T, static_cast<size_t>(M) * 64); A(tp.qkv, static_cast<size_t>(M) * 3 * d);
+    A(tp.h1, static_cast<size_t>(M) * d); A(tp.T, static_cast<size_t>(M) * 64 * c->Sm); A(tp.qkv, static_cast<size_t>(M) * 3 * d);
     A(tp.ao, static_cast<size_t>(M) * d); A(tp.h2, static_cast<size_t>(M) * d); A(tp.z, static_cast<size_t>(M) * F);
-    A(tp.g, static_cast<size_t>(M) * F); A(tp.lse, static_cast<size_t>(c->Vm) * c->H * c->tokens);
+    A(tp.g, static_cast<size_t>(M) * F); A(tp.lse, static_cast<size_t>(c->VVm) * c->H * c->tokens);
     A(tp.x_mid, static_cast<size_t>(M) * d); A(tp.x_out, static_cast<size_t>(M) * d);
   }
   A(c->DX, static_cast<size_t>(M) * d); A(c->DX2, static_cast<size_t>(M) * d); A(c->DH, static_cast<size_t>(M) * d);
   A(c->DXB, static_cast<size_t>(M) * d); A(c->DZ, static_cast<size_t>(M) * F); A(c->DAO, static_cast<size_t>(M) * d);
-  A(c->DQKV, static_cast<size_t>(M) * 3 * d); A(c->U, static_cast<size_t>(M) * 64);
-  A(c->ws, static_cast<size_t>((M + 127) / 128) * d * 32);
+  A(c->DQKV, static_cast<size_t>(M) * 3 * d); A(c->U, static_cast<size_t>(M) * 64 * c->Sm);
+  A(c->ws, static_cast<size_t>((M + 127) / 128 + c->Sm) * d * 32);
   c->lora_per_layer = 4LL * c->r * d;
   c->lora_total = c->lora_per_layer * c->n_lora;
-  A(c->lp, c->lora_total); A(c->lg, c->lora_total); A(c->l0, c->lora_total); A(c->lm, c->lora_total); A(c->lv, c->lora_total);
+  A(c->lp, c->lora_total * c->Sm); A(c->lg, c->lora_total * c->Sm); A(c->l0, c->lora_total);
+  A(c->lm, c->lora_total * c->Sm); A(c->lv, c->lora_total * c->Sm);
   c->pk.resize(c->n_lora);
   for (int i = 0; i < c->n_lora && rc == TTL_OK; ++i) {
-    A(c->pk[i].a_ext, 64 * d); A(c->pk[i].a_ext_t, d * 64); A(c->pk[i].b_ext, 3 * d * 64); A(c->pk[i].b_ext_t, 64 * 3 * d);
+    const size_t kcm = 64 * static_cast<size_t>(c->Sm);
+    A(c->pk[i].a_ext, kcm * d); A(c->pk[i].a_ext_t, d * kcm); A(c->pk[i].b_ext, 3 * d * kcm); A(c->pk[i].b_ext_t, kcm * 3 * d);
   }
 #undef A
   c->host_init.assign(c->lora_total, 0.f);
@@ -745,7 +793,7 @@ int ttl_lora_set_init(ttl_ctx* c, int32_t layer, int32_t which, const float* hos
 int ttl_lora_reset(ttl_ctx* c, void* stream) {
   if (!c) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
-  return lora_reset(c, static_cast<cudaStream_t>(stream));
+  return lora_reset(c, 1, static_cast<cudaStream_t>(stream));
 }
 
 int ttl_lora_get(ttl_ctx* c, int32_t layer, int32_t which, int32_t what, float* host_out, int64_t numel) {
@@ -774,13 +822,13 @@ int ttl_lora_touch(ttl_ctx* c, void* stream) {
   if (!c) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
   c->b_zero = false;  // factors were written from outside: assume B != 0
-  return repack(c, static_cast<cudaStream_t>(stream));
+  return repack(c, 1, static_cast<cudaStream_t>(stream));
 }
 
 int ttl_adamw_step(ttl_ctx* c, const ttl_hparams* hp, void* stream) {
   if (!c || !hp) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
-  return adamw(c, *hp, static_cast<cudaStream_t>(stream));
+  return adamw(c, *hp, 1, static_cast<cudaStream_t>(stream));
 }
 
 int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t train, float* logits_dev, void* stream) {
@@ -789,13 +837,14 @@ int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t tr
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->pack_samples != 1) RET_IF(repack(c, 1, st));
   RET_IF(forward_frozen(c, images_dev, n_views, st));
   if (train) {
-    RET_IF(forward_tail_train(c, c->XK, n_views, st));
+    RET_IF(forward_tail_train(c, c->XK, n_views, 1, st));
     launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits, c->entropy, n_views, c->C, c->P, st);
     c->launches += 2;
   } else {
-    RET_IF(forward_tail_infer(c, c->XK, n_views, c->feats, c->logits, c->entropy, st));
+    RET_IF(forward_tail_infer(c, c->XK, n_views, 1, c->feats, c->logits, c->entropy, st));
   }
   if (logits_dev) CK(cudaMemcpyAsync(logits_dev, c->logits, sizeof(float) * n_views * c->C, cudaMemcpyDeviceToDevice, st));
   return check_launch(c, "ttl_forward");
@@ -807,39 +856,50 @@ int ttl_backward(ttl_ctx* c, const float* dlogits_dev, void* stream) {
   return backward(c, dlogits_dev, c->last_train_views, static_cast<cudaStream_t>(stream));
 }
 
-int ttl_adapt_predict(ttl_ctx* c, const float* images_dev, int32_t n_views, const ttl_hparams* hp,
-                      const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream) {
-  RET_IF(validate_run(c, n_views, hp));
+int ttl_adapt_predict_batch(ttl_ctx* c, const float* images_dev, int32_t n_samples, int32_t n_views, const ttl_hparams* hp,
+                            const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream) {
+  RET_IF(validate_run(c, n_samples, n_views, hp));
   if (!images_dev) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int K = static_cast<int>(n_views * hp->selection_p);
   const bool forced = forced_idx_dev != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
-  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
-  RET_IF(adapt_predict_impl(c, images_dev, n_views, hp, forced, st));
-  return copy_outputs(c, out_dev, n_views, *hp, cudaMemcpyDeviceToDevice, st);
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K * n_samples, cudaMemcpyDeviceToDevice, st));
+  RET_IF(adapt_predict_impl(c, images_dev, n_samples, n_views, hp, forced, st));
+  return copy_outputs(c, out_dev, n_samples, n_views, *hp, cudaMemcpyDeviceToDevice, st);
 }
 
-int ttl_adapt_predict_host(ttl_ctx* c, const float* images_host, int32_t n_views, const ttl_hparams* hp,
-                           const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream) {
-  RET_IF(validate_run(c, n_views, hp));
+int ttl_adapt_predict(ttl_ctx* c, const float* images_dev, int32_t n_views, const ttl_hparams* hp,
+                      const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream) {
+  return ttl_adapt_predict_batch(c, images_dev, 1, n_views, hp, forced_idx_dev, out_dev, stream);
+}
+
+int ttl_adapt_predict_batch_host(ttl_ctx* c, const float* images_host, int32_t n_samples, int32_t n_views,
+                                 const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
+                                 void* stream) {
+  RET_IF(validate_run(c, n_samples, n_views, hp));
   if (!images_host) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // stage the views in TIN's tail?  No: a dedicated staging area is the (otherwise idle at this point) DZ buffer,
-  // which is >= V*3*S*S*4 bytes for every supported geometry (checked).
-  const size_t img_bytes = static_cast<size_t>(n_views) * 3 * c->cfg.image_size * c->cfg.image_size * sizeof(float);
+  // staging area for the views: the DZ buffer (idle until the backward; im2col has consumed the views long before),
+  // >= S*V*3*size*size*4 bytes for every supported geometry (checked).
+  const size_t img_bytes = static_cast<size_t>(n_samples) * n_views * 3 * c->cfg.image_size * c->cfg.image_size * sizeof(float);
   const size_t dz_bytes = static_cast<size_t>(c->Mm) * c->F * sizeof(bf16);
   if (img_bytes > dz_bytes) { c->err = "host staging buffer too small"; return TTL_E_SHAPE; }
   float* stage = reinterpret_cast<float*>(c->DZ);
   CK(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, st));
   const int K = static_cast<int>(n_views * hp->selection_p);
   const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
-  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K, cudaMemcpyHostToDevice, st));
-  RET_IF(adapt_predict_impl(c, stage, n_views, hp, forced, st));
-  RET_IF(copy_outputs(c, out_host, n_views, *hp, cudaMemcpyDeviceToHost, st));
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K * n_samples, cudaMemcpyHostToDevice, st));
+  RET_IF(adapt_predict_impl(c, stage, n_samples, n_views, hp, forced, st));
+  RET_IF(copy_outputs(c, out_host, n_samples, n_views, *hp, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return TTL_OK;
+}
+
+int ttl_adapt_predict_host(ttl_ctx* c, const float* images_host, int32_t n_views, const ttl_hparams* hp,
+                           const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream) {
+  return ttl_adapt_predict_batch_host(c, images_host, 1, n_views, hp, forced_idx_host, out_host, stream);
 }
 
 int ttl_set_graphs(ttl_ctx* c, int32_t enabled) {
@@ -969,7 +1029,7 @@ int ttl_op_skinny_reduce(const void* wide, int32_t ldw, int32_t nw, const void* 
                          int32_t M, float scale, float* out, int32_t transpose_out, float* ws, void* stream) {
   if (nw % 64 != 0 || (nn != 16 && nn != 32)) { g_create_err = "skinny_reduce: nw%64, nn in {16,32}"; return TTL_E_SHAPE; }
   launch_skinny_reduce(static_cast<const bf16*>(wide), ldw, nw, static_cast<const bf16*>(narrow), ldn, nn, M, scale, out,
-                       transpose_out, ws, static_cast<cudaStream_t>(stream));
+                       transpose_out, ws, 1, 0, 0, static_cast<cudaStream_t>(stream));
   return op_done("skinny_reduce");
 }
 

@@ -589,22 +589,11 @@ EncodeTiledFn get_encode() {
 
 bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* ptr, int inner, int rows, int ld,
                 int box_inner, int box_rows, CUtensorMapSwizzle swz) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_err("cuTensorMapEncodeTiled unavailable"); return false; }
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char b[200];
-    std::snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%d inner=%d ld=%d box=%dx%d", int(r), ptr,
-                  rows, inner, ld, box_inner, box_rows);
-    set_err(b);
-    return false;
-  }
-  return true;
+  const uint64_t dims[2] = {static_cast<uint64_t>(inner), static_cast<uint64_t>(rows)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ld) * elem_bytes};
+  const uint32_t box[2] = {static_cast<uint32_t>(box_inner), static_cast<uint32_t>(box_rows)};
+  return encode_tiled_map(m, dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 1 : 0, ptr, 2, dims, strides, box,
+                          swz == CU_TENSOR_MAP_SWIZZLE_128B ? 128 : (swz == CU_TENSOR_MAP_SWIZZLE_64B ? 64 : 0));
 }
 
 bool make_map(CUtensorMap* m, const GemmOperand& op, int box_rows) {
@@ -753,6 +742,29 @@ cudaError_t launch_n(const GemmArgs& g, cudaStream_t s, int sms) {
 }
 
 }  // namespace
+
+bool encode_tiled_map(void* map_out, int dtype, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_err("cuTensorMapEncodeTiled unavailable"); return false; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = enc(static_cast<CUtensorMap*>(map_out), dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[240];
+    std::snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d): ptr=%p rank=%d dims=%llu,%llu box=%u,%u swizzle=%d", int(r),
+                  ptr, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], swizzle_bytes);
+    set_err(msg);
+    return false;
+  }
+  return true;
+}
 
 const char* gemm_last_error() { return g_err; }
 

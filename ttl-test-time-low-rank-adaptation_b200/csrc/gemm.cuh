@@ -42,6 +42,12 @@ struct GemmArgs {
   int force_block_n = 0;               // 0 = heuristic
 };
 
+// Generic tiled tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point), shared with the
+// TMA-fed attention kernel.  dtype: 0 = bf16, 1 = fp32.  swizzle_bytes: 0 / 64 / 128.  dims/box innermost first;
+// strides_bytes has rank-1 entries (stride of dims 1..rank-1).  Returns false and sets gemm_last_error() on failure.
+bool encode_tiled_map(void* map_out, int dtype, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 // Returns cudaSuccess or an error; never synchronises.
 cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms);
 const char* gemm_last_error();

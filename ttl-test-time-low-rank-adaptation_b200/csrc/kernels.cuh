@@ -22,9 +22,11 @@ void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* 
 // dx = dres + LN'(x)^T (dy * gamma); statistics recomputed from x.  dres nullable.  dx_bf16 nullable.
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
                           bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st);
-// dst[g*tokens + t, :] = src[view_idx[g]*tokens + t, :]   (view_idx on device)
-void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int tokens, int d,
+// dst[g*tokens + t, :] = src[v(g)*tokens + t, :],  v(g) = view_idx[g] (device array) or g * view_stride when view_idx == nullptr
+void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int view_stride, int tokens, int d,
                          cudaStream_t st);
+// x bf16 [M, 64*S]: zero every 64-column block except the one of the row's own sample (row / rows_per_sample)
+void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStream_t st);
 
 // ---- attention.cu   qkv bf16 [V*tokens, 3d] (q | k | v, heads concatenated, 64 per head)
 // out bf16 [V*tokens, d]; lse (nullable) fp32 [V, heads, tokens] natural-log softmax normaliser of scale*q.k
@@ -57,21 +59,25 @@ void launch_head_bwd(const float* dlogits, const float* text, float scale, const
                      int P, int tokens, int d, float eps, cudaStream_t st);
 
 // ---- lora.cu   per-layer fp32 master tensors in the reference's tuple order (A_q[r,d], B_q[d,r], A_v[r,d], B_v[d,r])
-struct LoraPacked {       // bf16 operands consumed by the GEMM's second operand pair (64 = padded 2r)
-  bf16* a_ext;            // [64, d]   rows 0..r-1 = A_q, r..2r-1 = A_v, rest 0          (T = h1 @ a_ext^T)
-  bf16* a_ext_t;          // [d, 64]   transpose of a_ext                                  (dh1 += U @ a_ext_t^T)
-  bf16* b_ext;            // [3d, 64]  rows of q: s*B_q in cols 0..r-1; rows of v: s*B_v in cols r..2r-1   (qkv += T @ b_ext^T)
-  bf16* b_ext_t;          // [64, 3d]  transpose of b_ext                                  (U = dqkv @ b_ext_t^T)
+struct LoraPacked {       // bf16 operands consumed by the GEMM's second operand pair; kc = 64 * S (64 = padded 2r per sample)
+  bf16* a_ext;            // [kc, d]   per sample block: rows 0..r-1 = A_q, r..2r-1 = A_v, rest 0   (T = h1 @ a_ext^T)
+  bf16* a_ext_t;          // [d, kc]   transpose of a_ext                                  (dh1 += U @ a_ext_t^T)
+  bf16* b_ext;            // [3d, kc]  per sample block: rows of q: s*B_q in cols 0..r-1; rows of v: s*B_v in cols r..2r-1
+  bf16* b_ext_t;          // [kc, 3d]  transpose of b_ext                                  (U = dqkv @ b_ext_t^T)
 };
-void launch_lora_pack(const float* params, LoraPacked pk, int d, int r, float s, cudaStream_t st);
+// params: this layer's tensors of sample 0; sample i at params + i * sample_stride.  S samples are K-concatenated.
+void launch_lora_pack(const float* params, int64_t sample_stride, LoraPacked pk, int d, int r, float s, int S, cudaStream_t st);
 // out[w, j] (or out[j, w] if transpose_out) = scale * sum_m Wd[m, w] * Nr[m, j];  w < nw (multiple of 64), j < 16 * nj16
-// Deterministic two-pass reduction (partials in workspace `ws`, >= ceil(M/256)*nw*nn floats).
+// Deterministic two-pass reduction (partials in workspace `ws`, >= groups*ceil(M/128)*nw*nn floats).
+// groups > 1: group g reduces rows [g*M, (g+1)*M) with the narrow operand shifted by g*narrow_gstride columns and writes
+// out + g*out_gstride (the per-sample weight gradients of concurrently adapted samples).
 void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
-                          float* out, int transpose_out, float* ws, cudaStream_t st);
+                          float* out, int transpose_out, float* ws, int groups, int narrow_gstride, int64_t out_gstride,
+                          cudaStream_t st);
 // Fused AdamW (torch.optim.AdamW rule, ttl.py:218 defaults) over n contiguous fp32 elements.
 void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step, float lr, float b1, float b2,
                   float eps, float wd, cudaStream_t st);
-// p <- p0, m <- 0, v <- 0   (LoRA_AB.reset + optimizer.load_state_dict(optim_state), ttl.py:338-344)
-void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, cudaStream_t st);
+// p[i] <- p0[i % n0], m <- 0, v <- 0   (LoRA_AB.reset + optimizer.load_state_dict(optim_state), ttl.py:338-344; n = S * n0)
+void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, int n0, cudaStream_t st);
 
 }  // namespace ttl

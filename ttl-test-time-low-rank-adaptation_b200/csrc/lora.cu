@@ -10,9 +10,12 @@ namespace ttl {
 namespace {
 
 // params layout per layer: A_q[r,d] | B_q[d,r] | A_v[r,d] | B_v[d,r]   (fp32, contiguous)
-__global__ void lora_pack_kernel(const float* __restrict__ prm, LoraPacked pk, int d, int r, float s) {
-  const int n_a = 64 * d;          // a_ext / a_ext_t elements
-  const int n_b = 3 * d * 64;      // b_ext / b_ext_t elements
+__global__ void lora_pack_kernel(const float* __restrict__ prm0, int64_t sample_stride, LoraPacked pk, int d, int r,
+                                 float s, int S) {
+  const int n_a = 64 * d;          // a_ext / a_ext_t elements of one sample block
+  const int n_b = 3 * d * 64;      // b_ext / b_ext_t elements of one sample block
+  const int smp = blockIdx.y, kc = 64 * S, c0 = 64 * smp;   // this sample's 64-column block of the K-concatenation
+  const float* prm = prm0 + smp * sample_stride;
   const float* A_q = prm;
   const float* B_q = prm + r * d;
   const float* A_v = prm + 2 * r * d;
@@ -24,8 +27,8 @@ __global__ void lora_pack_kernel(const float* __restrict__ prm, LoraPacked pk, i
       if (j < r) v = A_q[j * d + k];
       else if (j < 2 * r) v = A_v[(j - r) * d + k];
       const bf16 b = __float2bfloat16(v);
-      pk.a_ext[i] = b;
-      pk.a_ext_t[k * 64 + j] = b;
+      pk.a_ext[static_cast<size_t>(c0 + j) * d + k] = b;
+      pk.a_ext_t[static_cast<size_t>(k) * kc + c0 + j] = b;
     } else {
       const int e = i - n_a;
       const int n = e / 64, j = e - n * 64;  // b_ext[n, j], n in [0, 3d)
@@ -33,8 +36,8 @@ __global__ void lora_pack_kernel(const float* __restrict__ prm, LoraPacked pk, i
       if (n < d) { if (j < r) v = s * B_q[n * r + j]; }
       else if (n >= 2 * d) { if (j >= r && j < 2 * r) v = s * B_v[(n - 2 * d) * r + (j - r)]; }
       const bf16 b = __float2bfloat16(v);
-      pk.b_ext[e] = b;
-      pk.b_ext_t[static_cast<size_t>(j) * 3 * d + n] = b;
+      pk.b_ext[static_cast<size_t>(n) * kc + c0 + j] = b;
+      pk.b_ext_t[static_cast<size_t>(c0 + j) * 3 * d + n] = b;
     }
   }
 }
@@ -44,10 +47,13 @@ constexpr int SR_MC = 128;  // rows per CTA
 template <int NN>           // narrow width (16 or 32)
 __global__ void __launch_bounds__(256)
 skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __restrict__ narrow, int ldn, int M, int nw,
-                      float* __restrict__ ws) {
+                      float* __restrict__ ws, int narrow_gstride) {
   __shared__ __align__(16) bf16 sW[SR_MC][64 + 8];
   __shared__ __align__(16) bf16 sN[SR_MC][NN + 8];
-  const int w0 = blockIdx.x * 64, m0 = blockIdx.y * SR_MC;
+  const int w0 = blockIdx.x * 64, m0 = blockIdx.y * SR_MC, grp = blockIdx.z;
+  wide += static_cast<size_t>(grp) * M * ldw;                              // this group's rows
+  narrow += static_cast<size_t>(grp) * M * ldn + grp * narrow_gstride;
+  ws += static_cast<size_t>(grp) * gridDim.y * nw * NN;
   for (int i = threadIdx.x; i < SR_MC * 8; i += blockDim.x) {
     const int r = i >> 3, c = (i & 7) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -77,9 +83,11 @@ skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __rest
 }
 
 __global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, int nw, int nn, float scale,
-                                    float* __restrict__ out, int transpose_out) {
+                                    float* __restrict__ out, int transpose_out, int64_t out_gstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nw * nn) return;
+  ws += static_cast<size_t>(blockIdx.y) * chunks * nw * nn;
+  out += blockIdx.y * out_gstride;
   float a = 0.f;
   for (int c = 0; c < chunks; ++c) a += ws[static_cast<size_t>(c) * nw * nn + i];
   const int w = i / nn, j = i - w * nn;
@@ -102,26 +110,28 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 }
 
 __global__ void lora_reset_kernel(float* __restrict__ p, const float* __restrict__ p0, float* __restrict__ m,
-                                  float* __restrict__ v, int n) {
+                                  float* __restrict__ v, int n, int n0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  p[i] = p0[i]; m[i] = 0.f; v[i] = 0.f;
+  p[i] = p0[i % n0]; m[i] = 0.f; v[i] = 0.f;
 }
 
 }  // namespace
 
-void launch_lora_pack(const float* params, LoraPacked pk, int d, int r, float s, cudaStream_t st) {
+void launch_lora_pack(const float* params, int64_t sample_stride, LoraPacked pk, int d, int r, float s, int S, cudaStream_t st) {
   const int total = 64 * d + 3 * d * 64;
-  lora_pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(params, pk, d, r, s);
+  lora_pack_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(params, sample_stride, pk, d, r, s, S);
 }
 
 void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
-                          float* out, int transpose_out, float* ws, cudaStream_t st) {
+                          float* out, int transpose_out, float* ws, int groups, int narrow_gstride, int64_t out_gstride,
+                          cudaStream_t st) {
   const int chunks = (M + SR_MC - 1) / SR_MC;
-  dim3 grid(nw / 64, chunks);
-  if (nn == 16) skinny_partial_kernel<16><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws);
-  else skinny_partial_kernel<32><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws);
-  skinny_final_kernel<<<(nw * nn + 255) / 256, 256, 0, st>>>(ws, chunks, nw, nn, scale, out, transpose_out);
+  dim3 grid(nw / 64, chunks, groups);
+  if (nn == 16) skinny_partial_kernel<16><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  else skinny_partial_kernel<32><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  skinny_final_kernel<<<dim3((nw * nn + 255) / 256, groups), 256, 0, st>>>(ws, chunks, nw, nn, scale, out, transpose_out,
+                                                                           out_gstride);
 }
 
 void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step, float lr, float b1, float b2,
@@ -132,8 +142,8 @@ void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step,
                                                 static_cast<float>(sqrt(bc2)));
 }
 
-void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, cudaStream_t st) {
-  lora_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, p0, m, v, n);
+void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, int n0, cudaStream_t st) {
+  lora_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, p0, m, v, n, n0);
 }
 
 }  // namespace ttl

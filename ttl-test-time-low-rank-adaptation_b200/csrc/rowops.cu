@@ -158,11 +158,20 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
-                                    const int* __restrict__ idx, int n_sel, int per_view4) {
+                                    const int* __restrict__ idx, int n_sel, int view_stride, int per_view4) {
   const int g = blockIdx.y;
-  const float4* s = src + static_cast<size_t>(idx[g]) * per_view4;
+  const float4* s = src + static_cast<size_t>(idx != nullptr ? idx[g] : g * view_stride) * per_view4;
   float4* o = dst + static_cast<size_t>(g) * per_view4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_view4; i += gridDim.x * blockDim.x) o[i] = s[i];
+}
+
+__global__ void block_mask_kernel(bf16* __restrict__ x, int M, int ncols, int rows_per_sample) {
+  const int chunks = ncols / 8;   // 16-byte chunks per row
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(M) * chunks;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / chunks), col = static_cast<int>(i % chunks) * 8;
+    if (col / 64 != row / rows_per_sample) *reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * ncols + col) = make_uint4(0, 0, 0, 0);
+  }
 }
 
 }  // namespace
@@ -194,12 +203,19 @@ void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, c
       dy, x, gamma, dres, dx, dx_bf16, rows, d, eps);
 }
 
-void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int tokens, int d,
+void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int view_stride, int tokens, int d,
                          cudaStream_t st) {
   const int per_view4 = tokens * d / 4;
   dim3 grid((per_view4 + 255) / 256 < 32 ? (per_view4 + 255) / 256 : 32, n_sel);
   gather_views_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
-                                            view_idx, n_sel, per_view4);
+                                            view_idx, n_sel, view_stride, per_view4);
+}
+
+void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(M) * (ncols / 8);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  block_mask_kernel<<<blocks, 256, 0, st>>>(x, M, ncols, rows_per_sample);
 }
 
 }  // namespace ttl

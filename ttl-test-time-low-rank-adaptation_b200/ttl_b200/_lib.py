@@ -21,7 +21,7 @@ class TtlConfig(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("proj_dim", C.c_int32), ("max_views", C.c_int32),
                 ("max_classes", C.c_int32), ("lora_rank", C.c_int32), ("lora_alpha", C.c_float),
                 ("lora_layer_lo", C.c_int32), ("lora_layer_hi", C.c_int32), ("ln_eps", C.c_float),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("max_samples", C.c_int32)]
 
 
 class TtlHparams(C.Structure):
@@ -64,6 +64,9 @@ _SIGS = {
     "ttl_backward": (C.c_int, [vp, vp, vp]),
     "ttl_adapt_predict": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_host": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
+    "ttl_adapt_predict_batch": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
+    "ttl_adapt_predict_batch_host": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs),
+                                               vp]),
     "ttl_set_graphs": (C.c_int, [vp, C.c_int32]),
     "ttl_last_launch_count": (C.c_int64, [vp]),
     "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),

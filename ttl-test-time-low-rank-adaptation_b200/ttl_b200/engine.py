@@ -56,20 +56,21 @@ class _DevAlias:
 class Engine:
     def __init__(self, arch: str = "ViT-B/16", max_views: int = 64, max_classes: int = 1000, lora_rank: int = 16,
                  lora_alpha: float = 32.0, layer_range: Sequence[int] = (9, 11), device: int = 0,
-                 geometry: Optional[dict] = None):
+                 geometry: Optional[dict] = None, max_samples: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("ttl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = L.load()
         g = dict(geometry or ARCH_GEOMETRY[arch])
         self.arch, self.geom = arch, g
         self.device = torch.device("cuda", device)
-        self.max_views, self.max_classes = max_views, max_classes
+        self.max_views, self.max_classes, self.max_samples = max_views, max_classes, max(1, int(max_samples))
         self.rank, self.alpha = lora_rank, lora_alpha
         self.layer_lo, self.layer_hi = int(layer_range[0]), int(layer_range[1])
         self.tokens = (g["image_size"] // g["patch"]) ** 2 + 1
         self.n_classes = 0
         cfg = L.TtlConfig(g["image_size"], g["patch"], g["width"], g["layers"], g["heads"], g["mlp_dim"], g["proj_dim"],
-                          max_views, max_classes, lora_rank, lora_alpha, self.layer_lo, self.layer_hi, 1e-5, device)
+                          max_views, max_classes, lora_rank, lora_alpha, self.layer_lo, self.layer_hi, 1e-5, device,
+                          self.max_samples)
         ctx = C.c_void_p()
         L.check(self.lib.ttl_create(C.byref(ctx), C.byref(cfg)))
         self.ctx = ctx
@@ -192,18 +193,27 @@ class Engine:
 
     def adapt_predict(self, images: torch.Tensor, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
                       want: Sequence[str] = ("pred_logits",)) -> Dict[str, torch.Tensor]:
-        """One test sample: reset -> adapt -> predict (ttl.py:338-352).  `images` may live on the device (fast path)
-        or in (pinned) host memory, in which case the library does the H2D/D2H itself and synchronises."""
-        V = int(images.shape[0])
+        """One test sample: reset -> adapt -> predict (ttl.py:338-352).  `images` [V,3,S,S] may live on the device (fast
+        path) or in (pinned) host memory, in which case the library does the H2D/D2H itself and synchronises."""
+        outs = self.adapt_predict_batch(images.unsqueeze(0), hp, None if forced_idx is None else forced_idx.unsqueeze(0), want)
+        return {k: v[0] for k, v in outs.items()}
+
+    def adapt_predict_batch(self, images: torch.Tensor, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
+                            want: Sequence[str] = ("pred_logits",)) -> Dict[str, torch.Tensor]:
+        """S independent test samples adapted concurrently (S <= max_samples), each exactly as adapt_predict would:
+        `images` [S,V,3,size,size] -> dict of per-sample results, leading dimension S."""
+        S, V = int(images.shape[0]), int(images.shape[1])
+        if S > self.max_samples:
+            raise ValueError(f"{S} samples > max_samples={self.max_samples}")
         K = int(V * hp.selection_p)
         host = not images.is_cuda
         dev = torch.device("cpu") if host else self.device
         images = images.to(torch.float32).contiguous()
         outs: Dict[str, torch.Tensor] = {}
         o = L.TtlOutputs()
-        shapes = {"logits0": ((V, self.n_classes), torch.float32), "entropy": ((V,), torch.float32),
-                  "idx": ((max(K, 1),), torch.int32), "loss": ((1,), torch.float32),
-                  "pred_logits": ((self.n_classes,), torch.float32)}
+        shapes = {"logits0": ((S, V, self.n_classes), torch.float32), "entropy": ((S, V), torch.float32),
+                  "idx": ((S, max(K, 1)), torch.int32), "loss": ((S,), torch.float32),
+                  "pred_logits": ((S, self.n_classes), torch.float32)}
         for name in want:
             shp, dt = shapes[name]
             t = torch.empty(shp, dtype=dt, device=dev, pin_memory=host)
@@ -214,18 +224,18 @@ class Engine:
             fidx = forced_idx.to(dev, torch.int32).contiguous()
         h = hp.to_c()
         if host:
-            L.check(self.lib.ttl_adapt_predict_host(self.ctx, images.data_ptr(), V, C.byref(h),
-                                                    fidx.data_ptr() if fidx is not None else None, C.byref(o),
-                                                    self._st()), self.ctx)
+            L.check(self.lib.ttl_adapt_predict_batch_host(self.ctx, images.data_ptr(), S, V, C.byref(h),
+                                                          fidx.data_ptr() if fidx is not None else None, C.byref(o),
+                                                          self._st()), self.ctx)
         else:
             self._sync_in()
-            L.check(self.lib.ttl_adapt_predict(self.ctx, images.data_ptr(), V, C.byref(h),
-                                               fidx.data_ptr() if fidx is not None else None, C.byref(o), self._st()),
-                    self.ctx)
+            L.check(self.lib.ttl_adapt_predict_batch(self.ctx, images.data_ptr(), S, V, C.byref(h),
+                                                     fidx.data_ptr() if fidx is not None else None, C.byref(o),
+                                                     self._st()), self.ctx)
             self._sync_out()
             images.record_stream(self.stream)
         if "idx" in outs:
-            outs["idx"] = outs["idx"][:K]
+            outs["idx"] = outs["idx"][:, :K]
         return outs
 
     def set_graphs(self, enabled: bool) -> None:
