@@ -283,9 +283,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(n_e2e):
-            o = eng.adapt_predict_batch(host[i % nh], hp, want=("pred_logits",))["pred_logits"]
-            _ = o.argmax(dim=1).tolist()
+        pending = None
+        for i in range(n_e2e):      # loader-style software pipeline: batch i+1 is submitted before batch i is read back
+            cur = eng.adapt_predict_batch(host[i % nh], hp, want=("pred_logits",), sync=False)
+            if pending is not None:
+                _ = pending.wait()["pred_logits"].argmax(dim=1).tolist()
+            pending = cur
+        _ = pending.wait()["pred_logits"].argmax(dim=1).tolist()
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -293,7 +297,9 @@ def main():
         e2e = {"value": world * n_e2e * S / float(dt), "unit": UNIT,
                "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": int(S * args.classes * 4),
                "steps": n_e2e, "samples_per_step": S,
-               "api": "ttl_b200.Engine.adapt_predict_batch(pinned host tensor [S,V,3,224,224]) -> ttl_adapt_predict_batch_host"}
+               "api": "ttl_b200.Engine.adapt_predict_batch(pinned host tensor [S,V,3,224,224], sync=False).wait() -> "
+                      "ttl_adapt_predict_batch_host_async; every step copies its own views H2D and its predictions D2H; "
+                      "the copy of step i+1 overlaps the kernels of step i (depth-2 pipeline)"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch, instrumented eager pass
     roof = None

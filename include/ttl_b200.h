@@ -152,6 +152,13 @@ int ttl_adapt_predict_batch(ttl_ctx* ctx, const float* images_dev, int32_t n_sam
 int ttl_adapt_predict_batch_host(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
                                  const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
                                  void* stream);
+/* As ttl_adapt_predict_batch_host but returns without synchronising: the views are copied on the library's copy stream
+ * into one of two staging buffers, so the H2D of this call overlaps the kernels of the previous one (the role of the
+ * reference's pin_memory + .cuda(non_blocking=True) loader, ttl.py:277,324-334).  images_host and out_host must stay
+ * valid (pinned for real overlap) until `stream` has been synchronised. */
+int ttl_adapt_predict_batch_host_async(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
+                                       const ttl_hparams* hp, const int32_t* forced_idx_host,
+                                       const ttl_outputs* out_host, void* stream);
 /* Toggle CUDA-graph replay of ttl_adapt_predict (default on). */
 int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
 /* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */

@@ -215,6 +215,17 @@ def test_concurrent_samples_host_path_and_partial_batch(b16_weights):
         dev = eng.adapt_predict_batch(imgs.cuda(), hp)["pred_logits"].cpu()          # S=2 on a max_samples=3 engine
         host = eng.adapt_predict_batch(imgs.pin_memory(), hp)["pred_logits"]
         assert host.device.type == "cpu" and _rel(host.numpy(), dev.numpy()) < 1e-6
+        # asynchronous submission: two batches in flight (double-buffered staging, copy stream), read back in order
+        imgs2 = torch.stack([O.make_synthetic_views(64, arch.image_size, seed=50 + i) for i in range(2)]).pin_memory()
+        ref2 = eng.adapt_predict_batch(imgs2, hp)["pred_logits"].clone()
+        pin1 = imgs.pin_memory()
+        for _ in range(2):
+            p1 = eng.adapt_predict_batch(pin1, hp, sync=False)
+            p2 = eng.adapt_predict_batch(imgs2, hp, sync=False)
+            p3 = eng.adapt_predict_batch(pin1, hp, sync=False)
+            assert _rel(p1.wait()["pred_logits"].numpy(), dev.numpy()) < 1e-6
+            assert _rel(p2.wait()["pred_logits"].numpy(), ref2.numpy()) < 1e-6
+            assert _rel(p3.wait()["pred_logits"].numpy(), dev.numpy()) < 1e-6
         with pytest.raises(ValueError):
             eng.adapt_predict_batch(torch.zeros(4, 64, 3, 224, 224), hp)
     finally:

@@ -117,6 +117,13 @@ struct ttl_ctx {
   struct ProfRec { cudaEvent_t e0, e1; int M, N, K, epi; };
   std::vector<ProfRec> prof_recs;
 
+  // host-input path: double-buffered staging of the views + a copy stream, so the H2D of call i+1 overlaps call i
+  float* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  int stage_next = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+
   // graphs
   bool graphs = true;
   std::vector<GraphEntry> gcache;
@@ -650,7 +657,16 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     const size_t kcm = 64 * static_cast<size_t>(c->Sm);
     A(c->pk[i].a_ext, kcm * d); A(c->pk[i].a_ext_t, d * kcm); A(c->pk[i].b_ext, 3 * d * kcm); A(c->pk[i].b_ext_t, kcm * 3 * d);
   }
+  c->stage_bytes = static_cast<size_t>(c->VVm) * 3 * cfg->image_size * cfg->image_size * sizeof(float);
+  A(c->stage[0], c->stage_bytes / sizeof(float)); A(c->stage[1], c->stage_bytes / sizeof(float));
 #undef A
+  if (rc == TTL_OK) {
+    bool ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { c->err = "could not create the copy stream / events"; rc = TTL_E_CUDA; }
+  }
   c->host_init.assign(c->lora_total, 0.f);
   if (rc != TTL_OK) {
     g_create_err = c->err;
@@ -667,6 +683,11 @@ void ttl_destroy(ttl_ctx* c) {
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   for (auto& e : c->gcache) if (e.exec) cudaGraphExecDestroy(e.exec);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
 }
@@ -874,26 +895,35 @@ int ttl_adapt_predict(ttl_ctx* c, const float* images_dev, int32_t n_views, cons
   return ttl_adapt_predict_batch(c, images_dev, 1, n_views, hp, forced_idx_dev, out_dev, stream);
 }
 
-int ttl_adapt_predict_batch_host(ttl_ctx* c, const float* images_host, int32_t n_samples, int32_t n_views,
-                                 const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
-                                 void* stream) {
+int ttl_adapt_predict_batch_host_async(ttl_ctx* c, const float* images_host, int32_t n_samples, int32_t n_views,
+                                       const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
+                                       void* stream) {
   RET_IF(validate_run(c, n_samples, n_views, hp));
   if (!images_host) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // staging area for the views: the DZ buffer (idle until the backward; im2col has consumed the views long before),
-  // >= S*V*3*size*size*4 bytes for every supported geometry (checked).
   const size_t img_bytes = static_cast<size_t>(n_samples) * n_views * 3 * c->cfg.image_size * c->cfg.image_size * sizeof(float);
-  const size_t dz_bytes = static_cast<size_t>(c->Mm) * c->F * sizeof(bf16);
-  if (img_bytes > dz_bytes) { c->err = "host staging buffer too small"; return TTL_E_SHAPE; }
-  float* stage = reinterpret_cast<float*>(c->DZ);
-  CK(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  if (img_bytes > c->stage_bytes) { c->err = "host staging buffer too small"; return TTL_E_SHAPE; }
+  // H2D on the copy stream into the staging buffer that is two calls old; it overlaps the previous call's kernels.
+  const int b = c->stage_next;
+  c->stage_next ^= 1;
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));   // no-op until the buffer has been used once
+  CK(cudaMemcpyAsync(c->stage[b], images_host, img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+  CK(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
   const int K = static_cast<int>(n_views * hp->selection_p);
   const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
   if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K * n_samples, cudaMemcpyHostToDevice, st));
-  RET_IF(adapt_predict_impl(c, stage, n_samples, n_views, hp, forced, st));
-  RET_IF(copy_outputs(c, out_host, n_samples, n_views, *hp, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  RET_IF(adapt_predict_impl(c, c->stage[b], n_samples, n_views, hp, forced, st));
+  CK(cudaEventRecord(c->ev_consumed[b], st));
+  return copy_outputs(c, out_host, n_samples, n_views, *hp, cudaMemcpyDeviceToHost, st);
+}
+
+int ttl_adapt_predict_batch_host(ttl_ctx* c, const float* images_host, int32_t n_samples, int32_t n_views,
+                                 const ttl_hparams* hp, const int32_t* forced_idx_host, const ttl_outputs* out_host,
+                                 void* stream) {
+  RET_IF(ttl_adapt_predict_batch_host_async(c, images_host, n_samples, n_views, hp, forced_idx_host, out_host, stream));
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return TTL_OK;
 }
 

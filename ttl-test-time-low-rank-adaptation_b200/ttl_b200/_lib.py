@@ -67,6 +67,8 @@ _SIGS = {
     "ttl_adapt_predict_batch": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_batch_host": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs),
                                                vp]),
+    "ttl_adapt_predict_batch_host_async": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp,
+                                                     C.POINTER(TtlOutputs), vp]),
     "ttl_set_graphs": (C.c_int, [vp, C.c_int32]),
     "ttl_last_launch_count": (C.c_int64, [vp]),
     "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),

@@ -53,6 +53,18 @@ class _DevAlias:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class Pending:
+    """Result of an asynchronous host-input call: pinned output tensors that are valid after wait()."""
+
+    def __init__(self, outs, event, keepalive):
+        self._outs, self._event, self._keep = outs, event, keepalive
+
+    def wait(self) -> Dict[str, torch.Tensor]:
+        self._event.synchronize()
+        self._keep = None
+        return self._outs
+
+
 class Engine:
     def __init__(self, arch: str = "ViT-B/16", max_views: int = 64, max_classes: int = 1000, lora_rank: int = 16,
                  lora_alpha: float = 32.0, layer_range: Sequence[int] = (9, 11), device: int = 0,
@@ -199,9 +211,11 @@ class Engine:
         return {k: v[0] for k, v in outs.items()}
 
     def adapt_predict_batch(self, images: torch.Tensor, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
-                            want: Sequence[str] = ("pred_logits",)) -> Dict[str, torch.Tensor]:
+                            want: Sequence[str] = ("pred_logits",), sync: bool = True):
         """S independent test samples adapted concurrently (S <= max_samples), each exactly as adapt_predict would:
-        `images` [S,V,3,size,size] -> dict of per-sample results, leading dimension S."""
+        `images` [S,V,3,size,size] -> dict of per-sample results, leading dimension S.
+        Host-resident `images` with sync=False return a `Pending` handle instead: the copy of this batch overlaps the
+        kernels of the previous one (software-pipelined loader loop); call .wait() for the dict."""
         S, V = int(images.shape[0]), int(images.shape[1])
         if S > self.max_samples:
             raise ValueError(f"{S} samples > max_samples={self.max_samples}")
@@ -224,9 +238,15 @@ class Engine:
             fidx = forced_idx.to(dev, torch.int32).contiguous()
         h = hp.to_c()
         if host:
-            L.check(self.lib.ttl_adapt_predict_batch_host(self.ctx, images.data_ptr(), S, V, C.byref(h),
-                                                          fidx.data_ptr() if fidx is not None else None, C.byref(o),
-                                                          self._st()), self.ctx)
+            fn = self.lib.ttl_adapt_predict_batch_host if sync else self.lib.ttl_adapt_predict_batch_host_async
+            L.check(fn(self.ctx, images.data_ptr(), S, V, C.byref(h), fidx.data_ptr() if fidx is not None else None,
+                       C.byref(o), self._st()), self.ctx)
+            if not sync:
+                if "idx" in outs:
+                    outs["idx"] = outs["idx"][:, :K]
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                return Pending(outs, ev, (images, fidx))
         else:
             self._sync_in()
             L.check(self.lib.ttl_adapt_predict_batch(self.ctx, images.data_ptr(), S, V, C.byref(h),
