@@ -117,25 +117,41 @@ def test_reference_control_flow_drives_the_module(model, b16_views, head):
 
 
 @pytest.mark.parametrize("head", ["tpt", "deyo"])
-def test_ttl_test_time_tuning_and_fused_path_agree(model, b16_views, head):
-    """Our ttl.test_time_tuning (kernel-backed heads, autograd, torch AdamW) vs the fused one-call path."""
+def test_ttl_test_time_tuning_and_fused_path_agree(model, b16_views, head, monkeypatch):
+    """Our ttl.test_time_tuning (kernel-backed heads, autograd, torch AdamW) vs the fused one-call path.  The top-6
+    selection is ill-conditioned end to end (the 6th/7th entropies of this sample differ by ~1e-3, a bf16
+    forward can swap them), so both paths are teacher-forced with the reference's selected views, as the north star words
+    it ("bit-exact given identical entropies"); the free-running selection itself is checked in test_gpu_e2e/test_gpu_ops."""
     import ttl
+    from ttl_b200 import Hparams
     g = np.load(os.path.join(GOLD, f"ref_b16_c10_{head}.npz"))
     args = _args(deyo_selection=True if head == "deyo" else '')
     opt = _optimizer(model)
     state = __import__("copy").deepcopy(opt.state_dict())
     scaler = torch.amp.GradScaler("cuda", init_scale=1000, enabled=False)
     imgs = b16_views.cuda()
+    forced = None
+    if head == "tpt":
+        forced = torch.from_numpy(g["idx_sorted"].astype(np.int64)).cuda()
+        monkeypatch.setattr(ttl, "select_confident_samples", lambda logits, top: (logits[forced], forced))
     with torch.no_grad():
         model.LoRA_reset()
     opt.load_state_dict(state)
     ttl.test_time_tuning(model, imgs, opt, scaler, args)
     with torch.no_grad():
         pred_compat = model(imgs[:1])[0].cpu().numpy()
-    pred_fused = model.adapt_and_predict(imgs, args)["pred_logits"].cpu().numpy()
+    hp = model.hparams_from_args(args)
+    pred_fused = model.engine.adapt_predict(imgs, hp, forced_idx=None if forced is None else forced.int(),
+                                            want=("pred_logits",))["pred_logits"].cpu().numpy()
     assert _rel(pred_compat, g["pred_logits"][0]) < 1e-2
     assert _rel(pred_fused, g["pred_logits"][0]) < 1e-2
     assert _rel(pred_fused, pred_compat) < 5e-3
+    # free-running fused call: when it selects the same SET of views it may still order them differently (entropy rank
+    # vs ascending index), which reorders the fp32 weight-gradient sums; step-1 Adam turns every gradient element into
+    # ~lr*sign(g), so the few elements with g ~ 0 can flip (SURVEY.md 7.3-1) -- hence a bf16-level bound, not equality
+    free = model.adapt_and_predict(imgs, args, want=("pred_logits", "idx"))
+    if head == "tpt" and sorted(free["idx"].cpu().tolist()) == sorted(g["idx_sorted"].tolist()):
+        assert _rel(free["pred_logits"].cpu().numpy(), pred_fused) < 1e-2
 
 
 def test_kernel_backed_head_functions():

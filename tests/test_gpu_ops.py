@@ -192,6 +192,26 @@ def test_attention_fwd_bwd(G, V, tokens, heads):
         assert gu.rel_err(got[:, i], g[:, i]) < 1.5e-2, nm   # bf16 P/dS operands; fp32 accumulation
 
 
+def test_attention_fwd_extreme_scores(G):
+    """Scores spanning hundreds of nats (keys 64.. scaled 40x): exact-max softmax must stay finite and accurate, and the
+    near one-hot rows exercise the 16-key tail block of P (32B-swizzled) and the last V rows of the MN-major operand."""
+    gu, L = G
+    V, tokens, heads = 3, 197, 12
+    d = heads * 64
+    qkv = torch.randn(V * tokens, 3 * d, device="cuda") * 1.5
+    kk = qkv.view(V, tokens, 3, heads, 64)
+    kk[:, 64:, 1] *= 40.0                      # K rows of the later tokens
+    qkv = qkv.bfloat16()
+    out = torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(V, heads, tokens, device="cuda")
+    gu.ok(gu.lib().ttl_op_attention_fwd(gu.ptr(qkv), gu.ptr(out), gu.ptr(lse), V, tokens, heads, 0.125, gu.stream()))
+    torch.cuda.synchronize()
+    ref, lse_ref = _attn_ref(qkv.float(), V, tokens, heads)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert gu.rel_err(out, ref) < 8e-3
+    assert float(((lse - lse_ref).abs() / lse_ref.abs().clamp_min(1.0)).max()) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ head
 @pytest.mark.parametrize("C_", [10, 200, 1000])
 def test_logits_entropy(G, C_):

@@ -189,7 +189,7 @@ class ClipTestTimeTuning(nn.Module):
     def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-B/16", n_ctx=16, ctx_init=None,
                  ctx_position="end", learned_cls=False, layer_range=[9, 11], init_method=None, lora_encoder="text",
                  rank=16, max_views: int = 64, weights: Optional[dict] = None, text_features: Optional[torch.Tensor] = None,
-                 logit_scale: float = math.log(100.0)):
+                 logit_scale: float = math.log(100.0), max_samples: int = 1):
         super().__init__()
         if lora_encoder != "image":
             raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
@@ -203,7 +203,7 @@ class ClipTestTimeTuning(nn.Module):
         d, n_layers = geo["width"], geo["layers"]
         self.layer_range = [int(layer_range[0]), int(layer_range[1])]
         self.engine = Engine(arch, max_views=max_views, max_classes=max(1000, len(classnames)), lora_rank=rank,
-                             lora_alpha=32.0, layer_range=self.layer_range, device=dev_index)
+                             lora_alpha=32.0, layer_range=self.layer_range, device=dev_index, max_samples=max_samples)
         self.engine.load_weights(weights if weights is not None else self._load_vision_weights(arch))
 
         # LoRA module tree.  Trainable-range tensors alias the library's device buffers.
@@ -328,6 +328,13 @@ class ClipTestTimeTuning(nn.Module):
         device or in pinned host memory.  Returns a dict with `pred_logits` [C] (+ anything else in `want`)."""
         hp = hparams or self.hparams_from_args(args)
         return self.engine.adapt_predict(images, hp, want=want)
+
+    def adapt_and_predict_batch(self, images: torch.Tensor, args=None, hparams: Optional[Hparams] = None,
+                                want=("pred_logits",), sync: bool = True):
+        """The same for S test samples adapted concurrently, each with its own adapter and optimiser state: `images`
+        [S,V,3,size,size] (S <= max_samples) -> per-sample results with leading dimension S."""
+        hp = hparams or self.hparams_from_args(args)
+        return self.engine.adapt_predict_batch(images, hp, want=want, sync=sync)
 
 
 def get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls=False, layer_range=[0, 11], init_method=None,

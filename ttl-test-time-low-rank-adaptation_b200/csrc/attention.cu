@@ -12,7 +12,9 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace ttl {
 
@@ -527,6 +529,285 @@ attention_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
   if (lane == 0) bulk_wait<0>();
 }
 
+
+// =============================================================================================== tcgen05 forward
+// Forward attention on the 5th-gen tensor cores.  Work item = (view, head, 128-query tile); two CTAs per SM (84 KB smem,
+// 256 TMEM columns each) so one CTA's softmax overlaps the other's loads and MMAs.
+//   warp 0 (one thread): TMA loads of Q tile / K / V (3-D maps, 128B swizzle, rows >= tokens zero-filled), then
+//                        S = Q K^T   : 4 x tcgen05.mma 128 x keys x 16 (both operands K-major)           -> TMEM cols [0, keys)
+//                        O = P V     : keys/16 x tcgen05.mma 128 x 64 x 16, A = P (bf16, smem, K-major), B = V as it sits
+//                                      in memory ([key][dh] = MN-major operand)                          -> TMEM cols [0, 64)
+//   warps 1-4: one thread per query row: two passes over the row in TMEM (max; exp2 + sum), P written as bf16 into the
+//              UMMA K-major swizzled layout (64-key blocks with 128B swizzle over the dead Q/K tiles + a 16-key tail block
+//              with 32B swizzle), then O / rowsum -> swizzled smem -> one TMA store per tile (rows >= tokens clipped).
+// fp32 softmax statistics as HF eager attention (modeling_clip.py:261-279); P rounded to bf16 like the mma.sync kernels.
+constexpr int TC_THREADS = 160;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
+                        int items, int q_tiles, int keys, float scale_log2, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_tc_raw[];
+#define TC_STAMP(k) do { if (dbg != nullptr && blockIdx.x < 8 && local_it < 16) dbg[(blockIdx.x * 16 + local_it) * 8 + (k)] = clock64(); } while (0)
+  int local_it = 0;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_tc_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = keys * 128;                                   // bytes of the K (or V) tile, multiple of 1024 (keys % 16 == 0, see launcher)
+  uint8_t* sQ = smem;                                          // 16 KB  [128 q][64 dh]      -> later P block 1
+  uint8_t* sK = smem + 16384;                                  // KB     [keys][64 dh]       -> later P block 0 (+ 16-key tail block)
+  uint8_t* sV = sK + KB;                                       // KB     [keys][64 dh]
+  uint8_t* sP2 = sV + KB;                                      // 16 KB  P block 2           -> later the output stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP2 + 16384);
+  uint64_t* bar_qk = bars;          // Q tile + K landed
+  uint64_t* bar_v = bars + 1;       // V landed
+  uint64_t* bar_s = bars + 2;       // S complete in TMEM
+  uint64_t* bar_o = bars + 3;       // O complete in TMEM (and every smem operand of the item is dead)
+  uint64_t* bar_tfree = bars + 4;   // O copied to registers: TMEM reusable (4 softmax warps)
+  uint64_t* bar_p = bars + 5;       // [4] P block b written (4 softmax warps each); index 3 = the 16-key tail block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * DH;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_tfree, 4);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_p[i], 4);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const int n_full = keys / 64, tail = keys - n_full * 64;     // 64-key P blocks + a 16-key tail block (tail in {0,16})
+  // P block b lives at: 0 -> sK, 1 -> sQ, 2 -> sP2 ; tail block -> sK + 16384
+  const uint32_t p_addr0 = smem_u32(sK), p_addr1 = smem_u32(sQ), p_addr2 = smem_u32(sP2);
+  const uint32_t p_tail = smem_u32(sK) + 16384;
+
+  uint32_t ph = 0;   // parity of the per-item barriers
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA + MMA issue (one thread)
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, static_cast<uint32_t>(keys));
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV);
+      const uint32_t v_lbo = static_cast<uint32_t>(KB);
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ph ^= 1, ++local_it) {
+        const int unit = item / q_tiles, qt = item - unit * q_tiles;
+        const int view = unit / heads, h = unit - view * heads;
+        // every smem operand of the previous item is dead (bar_o was waited at the end of the previous iteration)
+        TC_STAMP(0);
+        mbar_expect_tx(bar_qk, 16384 + KB);
+        tma_load_3d(&tmQ, bar_qk, sQ, h * DH, qt * 128, view);
+        tma_load_3d(&tmKV, bar_qk, sK, d + h * DH, 0, view);
+        mbar_expect_tx(bar_v, KB);
+        tma_load_3d(&tmKV, bar_v, sV, 2 * d + h * DH, 0, view);
+        mbar_wait(bar_qk, ph);
+        TC_STAMP(1);
+        if (local_it > 0) mbar_wait(bar_tfree, ph ^ 1);     // previous O has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)     // S = Q K^T
+          umma_bf16(tmem, umma_desc_k_sw128(qa + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(bar_s);
+        int kk = 0;                     // O = P V, block by block as the softmax warps deliver P
+        for (int b = 0; b < n_full; ++b) {
+          mbar_wait(&bar_p[b], ph);
+          if (b == 0) mbar_wait(bar_v, ph);
+          tc_fence_after();
+          const uint32_t pa = b == 0 ? p_addr0 : (b == 1 ? p_addr1 : p_addr2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j, ++kk)
+            umma_bf16(tmem, umma_desc_k_sw128(pa + j * 32), umma_desc(va + kk * 2048, 1024, v_lbo, 2), idesc_o, kk != 0 ? 1u : 0u);
+        }
+        if (tail) {
+          mbar_wait(&bar_p[3], ph);
+          if (n_full == 0) mbar_wait(bar_v, ph);
+          tc_fence_after();
+          umma_bf16(tmem, umma_desc(p_tail, 256, 0, 6), umma_desc(va + kk * 2048, 1024, v_lbo, 2), idesc_o, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_o);
+        mbar_wait(bar_o, ph);           // MMAs complete: Q/K/V/P regions may be overwritten by the next item's loads
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: one thread per query row
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const int n32 = keys / 32, rem16 = keys - n32 * 32;   // full 32-column chunks + optional 16-column chunk
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ph ^= 1, ++local_it) {
+      const int unit = item / q_tiles, qt = item - unit * q_tiles;
+      const int view = unit / heads, h = unit - view * heads;
+      const int r0 = qt * 128;
+      const bool active = r0 + quad * 32 < tokens;    // warp-uniform: at least one real query row
+      mbar_wait(bar_s, ph);
+      if (threadIdx.x == 32) TC_STAMP(2);
+      tc_fence_after();
+      float m = -INFINITY, l = 0.f;
+      if (active) {
+        // ---- pass 1: exact row maximum (ALU + TMEM only; it overlaps the other resident CTA's MUFU-bound pass 2).
+        // Columns >= tokens hold exact zeros (K rows beyond the view are zero-filled by the TMA): including them can only
+        // raise the subtracted constant to 0 when every real score is negative, which softmax is invariant to.
+        for (int c = 0; c < n32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(trow + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        }
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        }
+      }
+      if (threadIdx.x == 32) {
+        TC_STAMP(3);
+        bulk_wait_read<0>();          // the previous item's output store has finished reading sP2 (= P block 2)
+      }
+      named_bar_sync(2, 128);
+      if (active) {
+        // ---- pass 2: p = 2^(s*scale - m*scale), row sum, bf16 P into the UMMA K-major layout, block by block
+        const float ms = m * scale_log2;
+        float l0 = 0.f, l1 = 0.f;
+        for (int c = 0; c < n32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(trow + c * 32, r);
+          tmem_ld_wait();
+          const int blk = c >> 1;
+          const uint32_t base = (blk == 0 ? p_addr0 : (blk == 1 ? p_addr1 : p_addr2)) + row * 128;
+          if (c * 32 + 32 <= tokens) {     // warp-uniform: chunk entirely inside the real keys
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+              l0 += (e[0] + e[1]) + (e[2] + e[3]);
+              l1 += (e[4] + e[5]) + (e[6] + e[7]);
+              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((chunk ^ (row & 7)) << 4)),
+                           "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                           "r"(pack_bf16(e[6], e[7]))
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+                if (c * 32 + q4 * 8 + i >= tokens) v = 0.f;
+                e[i] = v;
+                l0 += v;
+              }
+              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((chunk ^ (row & 7)) << 4)),
+                           "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                           "r"(pack_bf16(e[6], e[7]))
+                           : "memory");
+            }
+          }
+          if (c & 1) {                  // a 64-key block is complete: hand it to the MMA thread
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            tc_fence_before();          // this warp's tcgen05.ld of S columns [0, 64*(blk+1)) are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[blk]);
+          }
+        }
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+          const uint32_t base = p_tail + row * 32;
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v = ex2_approx(fmaf(__uint_as_float(r[q2 * 8 + i]), scale_log2, -ms));
+              if (n32 * 32 + q2 * 8 + i >= tokens) v = 0.f;
+              e[i] = v;
+              l0 += v;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((q2 ^ ((row >> 2) & 1)) << 4)),
+                         "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                         "r"(pack_bf16(e[6], e[7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[3]);
+        }
+        l = l0 + l1;
+      } else {
+        tc_fence_before();
+        if (lane == 0) {
+          for (int b = 0; b < n_full; ++b) mbar_arrive(&bar_p[b]);
+          if (tail) mbar_arrive(&bar_p[3]);
+        }
+      }
+      if (threadIdx.x == 32) TC_STAMP(4);
+      mbar_wait(bar_o, ph);
+      if (threadIdx.x == 32) TC_STAMP(5);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (active) {
+        tmem_ld_32x32b_x32(trow, o0);
+        tmem_ld_32x32b_x32(trow + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfree);      // the next item's S may overwrite the TMEM columns
+      if (active) {
+        const float inv = 1.f / l;
+        const uint32_t obase = smem_u32(sP2) + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const uint32_t* r = q4 < 4 ? o0 + q4 * 8 : o1 + (q4 - 4) * 8;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (row & 7)) << 4)),
+                       "r"(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv))
+                       : "memory");
+        }
+        if (lse != nullptr && r0 + row < tokens)
+          lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + row] = (m * scale_log2 + log2f(l)) * LN2;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);       // the four softmax warps: output stage complete
+      if (threadIdx.x == 32) {
+        tma_store_3d(&tmOut, sP2, h * DH, r0, view);
+        bulk_commit();
+        TC_STAMP(6);
+      }
+    }
+    if (threadIdx.x == 32) bulk_wait<0>();
+  }
+#undef TC_STAMP
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 inline int pick_warps(int tiles) {
   const int rounds = (tiles + 7) / 8;
   return (tiles + rounds - 1) / rounds;
@@ -541,6 +822,64 @@ size_t attention_fwd_smem(int tokens) {
 size_t attention_bwd_smem(int tokens) {
   const int nkp = (tokens + 63) / 64 * 64;
   return static_cast<size_t>(4 * nkp) * LDS * sizeof(bf16) + 2 * nkp * sizeof(float);
+}
+
+static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                                    cudaStream_t st) {
+  const int keys = (tokens + 15) / 16 * 16;
+  const int tail = keys % 64;
+  if (keys < 64 || keys > 208 || (tail != 0 && tail != 16)) return false;   // P-block placement covers <= 3 blocks + 16-key tail
+  const int q_tiles = (tokens + 127) / 128;
+  const int d = heads * DH;
+  const size_t smem = 16384 + 2 * static_cast<size_t>(keys) * 128 + 16384 + 64 + 1024;
+  if (tail && 16384 + 4096 > keys * 128) return false;
+  CUtensorMap tq, tkv, to;
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+  const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
+  if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
+  const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+  const uint32_t obox[3] = {64, 128, 1};
+  if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
+  static size_t configured = 0;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem;
+  }
+  const int items = V * heads * q_tiles;
+  const int grid = items < 2 * num_sms ? items : 2 * num_sms;
+  static long long* dbg = nullptr;
+  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
+  if (want_dbg && dbg == nullptr) { cudaMallocManaged(&dbg, 8 * 16 * 8 * sizeof(long long)); }
+  if (want_dbg) std::memset(dbg, 0, 8 * 16 * 8 * sizeof(long long));
+  attention_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tq, tkv, to, lse, tokens, heads, items, q_tiles, keys, scale * LOG2E,
+                                                          want_dbg ? dbg : nullptr);
+  if (want_dbg) {   // development aid: per-stage clock64 deltas of the first items of CTAs 0..7
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (items >= 2000 && printed++ == 3) {
+      const char* nm[7] = {"issue", "landed", "S ready", "pass1", "pass2", "O ready", "retired"};
+      for (int cta = 0; cta < 8; cta += 7)
+        for (int it = 1; it < 6; ++it) {
+          const long long* t = dbg + (cta * 16 + it) * 8;
+          std::fprintf(stderr, "cta %d item %d:", cta, it);
+          for (int k = 1; k < 7; ++k) std::fprintf(stderr, " %s +%lld", nm[k], t[k] - t[0]);
+          std::fprintf(stderr, " | next issue +%lld\n", (dbg + (cta * 16 + it + 1) * 8)[0] - t[0]);
+        }
+    }
+  }
+  return true;
 }
 
 static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
@@ -589,8 +928,12 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
 
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                           cudaStream_t st) {
-  static const bool use_tma = std::getenv("TTL_ATTN_LEGACY") == nullptr;
-  if (use_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
+  // TTL_ATTN: unset / "tc" = tcgen05 kernel where the geometry allows, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
+  static const char* mode = std::getenv("TTL_ATTN");
+  const bool want_tc = mode == nullptr || mode[0] == 't';
+  const bool want_tma = mode == nullptr || mode[0] != 'l';
+  if (want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
+  if (want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_fwd_smem(tokens);
   static size_t configured = 0;

@@ -12,6 +12,7 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
   --compat        drive the module through autograd + torch.optim.AdamW (the reference's control flow) instead of
                   the fused per-sample call
   --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
+  --concurrent_samples S  adapt S test samples per library call (default 3; 1 = strictly one at a time)
 """
 from __future__ import annotations
 
@@ -141,6 +142,30 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
     rank, world = getattr(args, "rank_id", 0), getattr(args, "world_size", 1)
     counts = torch.zeros(3, dtype=torch.int64, device=model.device)
     end = time.time()
+    S = max(1, int(getattr(args, "concurrent_samples", 1))) if fused else 1
+    pend_imgs, pend_tgt, seen = [], [], 0
+
+    def score(output, target):
+        acc1, acc5 = accuracy(output, target, topk=(1, 5))
+        n = target.numel()
+        top1.update(float(acc1[0]), n)
+        top5.update(float(acc5[0]), n)
+        k1 = torch.round(acc1[0] * n / 100.0).long()
+        k5 = torch.round(acc5[0] * n / 100.0).long()
+        counts.add_(torch.stack([k1, k5, torch.full_like(k1, n)]).to(counts.device))
+
+    def flush():
+        """one fused library call for the pending samples (each: reset -> adapt -> predict, ttl.py:338-352)"""
+        nonlocal pend_imgs, pend_tgt
+        if not pend_imgs:
+            return
+        batch = torch.stack(pend_imgs)
+        if not batch.is_cuda and not getattr(args, "views_on_host", False):
+            batch = batch.to(model.device, non_blocking=True)
+        out = model.adapt_and_predict_batch(batch, args)["pred_logits"].to(model.device)
+        score(out, torch.cat(pend_tgt))
+        pend_imgs, pend_tgt = [], []
+
     for i, (images, target) in enumerate(val_loader):
         if isinstance(images, list):
             images = torch.cat([im if im.dim() == 4 else im[None] for im in images], dim=0)
@@ -148,9 +173,10 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
             images = images.squeeze(0)
         target = torch.as_tensor(target).view(-1)[:1].to(model.device)
         if fused:
-            if not images.is_cuda and not getattr(args, "views_on_host", False):
-                images = images.to(model.device, non_blocking=True)
-            output = model.adapt_and_predict(images, args)["pred_logits"].to(model.device)[None]
+            pend_imgs.append(images)
+            pend_tgt.append(target)
+            if len(pend_imgs) == S:
+                flush()
         else:
             images = images.to(model.device, non_blocking=True)
             image = images[:1]
@@ -161,14 +187,13 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
             test_time_tuning(model, images, optimizer, scaler, args)
             with torch.no_grad():
                 output = model(image)
-        acc1, acc5 = accuracy(output, target, topk=(1, 5))
-        top1.update(float(acc1[0]), 1)
-        top5.update(float(acc5[0]), 1)
-        counts += torch.stack([(acc1[0] > 0).long(), (acc5[0] > 0).long(), torch.ones((), dtype=torch.long, device=acc1.device)]).to(counts.device)
+            score(output, target)
+        seen += 1
         batch_time.update(time.time() - end)
         end = time.time()
         if (i + 1) % args.print_freq == 0 and rank == 0:
             print(f"Test: [{i + 1}/{len(val_loader)}]\t{batch_time}\t{top1}\t{top5}")
+    flush()
     tot = tdist.reduce_counts(counts, world)   # the only collective of the path: 3 int64 (utils/tools.py:40-44 semantics)
     n = max(tot[2], 1)
     if rank == 0:
@@ -207,7 +232,8 @@ def main_worker(gpu, args):
     first = args.test_sets.split("/")[0]
     model = get_coop(args.arch, args.test_sets, args.gpu, args.n_ctx, args.ctx_init, layer_range=args.layer_range,
                      init_method=args.init_method, lora_encoder=args.lora_encoder, rank=args.rank,
-                     classnames=_classnames_for(first, args), max_views=args.batch_size)
+                     classnames=_classnames_for(first, args), max_views=args.batch_size,
+                     max_samples=max(1, args.concurrent_samples))
     # requires-grad filter by parameter NAME, exactly the reference's rule (ttl.py:151-163)
     for name, param in model.named_parameters():
         ok = ('image_encoder' in name and ("lora_A" in name or "lora_B" in name)
@@ -307,6 +333,8 @@ def build_parser():
     p.add_argument('--synthetic', default=0, type=int, help='evaluate on N seeded synthetic samples')
     p.add_argument('--compat', action='store_true', default=False, help='autograd + torch.optim.AdamW control flow')
     p.add_argument('--views_on_host', action='store_true', default=False)
+    p.add_argument('--concurrent_samples', default=3, type=int,
+                   help='test samples adapted concurrently per library call (each keeps its own adapter/optimiser state)')
     return p
 
 
