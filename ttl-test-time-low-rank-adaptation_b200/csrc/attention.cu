@@ -229,8 +229,11 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   const float scale_log2 = scale * LOG2E;
   bf16* gdq = dqkv + static_cast<size_t>(view) * tokens * ld + h * DH;
 
+  // The two phases are independent given Q/K/V/dO/D in smem: blockIdx.z picks one, which doubles the number of CTAs of
+  // the (small: G <= 18 views) backward launches and halves the serial work per CTA.
+  const bool do_a = gridDim.z == 1 || blockIdx.z == 0, do_b = gridDim.z == 1 || blockIdx.z == 1;
   // ---------------- phase A: dQ for 16-query tiles
-  for (int qt = warp; qt < tiles; qt += nwarps) {
+  for (int qt = warp; do_a && qt < tiles; qt += nwarps) {
     uint32_t aq[4][4], ado[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -271,7 +274,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   }
 
   // ---------------- phase B: dK, dV for 16-key tiles (transposed problem: rows = keys, columns = queries)
-  for (int kt = warp; kt < tiles; kt += nwarps) {
+  for (int kt = warp; do_b && kt < tiles; kt += nwarps) {
     uint32_t ak[4][4], av[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -954,8 +957,8 @@ void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, co
     cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  attention_bwd_kernel<<<dim3(heads, V), pick_warps(tiles) * 32, smem, st>>>(qkv, out, dout, lse, dqkv, tokens, heads,
-                                                                             scale, tiles, nkp);
+  attention_bwd_kernel<<<dim3(heads, V, 2), pick_warps(tiles) * 32, smem, st>>>(qkv, out, dout, lse, dqkv, tokens, heads,
+                                                                                scale, tiles, nkp);
 }
 
 }  // namespace ttl

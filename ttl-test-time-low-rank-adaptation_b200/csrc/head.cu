@@ -51,38 +51,44 @@ cls_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     pooled[static_cast<size_t>(v) * d + i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
 }
 
-// out[m, n] = sum_k A[m, k] * B[n, k]      fp32, tile 16 x 64, K chunks of 64 staged in smem (padded, conflict-free)
-constexpr int SG_TM = 16, SG_TN = 64, SG_KC = 64;
+// out[m, n] = sum_k A[m, k] * B[n, k]      fp32.  A CTA stages 16 rows of A in smem; each of its 8 warps owns one row n of
+// B at a time (contiguous, read with float4 across the lanes) and keeps 16 running dot products, reduced with shuffles.
+// Grid (ceil(N/32), ceil(M/16)): >= 1000 CTAs for the [192 x 1000 x 512] logits GEMM, 32 for the 3-view prediction.
+constexpr int SG_TM = 16, SG_NPC = 32;   // rows of A per CTA, columns (rows of B) per CTA
 __global__ void __launch_bounds__(256)
 small_gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int M, int N,
                      int K) {
-  __shared__ float As[SG_TM][SG_KC + 1];
-  __shared__ float Bs[SG_TN][SG_KC + 1];
-  const int n0 = blockIdx.x * SG_TN, m0 = blockIdx.y * SG_TM;
-  const int tn = threadIdx.x & 63, tg = threadIdx.x >> 6;   // 4 groups x 4 rows
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += SG_KC) {
-    for (int i = threadIdx.x; i < SG_TM * SG_KC; i += 256) {
-      const int r = i / SG_KC, c = i % SG_KC;
-      As[r][c] = (m0 + r < M && k0 + c < K) ? A[static_cast<size_t>(m0 + r) * K + k0 + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < SG_TN * SG_KC; i += 256) {
-      const int r = i / SG_KC, c = i % SG_KC;
-      Bs[r][c] = (n0 + r < N && k0 + c < K) ? B[static_cast<size_t>(n0 + r) * K + k0 + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < SG_KC; ++kk) {
-      const float b = Bs[tn][kk];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] += As[tg * 4 + i][kk] * b;
-    }
-    __syncthreads();
+  extern __shared__ float sA[];            // [SG_TM][K]
+  const int m0 = blockIdx.y * SG_TM, n0 = blockIdx.x * SG_NPC;
+  const int K4 = K >> 2;
+  for (int i = threadIdx.x; i < SG_TM * K4; i += 256) {
+    const int r = i / K4, c = i - r * K4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + r < M) v = reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + r) * K)[c];
+    reinterpret_cast<float4*>(sA)[i] = v;
   }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int nn = warp; nn < SG_NPC; nn += 8) {
+    const int n = n0 + nn;
+    if (n >= N) break;
+    const float4* b4 = reinterpret_cast<const float4*>(B + static_cast<size_t>(n) * K);
+    float acc[SG_TM];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + tg * 4 + i;
-    if (m < M && n0 + tn < N) out[static_cast<size_t>(m) * N + n0 + tn] = acc[i];
+    for (int i = 0; i < SG_TM; ++i) acc[i] = 0.f;
+    for (int c = lane; c < K4; c += 32) {
+      const float4 b = __ldg(b4 + c);
+#pragma unroll
+      for (int i = 0; i < SG_TM; ++i) {
+        const float4 a = reinterpret_cast<const float4*>(sA)[i * K4 + c];
+        acc[i] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < SG_TM; ++i) {
+      const float v = warp_sum(acc[i]);
+      if (lane == 0 && m0 + i < M) out[static_cast<size_t>(m0 + i) * N + n] = v;
+    }
   }
 }
 
@@ -310,14 +316,24 @@ cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, 
 
 }  // namespace
 
+static void small_gemm_nt_smem(size_t bytes) {
+  static size_t configured = 48 * 1024;
+  if (bytes > configured) {
+    cudaFuncSetAttribute(small_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    configured = bytes;
+  }
+}
+
 void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
                          float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st) {
+  small_gemm_nt_smem(SG_TM * d * sizeof(float));
   cls_ln_kernel<<<V, HT, 0, st>>>(x, gamma, beta, pooled, tokens, d, eps);
-  small_gemm_nt_kernel<<<dim3((P + SG_TN - 1) / SG_TN, (V + SG_TM - 1) / SG_TM), 256, 0, st>>>(pooled, Wp, feats, V, P, d);
+  small_gemm_nt_kernel<<<dim3((P + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM), 256, SG_TM * d * sizeof(float), st>>>(pooled, Wp, feats, V, P, d);
 }
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st) {
-  small_gemm_nt_kernel<<<dim3((C + SG_TN - 1) / SG_TN, (V + SG_TM - 1) / SG_TM), 256, 0, st>>>(feats, text, logits, V, C, P);
+  small_gemm_nt_smem(SG_TM * P * sizeof(float));
+  small_gemm_nt_kernel<<<dim3((C + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM), 256, SG_TM * P * sizeof(float), st>>>(feats, text, logits, V, C, P);
   scale_entropy_kernel<<<V, HT, 0, st>>>(feats, scale, logits, entropy, C, P);
 }
 void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st) {

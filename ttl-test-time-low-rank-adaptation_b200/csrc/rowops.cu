@@ -12,22 +12,40 @@ namespace {
 constexpr int MAXV = 8;            // d <= 1024, d % 128 == 0
 constexpr int ROWS_PER_BLOCK = 8;  // 8 warps per CTA
 
+// One thread per 8 consecutive output columns = 8 consecutive pixels of one patch row (p % 8 == 0) or a generic
+// 2-pixel path (p = 14).  Reads 32 B, writes 16 B; padding columns (K..Kp) are zero.
+template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int V, int S, int p, int Kp) {
   const int gp = S / p, T = gp * gp, K = 3 * p * p;
-  const size_t total = static_cast<size_t>(V) * T * (Kp / 2);
+  const int cols = Kp / VEC;
+  const size_t total = static_cast<size_t>(V) * T * cols;
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int col = static_cast<int>(e % (Kp / 2)) * 2;
-    const size_t row = e / (Kp / 2);
-    float2 v = make_float2(0.f, 0.f);
+    const int col = static_cast<int>(e % cols) * VEC;
+    const size_t row = e / cols;
+    float v[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = 0.f;
     if (col < K) {
       const int view = static_cast<int>(row / T), patch = static_cast<int>(row % T);
       const int py = patch / gp, px = patch % gp;
       const int c = col / (p * p), rem = col % (p * p), i = rem / p, j = rem % p;
-      const size_t src = ((static_cast<size_t>(view) * 3 + c) * S + (py * p + i)) * S + px * p + j;
-      v = *reinterpret_cast<const float2*>(img + src);
+      const float* src = img + ((static_cast<size_t>(view) * 3 + c) * S + (py * p + i)) * S + px * p + j;
+      if (VEC == 8) {
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(src);
+        v[0] = a.x; v[1] = a.y;
+      }
     }
-    *reinterpret_cast<__nv_bfloat162*>(out + row * Kp + col) = __floats2bfloat162_rn(v.x, v.y);
+    if (VEC == 8) {
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(out + row * Kp + col) = o;
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(out + row * Kp + col) = __floats2bfloat162_rn(v[0], v[1]);
+    }
   }
 }
 
@@ -178,10 +196,12 @@ __global__ void block_mask_kernel(bf16* __restrict__ x, int M, int ncols, int ro
 
 void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cudaStream_t st) {
   const int K = 3 * p * p, Kp = (K + 63) / 64 * 64;
-  const size_t total = static_cast<size_t>(V) * (S / p) * (S / p) * (Kp / 2);
+  const bool vec8 = (p % 8 == 0) && (S % 4 == 0);
+  const size_t total = static_cast<size_t>(V) * (S / p) * (S / p) * (Kp / (vec8 ? 8 : 2));
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  im2col_kernel<<<blocks, 256, 0, st>>>(images, patches, V, S, p, Kp);
+  if (vec8) im2col_kernel<8><<<blocks, 256, 0, st>>>(images, patches, V, S, p, Kp);
+  else im2col_kernel<2><<<blocks, 256, 0, st>>>(images, patches, V, S, p, Kp);
 }
 
 void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
