@@ -234,3 +234,41 @@ def test_concurrent_samples_host_path_and_partial_batch(b16_weights):
             eng.adapt_predict_batch(torch.zeros(4, 64, 3, 224, 224), hp)
     finally:
         eng.close()
+
+
+def test_adapted_top1_agreement_with_oracle(b16_weights):
+    """North-star accuracy parity: adapted top-1 predictions agree with the fp32 oracle on >= 99 % of a synthetic set.
+    Free-running on both sides (own entropies, own selection); samples whose fp32 adapted top-1 margin is below 3 logits
+    are not counted (a bf16 forward legitimately flips near-ties).  16 views per sample keep the CPU
+    oracle at ~0.6 s/sample."""
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-B/16"]
+    spec = O.LoraSpec()
+    lora0 = O.lora_init(arch, spec, seed=0)
+    V, n, S = 16, 36, 3
+    text = O.make_text_features(10, arch.proj, seed=3)
+    eng = Engine("ViT-B/16", max_views=V, max_classes=16, layer_range=(9, 11), max_samples=S)
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(lora0)
+        eng.set_text_features(text, math.log(100.0))
+        hp = Hparams(head="tpt", selection_p=0.25)
+        imgs = [O.make_synthetic_views(V, arch.image_size, seed=300 + i) for i in range(n)]
+        got = []
+        for b in range(0, n, S):
+            out = eng.adapt_predict_batch(torch.stack(imgs[b:b + S]).cuda(), hp)["pred_logits"].cpu()
+            got += out.argmax(dim=1).tolist()
+        counted = agree = 0
+        for i in range(n):
+            ref = O.adapt_and_predict(arch, b16_weights, imgs[i], text, math.log(100.0), lora0, spec, head="tpt",
+                                      selection_p=0.25).pred_logits[0]
+            top2 = ref.topk(2).values
+            if float(top2[0] - top2[1]) < 3.0:
+                continue
+            counted += 1
+            agree += int(int(ref.argmax()) == got[i])
+        assert counted >= 8, counted
+        assert agree >= math.ceil(0.99 * counted), (agree, counted)
+        print(f"adapted top-1 agreement {agree}/{counted} (of {n} samples)")
+    finally:
+        eng.close()
