@@ -27,3 +27,24 @@ for (V, tokens, heads) in ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197,
     fl = 4.0 * tokens * tokens * 64 * heads * V
     by = V * tokens * d * 2 * 4
     print(f"attention fwd V={V} tokens={tokens} heads={heads}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
+
+for (V, tokens, heads) in ((18, 197, 12), (6, 197, 12), (64, 197, 12)):
+    d = heads * 64
+    qkv = (torch.randn(V * tokens, 3 * d, device="cuda") * 1.5).bfloat16()
+    out = torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(V, heads, tokens, device="cuda")
+    dout = torch.randn(V * tokens, d, device="cuda").bfloat16()
+    dqkv = torch.empty_like(qkv)
+    gu.ok(lib.ttl_op_attention_fwd(gu.ptr(qkv), gu.ptr(out), gu.ptr(lse), V, tokens, heads, 0.125, gu.stream()))
+    def runb():
+        gu.ok(lib.ttl_op_attention_bwd(gu.ptr(qkv), gu.ptr(out), gu.ptr(dout), gu.ptr(lse), gu.ptr(dqkv), V, tokens, heads, 0.125, gu.stream()))
+    for i in range(3):
+        runb()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        runb()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"attention bwd V={V}: {e0.elapsed_time(e1) * 1e3 / 20:8.1f} us", flush=True)

@@ -91,12 +91,23 @@ __device__ __forceinline__ void zero_acc(float (&a)[8][4]) {
 }
 
 // Copy one head's [tokens x 64] slice (row pitch ld elements) into smem [rows_pad][LDS], zero-filling the padding rows.
+// Four independent 16-byte loads are in flight per thread before the first store (the plain loop serialised on the
+// global-load latency: ~9 dependent round trips per operand).
 __device__ __forceinline__ void load_head_tile(bf16* s, const bf16* g, int ld, int tokens, int rows_pad) {
-  for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {
-    const int r = i >> 3, c = (i & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < tokens) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
-    *reinterpret_cast<uint4*>(s + r * LDS + c) = v;
+  const int total = rows_pad * 8, step = blockDim.x;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * step) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * step, r = i >> 3, c = (i & 7) * 8;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < total && r < tokens) v[u] = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * step, r = i >> 3, c = (i & 7) * 8;
+      if (i < total) *reinterpret_cast<uint4*>(s + r * LDS + c) = v[u];
+    }
   }
 }
 // Write a warp-owned 16x64 fp32 tile as bf16 to global rows row0.. (< tokens), staging through the warp's own smem rows.
@@ -211,19 +222,29 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   load_head_tile(sDO, gDO, d, tokens, nkp);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float* L = lse + (static_cast<size_t>(view) * heads + h) * tokens;
-  for (int r = warp; r < nkp; r += nwarps) {
+  // D[r] = rowsum(dO[r,:] * O[r,:]) and the log-sum-exp in log2 units: one thread per row, eight independent 16-byte loads
+  for (int r = threadIdx.x; r < nkp; r += blockDim.x) {
     float acc = 0.f;
     if (r < tokens) {
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(gO + static_cast<size_t>(r) * d + lane * 2);
-      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(gDO + static_cast<size_t>(r) * d + lane * 2);
-      const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
-      acc = fa.x * fb.x + fa.y * fb.y;
+      uint4 a[8], b[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        a[c] = *reinterpret_cast<const uint4*>(gO + static_cast<size_t>(r) * d + c * 8);
+        b[c] = *reinterpret_cast<const uint4*>(gDO + static_cast<size_t>(r) * d + c * 8);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[c]);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b[c]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(pa[e]), fb = __bfloat1622float2(pb[e]);
+          acc += fa.x * fb.x + fa.y * fb.y;
+        }
+      }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      sD[r] = acc;
-      sL[r] = r < tokens ? L[r] * LOG2E : INFINITY;   // +inf -> exp2(x - inf) = 0 for padding rows
-    }
+    sD[r] = acc;
+    sL[r] = r < tokens ? L[r] * LOG2E : INFINITY;   // +inf -> exp2(x - inf) = 0 for padding rows
   }
   __syncthreads();
   const float scale_log2 = scale * LOG2E;
@@ -614,6 +635,13 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(&tmKV, bar_qk, sK, d + h * DH, 0, view);
         mbar_expect_tx(bar_v, KB);
         tma_load_3d(&tmKV, bar_v, sV, 2 * d + h * DH, 0, view);
+        if (item + static_cast<int>(gridDim.x) < items) {   // pull the next item's operands into L2 behind this item's compute
+          const int nu = (item + gridDim.x) / q_tiles, nq = (item + gridDim.x) - nu * q_tiles;
+          const int nv = nu / heads, nh = nu - nv * heads;
+          tma_prefetch_l2_3d(&tmQ, nh * DH, nq * 128, nv);
+          tma_prefetch_l2_3d(&tmKV, d + nh * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmKV, 2 * d + nh * DH, 0, nv);
+        }
         mbar_wait(bar_qk, ph);
         TC_STAMP(1);
         if (local_it > 0) mbar_wait(bar_tfree, ph ^ 1);     // previous O has left TMEM
