@@ -272,3 +272,32 @@ def test_adapted_top1_agreement_with_oracle(b16_weights):
         print(f"adapted top-1 agreement {agree}/{counted} (of {n} samples)")
     finally:
         eng.close()
+
+
+def test_vit_l14_geometry_forward_and_adapt():
+    """BASELINE config 4 geometry (ViT-L/14 @224: 257 tokens, d=1024, 24 layers, 16 heads, proj 768; adapters on the last
+    three layers): first-forward logits against the fp32 oracle on 4 views, then one fused adapt+predict runs and moves
+    the prediction.  (257 tokens exceed the tcgen05 attention tile plan; the mma.sync kernel serves this geometry.)"""
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-L/14"]
+    spec = O.LoraSpec(rank=16, alpha=32.0, layer_lo=21, layer_hi=23)
+    w = O.make_synthetic_weights(arch, 3)
+    lora0 = O.lora_init(arch, spec, 0)
+    V = 10
+    imgs = O.make_synthetic_views(V, arch.image_size, seed=4)
+    text = O.make_text_features(10, arch.proj, seed=5)
+    eng = Engine("ViT-L/14", max_views=V, max_classes=16, layer_range=(21, 23))
+    try:
+        eng.load_weights(w)
+        eng.set_lora_init(lora0)
+        eng.set_text_features(text, math.log(100.0))
+        eng.lora_reset()
+        logits = eng.forward(imgs[:4].cuda()).cpu()
+        feats = O.vision_forward(arch, w, imgs[:4])
+        ref = O.clip_logits(feats, text, math.log(100.0))
+        assert _rel(logits.numpy(), ref.detach().numpy()) < 1.5e-2     # 24 layers of bf16 operands
+        out = eng.adapt_predict(imgs.cuda(), Hparams(head="tpt", selection_p=0.3), want=("logits0", "pred_logits", "idx", "loss"))
+        assert torch.isfinite(out["pred_logits"]).all() and out["idx"].numel() == 3
+        assert _rel(out["pred_logits"].cpu().numpy(), out["logits0"][0].cpu().numpy()) > 1e-4   # the adapter moved it
+    finally:
+        eng.close()
