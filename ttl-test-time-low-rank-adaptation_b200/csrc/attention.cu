@@ -839,6 +839,67 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+
+// =============================================================================================== CLS-query attention
+// Last encoder layer in inference: only the CLS token of each view feeds post_layernorm / visual_projection
+// (HF CLIPVisionTransformer.forward: pooled_output = last_hidden_state[:, 0]), so only its query row is needed.
+// One CTA per (head, view): phase 1 one thread per key (q . k_j, fp32), block softmax, phase 2 one thread per output
+// dimension (sum_j p_j v_j[d], coalesced over d).  q comes from a compact [V, d] tensor, K/V from the usual qkv rows.
+__global__ void __launch_bounds__(128)
+attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qkv, bf16* __restrict__ out_cls, int tokens,
+                     int heads, float scale_log2) {
+  extern __shared__ float sh_cls[];
+  float* sq = sh_cls;            // [64]
+  float* sp = sh_cls + 64;       // [tokens]
+  __shared__ float red[8];
+  const int h = blockIdx.x, view = blockIdx.y, d = heads * DH, ld = 3 * d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < DH) sq[tid] = __bfloat162float(q_cls[static_cast<size_t>(view) * d + h * DH + tid]);
+  __syncthreads();
+  const bf16* kbase = qkv + static_cast<size_t>(view) * tokens * ld + d + h * DH;
+  float mx = -INFINITY;
+  for (int j = tid; j < tokens; j += blockDim.x) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = kr[c];
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(p2[e]);
+        acc += f.x * sq[c * 8 + 2 * e] + f.y * sq[c * 8 + 2 * e + 1];
+      }
+    }
+    acc *= scale_log2;
+    sp[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float sum = 0.f;
+  for (int j = tid; j < tokens; j += blockDim.x) {
+    const float e = exp2f(sp[j] - mx);
+    sp[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[4] + red[5] + red[6] + red[7]);
+  // phase 2: threads 0..63 take the even keys, 64..127 the odd keys of output dimension tid & 63
+  const int dd = tid & 63, half = tid >> 6;
+  const bf16* vbase = qkv + static_cast<size_t>(view) * tokens * ld + 2 * d + h * DH + dd;
+  float o = 0.f;
+  for (int j = half; j < tokens; j += 2) o += sp[j] * __bfloat162float(vbase[static_cast<size_t>(j) * ld]);
+  __syncthreads();
+  if (half == 1) sq[dd] = o;
+  __syncthreads();
+  if (half == 0) out_cls[static_cast<size_t>(view) * d + h * DH + dd] = __float2bfloat16((o + sq[dd]) * inv);
+}
+
 inline int pick_warps(int tiles) {
   const int rounds = (tiles + 7) / 8;
   return (tiles + rounds - 1) / rounds;
@@ -974,6 +1035,12 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   }
   attention_fwd_kernel<<<dim3(heads, V), pick_warps(q_tiles) * 32, smem, st>>>(qkv, out, lse, tokens, heads,
                                                                                scale * LOG2E, q_tiles, nkp);
+}
+
+void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
+                          cudaStream_t st) {
+  attention_cls_kernel<<<dim3(heads, V), 128, (64 + tokens) * sizeof(float), st>>>(q_cls, qkv, out_cls, tokens, heads,
+                                                                                    scale * LOG2E);
 }
 
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,

@@ -90,6 +90,10 @@ struct ttl_ctx {
   // activations
   bf16 *patches = nullptr, *Hb = nullptr, *QKV = nullptr, *AO = nullptr, *Gb = nullptr, *Tm = nullptr;
   float *XK = nullptr, *XA = nullptr, *XB = nullptr, *TIN = nullptr, *PIN = nullptr;
+  // last layer in inference: only the CLS row of each view is carried past the K/V projection
+  bf16 *QC = nullptr, *AOC = nullptr, *HC = nullptr, *GC = nullptr;
+  float *XCm = nullptr, *XCo = nullptr;
+  bool cls_shortcut = true;
   float *feats = nullptr, *feats_c = nullptr, *logits = nullptr, *logits_c = nullptr, *entropy = nullptr,
         *entropy_c = nullptr, *loss = nullptr, *dlogits = nullptr, *pred = nullptr, *pred_feats = nullptr,
         *pred_entropy = nullptr, *pooled = nullptr, *dfh = nullptr, *dpool = nullptr;
@@ -289,15 +293,96 @@ int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
   return TTL_OK;
 }
 
+// Last encoder layer in inference mode.  Only the CLS token of each view reaches post_layernorm / visual_projection
+// (HF CLIPVisionTransformer.forward pools last_hidden_state[:, 0]), so after the K/V projection of all tokens everything
+// else (Q, attention, out_proj, MLP) is computed for the V CLS rows only: exact, and 5/6 of the layer's GEMM work less.
+// Result: x_out_cls fp32 [V, d] (compact, one row per view).
+int run_last_layer_cls(ttl_ctx* c, int layer, const float* x_in, int V, int S, bool lora_on, cudaStream_t st) {
+  const LayerW& w = c->lw[layer];
+  const int M = V * c->tokens, d = c->d, F = c->F, tk = c->tokens;
+  const int kc = 64 * c->pack_samples;
+  const bool lora = has_lora(c, layer) && lora_on;
+  launch_layernorm(x_in, c->Hb, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+  c->launches++;
+  if (lora) {
+    if (S != c->pack_samples) { c->err = "run_last_layer_cls: adapter packs were built for another sample count"; return TTL_E_STATE; }
+    GemmArgs g;
+    g.a1 = opnd(c->Hb, M, d, d);
+    g.b1 = opnd(c->pk[layer - c->lo].a_ext, kc, d, d);
+    g.M = M; g.N = kc; g.epi = EPI_BF16; g.out = c->Tm; g.ldo = kc;
+    RET_IF(gemm(c, g, st));
+    if (S > 1) {
+      launch_block_mask(c->Tm, M, kc, M / S, st);
+      c->launches++;
+    }
+  }
+  {  // K, V of every token: columns [d, 3d) of the qkv rows
+    GemmArgs g;
+    g.a1 = opnd(c->Hb, M, d, d);
+    g.b1 = opnd(w.wqkv + static_cast<size_t>(d) * d, 2 * d, d, d);
+    if (lora) {
+      g.a2 = opnd(c->Tm, M, kc, kc);
+      g.b2 = opnd(c->pk[layer - c->lo].b_ext + static_cast<size_t>(d) * kc, 2 * d, kc, kc);
+    }
+    g.M = M; g.N = 2 * d; g.epi = EPI_BF16; g.bias = w.bqkv + d; g.out = c->QKV + d; g.ldo = 3 * d;
+    RET_IF(gemm(c, g, st));
+  }
+  {  // Q of the CLS rows (row v * tokens of h1) -> compact [V, d]
+    GemmArgs g;
+    g.a1 = opnd(c->Hb, V, d, tk * d);
+    g.b1 = opnd(w.wqkv, d, d, d);
+    if (lora) {
+      g.a2 = opnd(c->Tm, V, kc, tk * kc);
+      g.b2 = opnd(c->pk[layer - c->lo].b_ext, d, kc, kc);
+    }
+    g.M = V; g.N = d; g.epi = EPI_BF16; g.bias = w.bqkv; g.out = c->QC; g.ldo = d;
+    RET_IF(gemm(c, g, st));
+  }
+  launch_attention_cls(c->QC, c->QKV, c->AOC, V, tk, c->H, 0.125f, st);
+  c->launches++;
+  {
+    GemmArgs g;
+    g.a1 = opnd(c->AOC, V, d, d);
+    g.b1 = opnd(w.wo, d, d, d);
+    g.M = V; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.bo; g.out = c->XCm; g.ldo = d; g.resid = x_in; g.ldr = tk * d;
+    RET_IF(gemm(c, g, st));
+  }
+  launch_layernorm(c->XCm, c->HC, w.ln2g, w.ln2b, V, d, c->cfg.ln_eps, st);
+  c->launches++;
+  {
+    GemmArgs g;
+    g.a1 = opnd(c->HC, V, d, d);
+    g.b1 = opnd(w.w1, F, d, d);
+    g.M = V; g.N = F; g.epi = EPI_GELU; g.bias = w.b1; g.out = c->GC; g.ldo = F;
+    RET_IF(gemm(c, g, st));
+  }
+  {
+    GemmArgs g;
+    g.a1 = opnd(c->GC, V, F, F);
+    g.b1 = opnd(w.w2, d, F, F);
+    g.M = V; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.b2; g.out = c->XCo; g.ldo = d; g.resid = c->XCm; g.ldr = d;
+    RET_IF(gemm(c, g, st));
+  }
+  return check_launch(c, "run_last_layer_cls");
+}
+
 // layers [lo, L) in inference mode from x_in (V views of S samples) -> feats/logits/entropy written to the given buffers
 int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats, float* logits, float* entropy,
                        cudaStream_t st) {
   const float* cur = x_in;
+  const int last = c->L - 1;
+  const bool shortcut = c->cls_shortcut && last >= c->lo;
   for (int l = c->lo; l < c->L; ++l) {
+    if (shortcut && l == last) break;
     RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, S, !c->b_zero, nullptr, st));
     cur = c->XA;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  if (shortcut) {
+    RET_IF(run_last_layer_cls(c, last, cur, V, S, !c->b_zero, st));
+    launch_pool_project(c->XCo, c->postg, c->postb, c->Wp, c->pooled, feats, V, 1, c->d, c->P, c->cfg.ln_eps, st);
+  } else {
+    launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  }
   launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
   c->launches += 4;
   return check_launch(c, "forward_tail_infer");
@@ -631,6 +716,8 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64 * c->Sm);
   A(c->XK, static_cast<size_t>(M) * d); A(c->XA, static_cast<size_t>(M) * d); A(c->XB, static_cast<size_t>(M) * d);
   A(c->TIN, static_cast<size_t>(M) * d); A(c->PIN, static_cast<size_t>(c->Sm) * c->tokens * d);
+  A(c->QC, static_cast<size_t>(c->VVm) * d); A(c->AOC, static_cast<size_t>(c->VVm) * d); A(c->HC, static_cast<size_t>(c->VVm) * d);
+  A(c->GC, static_cast<size_t>(c->VVm) * F); A(c->XCm, static_cast<size_t>(c->VVm) * d); A(c->XCo, static_cast<size_t>(c->VVm) * d);
   const size_t VV = c->VVm;
   A(c->feats, VV * c->P); A(c->feats_c, VV * c->P); A(c->logits, VV * c->Cm); A(c->logits_c, VV * c->Cm);
   A(c->entropy, VV); A(c->entropy_c, VV); A(c->loss, c->Sm + 4); A(c->dlogits, VV * c->Cm); A(c->pred, static_cast<size_t>(c->Sm) * c->Cm);

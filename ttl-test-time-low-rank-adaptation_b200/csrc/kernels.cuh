@@ -35,6 +35,10 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
 // dqkv bf16 [V*tokens, 3d]  from dout bf16 [V*tokens, d], qkv, out, lse
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
                           int tokens, int heads, float scale, cudaStream_t st);
+// CLS-query attention of the last layer in inference: q_cls bf16 [V, d] (one query row per view), K/V from qkv rows;
+// out_cls bf16 [V, d]
+void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
+                          cudaStream_t st);
 size_t attention_fwd_smem(int tokens);
 size_t attention_bwd_smem(int tokens);
 
