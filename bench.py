@@ -46,8 +46,8 @@ def parse_args():
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--ring", type=int, default=4, help="distinct pre-staged batches (ring * S * 38.5 MB > L2)")
-    ap.add_argument("--concurrent", type=int, default=3,
-                    help="test samples adapted concurrently per step (BASELINE config 5); 3 x 64 x 197 rows = 147.75 "
+    ap.add_argument("--concurrent", type=int, default=6,
+                    help="test samples adapted concurrently per step (BASELINE config 5); every multiple of 3 x 64 x 197 rows = 147.75 "
                          "tiles of 256 rows, one full wave of the 74 CTA pairs per 256-column block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
