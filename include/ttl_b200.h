@@ -159,6 +159,32 @@ int ttl_adapt_predict_batch_host(ttl_ctx* ctx, const float* images_host, int32_t
 int ttl_adapt_predict_batch_host_async(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
                                        const ttl_hparams* hp, const int32_t* forced_idx_host,
                                        const ttl_outputs* out_host, void* stream);
+/* ---- view generator on the device ------------------------------------------------------
+ * Stands in for the host-side AugMixAugmenter the reference's DataLoader workers run per test image
+ * (data/datautils.py:98-157 with the empty augmentation list; ttl.py:232-241): the caller ships the decoded uint8 RGB
+ * image [H,W,3] plus one spec per view, and the library resamples on the GPU, bit-exactly as Pillow's 8-bit antialiased
+ * resampler + torchvision's ToTensor/Normalize would on the host.
+ *   TTL_VIEW_CLEAN: Resize(image_size, BICUBIC, antialias) + CenterCrop(image_size)   (ttl.py:232-234); box ignored
+ *   TTL_VIEW_CROP : RandomResizedCrop box (top, left, height, width) as drawn by torchvision's
+ *                   RandomResizedCrop.get_params, bilinear resize to image_size, optional horizontal flip
+ *                   (data/datautils.py:98-101).  The RNG stays on the host so the torch seed (ttl.py:114) still decides. */
+enum ttl_view_kind { TTL_VIEW_CLEAN = 0, TTL_VIEW_CROP = 1 };
+typedef struct ttl_view_spec { int32_t kind, top, left, height, width, flip; } ttl_view_spec;
+/* transforms.Normalize(mean, std) of ttl.py:226-227; the CLIP constants are the default. */
+int ttl_set_pixel_norm(ttl_ctx* ctx, const float* mean3, const float* std3);
+/* n_images host images (uint8 [H_i, W_i, 3]) x n_views specs each (specs_host [n_images, n_views]) ->
+ * normalised fp32 views on the device [n_images * n_views, 3, S, S].  Enqueued on `stream`; the host buffers may be
+ * reused once the call returns only if they are pageable (pinned buffers: after the stream has been synchronised). */
+int ttl_make_views(ttl_ctx* ctx, const uint8_t* const* images_host, const int32_t* heights, const int32_t* widths,
+                   int32_t n_images, const ttl_view_spec* specs_host, int32_t n_views, float* views_dev, void* stream);
+/* ttl_adapt_predict_batch_host_async fed by uint8 images: H2D of the images (not of 64 fp32 views each), view
+ * generation straight into the patch-embedding operand (bf16 patch matrix; the fp32 views never exist), then the
+ * adapt/predict graph.  Same staging/overlap and lifetime rules as ttl_adapt_predict_batch_host_async. */
+int ttl_adapt_predict_images_async(ttl_ctx* ctx, const uint8_t* const* images_host, const int32_t* heights,
+                                   const int32_t* widths, int32_t n_samples, const ttl_view_spec* specs_host,
+                                   int32_t n_views, const ttl_hparams* hp, const int32_t* forced_idx_host,
+                                   const ttl_outputs* out_host, void* stream);
+
 /* Toggle CUDA-graph replay of ttl_adapt_predict (default on). */
 int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
 /* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */

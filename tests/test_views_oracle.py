@@ -55,3 +55,24 @@ def test_views_match_the_reference_transform_stack():
     ref = torch.stack(ref).numpy()
     assert got.shape == ref.shape
     np.testing.assert_allclose(got, ref, rtol=0, atol=3e-7)
+
+
+def test_spec_sampler_consumes_the_rng_like_the_reference_transforms():
+    """ttl_b200.views.ViewSpecSampler (host half of the GPU view generator) draws exactly what
+    RandomResizedCrop.forward + RandomHorizontalFlip.forward draw from the torch RNG (data/datautils.py:98-101)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "ttl-test-time-low-rank-adaptation_b200"))
+    from ttl_b200.views import ViewSpecSampler
+    pil = Image.fromarray(_img(333, 500, 9))
+    torch.manual_seed(3)
+    arr, specs = ViewSpecSampler(12)(pil)
+    torch.manual_seed(3)
+    ref = []
+    for _ in range(12):
+        i, j, h, w = T.RandomResizedCrop.get_params(pil, scale=[0.08, 1.0], ratio=[3.0 / 4.0, 4.0 / 3.0])
+        ref.append([1, i, j, h, w, int(torch.rand(1) < 0.5)])
+    assert arr.shape == (333, 500, 3) and arr.dtype == np.uint8
+    assert specs[0].tolist() == [0, 0, 0, 333, 500, 0]
+    assert specs[1:].tolist() == ref

@@ -132,6 +132,8 @@ __device__ __forceinline__ void store_tile(bf16* stage, const float (&acc)[8][4]
 
 __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                                      int tokens, int heads, float scale_log2, int q_tiles, int nkp) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
   bf16* sK = sQ + q_tiles * 16 * LDS;
@@ -205,6 +207,8 @@ __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restr
 __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                      const bf16* __restrict__ dout, const float* __restrict__ lse,
                                      bf16* __restrict__ dqkv, int tokens, int heads, float scale, int tiles, int nkp) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t smem_att[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_att);
   bf16* sK = sQ + nkp * LDS;
@@ -518,6 +522,8 @@ attention_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
     fence_proxy_async_smem();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   auto issue = [&](int unit, int buf) {   // thread 0 only
     const int view = unit / heads, h = unit - view * heads;
     uint8_t* dst = smem + buf * 3 * RB;
@@ -612,6 +618,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();      // the prologue above overlaps the tail of the previous kernel
+  pdl_trigger();
   const int n_full = keys / 64, tail = keys - n_full * 64;     // 64-key P blocks + a 16-key tail block (tail in {0,16})
   // P block b lives at: 0 -> sK, 1 -> sQ, 2 -> sP2 ; tail block -> sK + 16384
   const uint32_t p_addr0 = smem_u32(sK), p_addr1 = smem_u32(sQ), p_addr2 = smem_u32(sP2);
@@ -848,6 +856,8 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 __global__ void __launch_bounds__(128)
 attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qkv, bf16* __restrict__ out_cls, int tokens,
                      int heads, float scale_log2) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh_cls[];
   float* sq = sh_cls;            // [64]
   float* sp = sh_cls + 64;       // [tokens]
@@ -955,8 +965,8 @@ static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int 
   static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
   if (want_dbg && dbg == nullptr) { cudaMallocManaged(&dbg, 8 * 16 * 8 * sizeof(long long)); }
   if (want_dbg) std::memset(dbg, 0, 8 * 16 * 8 * sizeof(long long));
-  attention_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tq, tkv, to, lse, tokens, heads, items, q_tiles, keys, scale * LOG2E,
-                                                          want_dbg ? dbg : nullptr);
+  launch_pdl(attention_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, items, q_tiles, keys,
+             scale * LOG2E, want_dbg ? dbg : nullptr);
   if (want_dbg) {   // development aid: per-stage clock64 deltas of the first items of CTAs 0..7
     cudaStreamSynchronize(st);
     static int printed = 0;
@@ -1013,8 +1023,8 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
   }
   const int units = V * heads;
   const int grid = units < num_sms ? units : num_sms;
-  attention_fwd_tma_kernel<<<grid, (rows_alloc / 32) * 32, smem, st>>>(tq, to, lse, tokens, heads, units, scale * LOG2E, rows_alloc,
-                                                                      rows_pad, nbox, box_rows);
+  launch_pdl(attention_fwd_tma_kernel, dim3(grid), dim3((rows_alloc / 32) * 32), smem, st, tq, to, lse, tokens, heads, units,
+             scale * LOG2E, rows_alloc, rows_pad, nbox, box_rows);
   return true;
 }
 
@@ -1033,14 +1043,14 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
     cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  attention_fwd_kernel<<<dim3(heads, V), pick_warps(q_tiles) * 32, smem, st>>>(qkv, out, lse, tokens, heads,
-                                                                               scale * LOG2E, q_tiles, nkp);
+  launch_pdl(attention_fwd_kernel, dim3(heads, V), dim3(pick_warps(q_tiles) * 32), smem, st, qkv, out, lse, tokens, heads,
+             scale * LOG2E, q_tiles, nkp);
 }
 
 void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
                           cudaStream_t st) {
-  attention_cls_kernel<<<dim3(heads, V), 128, (64 + tokens) * sizeof(float), st>>>(q_cls, qkv, out_cls, tokens, heads,
-                                                                                    scale * LOG2E);
+  launch_pdl(attention_cls_kernel, dim3(heads, V), dim3(128), (64 + tokens) * sizeof(float), st, q_cls, qkv, out_cls, tokens,
+             heads, scale * LOG2E);
 }
 
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
@@ -1052,8 +1062,8 @@ void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, co
     cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  attention_bwd_kernel<<<dim3(heads, V, 2), pick_warps(tiles) * 32, smem, st>>>(qkv, out, dout, lse, dqkv, tokens, heads,
-                                                                                scale, tiles, nkp);
+  launch_pdl(attention_bwd_kernel, dim3(heads, V, 2), dim3(pick_warps(tiles) * 32), smem, st, qkv, out, dout, lse, dqkv, tokens,
+             heads, scale, tiles, nkp);
 }
 
 }  // namespace ttl

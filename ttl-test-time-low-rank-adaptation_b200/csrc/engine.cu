@@ -16,6 +16,7 @@
 #include "../../include/ttl_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "views.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -127,6 +128,19 @@ struct ttl_ctx {
   int stage_next = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+
+  // view generator (views.cu): double-buffered image / descriptor staging, single coefficient + horizontal-pass scratch
+  uint8_t* vg_img[2] = {nullptr, nullptr};
+  size_t vg_img_cap[2] = {0, 0};
+  ViewDesc* vg_desc[2] = {nullptr, nullptr};
+  ViewDesc* vg_desc_host[2] = {nullptr, nullptr};   // pinned
+  size_t vg_desc_cap = 0;
+  int* vg_coef = nullptr;
+  size_t vg_coef_cap = 0;
+  uint8_t* vg_tmp = nullptr;
+  size_t vg_tmp_cap = 0;
+  float pix_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // ttl.py:226-227
+  float pix_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
   // graphs
   bool graphs = true;
@@ -605,6 +619,7 @@ int validate_run(ttl_ctx* c, int S, int V, const ttl_hparams* hp) {
   return TTL_OK;
 }
 
+// images_dev == nullptr: the bf16 patch matrix c->patches is already in place (view generator).
 int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
   const int64_t before = c->launches;
   if (!c->graphs || c->prof || st == nullptr) {  // the legacy default stream cannot be captured
@@ -646,7 +661,7 @@ int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const 
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { c->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return TTL_E_CUDA; }
   }
-  launch_im2col(images_dev, c->patches, S * V, c->cfg.image_size, c->cfg.patch, st);
+  if (images_dev != nullptr) launch_im2col(images_dev, c->patches, S * V, c->cfg.image_size, c->cfg.patch, st);
   CK(cudaGraphLaunch(ge->exec, st));
   c->launches = before + ge->launches;
   c->last_launches = ge->launches;
@@ -775,6 +790,13 @@ void ttl_destroy(ttl_ctx* c) {
     if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (c->vg_img[i]) cudaFree(c->vg_img[i]);
+    if (c->vg_desc[i]) cudaFree(c->vg_desc[i]);
+    if (c->vg_desc_host[i]) cudaFreeHost(c->vg_desc_host[i]);
+  }
+  if (c->vg_coef) cudaFree(c->vg_coef);
+  if (c->vg_tmp) cudaFree(c->vg_tmp);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
 }
@@ -1017,6 +1039,132 @@ int ttl_adapt_predict_batch_host(ttl_ctx* c, const float* images_host, int32_t n
 int ttl_adapt_predict_host(ttl_ctx* c, const float* images_host, int32_t n_views, const ttl_hparams* hp,
                            const int32_t* forced_idx_host, const ttl_outputs* out_host, void* stream) {
   return ttl_adapt_predict_batch_host(c, images_host, 1, n_views, hp, forced_idx_host, out_host, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------- view generator (views.cu)
+namespace {
+
+template <typename Tp>
+int vg_grow(ttl_ctx* c, Tp** p, size_t* cap, size_t need) {
+  if (need <= *cap) return TTL_OK;
+  CK(cudaDeviceSynchronize());          // the old buffer may still be in use by an earlier call
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  const size_t n = need + need / 4 + 4096;
+  void* q = nullptr;
+  if (cudaMalloc(&q, n * sizeof(Tp)) != cudaSuccess) { cudaGetLastError(); c->err = "view generator: cudaMalloc failed"; return TTL_E_NOMEM; }
+  *p = static_cast<Tp*>(q);
+  *cap = n;
+  return TTL_OK;
+}
+
+// Plans the views of n_images images, stages images + descriptors into buffer set b on `cs`; returns the largest source
+// window height (grid sizing) through max_h.
+int vg_stage(ttl_ctx* c, const uint8_t* const* images_host, const int32_t* heights, const int32_t* widths,
+                    int n_images, const ttl_view_spec* specs, int n_views, int b, cudaStream_t cs, int* max_h) {
+  if (!images_host || !heights || !widths || !specs) return TTL_E_INVALID;
+  if (n_images <= 0 || n_views <= 0) { c->err = "view generator: n_images / n_views must be positive"; return TTL_E_SHAPE; }
+  const size_t nd = static_cast<size_t>(n_images) * n_views;
+  CK(cudaEventSynchronize(c->ev_copied[b]));   // the pinned descriptor buffer of this set has been read by its last copy
+  if (nd > c->vg_desc_cap) {
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      if (c->vg_desc[i]) cudaFree(c->vg_desc[i]);
+      if (c->vg_desc_host[i]) cudaFreeHost(c->vg_desc_host[i]);
+      c->vg_desc[i] = nullptr; c->vg_desc_host[i] = nullptr;
+    }
+    c->vg_desc_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+      if (cudaMalloc(reinterpret_cast<void**>(&c->vg_desc[i]), nd * sizeof(ViewDesc)) != cudaSuccess ||
+          cudaMallocHost(reinterpret_cast<void**>(&c->vg_desc_host[i]), nd * sizeof(ViewDesc)) != cudaSuccess) {
+        cudaGetLastError();
+        c->err = "view generator: descriptor allocation failed";
+        return TTL_E_NOMEM;
+      }
+    }
+    c->vg_desc_cap = nd;
+  }
+  size_t img_bytes = 0, coef_ints = 0, tmp_bytes = 0;
+  int mh = 1;
+  for (int i = 0; i < n_images; ++i) {
+    if (!images_host[i]) { c->err = "view generator: null image"; return TTL_E_INVALID; }
+    const char* e = views_plan(specs + static_cast<size_t>(i) * n_views, n_views, heights[i], widths[i], c->cfg.image_size,
+                               static_cast<long long>(img_bytes), c->vg_desc_host[b] + static_cast<size_t>(i) * n_views,
+                               &coef_ints, &tmp_bytes);
+    if (e) { c->err = e; return TTL_E_SHAPE; }
+    img_bytes += (static_cast<size_t>(heights[i]) * widths[i] * 3 + 255) / 256 * 256;
+    if (heights[i] > mh) mh = heights[i];
+  }
+  *max_h = mh;
+  RET_IF(vg_grow(c, &c->vg_img[b], &c->vg_img_cap[b], img_bytes));
+  RET_IF(vg_grow(c, &c->vg_coef, &c->vg_coef_cap, coef_ints));
+  RET_IF(vg_grow(c, &c->vg_tmp, &c->vg_tmp_cap, tmp_bytes));
+  size_t off = 0;
+  for (int i = 0; i < n_images; ++i) {
+    const size_t nb = static_cast<size_t>(heights[i]) * widths[i] * 3;
+    CK(cudaMemcpyAsync(c->vg_img[b] + off, images_host[i], nb, cudaMemcpyHostToDevice, cs));
+    off += (nb + 255) / 256 * 256;
+  }
+  CK(cudaMemcpyAsync(c->vg_desc[b], c->vg_desc_host[b], nd * sizeof(ViewDesc), cudaMemcpyHostToDevice, cs));
+  return TTL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ttl_set_pixel_norm(ttl_ctx* c, const float* mean3, const float* std3) {
+  if (!c || !mean3 || !std3) return TTL_E_INVALID;
+  for (int i = 0; i < 3; ++i) {
+    if (!(std3[i] > 0.f)) { c->err = "pixel std must be positive"; return TTL_E_INVALID; }
+    c->pix_mean[i] = mean3[i];
+    c->pix_std[i] = std3[i];
+  }
+  return TTL_OK;
+}
+
+int ttl_make_views(ttl_ctx* c, const uint8_t* const* images_host, const int32_t* heights, const int32_t* widths,
+                   int32_t n_images, const ttl_view_spec* specs_host, int32_t n_views, float* views_dev, void* stream) {
+  if (!c || !views_dev) return TTL_E_INVALID;
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int b = c->stage_next;
+  c->stage_next ^= 1;
+  int max_h = 1;
+  CK(cudaStreamWaitEvent(st, c->ev_consumed[b], 0));
+  RET_IF(vg_stage(c, images_host, heights, widths, n_images, specs_host, n_views, b, st, &max_h));
+  CK(cudaEventRecord(c->ev_copied[b], st));
+  launch_views(c->vg_img[b], c->vg_desc[b], n_images * n_views, max_h, c->vg_coef, c->vg_tmp, views_dev, nullptr,
+               c->cfg.image_size, c->cfg.patch, c->pix_mean, c->pix_std, st);
+  CK(cudaEventRecord(c->ev_consumed[b], st));
+  return check_launch(c, "make_views");
+}
+
+int ttl_adapt_predict_images_async(ttl_ctx* c, const uint8_t* const* images_host, const int32_t* heights,
+                                   const int32_t* widths, int32_t n_samples, const ttl_view_spec* specs_host,
+                                   int32_t n_views, const ttl_hparams* hp, const int32_t* forced_idx_host,
+                                   const ttl_outputs* out_host, void* stream) {
+  RET_IF(validate_run(c, n_samples, n_views, hp));
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int b = c->stage_next;
+  c->stage_next ^= 1;
+  int max_h = 1;
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));   // staging set b was last read two calls ago
+  RET_IF(vg_stage(c, images_host, heights, widths, n_samples, specs_host, n_views, b, c->copy_stream, &max_h));
+  CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+  CK(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
+  const int K = static_cast<int>(n_views * hp->selection_p);
+  const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K * n_samples, cudaMemcpyHostToDevice, st));
+  launch_views(c->vg_img[b], c->vg_desc[b], n_samples * n_views, max_h, c->vg_coef, c->vg_tmp, nullptr, c->patches,
+               c->cfg.image_size, c->cfg.patch, c->pix_mean, c->pix_std, st);
+  c->launches += 3;
+  RET_IF(adapt_predict_impl(c, nullptr, n_samples, n_views, hp, forced, st));
+  CK(cudaEventRecord(c->ev_consumed[b], st));
+  return copy_outputs(c, out_host, n_samples, n_views, *hp, cudaMemcpyDeviceToHost, st);
 }
 
 int ttl_set_graphs(ttl_ctx* c, int32_t enabled) {

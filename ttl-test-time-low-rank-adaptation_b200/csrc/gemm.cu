@@ -193,6 +193,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();      // prologue above overlaps the tail of the previous kernel; global memory is touched only below
+  pdl_trigger();
 
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = p.N / BLOCK_N;
@@ -381,6 +383,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();      // prologue above overlaps the tail of the previous kernel; global memory is touched only below
+  pdl_trigger();
 
   const int m_pairs = (p.M + 255) / 256;
   const int n_tiles = p.N / BLOCK_N;
@@ -661,8 +665,7 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   }
   const int tiles = ((g.M + 255) / 256) * (g.N / BLOCK_N);
   const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-  kern<<<grid, G2_THREADS, C::SMEM_BYTES, stream>>>(tA1, tB1, tA2, tB2, tOut, tRes, p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(G2_THREADS), C::SMEM_BYTES, stream, tA1, tB1, tA2, tB2, tOut, tRes, p);
 }
 
 template <int BLOCK_N>
@@ -724,8 +727,7 @@ cudaError_t launch_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = m_tiles * (g.N / BLOCK_N);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA1, tB1, tA2, tB2, p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, tA1, tB1, tA2, tB2, p);
 }
 
 template <int BLOCK_N>

@@ -38,6 +38,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __global__ void __launch_bounds__(HT)
 cls_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               float* __restrict__ pooled, int tokens, int d, float eps) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int v = blockIdx.x;
   const float* xr = x + static_cast<size_t>(v) * tokens * d;
@@ -58,6 +60,8 @@ constexpr int SG_TM = 16, SG_NPC = 32;   // rows of A per CTA, columns (rows of 
 __global__ void __launch_bounds__(256)
 small_gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int M, int N,
                      int K) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sA[];            // [SG_TM][K]
   const int m0 = blockIdx.y * SG_TM, n0 = blockIdx.x * SG_NPC;
   const int K4 = K >> 2;
@@ -96,6 +100,8 @@ small_gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 __global__ void __launch_bounds__(256)
 small_gemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int M, int N,
                      int K, float alpha) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh[];
   float* As = sh;                    // [8][K]
   float* part = sh + 8 * K;          // [4][8][64]
@@ -132,6 +138,8 @@ small_gemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 __global__ void __launch_bounds__(HT)
 scale_entropy_kernel(const float* __restrict__ feats, float scale, float* __restrict__ logits,
                      float* __restrict__ entropy, int C, int P) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int v = blockIdx.x;
   float mul = 1.f;   // feats == nullptr: logits are final, only the entropy is wanted
@@ -156,6 +164,8 @@ scale_entropy_kernel(const float* __restrict__ feats, float scale, float* __rest
 // rank-by-counting stable argsort prefix: idx[rank] = v for rank < K
 __global__ void select_kernel(const float* __restrict__ entropy, int V, int K, const int* __restrict__ forced,
                               int* __restrict__ idx) {
+  pdl_wait();
+  pdl_trigger();
   if (forced != nullptr) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) idx[k] = forced[k];
     return;
@@ -175,6 +185,8 @@ __global__ void select_kernel(const float* __restrict__ entropy, int V, int K, c
 __global__ void __launch_bounds__(1024)
 tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, int K, int C, float* __restrict__ loss,
                 float* __restrict__ dlogits) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh[];
   float* lse = sh;            // [K]
   float* sk = sh + K;         // [K]  sum_j p[k,j] a_j
@@ -226,6 +238,8 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
 __global__ void __launch_bounds__(1024)
 deyo_loss_kernel(const float* __restrict__ logits, int V, int C, float e0, float* __restrict__ loss,
                  float* __restrict__ dlogits) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh[];
   float* lse = sh;          // [V]
   float* H = sh + V;        // [V]
@@ -270,6 +284,8 @@ deyo_loss_kernel(const float* __restrict__ logits, int V, int C, float e0, float
 // d/d f from d/d fhat:  df = (dfh - fhat <fhat, dfh>) / |f|     (in place on dfh); one CTA per compact view
 __global__ void __launch_bounds__(HT)
 l2norm_bwd_kernel(const float* __restrict__ feats, float* __restrict__ dfh, int P) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int g = blockIdx.x;
   const float* f = feats + static_cast<size_t>(g) * P;
@@ -287,6 +303,8 @@ l2norm_bwd_kernel(const float* __restrict__ feats, float* __restrict__ dfh, int 
 __global__ void __launch_bounds__(HT)
 cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, const float* __restrict__ gamma,
                   float* __restrict__ dx, bf16* __restrict__ dxb, int tokens, int d, float eps) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   const int g = blockIdx.x;
   const float* xr = x + static_cast<size_t>(g) * tokens * d;
@@ -327,26 +345,26 @@ static void small_gemm_nt_smem(size_t bytes) {
 void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
                          float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st) {
   small_gemm_nt_smem(SG_TM * d * sizeof(float));
-  cls_ln_kernel<<<V, HT, 0, st>>>(x, gamma, beta, pooled, tokens, d, eps);
-  small_gemm_nt_kernel<<<dim3((P + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM), 256, SG_TM * d * sizeof(float), st>>>(pooled, Wp, feats, V, P, d);
+  launch_pdl(cls_ln_kernel, dim3(V), dim3(HT), 0, st, x, gamma, beta, pooled, tokens, d, eps);
+  launch_pdl(small_gemm_nt_kernel, dim3(dim3((P + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM)), dim3(256), SG_TM * d * sizeof(float), st, pooled, Wp, feats, V, P, d);
 }
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st) {
   small_gemm_nt_smem(SG_TM * P * sizeof(float));
-  small_gemm_nt_kernel<<<dim3((C + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM), 256, SG_TM * P * sizeof(float), st>>>(feats, text, logits, V, C, P);
-  scale_entropy_kernel<<<V, HT, 0, st>>>(feats, scale, logits, entropy, C, P);
+  launch_pdl(small_gemm_nt_kernel, dim3(dim3((C + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM)), dim3(256), SG_TM * P * sizeof(float), st, feats, text, logits, V, C, P);
+  launch_pdl(scale_entropy_kernel, dim3(V), dim3(HT), 0, st, feats, scale, logits, entropy, C, P);
 }
 void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st) {
-  scale_entropy_kernel<<<V, HT, 0, st>>>(nullptr, 1.f, logits, entropy, C, 0);
+  launch_pdl(scale_entropy_kernel, dim3(V), dim3(HT), 0, st, nullptr, 1.f, logits, entropy, C, 0);
 }
 void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st) {
-  select_kernel<<<1, 256, 0, st>>>(entropy, V, K, forced_idx, idx);
+  launch_pdl(select_kernel, dim3(1), dim3(256), 0, st, entropy, V, K, forced_idx, idx);
 }
 void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st) {
-  tpt_loss_kernel<<<1, 1024, (2 * K + 32 + C) * sizeof(float), st>>>(logits, idx, K, C, loss, dlogits);
+  launch_pdl(tpt_loss_kernel, dim3(1), dim3(1024), (2 * K + 32 + C) * sizeof(float), st, logits, idx, K, C, loss, dlogits);
 }
 void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st) {
-  deyo_loss_kernel<<<1, 1024, 3 * V * sizeof(float), st>>>(logits, V, C, margin_e0, loss, dlogits);
+  launch_pdl(deyo_loss_kernel, dim3(1), dim3(1024), 3 * V * sizeof(float), st, logits, V, C, margin_e0, loss, dlogits);
 }
 void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
                      const float* x, const float* gamma, float* dfh, float* dpool, float* dx, bf16* dx_bf16, int G, int C,
@@ -354,12 +372,12 @@ void launch_head_bwd(const float* dlogits, const float* text, float scale, const
   cudaMemsetAsync(dx, 0, static_cast<size_t>(G) * tokens * d * sizeof(float), st);
   cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(G) * tokens * d * sizeof(bf16), st);
   // d fhat = scale * dlogits @ T ; d f ; d pooled = d f @ Wp ; LN backward on the CLS rows
-  small_gemm_nn_kernel<<<dim3((P + 63) / 64, (G + 7) / 8), 256, (8 * C + 4 * 8 * 64) * sizeof(float), st>>>(
+  launch_pdl(small_gemm_nn_kernel, dim3(dim3((P + 63) / 64, (G + 7) / 8)), dim3(256), (8 * C + 4 * 8 * 64) * sizeof(float), st, 
       dlogits, text, dfh, G, P, C, scale);
-  l2norm_bwd_kernel<<<G, HT, 0, st>>>(feats, dfh, P);
-  small_gemm_nn_kernel<<<dim3((d + 63) / 64, (G + 7) / 8), 256, (8 * P + 4 * 8 * 64) * sizeof(float), st>>>(
+  launch_pdl(l2norm_bwd_kernel, dim3(G), dim3(HT), 0, st, feats, dfh, P);
+  launch_pdl(small_gemm_nn_kernel, dim3(dim3((d + 63) / 64, (G + 7) / 8)), dim3(256), (8 * P + 4 * 8 * 64) * sizeof(float), st, 
       dfh, Wp, dpool, G, d, P, 1.0f);
-  cls_ln_bwd_kernel<<<G, HT, 0, st>>>(dpool, x, gamma, dx, dx_bf16, tokens, d, eps);
+  launch_pdl(cls_ln_bwd_kernel, dim3(G), dim3(HT), 0, st, dpool, x, gamma, dx, dx_bf16, tokens, d, eps);
 }
 
 }  // namespace ttl

@@ -12,6 +12,8 @@ namespace {
 // params layout per layer: A_q[r,d] | B_q[d,r] | A_v[r,d] | B_v[d,r]   (fp32, contiguous)
 __global__ void lora_pack_kernel(const float* __restrict__ prm0, int64_t sample_stride, LoraPacked pk, int d, int r,
                                  float s, int S) {
+  pdl_wait();
+  pdl_trigger();
   const int n_a = 64 * d;          // a_ext / a_ext_t elements of one sample block
   const int n_b = 3 * d * 64;      // b_ext / b_ext_t elements of one sample block
   const int smp = blockIdx.y, kc = 64 * S, c0 = 64 * smp;   // this sample's 64-column block of the K-concatenation
@@ -48,6 +50,8 @@ template <int NN>           // narrow width (16 or 32)
 __global__ void __launch_bounds__(256)
 skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __restrict__ narrow, int ldn, int M, int nw,
                       float* __restrict__ ws, int narrow_gstride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) bf16 sW[SR_MC][64 + 8];
   __shared__ __align__(16) bf16 sN[SR_MC][NN + 8];
   const int w0 = blockIdx.x * 64, m0 = blockIdx.y * SR_MC, grp = blockIdx.z;
@@ -84,6 +88,8 @@ skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __rest
 
 __global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, int nw, int nn, float scale,
                                     float* __restrict__ out, int transpose_out, int64_t out_gstride) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nw * nn) return;
   ws += static_cast<size_t>(blockIdx.y) * chunks * nw * nn;
@@ -98,6 +104,8 @@ __global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, in
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, int n, float lr, float b1, float b2, float eps, float wd,
                              float step_size, float bc2_sqrt) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i];
@@ -111,6 +119,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 
 __global__ void lora_reset_kernel(float* __restrict__ p, const float* __restrict__ p0, float* __restrict__ m,
                                   float* __restrict__ v, int n, int n0) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   p[i] = p0[i % n0]; m[i] = 0.f; v[i] = 0.f;
@@ -120,7 +130,7 @@ __global__ void lora_reset_kernel(float* __restrict__ p, const float* __restrict
 
 void launch_lora_pack(const float* params, int64_t sample_stride, LoraPacked pk, int d, int r, float s, int S, cudaStream_t st) {
   const int total = 64 * d + 3 * d * 64;
-  lora_pack_kernel<<<dim3((total + 255) / 256, S), 256, 0, st>>>(params, sample_stride, pk, d, r, s, S);
+  launch_pdl(lora_pack_kernel, dim3(dim3((total + 255) / 256, S)), dim3(256), 0, st, params, sample_stride, pk, d, r, s, S);
 }
 
 void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
@@ -128,9 +138,9 @@ void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow,
                           cudaStream_t st) {
   const int chunks = (M + SR_MC - 1) / SR_MC;
   dim3 grid(nw / 64, chunks, groups);
-  if (nn == 16) skinny_partial_kernel<16><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
-  else skinny_partial_kernel<32><<<grid, 256, 0, st>>>(wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
-  skinny_final_kernel<<<dim3((nw * nn + 255) / 256, groups), 256, 0, st>>>(ws, chunks, nw, nn, scale, out, transpose_out,
+  if (nn == 16) launch_pdl(skinny_partial_kernel<16>, dim3(grid), dim3(256), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  else launch_pdl(skinny_partial_kernel<32>, dim3(grid), dim3(256), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  launch_pdl(skinny_final_kernel, dim3(dim3((nw * nn + 255) / 256, groups)), dim3(256), 0, st, ws, chunks, nw, nn, scale, out, transpose_out,
                                                                            out_gstride);
 }
 
@@ -138,12 +148,12 @@ void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step,
                   float eps, float wd, cudaStream_t st) {
   const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
-  adamw_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, static_cast<float>(lr / bc1),
+  launch_pdl(adamw_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p, g, m, v, n, lr, b1, b2, eps, wd, static_cast<float>(lr / bc1),
                                                 static_cast<float>(sqrt(bc2)));
 }
 
 void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, int n0, cudaStream_t st) {
-  lora_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, p0, m, v, n, n0);
+  launch_pdl(lora_reset_kernel, dim3((n + 255) / 256), dim3(256), 0, st, p, p0, m, v, n, n0);
 }
 
 }  // namespace ttl

@@ -16,6 +16,8 @@ constexpr int ROWS_PER_BLOCK = 8;  // 8 warps per CTA
 // 2-pixel path (p = 14).  Reads 32 B, writes 16 B; padding columns (K..Kp) are zero.
 template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int V, int S, int p, int Kp) {
+  pdl_wait();
+  pdl_trigger();
   const int gp = S / p, T = gp * gp, K = 3 * p * p;
   const int cols = Kp / VEC;
   const size_t total = static_cast<size_t>(V) * T * cols;
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int tokens, int d,
                    float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nv = d / 128;
@@ -101,6 +105,8 @@ embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const f
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
                  const float* __restrict__ beta, int rows, int d, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nv = d / 128;
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ dres, float* __restrict__ dx, bf16* __restrict__ dxb, int rows, int d,
                      float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nv = d / 128;
@@ -177,6 +185,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 
 __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                     const int* __restrict__ idx, int n_sel, int view_stride, int per_view4) {
+  pdl_wait();
+  pdl_trigger();
   const int g = blockIdx.y;
   const float4* s = src + static_cast<size_t>(idx != nullptr ? idx[g] : g * view_stride) * per_view4;
   float4* o = dst + static_cast<size_t>(g) * per_view4;
@@ -184,6 +194,8 @@ __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __re
 }
 
 __global__ void block_mask_kernel(bf16* __restrict__ x, int M, int ncols, int rows_per_sample) {
+  pdl_wait();
+  pdl_trigger();
   const int chunks = ncols / 8;   // 16-byte chunks per row
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(M) * chunks;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -207,19 +219,19 @@ void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cuda
 void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
                         int tokens, int d, float eps, cudaStream_t st) {
   const int rows = V * tokens;
-  embed_preln_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(
+  launch_pdl(embed_preln_kernel, dim3((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, st, 
       x, cls, pos, gamma, beta, rows, tokens, d, eps);
 }
 
 void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
                       cudaStream_t st) {
-  layernorm_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(x, y, gamma, beta,
+  launch_pdl(layernorm_kernel, dim3((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, st, x, y, gamma, beta,
                                                                                                 rows, d, eps);
 }
 
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
                           bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st) {
-  layernorm_bwd_kernel<<<(rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, st>>>(
+  launch_pdl(layernorm_bwd_kernel, dim3((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, st, 
       dy, x, gamma, dres, dx, dx_bf16, rows, d, eps);
 }
 
@@ -227,7 +239,7 @@ void launch_gather_views(const float* src, float* dst, const int* view_idx, int 
                          cudaStream_t st) {
   const int per_view4 = tokens * d / 4;
   dim3 grid((per_view4 + 255) / 256 < 32 ? (per_view4 + 255) / 256 : 32, n_sel);
-  gather_views_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
+  launch_pdl(gather_views_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
                                             view_idx, n_sel, view_stride, per_view4);
 }
 
@@ -235,7 +247,7 @@ void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStrea
   const size_t total = static_cast<size_t>(M) * (ncols / 8);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  block_mask_kernel<<<blocks, 256, 0, st>>>(x, M, ncols, rows_per_sample);
+  launch_pdl(block_mask_kernel, dim3(blocks), dim3(256), 0, st, x, M, ncols, rows_per_sample);
 }
 
 }  // namespace ttl

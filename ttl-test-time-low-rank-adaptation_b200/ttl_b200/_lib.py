@@ -34,6 +34,11 @@ class TtlGemmRecord(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("epi", C.c_int32), ("ms", C.c_float)]
 
 
+class TtlViewSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("top", C.c_int32), ("left", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("flip", C.c_int32)]
+
+
 class TtlOutputs(C.Structure):
     _fields_ = [("logits0", vp), ("entropy", vp), ("idx", vp), ("loss", vp), ("pred_logits", vp)]
 
@@ -45,6 +50,7 @@ W_CLASS_EMB, W_PATCH_EMB, W_POS_EMB, W_PRE_LN_G, W_PRE_LN_B, W_POST_LN_G, W_POST
 LORA_A_Q, LORA_B_Q, LORA_A_V, LORA_B_V = range(4)
 LORA_PARAM, LORA_GRAD, LORA_INIT = range(3)
 HEAD_TPT, HEAD_DEYO = 0, 1
+VIEW_CLEAN, VIEW_CROP = 0, 1
 EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_PATCH_F32, EPI_F32, EPI_GELU_BWD = range(6)
 
 _SIGS = {
@@ -69,6 +75,10 @@ _SIGS = {
                                                vp]),
     "ttl_adapt_predict_batch_host_async": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp,
                                                      C.POINTER(TtlOutputs), vp]),
+    "ttl_set_pixel_norm": (C.c_int, [vp, vp, vp]),
+    "ttl_make_views": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
+    "ttl_adapt_predict_images_async": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(TtlHparams), vp,
+                                                 C.POINTER(TtlOutputs), vp]),
     "ttl_set_graphs": (C.c_int, [vp, C.c_int32]),
     "ttl_last_launch_count": (C.c_int64, [vp]),
     "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),

@@ -258,6 +258,73 @@ class Engine:
             outs["idx"] = outs["idx"][:, :K]
         return outs
 
+    # ------------------------------------------------------------------ views generated on the device (views.cu)
+    @staticmethod
+    def _image_table(images):
+        arrs = [np.ascontiguousarray(np.asarray(im, dtype=np.uint8)) for im in images]
+        for a in arrs:
+            if a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("images must be uint8 [H,W,3]")
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        hs = (C.c_int32 * n)(*[a.shape[0] for a in arrs])
+        ws = (C.c_int32 * n)(*[a.shape[1] for a in arrs])
+        return arrs, ptrs, hs, ws
+
+    def set_pixel_norm(self, mean, std) -> None:
+        m, s = _f32(mean), _f32(std)
+        L.check(self.lib.ttl_set_pixel_norm(self.ctx, m.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)), self.ctx)
+
+    def make_views(self, images, specs) -> torch.Tensor:
+        """uint8 images [H_i,W_i,3] + specs [n_images, n_views, 6] (views.ViewSpecSampler) -> fp32 views on the device
+        [n_images, n_views, 3, S, S]: what AugMixAugmenter + torch.cat produce on the host (ttl.py:324-336)."""
+        from .views import pack_specs
+        arrs, ptrs, hs, ws = self._image_table(images)
+        sp = pack_specs(specs)
+        n, v, size = len(arrs), int(sp.shape[1]), self.geom["image_size"]
+        out = torch.empty(n, v, 3, size, size, device=self.device, dtype=torch.float32)
+        self._sync_in()
+        L.check(self.lib.ttl_make_views(self.ctx, ptrs, hs, ws, n, sp.ctypes.data_as(C.c_void_p), v, out.data_ptr(),
+                                        self._st()), self.ctx)
+        self._sync_out()
+        out.record_stream(self.stream)
+        return out
+
+    def adapt_predict_images(self, images, specs, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
+                             want: Sequence[str] = ("pred_logits",), sync: bool = True):
+        """adapt_predict_batch fed by decoded uint8 images: the host ships H*W*3 bytes + the view specs per sample, the
+        views are generated on the device straight into the patch-embedding operand.  sync=False returns a Pending."""
+        from .views import pack_specs
+        arrs, ptrs, hs, ws = self._image_table(images)
+        sp = pack_specs(specs)
+        S, V = len(arrs), int(sp.shape[1])
+        if S > self.max_samples:
+            raise ValueError(f"{S} samples > max_samples={self.max_samples}")
+        if V > self.max_views:
+            raise ValueError(f"{V} views > max_views={self.max_views}")
+        K = int(V * hp.selection_p)
+        outs: Dict[str, torch.Tensor] = {}
+        o = L.TtlOutputs()
+        shapes = {"logits0": ((S, V, self.n_classes), torch.float32), "entropy": ((S, V), torch.float32),
+                  "idx": ((S, max(K, 1)), torch.int32), "loss": ((S,), torch.float32),
+                  "pred_logits": ((S, self.n_classes), torch.float32)}
+        for name in want:
+            shp, dt = shapes[name]
+            t = torch.empty(shp, dtype=dt, pin_memory=True)
+            outs[name] = t
+            setattr(o, name, t.data_ptr())
+        fidx = None if forced_idx is None else forced_idx.to("cpu", torch.int32).contiguous()
+        h = hp.to_c()
+        L.check(self.lib.ttl_adapt_predict_images_async(self.ctx, ptrs, hs, ws, S, sp.ctypes.data_as(C.c_void_p), V,
+                                                        C.byref(h), fidx.data_ptr() if fidx is not None else None,
+                                                        C.byref(o), self._st()), self.ctx)
+        if "idx" in outs:
+            outs["idx"] = outs["idx"][:, :K]
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        pending = Pending(outs, ev, (arrs, sp, fidx))
+        return pending.wait() if sync else pending
+
     def set_graphs(self, enabled: bool) -> None:
         L.check(self.lib.ttl_set_graphs(self.ctx, int(enabled)), self.ctx)
 
