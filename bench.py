@@ -301,6 +301,51 @@ def main():
                       "ttl_adapt_predict_batch_host_async; every step copies its own views H2D and its predictions D2H; "
                       "the copy of step i+1 overlaps the kernels of step i (depth-2 pipeline)"}
 
+    # ---- the same from decoded uint8 images: views generated on the device (csrc/views.cu); the host ships
+    #      H*W*3 bytes + 64 view specs per sample instead of 64 fp32 views
+    e2e_img = None
+    if not args.no_e2e:
+        import numpy as np
+        from ttl_b200.views import ViewSpecSampler
+        sampler = ViewSpecSampler(args.views - 1)
+        rng = np.random.default_rng(5 + rank)
+        torch.manual_seed(1234 + rank)
+        batches = []
+        for _ in range(4):
+            imgs, specs = [], []
+            for _ in range(S):
+                lo = rng.integers(0, 256, size=(375 // 25 + 1, 500 // 25 + 1, 3), dtype=np.uint8)
+                img = np.clip(np.kron(lo, np.ones((25, 25, 1), dtype=np.uint8))[:375, :500].astype(np.int16)
+                              + rng.integers(-25, 26, size=(375, 500, 3)), 0, 255).astype(np.uint8)   # ImageNet-like 500x375
+                a, sp = sampler(img)
+                imgs.append(a)
+                specs.append(sp)
+            batches.append((imgs, specs))
+        for i in range(3):
+            eng.adapt_predict_images(*batches[i % 4], hp)
+        n_img = max(10, args.steps // 4)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pending = None
+        for i in range(n_img):
+            cur = eng.adapt_predict_images(*batches[i % 4], hp, sync=False)
+            if pending is not None:
+                _ = pending.wait()["pred_logits"].argmax(dim=1).tolist()
+            pending = cur
+        _ = pending.wait()["pred_logits"].argmax(dim=1).tolist()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_img = {"value": world * n_img * S / float(dt), "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(a.nbytes for a in batches[0][0]) + sum(sp.nbytes for sp in batches[0][1])),
+                   "d2h_bytes_per_step": int(S * args.classes * 4), "steps": n_img, "samples_per_step": S,
+                   "api": "ttl_b200.Engine.adapt_predict_images(uint8 images [375,500,3] + view specs, sync=False).wait() -> "
+                          "ttl_adapt_predict_images_async: H2D of the image, Pillow-exact view generation on the device "
+                          "straight into the bf16 patch matrix, adapt, predict, D2H"}
+
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch, instrumented eager pass
     roof = None
     if not args.no_roofline and rank == 0:
@@ -333,7 +378,8 @@ def main():
                                       "peaks": peaks["src"]},
                 "accuracy": {"top1": 100.0 * counts[0] / max(counts[2], 1), "top5": 100.0 * counts[1] / max(counts[2], 1),
                              "n": counts[2], "note": "labels = zero-shot prediction of the un-adapted random-init model"},
-                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu_base}
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "e2e_from_images": e2e_img, "roofline": roof,
+                "cpu_baseline": cpu_base}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -182,3 +182,12 @@ def test_cli_synthetic_fused_and_compat():
     compat = ttl.main(common + ['--compat'])
     assert set(fused) == {'A'} and len(fused['A']) == 2
     assert fused['A'] == compat['A']      # same per-sample predictions -> same accuracy counters
+
+
+def test_cli_views_on_device():
+    """--views_on_device: the loader ships uint8 images + drawn crop boxes, the library generates the 64 views on the GPU
+    (csrc/views.cu) and adapts 3 samples per call; a ragged tail (7 = 3 + 3 + 1 samples) is flushed too."""
+    import ttl
+    res = ttl.main(['--synthetic', '7', '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0',
+                    '--print_freq', '100', '--views_on_device'])
+    assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0

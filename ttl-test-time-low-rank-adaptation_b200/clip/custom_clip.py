@@ -337,6 +337,15 @@ class ClipTestTimeTuning(nn.Module):
         return self.engine.adapt_predict_batch(images, hp, want=want, sync=sync)
 
 
+    def adapt_and_predict_images(self, images, specs, args=None, hparams: Optional[Hparams] = None,
+                                 want=("pred_logits",), sync: bool = True):
+        """adapt_and_predict_batch fed by decoded uint8 images [H,W,3] and the view specs the host drew
+        (ttl_b200.views.ViewSpecSampler = the RNG half of AugMixAugmenter, data/datautils.py:129-157): the 64 views of
+        each sample are generated on the device, bit-exactly as the reference's PIL/torchvision pipeline would."""
+        hp = hparams or self.hparams_from_args(args)
+        return self.engine.adapt_predict_images(images, specs, hp, want=want, sync=sync)
+
+
 def get_coop(clip_arch, test_set, device, n_ctx, ctx_init, learned_cls=False, layer_range=[0, 11], init_method=None,
              lora_encoder="text", rank=16, classnames: Optional[Sequence[str]] = None, **kw):
     """clip/custom_clip.py:706-723.  Class names come from the reference's `data` package when importable."""

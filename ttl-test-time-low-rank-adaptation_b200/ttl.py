@@ -13,6 +13,8 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
                   the fused per-sample call
   --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
   --concurrent_samples S  adapt S test samples per library call (default 3; 1 = strictly one at a time)
+  --views_on_device  ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
+                  (bit-exact with the reference's PIL/torchvision AugMixAugmenter) instead of 64 fp32 views per sample
 """
 from __future__ import annotations
 
@@ -128,6 +130,48 @@ class SyntheticViews(torch.utils.data.Dataset):
         return views, label
 
 
+class SyntheticImages(torch.utils.data.Dataset):
+    """Seeded stand-in for ImageFolder + ViewSpecSampler (--views_on_device): item i is (uint8 image [H,W,3], int32 view
+    specs [n_views, 6], label) -- what the loader ships when the views are generated on the GPU."""
+
+    def __init__(self, n_samples, n_views=64, n_classes=1000, seed=0):
+        from ttl_b200.views import ViewSpecSampler
+        self.n, self.c, self.seed = n_samples, n_classes, seed
+        self.sampler = ViewSpecSampler(n_views - 1)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        import numpy as np
+        g = np.random.default_rng(self.seed * 1000003 + i)
+        h, w = int(g.integers(256, 513)), int(g.integers(256, 513))
+        lo = g.integers(0, 256, size=(h // 32 + 2, w // 32 + 2, 3)).astype(np.float32)
+        ys, xs = np.arange(h) / 32.0, np.arange(w) / 32.0
+        y0, x0 = ys.astype(int), xs.astype(int)
+        fy, fx = (ys - y0)[:, None, None], (xs - x0)[None, :, None]
+        img = ((lo[y0][:, x0] * (1 - fx) + lo[y0][:, x0 + 1] * fx) * (1 - fy)
+               + (lo[y0 + 1][:, x0] * (1 - fx) + lo[y0 + 1][:, x0 + 1] * fx) * fy)
+        img = np.clip(img + g.normal(0, 12, size=img.shape), 0, 255).astype(np.uint8)
+        st = torch.random.get_rng_state()
+        torch.manual_seed(self.seed * 7919 + i)          # the sampler draws from the global torch RNG like torchvision
+        arr, specs = self.sampler(img)
+        torch.random.set_rng_state(st)
+        return torch.from_numpy(arr), torch.from_numpy(specs), int(g.integers(0, self.c))
+
+
+class _ImageSpecTransform:
+    """`transform=` for the reference's build_dataset when --views_on_device is set: PIL image -> (uint8, specs)."""
+
+    def __init__(self, n_views):
+        from ttl_b200.views import ViewSpecSampler
+        self.sampler = ViewSpecSampler(n_views)
+
+    def __call__(self, img):
+        arr, specs = self.sampler(img)
+        return torch.from_numpy(arr), torch.from_numpy(specs)
+
+
 @torch.enable_grad()
 def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state, scaler, args):
     """ttl.py:300-363.  With default flags each sample is ONE fused library call (reset -> adapt -> predict); `--compat`
@@ -159,6 +203,12 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
         nonlocal pend_imgs, pend_tgt
         if not pend_imgs:
             return
+        if isinstance(pend_imgs[0], tuple):     # --views_on_device: (uint8 image, view specs) per sample
+            out = model.adapt_and_predict_images([im.numpy() for im, _ in pend_imgs], [sp.numpy() for _, sp in pend_imgs],
+                                                 args)["pred_logits"].to(model.device)
+            score(out, torch.cat(pend_tgt))
+            pend_imgs, pend_tgt = [], []
+            return
         batch = torch.stack(pend_imgs)
         if not batch.is_cuda and not getattr(args, "views_on_host", False):
             batch = batch.to(model.device, non_blocking=True)
@@ -166,8 +216,18 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
         score(out, torch.cat(pend_tgt))
         pend_imgs, pend_tgt = [], []
 
-    for i, (images, target) in enumerate(val_loader):
-        if isinstance(images, list):
+    for i, item in enumerate(val_loader):
+        if len(item) == 3:                      # --views_on_device: uint8 image [1,H,W,3], specs [1,V,6], label
+            if not fused:
+                raise NotImplementedError("--views_on_device needs the fused path (default flags, no --compat)")
+            images, target = (item[0][0], item[1][0]), item[2]
+        else:
+            images, target = item
+            if isinstance(images, (list, tuple)) and len(images) == 2 and images[0].dtype == torch.uint8:
+                images = (images[0][0], images[1][0])   # build_dataset(transform=_ImageSpecTransform) item
+        if isinstance(images, tuple):
+            pass
+        elif isinstance(images, list):
             images = torch.cat([im if im.dim() == 4 else im[None] for im in images], dim=0)
         elif images.dim() > 4:
             images = images.squeeze(0)
@@ -254,8 +314,13 @@ def main_worker(gpu, args):
     for set_id in args.test_sets.split("/"):
         classnames = _classnames_for(set_id, args)
         model.reset_classnames(classnames, args.arch)
-        if args.synthetic > 0:
+        if args.synthetic > 0 and args.views_on_device:
+            ds = SyntheticImages(args.synthetic, args.batch_size, len(classnames), seed=args.seed)
+        elif args.synthetic > 0:
             ds = SyntheticViews(args.synthetic, args.batch_size, args.resolution, len(classnames), seed=args.seed)
+        elif args.views_on_device:
+            from data.datautils import build_dataset   # the reference's dataset tree (not vendored)
+            ds = build_dataset(set_id=set_id, transform=_ImageSpecTransform(args.batch_size - 1), args=args)
         else:
             from data.datautils import AugMixAugmenter, build_dataset   # the reference's data pipeline (not vendored)
             import torchvision.transforms as T
@@ -333,6 +398,8 @@ def build_parser():
     p.add_argument('--synthetic', default=0, type=int, help='evaluate on N seeded synthetic samples')
     p.add_argument('--compat', action='store_true', default=False, help='autograd + torch.optim.AdamW control flow')
     p.add_argument('--views_on_host', action='store_true', default=False)
+    p.add_argument('--views_on_device', action='store_true', default=False,
+                   help='generate the views on the GPU from the uint8 image (bit-exact with PIL/torchvision)')
     p.add_argument('--concurrent_samples', default=3, type=int,
                    help='test samples adapted concurrently per library call (each keeps its own adapter/optimiser state)')
     return p
