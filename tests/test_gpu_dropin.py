@@ -191,3 +191,14 @@ def test_cli_views_on_device():
     res = ttl.main(['--synthetic', '7', '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0',
                     '--print_freq', '100', '--views_on_device'])
     assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+
+
+@pytest.mark.parametrize("extra", [["--filter_ent", "1"], ["--filter_plpd", "1", "--aug_type", "occ", "--plpd_threshold", "-1"],
+                                   ["--filter_plpd", "1", "--aug_type", "patch", "--plpd_threshold", "-1"]])
+def test_cli_deyo_optional_branches_run_in_compat_mode(extra):
+    """filter_ent / filter_plpd (deyo.py:103-151) are not covered by the fused call: the CLI must route them through
+    compat mode (library forward/backward under the reference's control flow) and still adapt + predict.  The branch logic
+    itself is pinned to the reference in tests/test_deyo_variants_cpu.py."""
+    import ttl
+    res = ttl.main(['--synthetic', '2', '--test_sets', 'A', '--gpu', '0', '--workers', '0', '--print_freq', '100'] + extra)
+    assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0

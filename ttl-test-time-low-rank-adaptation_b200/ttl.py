@@ -13,6 +13,7 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
                   the fused per-sample call
   --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
   --concurrent_samples S  adapt S test samples per library call (default 3; 1 = strictly one at a time)
+  --vision_checkpoint F  load the image tower from a checkpoint file (HF or OpenAI format) instead of the local HF cache
   --views_on_device  ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
                   (bit-exact with the reference's PIL/torchvision AugMixAugmenter) instead of 64 fp32 views per sample
 """
@@ -290,10 +291,14 @@ def main_worker(gpu, args):
     from clip.custom_clip import get_coop
     rank, world = args.rank_id, args.world_size
     first = args.test_sets.split("/")[0]
+    extra = {}
+    if args.vision_checkpoint:      # HF safetensors/bin or OpenAI-format .pt (ttl_b200/weights.py); default: local HF cache
+        from ttl_b200.weights import load_vision_checkpoint
+        extra["weights"] = load_vision_checkpoint(args.vision_checkpoint)
     model = get_coop(args.arch, args.test_sets, args.gpu, args.n_ctx, args.ctx_init, layer_range=args.layer_range,
                      init_method=args.init_method, lora_encoder=args.lora_encoder, rank=args.rank,
                      classnames=_classnames_for(first, args), max_views=args.batch_size,
-                     max_samples=max(1, args.concurrent_samples))
+                     max_samples=max(1, args.concurrent_samples), **extra)
     # requires-grad filter by parameter NAME, exactly the reference's rule (ttl.py:151-163)
     for name, param in model.named_parameters():
         ok = ('image_encoder' in name and ("lora_A" in name or "lora_B" in name)
@@ -400,6 +405,8 @@ def build_parser():
     p.add_argument('--views_on_host', action='store_true', default=False)
     p.add_argument('--views_on_device', action='store_true', default=False,
                    help='generate the views on the GPU from the uint8 image (bit-exact with PIL/torchvision)')
+    p.add_argument('--vision_checkpoint', default=None, type=str,
+                   help='CLIP checkpoint file for the image tower: HF model.safetensors / pytorch_model.bin or OpenAI ViT-*.pt')
     p.add_argument('--concurrent_samples', default=3, type=int,
                    help='test samples adapted concurrently per library call (each keeps its own adapter/optimiser state)')
     return p
