@@ -185,6 +185,34 @@ int ttl_adapt_predict_images_async(ttl_ctx* ctx, const uint8_t* const* images_ho
                                    int32_t n_views, const ttl_hparams* hp, const int32_t* forced_idx_host,
                                    const ttl_outputs* out_host, void* stream);
 
+/* ---- class-feature builder: the text tower, once per class-name set --------------------------
+ * Stands in for ClipTestTimeTuning.get_text_features (clip/custom_clip.py:651-663) -> PromptEncoder (:73-82) -> HF
+ * CLIPModel.get_text_features, which the reference re-runs inside every forward although nothing in it is trainable on
+ * the TTL path.  Own context (own geometry and weights); the result feeds ttl_set_text_features. */
+typedef struct ttl_text_ctx ttl_text_ctx;
+typedef struct ttl_text_config {
+  int32_t vocab;        /* 49408 */
+  int32_t context;      /* 77 (<= 128) */
+  int32_t width;        /* 512 (B/16) / 768 (L/14); multiple of 128, head_dim 64 */
+  int32_t layers;       /* 12 */
+  int32_t heads;        /* 8 / 12 */
+  int32_t mlp_dim;      /* 2048 / 3072 */
+  int32_t proj_dim;     /* 512 / 768 */
+  int32_t max_prompts;  /* prompts encoded per pass (buffer sizing; longer lists are chunked) */
+  float ln_eps;         /* 1e-5 */
+  int32_t device;
+} ttl_text_config;
+/* Non-layer slots (HF names: text_model.embeddings.token_embedding.weight [vocab,d], .position_embedding.weight [ctx,d],
+ * text_model.final_layer_norm.{weight,bias}, text_projection.weight [P,d]); per-layer slots reuse TTL_W_LN1_G..TTL_W_FC2_B. */
+enum ttl_text_weight_kind { TTL_TW_TOKEN_EMB = 0, TTL_TW_POS_EMB = 1, TTL_TW_FINAL_LN_G = 2, TTL_TW_FINAL_LN_B = 3, TTL_TW_TEXT_PROJ = 4 };
+int ttl_text_create(ttl_text_ctx** out, const ttl_text_config* cfg);
+void ttl_text_destroy(ttl_text_ctx* ctx);
+const char* ttl_text_last_error(const ttl_text_ctx* ctx);
+int ttl_text_set_weight(ttl_text_ctx* ctx, int32_t layer, int32_t kind, const float* host, int64_t numel);
+/* tokens_host int32 [n_prompts, context] (clip.tokenize layout: SOT, ids, EOT = highest id, zero padding) ->
+ * feats_host fp32 [n_prompts, proj_dim], L2-normalised.  Synchronises `stream`. */
+int ttl_text_encode(ttl_text_ctx* ctx, const int32_t* tokens_host, int32_t n_prompts, float* feats_host, void* stream);
+
 /* Toggle CUDA-graph replay of ttl_adapt_predict (default on). */
 int ttl_set_graphs(ttl_ctx* ctx, int32_t enabled);
 /* Kernel launches issued by the last ttl_adapt_predict* call (for bench.py's gpu_launches). */

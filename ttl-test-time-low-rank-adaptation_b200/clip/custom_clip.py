@@ -106,7 +106,7 @@ class _PromptState:
     def set(self, classnames):
         self.classnames = [c.replace("_", " ") for c in classnames]
         self.prompts = [f"{self.ctx_init} {c}." for c in self.classnames]
-        self.tokenized_prompts = None      # tokeniser + text tower are the "next" row N2
+        self.tokenized_prompts = None      # filled by _refresh_text_features when a BPE merge table is available
 
     def reset_classnames(self, classnames, arch):
         self.set(classnames)
@@ -189,7 +189,8 @@ class ClipTestTimeTuning(nn.Module):
     def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-B/16", n_ctx=16, ctx_init=None,
                  ctx_position="end", learned_cls=False, layer_range=[9, 11], init_method=None, lora_encoder="text",
                  rank=16, max_views: int = 64, weights: Optional[dict] = None, text_features: Optional[torch.Tensor] = None,
-                 logit_scale: float = math.log(100.0), max_samples: int = 1):
+                 logit_scale: float = math.log(100.0), max_samples: int = 1, text_weights: Optional[dict] = None,
+                 bpe_path: Optional[str] = None, tokenizer=None):
         super().__init__()
         if lora_encoder != "image":
             raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
@@ -204,7 +205,10 @@ class ClipTestTimeTuning(nn.Module):
         self.layer_range = [int(layer_range[0]), int(layer_range[1])]
         self.engine = Engine(arch, max_views=max_views, max_classes=max(1000, len(classnames)), lora_rank=rank,
                              lora_alpha=32.0, layer_range=self.layer_range, device=dev_index, max_samples=max_samples)
+        self._text_weights, self._bpe_path, self._text_encoder, self._tokenizer = text_weights, bpe_path, None, tokenizer
         self.engine.load_weights(weights if weights is not None else self._load_vision_weights(arch))
+        if self._text_weights is None and weights is None:
+            self._text_weights = getattr(ClipTestTimeTuning, "_hf_text_weights", None)
 
         # LoRA module tree.  Trainable-range tensors alias the library's device buffers.
         layers: List[_Layer] = []
@@ -245,6 +249,8 @@ class ClipTestTimeTuning(nn.Module):
             m = CLIPModel.from_pretrained(_HF_NAME[arch], local_files_only=True)
             sd = {k: v for k, v in m.state_dict().items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
             ClipTestTimeTuning._hf_logit_scale = float(m.logit_scale)
+            ClipTestTimeTuning._hf_text_weights = {k: v for k, v in m.state_dict().items()
+                                                   if k.startswith("text_model.") or k == "text_projection.weight"}
             return sd
         except Exception:
             if os.environ.get("TTL_SYNTHETIC_WEIGHTS", "1") == "0":
@@ -258,8 +264,20 @@ class ClipTestTimeTuning(nn.Module):
         P = ARCH_GEOMETRY[self.arch]["proj_dim"]
         if self._given_text is not None and self._given_text.shape[0] == len(names):
             t = self._given_text.detach().float().cpu()
+        elif self._text_weights is not None:
+            # the real thing (row N2): tokenise the hand-crafted prompts, run the text tower ONCE on the device
+            from ttl_b200.text import TextEncoder
+            from ttl_b200.tokenizer import SimpleTokenizer
+            if self._tokenizer is None:
+                self._tokenizer = SimpleTokenizer(self._bpe_path)
+            if self._text_encoder is None:
+                self._text_encoder = TextEncoder(self.arch, device=self.device.index or 0)
+                self._text_encoder.load_weights(self._text_weights)
+            self.prompt_learner.tokenized_prompts = self._tokenizer(self.prompt_learner.prompts).to(self.device)
+            self.tokenized_prompts = self.prompt_learner.tokenized_prompts
+            t = self._text_encoder.encode(self.prompt_learner.tokenized_prompts)
         else:
-            # No tokenizer/text tower offline: deterministic unit vectors keyed by the prompt text.
+            # synthetic mode (no text-tower weights given): deterministic unit vectors keyed by the prompt text
             rows = []
             for p in self.prompt_learner.prompts:
                 g = torch.Generator().manual_seed(zlib.crc32(p.encode()))

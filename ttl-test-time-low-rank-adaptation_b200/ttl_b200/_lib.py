@@ -39,6 +39,12 @@ class TtlViewSpec(C.Structure):
                 ("width", C.c_int32), ("flip", C.c_int32)]
 
 
+class TtlTextConfig(C.Structure):
+    _fields_ = [("vocab", C.c_int32), ("context", C.c_int32), ("width", C.c_int32), ("layers", C.c_int32),
+                ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("proj_dim", C.c_int32), ("max_prompts", C.c_int32),
+                ("ln_eps", C.c_float), ("device", C.c_int32)]
+
+
 class TtlOutputs(C.Structure):
     _fields_ = [("logits0", vp), ("entropy", vp), ("idx", vp), ("loss", vp), ("pred_logits", vp)]
 
@@ -51,6 +57,7 @@ LORA_A_Q, LORA_B_Q, LORA_A_V, LORA_B_V = range(4)
 LORA_PARAM, LORA_GRAD, LORA_INIT = range(3)
 HEAD_TPT, HEAD_DEYO = 0, 1
 VIEW_CLEAN, VIEW_CROP = 0, 1
+TW_TOKEN_EMB, TW_POS_EMB, TW_FINAL_LN_G, TW_FINAL_LN_B, TW_TEXT_PROJ = range(5)
 EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_PATCH_F32, EPI_F32, EPI_GELU_BWD = range(6)
 
 _SIGS = {
@@ -79,6 +86,11 @@ _SIGS = {
     "ttl_make_views": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "ttl_adapt_predict_images_async": (C.c_int, [vp, vp, vp, vp, C.c_int32, vp, C.c_int32, C.POINTER(TtlHparams), vp,
                                                  C.POINTER(TtlOutputs), vp]),
+    "ttl_text_create": (C.c_int, [C.POINTER(vp), C.POINTER(TtlTextConfig)]),
+    "ttl_text_destroy": (None, [vp]),
+    "ttl_text_last_error": (C.c_char_p, [vp]),
+    "ttl_text_set_weight": (C.c_int, [vp, C.c_int32, C.c_int32, vp, C.c_int64]),
+    "ttl_text_encode": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
     "ttl_set_graphs": (C.c_int, [vp, C.c_int32]),
     "ttl_last_launch_count": (C.c_int64, [vp]),
     "ttl_profile_gemm": (C.c_int, [vp, C.c_int32]),
