@@ -175,7 +175,8 @@ def run_reference_arm(args):
     timed = times[args.warmup:]
     per_step = sum(timed) / len(timed)
     value = (views / args.views) / per_step
-    sample = (f"{len(timed)} timed steps of {views}-view adapt+predict, fp32, oracle port of ttl.py:338-352"
+    sample = (f"{len(timed)} timed steps of {views}-view adapt+predict, fp32, oracle port of ttl.py:338-352 with the class "
+              f"features cached (the reference re-runs its text tower twice per sample on top of this)"
               + (f"; bounded: scaled by {views}/{args.views} views" if bounded else ""))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3 * (args.views / views), "higher_is_better": True,
@@ -359,7 +360,7 @@ def main():
         per = sum(times) / len(times)
         cpu_base = {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{len(times)} samples of the same workload, oracle port (fp32 PyTorch CPU, autograd) of "
-                              f"ttl.py:338-352, {per:.2f} s/sample"}
+                              f"ttl.py:338-352 with cached class features, {per:.2f} s/sample"}
 
     if rank == 0:
         f_alg = F_ALG_TFLOP if args.head == "tpt" else F_ALG_TFLOP_DEYO

@@ -59,7 +59,9 @@ def gemm_roofline(eng, hp, ring, peaks: Dict[str, float], batches: int = 3, traf
     peak = peaks["tf_sus"]
     return {"bound": "tensor", "kernel": "gemm2_kernel<BLOCK_N,EPI> (cta_group::2 tcgen05 GEMM; all launches with M >= 4096 "
                                          "of the adapted batch)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": traffic.get("bytes_per_launch_avg") if isinstance(traffic, dict) else None,
+            "traffic_detail": traffic,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
             "launches_timed": n_big, "avg_launch_ms": big_ms / max(n_big, 1),
             "flop_per_launch_avg": big_flops / max(n_big, 1),
