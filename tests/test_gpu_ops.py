@@ -71,6 +71,29 @@ def test_gemm_cta_pair_lora_pair_and_guard_rows(G):
     assert float(out[M:].float().abs().max()) == 0.0          # TMA clips rows >= M
 
 
+@pytest.mark.parametrize("M,N,K", [(12608, 2304, 768), (1182, 768, 3072), (2100, 768, 256), (300, 256, 128), (37824, 768, 768)])
+def test_gemm_four_cta_cluster_multicast(G, M, N, K):
+    """block_n = 2256: two CTA pairs per cluster share every B tile through TMA multicast (quarter tiles, forwarded
+    arrivals, slot release counted over both pairs).  Odd numbers of 256-row blocks leave a pair of the last cluster on
+    rows >= M (zero-filled loads, clipped stores); the LoRA second operand pair rides along."""
+    gu, L = G
+    a, b = _bf(M, K, seed=21), _bf(N, K, scale=K ** -0.5, seed=22)
+    bias = torch.randn(N, device="cuda") * 0.2
+    acc = a.float() @ b.float().t()
+    out, _ = gu.gemm(a, b, L.EPI_BF16, bias=bias, block_n=2256, out_rows=M + 8)
+    assert gu.rel_err(out[:M], acc + bias) < 4e-3 and float(out[M:].float().abs().max()) == 0.0
+    resid = torch.randn(M, N, device="cuda")
+    out, _ = gu.gemm(a, b, L.EPI_RESID_F32, bias=bias, resid=resid, block_n=2256)
+    assert gu.rel_err(out, resid + acc + bias) < 1e-5
+    a2, b2 = _bf(M, 64, seed=3), _bf(N, 64, scale=0.1, seed=4)
+    out, _ = gu.gemm(a, b, L.EPI_GELU, bias=bias, a2=a2, b2=b2, block_n=2256)
+    z = acc + a2.float() @ b2.float().t() + bias
+    assert gu.rel_err(out, z * torch.sigmoid(1.702 * z)) < 6e-3
+    pair, _ = gu.gemm(a, b, L.EPI_F32, block_n=1256)
+    quad, _ = gu.gemm(a, b, L.EPI_F32, block_n=2256)
+    assert torch.equal(pair, quad)      # same MMA order per output tile: bit-identical to the pair kernel
+
+
 def test_gemm_lora_second_pair(G):
     gu, L = G
     M, N, K = 1182, 2304, 768

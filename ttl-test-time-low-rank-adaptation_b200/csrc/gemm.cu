@@ -314,7 +314,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EBUF_BYTES = OUT_F32 ? 4096 : 2048;          // 32 rows x 32 columns
   static constexpr int EPI_BYTES = G2_EPI_WARPS * 2 * EBUF_BYTES;   // two buffers per epilogue warp
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 512;   // (3 * STAGES + 4 + 2 * G2_EPI_WARPS) mbarriers + the TMEM slot: <= 44 * 8 + 4
   static constexpr int STAGES_RAW = (G2_SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
@@ -330,8 +330,14 @@ struct Epi2Params {
   int dbg;   // TTL_GEMM_DBG bits (development only): 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
 };
 
-template <int BLOCK_N, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+// CL = 2: one CTA pair per cluster (above).  CL = 4: two pairs stacked along M share every B tile: each CTA loads a QUARTER of
+// the B tile and TMA-multicasts it to the CTA of the same parity in the other pair, so a pair pulls (256 + BLOCK_N/2) x 64
+// bf16 from L2 per 256 x BLOCK_N x 64 MMA block instead of (256 + BLOCK_N) x 64.  Parity-0 CTAs are the pair leaders: their
+// B quarters signal the leaders' `full` barriers directly; parity-1 CTAs collect theirs on a local `fullB` barrier and the
+// (otherwise idle) MMA warp of the non-leader forwards one remote arrival per stage to its leader.  A smem slot is
+// released to all four producers only when BOTH pairs' MMAs have read it (`empty` counts two multicast commits).
+template <int BLOCK_N, int EPI, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -347,11 +353,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint64_t* tfull = empty + C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* lbar = tempty + 2;                       // [G2_EPI_WARPS][2] residual-tile arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 2 * G2_EPI_WARPS);
+  uint64_t* fullB = lbar + 2 * G2_EPI_WARPS;         // [STAGES] CL == 4, parity-1 CTAs: this CTA's B half has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fullB + C::STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();          // 0 .. CL-1
+  const uint32_t rank = crank & 1;                   // parity inside the pair: 0 = leader
+  const uint32_t pair = crank >> 1;                  // 0 (CL == 2) or 0/1 (CL == 4)
+  const uint32_t lead_rank = crank & ~1u;            // cluster rank of this pair's leader
   const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
@@ -364,8 +374,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tma_prefetch_desc(&tmB2);
     }
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], 2);    // one arrival per CTA's producer (used in the leader only)
-      mbar_init(&empty[s], 1);   // multicast tcgen05.commit
+      mbar_init(&full[s], CL == 4 ? 3 : 2);   // one arrival per CTA's producer (+ the peer's B forwarder), leader's copy is used
+      mbar_init(&empty[s], CL == 4 ? 2 : 1);  // multicast tcgen05.commit of every pair in the cluster
+      mbar_init(&fullB[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);                      // multicast tcgen05.commit
@@ -386,36 +397,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   pdl_wait();      // prologue above overlaps the tail of the previous kernel; global memory is touched only below
   pdl_trigger();
 
-  const int m_pairs = (p.M + 255) / 256;
+  constexpr int PAIRS = CL / 2;                       // pairs per cluster, stacked along M
+  const int m_pairs = ((p.M + 255) / 256 + PAIRS - 1) / PAIRS;   // row blocks of 256 * PAIRS rows
   const int n_tiles = p.N / BLOCK_N;
   const int num_tiles = m_pairs * n_tiles;
   const int num_kb = p.kb1 + p.kb2;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer (one thread per CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t full0 = mapa_u32(smem_u32(&full[0]), 0);   // the LEADER's full barriers
+      const uint32_t full0 = mapa_u32(smem_u32(&full[0]), lead_rank);   // the pair LEADER's full barriers
+      const uint16_t bmask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));   // CL == 4: same parity, both pairs
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
-        const int a_row = m_pair * 256 + static_cast<int>(rank) * 128;
-        const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        const int a_row = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128;
+        const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) +
+                          (CL == 4 ? static_cast<int>(pair) * (BLOCK_N / 4) : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t fb = full0 + stage * 8;
-          if (leader) mbar_expect_tx(&full[stage], (p.dbg & 4) ? 0 : 2 * C::STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full[stage], (p.dbg & 4) ? 0 : 2 * C::A_BYTES + (CL == 4 ? 1 : 2) * C::B_BYTES);
           else mbar_arrive_cluster(fb);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
-          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES + (CL == 4 ? pair * (C::B_BYTES / 2) : 0);
+          const void* tA = kb < p.kb1 ? static_cast<const void*>(&tmA1) : static_cast<const void*>(&tmA2);
+          const void* tB = kb < p.kb1 ? static_cast<const void*>(&tmB1) : static_cast<const void*>(&tmB2);
+          const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BLOCK_K;
           if (p.dbg & 4) {
-          } else if (kb < p.kb1) {
-            tma_load_2d_cg2(&tmA1, fb, a_dst, kb * BLOCK_K, a_row);
-            tma_load_2d_cg2(&tmB1, fb, b_dst, kb * BLOCK_K, b_row);
           } else {
-            tma_load_2d_cg2(&tmA2, fb, a_dst, (kb - p.kb1) * BLOCK_K, a_row);
-            tma_load_2d_cg2(&tmB2, fb, b_dst, (kb - p.kb1) * BLOCK_K, b_row);
+            tma_load_2d_cg2(tA, fb, a_dst, kc, a_row);
+            if (CL == 4) tma_load_2d_mc(tB, leader ? &full[stage] : &fullB[stage], b_dst, kc, b_row, bmask);
+            else tma_load_2d_cg2(tB, fb, b_dst, kc, b_row);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -445,10 +461,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             umma_bf16_cg2(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
                           idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_mc2(&empty[stage], 3);   // frees the slot in BOTH CTAs
+          umma_commit_mc2(&empty[stage], CL == 4 ? 0xF : 3);   // frees the slot in every CTA that loads into it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_mc2(&tfull[as], 3);        // accumulator complete -> both CTAs' epilogues
+        umma_commit_mc2(&tfull[as], pair_mask);   // accumulator complete -> both CTAs' epilogues
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -457,6 +473,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         mbar_wait(&tempty[as], aphase ^ 1);
         as ^= 1;
         if (as == 0) aphase ^= 1;
+      }
+    } else if (CL == 4 && !leader && lane == 0 && !(p.dbg & 4)) {
+      // B forwarder of the non-leader CTA: its half of the B tile arrives as two multicast quarters on the local fullB
+      // barrier; one remote arrival per stage tells the leader's MMA thread that this CTA's operands are complete.
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0 = mapa_u32(smem_u32(&full[0]), lead_rank);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_expect_tx(&fullB[stage], C::B_BYTES);
+          mbar_wait(&fullB[stage], phase);
+          mbar_arrive_cluster(full0 + stage * 8);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -467,13 +497,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     const int half = ew >> 2;           // which half of the BLOCK_N columns
     uint8_t* ebuf = sE + ew * 2 * C::EBUF_BYTES;
     uint64_t* lb = lbar + ew * 2;
-    const uint32_t tempty0 = mapa_u32(smem_u32(&tempty[0]), 0);
+    const uint32_t tempty0 = mapa_u32(smem_u32(&tempty[0]), lead_rank);
     int as = 0;
     uint32_t aphase = 0;
     uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
-      const int row0 = m_pair * 256 + static_cast<int>(rank) * 128 + quad * 32;
+      const int row0 = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
       const bool live = row0 < p.M;     // warp-uniform
       if (EPI == EPI_RESID_F32 && live && lane == 0 && !(p.dbg & 1)) {
@@ -577,6 +607,7 @@ thread_local char g_err[256] = "";
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 int g_pairs_hint = 0;   // co-resident CTA pairs reported by the occupancy API (0 until the first pair launch)
+int g_quads_hint = 0;   // co-resident 4-CTA clusters
 
 void set_err(const char* msg) { std::snprintf(g_err, sizeof(g_err), "%s", msg); }
 
@@ -605,14 +636,14 @@ bool make_map(CUtensorMap* m, const GemmOperand& op, int box_rows) {
                     CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CL>
 cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   using C = Cfg2<BLOCK_N, EPI>;
   CUtensorMap tA1, tB1, tA2, tB2, tOut, tRes;
-  if (!make_map(&tA1, g.a1, 128) || !make_map(&tB1, g.b1, BLOCK_N / 2)) return cudaErrorInvalidValue;
+  if (!make_map(&tA1, g.a1, 128) || !make_map(&tB1, g.b1, BLOCK_N / CL)) return cudaErrorInvalidValue;
   const bool two = g.a2.ptr != nullptr && g.a2.k > 0;
   if (two) {
-    if (!make_map(&tA2, g.a2, 128) || !make_map(&tB2, g.b2, BLOCK_N / 2)) return cudaErrorInvalidValue;
+    if (!make_map(&tA2, g.a2, 128) || !make_map(&tB2, g.b2, BLOCK_N / CL)) return cudaErrorInvalidValue;
   } else {
     tA2 = tA1;
     tB2 = tB1;
@@ -637,7 +668,7 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   p.bias = g.bias;
   static const char* dbg_env = std::getenv("TTL_GEMM_DBG");
   p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
-  auto kern = gemm2_kernel<BLOCK_N, EPI>;
+  auto kern = gemm2_kernel<BLOCK_N, EPI, CL>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -649,32 +680,33 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   static int max_pairs = 0;
   if (max_pairs == 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(num_sms & ~1);
+    cfg.gridDim = dim3(num_sms / CL * CL);
     cfg.blockDim = dim3(G2_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
-    max_pairs = n < num_sms / 2 ? n : num_sms / 2;
-    g_pairs_hint = max_pairs;
-    if (std::getenv("TTL_DEBUG")) std::fprintf(stderr, "ttl: gemm2<%d,%d> co-resident CTA pairs: %d (SMs %d)\n", BLOCK_N, EPI, n, num_sms);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / CL; }
+    max_pairs = n < num_sms / CL ? n : num_sms / CL;
+    if (CL == 2) g_pairs_hint = max_pairs;
+    else g_quads_hint = max_pairs;
+    if (std::getenv("TTL_DEBUG")) std::fprintf(stderr, "ttl: gemm2<%d,%d,%d> co-resident clusters: %d (SMs %d)\n", BLOCK_N, EPI, CL, n, num_sms);
   }
-  const int tiles = ((g.M + 255) / 256) * (g.N / BLOCK_N);
-  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  const int tiles = (((g.M + 255) / 256 + CL / 2 - 1) / (CL / 2)) * (g.N / BLOCK_N);
+  const int grid = CL * (tiles < max_pairs ? tiles : max_pairs);
   return launch_pdl(kern, dim3(grid), dim3(G2_THREADS), C::SMEM_BYTES, stream, tA1, tB1, tA2, tB2, tOut, tRes, p);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CL = 2>
 cudaError_t launch2_n(const GemmArgs& g, cudaStream_t s, int sms) {
   switch (g.epi) {
-    case EPI_BF16: return launch2_t<BLOCK_N, EPI_BF16>(g, s, sms);
-    case EPI_GELU: return launch2_t<BLOCK_N, EPI_GELU>(g, s, sms);
-    case EPI_RESID_F32: return launch2_t<BLOCK_N, EPI_RESID_F32>(g, s, sms);
-    case EPI_F32: return launch2_t<BLOCK_N, EPI_F32>(g, s, sms);
+    case EPI_BF16: return launch2_t<BLOCK_N, EPI_BF16, CL>(g, s, sms);
+    case EPI_GELU: return launch2_t<BLOCK_N, EPI_GELU, CL>(g, s, sms);
+    case EPI_RESID_F32: return launch2_t<BLOCK_N, EPI_RESID_F32, CL>(g, s, sms);
+    case EPI_F32: return launch2_t<BLOCK_N, EPI_F32, CL>(g, s, sms);
     default: set_err("gemm2: epilogue not supported by the CTA-pair kernel"); return cudaErrorInvalidValue;
   }
 }
@@ -781,7 +813,12 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   if (g.a1.rows < g.M || g.b1.rows < g.N) { set_err("gemm_launch: operand rows smaller than M/N"); return cudaErrorInvalidValue; }
   int bn = g.force_block_n;
   {
-    // force_block_n: 0 = heuristic; 64/128/256 = 1-CTA kernel; 1000 + {128,192,256} = CTA-pair kernel
+    // force_block_n: 0 = heuristic; 64/128/256 = 1-CTA kernel; 1000 + {128,192,256} = CTA-pair kernel;
+    // 2256 = 4-CTA cluster (two pairs, multicast B tiles), BLOCK_N = 256
+    if (bn == 2256) {
+      if (g.N % 256 != 0 || g.out2 != nullptr) { set_err("gemm_launch: 4-CTA cluster kernel needs N % 256 == 0, no out2"); return cudaErrorInvalidValue; }
+      return launch2_n<256, 4>(g, stream, num_sms);
+    }
     int bn2 = bn >= 1000 ? bn - 1000 : (bn == 0 ? pick_pair_block_n(g, num_sms) : 0);
     static const char* env = std::getenv("TTL_GEMM_PAIR");
     if (bn == 0 && env != nullptr) {
@@ -791,6 +828,12 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
     }
     if (bn2 != 0) {
       if (g.N % bn2 != 0 || g.out2 != nullptr) { set_err("gemm_launch: CTA-pair kernel: bad BLOCK_N / out2"); return cudaErrorInvalidValue; }
+      // 4-CTA clusters with multicast B tiles: TTL_GEMM_CLUSTER=4 (BLOCK_N = 256, at least two row blocks of 256).  Opt-in:
+      // measured on B200 (gpurun s59/s60) only 33 clusters of 4 are co-resident (132 of 148 SMs): +6-7 % per SM from the
+      // smaller L2->SM operand traffic, but -4 % per kernel and -2 % per adapted sample with 16 SMs stranded.
+      static const char* cl_env = std::getenv("TTL_GEMM_CLUSTER");
+      static const int cl = cl_env ? std::atoi(cl_env) : 2;
+      if (cl == 4 && bn2 == 256 && g.M > 2048) return launch2_n<256, 4>(g, stream, num_sms);
       switch (bn2) {
         case 256: return launch2_n<256>(g, stream, num_sms);
         case 192: return launch2_n<192>(g, stream, num_sms);

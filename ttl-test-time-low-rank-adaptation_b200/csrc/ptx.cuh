@@ -235,6 +235,16 @@ __device__ __forceinline__ void tma_load_2d_cg2(const void* tmap, uint32_t bar_c
       "r"(c_outer)
       : "memory");
 }
+// TMA load multicast to every CTA of `cta_mask` in the cluster: the tile lands at the same CTA-relative smem offset in each
+// destination and completes bytes on the mbarrier at the same CTA-relative offset there.
+__device__ __forceinline__ void tma_load_2d_mc(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c_inner,
+                                               int32_t c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer),
+      "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {  // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)
