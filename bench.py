@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--head", default="tpt", choices=["tpt", "deyo"])
+    ap.add_argument("--arch", default="ViT-B/16", choices=["ViT-B/16", "ViT-L/14"],
+                    help="ViT-B/16 is the metric's configuration; ViT-L/14 (BASELINE config 4, layers 21-23) is informational")
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--views", type=int, default=64)
     ap.add_argument("--ring", type=int, default=4, help="distinct pre-staged batches (ring * S * 38.5 MB > L2)")
@@ -217,10 +219,14 @@ def main():
     # ---- model: random-init ViT-B/16 (seed 1234), synthetic unit text features, Xavier LoRA A / zero B
     from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features
     S = args.concurrent
-    eng = Engine("ViT-B/16", max_views=args.views, max_classes=max(args.classes, 16), device=local_rank, max_samples=S)
-    eng.load_weights(synthetic_vit_weights("ViT-B/16", seed=1234))
-    eng.set_text_features(synthetic_text_features(args.classes, 512, seed=11), math.log(100.0))
-    eng.set_lora_init(synthetic_lora_init("ViT-B/16", rank=16, layers=(9, 11), seed=0))
+    from ttl_b200 import ARCH_GEOMETRY
+    geo = ARCH_GEOMETRY[args.arch]
+    lora_layers = (geo["layers"] - 3, geo["layers"] - 1)      # the last three layers: 9-11 (B/16, ttl.py:402), 21-23 (L/14)
+    eng = Engine(args.arch, max_views=args.views, max_classes=max(args.classes, 16), device=local_rank, max_samples=S,
+                 layer_range=lora_layers)
+    eng.load_weights(synthetic_vit_weights(args.arch, seed=1234))
+    eng.set_text_features(synthetic_text_features(args.classes, geo["proj_dim"], seed=11), math.log(100.0))
+    eng.set_lora_init(synthetic_lora_init(args.arch, rank=16, layers=lora_layers, seed=0))
     hp = Hparams(head=args.head)
 
     # ---- data: this rank's shard of a seeded synthetic evaluation set, pre-staged in HBM (ring > L2)
@@ -364,11 +370,13 @@ def main():
 
     if rank == 0:
         f_alg = F_ALG_TFLOP if args.head == "tpt" else F_ALG_TFLOP_DEYO
+        if args.arch == "ViT-L/14":
+            f_alg = 10.67 if args.head == "tpt" else 11.90
         per_gpu_tflops = value / world * f_alg
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head), "
+                "config": {"workload": f"TTL {args.arch}, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head), "
                                        f"random-init weights", "samples_per_rank": args.steps * S,
                            "concurrent_samples_per_step": S,
                            "l2": f"inputs larger than L2: ring of {args.ring} pre-staged batches x {ring[0].numel() * 4 / 1e6:.1f} MB",
