@@ -945,13 +945,12 @@ static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int 
   const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
   const uint32_t obox[3] = {64, 128, 1};
   if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
-  static size_t configured = 0;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int dv = current_device_slot();
+  static size_t configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[dv];
+  int& num_sms = num_sms_dev[dv];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
   if (smem > configured) {
     if (cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
       cudaGetLastError();
@@ -1007,13 +1006,12 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
     const uint32_t box[3] = {64, 32, 1};
     if (!encode_tiled_map(&to, 0, out, 3, dims, strides, box, 128)) return false;
   }
-  static size_t configured = 0;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int dv = current_device_slot();
+  static size_t configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[dv];
+  int& num_sms = num_sms_dev[dv];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
   if (smem > configured) {
     if (cudaFuncSetAttribute(attention_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
       cudaGetLastError();
@@ -1038,7 +1036,8 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   if (want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_fwd_smem(tokens);
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
@@ -1057,7 +1056,8 @@ void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, co
                           int tokens, int heads, float scale, cudaStream_t st) {
   const int tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_bwd_smem(tokens);
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
     cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;

@@ -669,15 +669,17 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   static const char* dbg_env = std::getenv("TTL_GEMM_DBG");
   p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
   auto kern = gemm2_kernel<BLOCK_N, EPI, CL>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  const int dv = current_device_slot();
+  static bool attr_done[MAX_DEVICES] = {};  // per instantiation and device
+  if (!attr_done[dv]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem) failed (gemm2)"); return e; }
-    attr_done = true;
+    attr_done[dv] = true;
   }
   // A persistent grid must be co-resident: not every TPC of a B200 has both SMs enabled, so the number of CTA pairs
   // that fit at once can be below num_sms / 2 -- ask the occupancy API once per instantiation.
-  static int max_pairs = 0;
+  static int max_pairs_dev[MAX_DEVICES] = {};
+  int& max_pairs = max_pairs_dev[dv];
   if (max_pairs == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms / CL * CL);
@@ -750,11 +752,12 @@ cudaError_t launch_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   p.bias = g.bias; p.out = g.out; p.ldo = g.ldo; p.out2 = g.out2;
   p.resid = g.resid; p.ldr = g.ldr; p.aux = g.aux; p.pos = g.pos; p.tpv = g.tokens_per_view;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static bool attr_done[MAX_DEVICES] = {};  // per instantiation and device
+  const int dv = current_device_slot();
+  if (!attr_done[dv]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem) failed"); return e; }
-    attr_done = true;
+    attr_done[dv] = true;
   }
   const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles = m_tiles * (g.N / BLOCK_N);

@@ -335,7 +335,9 @@ cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, 
 }  // namespace
 
 static void small_gemm_nt_smem(size_t bytes) {
-  static size_t configured = 48 * 1024;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
+  if (configured == 0) configured = 48 * 1024;
   if (bytes > configured) {
     cudaFuncSetAttribute(small_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
     configured = bytes;

@@ -31,6 +31,15 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
+// Function-local launch state (max dynamic smem already configured, co-resident cluster counts, SM counts) is PER DEVICE:
+// cudaFuncSetAttribute applies to the current device only.  One slot per CUDA ordinal.
+constexpr int MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

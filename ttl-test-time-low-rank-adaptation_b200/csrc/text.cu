@@ -215,7 +215,8 @@ int encode_chunk(ttl_text_ctx* c, int n, cudaStream_t st) {
                static_cast<const float*>(c->tok), static_cast<const float*>(c->pos), c->XA, M, c->ctx, d / 4, c->vocab);
   }
   const size_t att_smem = (2 * static_cast<size_t>(c->ctx) * (DH + 1) + 8 * DH) * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (att_smem > configured) {
     cudaFuncSetAttribute(text_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(att_smem));
     configured = att_smem;
