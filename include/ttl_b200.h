@@ -53,7 +53,11 @@ typedef struct ttl_config {
   float ln_eps;          /* 1e-5 */
   int32_t device;        /* CUDA ordinal (--gpu) */
   int32_t max_samples;   /* test samples adapted concurrently per call (BASELINE config 5); 0 or 1 = one at a time */
+  int32_t precision;     /* enum ttl_precision: 0 = bf16 operands / fp32 accumulation on the tensor cores (the product);
+                            1 = fp32 validation mode: every activation and contraction in fp32 on the CUDA cores, one sample
+                            per call, no graphs -- held to the fp32 tolerance (1e-4) against the reference's fp32 CPU run */
 } ttl_config;
+enum ttl_precision { TTL_PRECISION_BF16 = 0, TTL_PRECISION_FP32 = 1 };
 
 /* Frozen-weight slots; names follow the HF CLIP vision tower state_dict that
  * CLIPModel.from_pretrained (clip/custom_clip.py:581) yields. */

@@ -190,7 +190,7 @@ class ClipTestTimeTuning(nn.Module):
                  ctx_position="end", learned_cls=False, layer_range=[9, 11], init_method=None, lora_encoder="text",
                  rank=16, max_views: int = 64, weights: Optional[dict] = None, text_features: Optional[torch.Tensor] = None,
                  logit_scale: float = math.log(100.0), max_samples: int = 1, text_weights: Optional[dict] = None,
-                 bpe_path: Optional[str] = None, tokenizer=None):
+                 bpe_path: Optional[str] = None, tokenizer=None, precision: str = "bf16"):
         super().__init__()
         if lora_encoder != "image":
             raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
@@ -204,7 +204,8 @@ class ClipTestTimeTuning(nn.Module):
         d, n_layers = geo["width"], geo["layers"]
         self.layer_range = [int(layer_range[0]), int(layer_range[1])]
         self.engine = Engine(arch, max_views=max_views, max_classes=max(1000, len(classnames)), lora_rank=rank,
-                             lora_alpha=32.0, layer_range=self.layer_range, device=dev_index, max_samples=max_samples)
+                             lora_alpha=32.0, layer_range=self.layer_range, device=dev_index,
+                             max_samples=1 if precision == "fp32" else max_samples, precision=precision)
         self._text_weights, self._bpe_path, self._text_encoder, self._tokenizer = text_weights, bpe_path, None, tokenizer
         self.engine.load_weights(weights if weights is not None else self._load_vision_weights(arch))
         if self._text_weights is None and weights is None:

@@ -44,6 +44,11 @@ struct LayerW {
   bf16 *wqkvT = nullptr, *woT = nullptr, *w1T = nullptr, *w2T = nullptr;   // transposes (train layers only)
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  float *wqkv_f = nullptr, *wo_f = nullptr, *w1_f = nullptr, *w2_f = nullptr;   // fp32 validation mode: untransposed fp32 copies
+};
+
+struct TapeF {  // one train-mode layer of the fp32 validation mode (x_mid / x_out / lse live in the regular Tape)
+  float *h1 = nullptr, *qkv = nullptr, *ao = nullptr, *h2 = nullptr, *z = nullptr, *g = nullptr, *Tq = nullptr, *Tv = nullptr;
 };
 
 struct Tape {  // one train-mode layer
@@ -116,6 +121,12 @@ struct ttl_ctx {
   int last_train_views = 0, last_train_samples = 1;   // total views / samples of the last train-mode forward
   const float* last_train_in = nullptr;
   int pack_samples = 1;                                // K-concatenation width (in samples) of the current bf16 packs
+
+  // fp32 validation mode (cfg.precision == TTL_PRECISION_FP32): fp32 twins of every bf16 buffer
+  bool f32 = false;
+  float *wpatch_f = nullptr, *patches_f = nullptr, *Hf = nullptr, *QKVf = nullptr, *AOf = nullptr, *Gf = nullptr, *Tqf = nullptr,
+        *Tvf = nullptr, *DZf = nullptr, *DAOf = nullptr, *DQKVf = nullptr, *Uqf = nullptr, *Uvf = nullptr;
+  std::vector<TapeF> tapef;
 
   // per-launch GEMM timing (bench.py roofline): CUDA events around every gemm launch while enabled
   bool prof = false;
@@ -508,6 +519,155 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   return check_launch(c, "backward");
 }
 
+// ================================================================================ fp32 validation mode
+// Same path, every activation and contraction in fp32 (fp32.cu): one sample per call, the adapter applied as two explicit
+// rank-r products per projection instead of the K-concatenated operand pair, no CLS shortcut, no graphs.
+int sg(ttl_ctx* c, const float* A, int lda, const float* B, int ldb, int b_kn, int M, int N, int K, float alpha,
+       const float* bias, const float* resid, int ldr, float* out, int ldo, int epi, float* out2, const float* aux,
+       cudaStream_t st) {
+  SgemmArgs a;
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.b_kn = b_kn; a.M = M; a.N = N; a.K = K; a.alpha = alpha; a.bias = bias;
+  a.resid = resid; a.ldr = ldr; a.out = out; a.ldo = ldo; a.epi = epi; a.out2 = out2; a.aux = aux;
+  c->launches++;
+  cudaError_t e = launch_sgemm(a, st);
+  if (e != cudaSuccess) { c->err = std::string("sgemm: ") + cudaGetErrorString(e); return e == cudaErrorInvalidValue ? TTL_E_SHAPE : TTL_E_CUDA; }
+  return TTL_OK;
+}
+
+const float* lora_ptr(const ttl_ctx* c, int layer, int which) {   // live fp32 factors of sample 0
+  return c->lp + static_cast<int64_t>(layer - c->lo) * c->lora_per_layer + static_cast<int64_t>(which) * c->r * c->d;
+}
+
+int f32_embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
+  launch_im2col_f32(images, c->patches_f, V, c->cfg.image_size, c->cfg.patch, st);
+  SgemmArgs a;
+  a.A = c->patches_f; a.lda = c->Kp; a.B = c->wpatch_f; a.ldb = c->Kp; a.M = V * c->T; a.N = c->d; a.K = c->Kp;
+  a.out = x; a.ldo = c->d; a.epi = SE_PATCH; a.pos = c->pos; a.tpv = c->T;
+  if (launch_sgemm(a, st) != cudaSuccess) { c->err = "sgemm (patch embedding) failed"; return TTL_E_CUDA; }
+  launch_embed_preln(x, c->cls, c->pos, c->preg, c->preb, V, c->tokens, c->d, c->cfg.ln_eps, st);
+  c->launches += 3;
+  return check_launch(c, "f32_embed");
+}
+
+int f32_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_out, int V, bool lora_on, Tape* tp, TapeF* tf,
+              cudaStream_t st) {
+  const LayerW& w = c->lw[layer];
+  const int M = V * c->tokens, d = c->d, F = c->F, r = c->r;
+  float* h1 = tf ? tf->h1 : c->Hf;
+  float* qkv = tf ? tf->qkv : c->QKVf;
+  float* ao = tf ? tf->ao : c->AOf;
+  float* h2 = tf ? tf->h2 : c->Hf;
+  float* g = tf ? tf->g : c->Gf;
+  float* Tq = tf ? tf->Tq : c->Tqf;
+  float* Tv = tf ? tf->Tv : c->Tvf;
+  const bool lora = has_lora(c, layer);
+  launch_layernorm_f32(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+  RET_IF(sg(c, h1, d, w.wqkv_f, d, 0, M, 3 * d, d, 1.f, w.bqkv, nullptr, 0, qkv, 3 * d, SE_LINEAR, nullptr, nullptr, st));
+  if (lora && (lora_on || tf)) {   // T = h1 A^T (needed by dB even while B == 0)
+    RET_IF(sg(c, h1, d, lora_ptr(c, layer, TTL_LORA_A_Q), d, 0, M, r, d, 1.f, nullptr, nullptr, 0, Tq, r, SE_LINEAR, nullptr, nullptr, st));
+    RET_IF(sg(c, h1, d, lora_ptr(c, layer, TTL_LORA_A_V), d, 0, M, r, d, 1.f, nullptr, nullptr, 0, Tv, r, SE_LINEAR, nullptr, nullptr, st));
+  }
+  if (lora && lora_on) {           // q += s T_q B_q^T ; v += s T_v B_v^T   (peft: base(x) + B(A(x)) * scaling)
+    RET_IF(sg(c, Tq, r, lora_ptr(c, layer, TTL_LORA_B_Q), r, 0, M, d, r, c->s, nullptr, qkv, 3 * d, qkv, 3 * d, SE_LINEAR, nullptr, nullptr, st));
+    RET_IF(sg(c, Tv, r, lora_ptr(c, layer, TTL_LORA_B_V), r, 0, M, d, r, c->s, nullptr, qkv + 2 * d, 3 * d, qkv + 2 * d, 3 * d, SE_LINEAR,
+              nullptr, nullptr, st));
+  }
+  launch_attention_f32_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
+  RET_IF(sg(c, ao, d, w.wo_f, d, 0, M, d, d, 1.f, w.bo, x_in, d, x_mid, d, SE_LINEAR, nullptr, nullptr, st));
+  launch_layernorm_f32(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
+  RET_IF(sg(c, h2, d, w.w1_f, d, 0, M, F, d, 1.f, w.b1, nullptr, 0, g, F, SE_GELU, tf ? tf->z : nullptr, nullptr, st));
+  RET_IF(sg(c, g, F, w.w2_f, F, 0, M, d, F, 1.f, w.b2, x_mid, d, x_out, d, SE_LINEAR, nullptr, nullptr, st));
+  c->launches += 3;
+  return check_launch(c, "f32_layer");
+}
+
+int f32_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
+  RET_IF(f32_embed(c, images, V, c->XK, st));
+  for (int l = 0; l < c->lo; ++l) RET_IF(f32_layer(c, l, c->XK, c->XB, c->XK, V, false, nullptr, nullptr, st));
+  return TTL_OK;
+}
+
+int f32_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float* logits, float* entropy, cudaStream_t st) {
+  const float* cur = x_in;
+  for (int l = c->lo; l < c->L; ++l) {
+    RET_IF(f32_layer(c, l, cur, c->XB, c->XA, V, !c->b_zero, nullptr, nullptr, st));
+    cur = c->XA;
+  }
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
+  c->launches += 4;
+  return check_launch(c, "f32_tail_infer");
+}
+
+int f32_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
+  const float* cur = x_in;
+  for (int l = c->lo; l < c->L; ++l) {
+    Tape& tp = c->tape[l - c->lo];
+    RET_IF(f32_layer(c, l, cur, tp.x_mid, tp.x_out, G, !c->b_zero, &tp, &c->tapef[l - c->lo], st));
+    cur = tp.x_out;
+  }
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  c->launches += 2;
+  c->last_train_views = G;
+  c->last_train_samples = 1;
+  c->last_train_in = x_in;
+  return check_launch(c, "f32_tail_train");
+}
+
+int f32_backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
+  if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
+  const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
+  const float* x_last = c->tape[c->n_train - 1].x_out;
+  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX, c->DXB, G,
+                  c->C, c->P, c->tokens, d, c->cfg.ln_eps, st);
+  c->launches += 4;
+  float* dx = c->DX;
+  float* dx2 = c->DX2;
+  for (int l = c->L - 1; l >= c->lo; --l) {
+    const LayerW& w = c->lw[l];
+    Tape& tp = c->tape[l - c->lo];
+    TapeF& tf = c->tapef[l - c->lo];
+    const float* x_in = (l == c->lo) ? c->last_train_in : c->tape[l - c->lo - 1].x_out;
+    // dz = (dx_out W2) * gelu'(z) ; dh2 = dz W1 ; dx_mid = dx_out + LN2'(dh2)
+    RET_IF(sg(c, dx, d, w.w2_f, F, 1, Mg, F, d, 1.f, nullptr, nullptr, 0, c->DZf, F, SE_GELU_BWD, nullptr, tf.z, st));
+    RET_IF(sg(c, c->DZf, F, w.w1_f, d, 1, Mg, d, F, 1.f, nullptr, nullptr, 0, c->DH, d, SE_LINEAR, nullptr, nullptr, st));
+    launch_layernorm_bwd(c->DH, tp.x_mid, w.ln2g, dx, dx2, c->DXB, Mg, d, c->cfg.ln_eps, st);
+    // d attn_out = dx_mid Wo ; attention backward
+    RET_IF(sg(c, dx2, d, w.wo_f, d, 1, Mg, d, d, 1.f, nullptr, nullptr, 0, c->DAOf, d, SE_LINEAR, nullptr, nullptr, st));
+    launch_attention_f32_bwd(tf.qkv, tf.ao, c->DAOf, tp.lse, c->DQKVf, G, c->tokens, c->H, 0.125f, st);
+    c->launches += 2;
+    const bool lora = has_lora(c, l);
+    if (lora) {
+      float* gl = c->lg + static_cast<int64_t>(l - c->lo) * c->lora_per_layer;
+      float *gAq = gl, *gBq = gl + r * d, *gAv = gl + 2 * r * d, *gBv = gl + 3 * r * d;
+      // dB = s dY^T (X A^T)
+      launch_reduce_tn_f32(c->DQKVf, 3 * d, d, tf.Tq, r, r, Mg, c->s, gBq, 0, st);
+      launch_reduce_tn_f32(c->DQKVf + 2 * d, 3 * d, d, tf.Tv, r, r, Mg, c->s, gBv, 0, st);
+      c->launches += 2;
+      if (!c->b_zero) {   // U = s dY B ; dA = U^T X
+        RET_IF(sg(c, c->DQKVf, 3 * d, lora_ptr(c, l, TTL_LORA_B_Q), r, 1, Mg, r, d, c->s, nullptr, nullptr, 0, c->Uqf, r, SE_LINEAR, nullptr, nullptr, st));
+        RET_IF(sg(c, c->DQKVf + 2 * d, 3 * d, lora_ptr(c, l, TTL_LORA_B_V), r, 1, Mg, r, d, c->s, nullptr, nullptr, 0, c->Uvf, r, SE_LINEAR, nullptr, nullptr, st));
+        launch_reduce_tn_f32(tf.h1, d, d, c->Uqf, r, r, Mg, 1.f, gAq, 1, st);
+        launch_reduce_tn_f32(tf.h1, d, d, c->Uvf, r, r, Mg, 1.f, gAv, 1, st);
+        c->launches += 2;
+      } else {
+        cudaMemsetAsync(gAq, 0, sizeof(float) * r * d, st);
+        cudaMemsetAsync(gAv, 0, sizeof(float) * r * d, st);
+      }
+    }
+    if (l > c->lo) {   // dh1 = dqkv Wqkv (+ U_q A_q + U_v A_v) ; dx_in = dx_mid + LN1'(dh1)
+      RET_IF(sg(c, c->DQKVf, 3 * d, w.wqkv_f, d, 1, Mg, d, 3 * d, 1.f, nullptr, nullptr, 0, c->DH, d, SE_LINEAR, nullptr, nullptr, st));
+      if (lora && !c->b_zero) {
+        RET_IF(sg(c, c->Uqf, r, lora_ptr(c, l, TTL_LORA_A_Q), d, 1, Mg, d, r, 1.f, nullptr, c->DH, d, c->DH, d, SE_LINEAR, nullptr, nullptr, st));
+        RET_IF(sg(c, c->Uvf, r, lora_ptr(c, l, TTL_LORA_A_V), d, 1, Mg, d, r, 1.f, nullptr, c->DH, d, c->DH, d, SE_LINEAR, nullptr, nullptr, st));
+      }
+      launch_layernorm_bwd(c->DH, x_in, w.ln1g, dx2, dx, c->DXB, Mg, d, c->cfg.ln_eps, st);
+      c->launches++;
+    }
+  }
+  return check_launch(c, "f32_backward");
+}
+
 // bf16 operand packs of the live factors of samples [0, S), K-concatenated
 int repack(ttl_ctx* c, int S, cudaStream_t st) {
   for (int i = 0; i < c->n_lora; ++i) {
@@ -597,6 +757,49 @@ int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams&
   return TTL_OK;
 }
 
+// adapt_body in the fp32 validation mode: one sample (S == 1), same sequence, same head / optimiser kernels (they are fp32)
+int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
+  RET_IF(lora_reset(c, 1, st));
+  RET_IF(f32_frozen(c, images, V, st));
+  const int K = static_cast<int>(V * hp.selection_p);
+  const size_t view_elems = static_cast<size_t>(c->tokens) * c->d;
+  if (hp.head == TTL_HEAD_TPT) {
+    RET_IF(f32_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    if (hp.tta_steps > 0 && K > 0) {
+      launch_select(c->entropy, V, K, forced ? c->idx : nullptr, c->idx, st);
+      launch_gather_views(c->XK, c->TIN, c->idx, K, 0, c->tokens, c->d, st);
+      c->launches += 2;
+      for (int step = 0; step < hp.tta_steps; ++step) {
+        RET_IF(f32_tail_train(c, c->TIN, K, st));
+        if (step == 0) {
+          launch_tpt_loss(c->logits, c->idx, K, c->C, c->loss, c->dlogits, st);
+        } else {
+          launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, K, c->C, c->P, st);
+          launch_tpt_loss(c->logits_c, nullptr, K, c->C, c->loss, c->dlogits, st);
+        }
+        c->launches += 3;
+        RET_IF(f32_backward(c, c->dlogits, K, st));
+        RET_IF(adamw(c, hp, 1, st));
+      }
+    }
+  } else {
+    const int nsteps = hp.tta_steps * hp.tta_steps;
+    if (nsteps == 0) RET_IF(f32_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
+    for (int step = 0; step < nsteps; ++step) {
+      RET_IF(f32_tail_train(c, c->XK, V, st));
+      float* lg = step == 0 ? c->logits : c->logits_c;
+      float* en = step == 0 ? c->entropy : c->entropy_c;
+      launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, V, c->C, c->P, st);
+      launch_deyo_loss(lg, V, c->C, hp.deyo_margin_e0, c->loss, c->dlogits, st);
+      c->launches += 3;
+      RET_IF(f32_backward(c, c->dlogits, V, st));
+      RET_IF(adamw(c, hp, 1, st));
+    }
+  }
+  (void)view_elems;
+  return f32_tail_infer(c, c->XK, 1, c->pred_feats, c->pred, c->pred_entropy, st);   // view 0 with the adapted factors
+}
+
 int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int S, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
   if (!o) return TTL_OK;
   const int K = static_cast<int>(V * hp.selection_p);
@@ -622,6 +825,12 @@ int validate_run(ttl_ctx* c, int S, int V, const ttl_hparams* hp) {
 // images_dev == nullptr: the bf16 patch matrix c->patches is already in place (view generator).
 int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
   const int64_t before = c->launches;
+  if (c->f32) {
+    if (S != 1 || images_dev == nullptr) { c->err = "fp32 validation mode: one sample per call, fp32 views as input"; return TTL_E_SHAPE; }
+    int r = adapt_body_f32(c, images_dev, V, *hp, forced, st);
+    c->last_launches = c->launches - before;
+    return r;
+  }
   if (!c->graphs || c->prof || st == nullptr) {  // the legacy default stream cannot be captured
     int r = adapt_body(c, images_dev, S, V, *hp, forced, st);
     c->last_launches = c->launches - before;
@@ -700,6 +909,18 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     g_create_err = "unsupported geometry (width%128, head_dim 64, rank 16/32, layer range, even patch, max_samples <= 16)";
     return TTL_E_SHAPE;
   }
+  if (cfg->precision != TTL_PRECISION_BF16 && cfg->precision != TTL_PRECISION_FP32) { g_create_err = "unknown precision"; return TTL_E_INVALID; }
+  if (cfg->precision == TTL_PRECISION_FP32 && cfg->max_samples > 1) {
+    g_create_err = "the fp32 validation mode adapts one sample per call (max_samples <= 1)";
+    return TTL_E_SHAPE;
+  }
+  if (cfg->precision == TTL_PRECISION_FP32) {
+    const int tk = (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch) + 1;
+    if (attention_f32_bwd_smem(tk) > 227 * 1024) {
+      g_create_err = "the fp32 validation mode stages Q/K/V/dO of one (view, head) in shared memory: too many tokens";
+      return TTL_E_SHAPE;
+    }
+  }
   cudaSetDevice(cfg->device);
   ttl_ctx* c = new ttl_ctx();
   c->cfg = *cfg;
@@ -713,6 +934,7 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   c->Vm = cfg->max_views; c->Sm = cfg->max_samples > 0 ? cfg->max_samples : 1;
   c->VVm = c->Vm * c->Sm; c->Mm = c->VVm * c->tokens; c->Cm = cfg->max_classes;
   c->n_train = c->L - c->lo; c->n_lora = c->hi - c->lo + 1;
+  c->f32 = cfg->precision == TTL_PRECISION_FP32;
   const int d = c->d, F = c->F, M = c->Mm;
   int rc = TTL_OK;
 #define A(p, n) if (rc == TTL_OK) rc = dalloc(c, &(p), static_cast<size_t>(n))
@@ -750,6 +972,22 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   A(c->DXB, static_cast<size_t>(M) * d); A(c->DZ, static_cast<size_t>(M) * F); A(c->DAO, static_cast<size_t>(M) * d);
   A(c->DQKV, static_cast<size_t>(M) * 3 * d); A(c->U, static_cast<size_t>(M) * 64 * c->Sm);
   A(c->ws, static_cast<size_t>((M + 127) / 128 + c->Sm) * d * 32);
+  if (c->f32) {
+    const size_t Mz = static_cast<size_t>(M);
+    A(c->wpatch_f, static_cast<size_t>(d) * c->Kp); A(c->patches_f, static_cast<size_t>(c->VVm) * c->T * c->Kp);
+    A(c->Hf, Mz * d); A(c->QKVf, Mz * 3 * d); A(c->AOf, Mz * d); A(c->Gf, Mz * F); A(c->Tqf, Mz * c->r); A(c->Tvf, Mz * c->r);
+    A(c->DZf, Mz * F); A(c->DAOf, Mz * d); A(c->DQKVf, Mz * 3 * d); A(c->Uqf, Mz * c->r); A(c->Uvf, Mz * c->r);
+    for (int l = 0; l < c->L && rc == TTL_OK; ++l) {
+      LayerW& w = c->lw[l];
+      A(w.wqkv_f, 3 * d * d); A(w.wo_f, d * d); A(w.w1_f, F * d); A(w.w2_f, d * F);
+    }
+    c->tapef.resize(c->n_train);
+    for (int t = 0; t < c->n_train && rc == TTL_OK; ++t) {
+      TapeF& tf = c->tapef[t];
+      A(tf.h1, Mz * d); A(tf.qkv, Mz * 3 * d); A(tf.ao, Mz * d); A(tf.h2, Mz * d); A(tf.z, Mz * F); A(tf.g, Mz * F);
+      A(tf.Tq, Mz * c->r); A(tf.Tv, Mz * c->r);
+    }
+  }
   c->lora_per_layer = 4LL * c->r * d;
   c->lora_total = c->lora_per_layer * c->n_lora;
   A(c->lp, c->lora_total * c->Sm); A(c->lg, c->lora_total * c->Sm); A(c->l0, c->lora_total);
@@ -840,6 +1078,8 @@ int ttl_set_weight(ttl_ctx* c, int32_t layer, int32_t kind, const float* host, i
       case TTL_W_PATCH_EMB: {
         const int K = 3 * c->cfg.patch * c->cfg.patch;
         if (!need(static_cast<int64_t>(d) * K)) return TTL_E_SHAPE;
+        if (c->f32) CK(cudaMemcpy2D(c->wpatch_f, sizeof(float) * c->Kp, host, sizeof(float) * K, sizeof(float) * K, d,
+                                    cudaMemcpyHostToDevice));
         return upload_bf16(c, c->wpatch, c->Kp, nullptr, 0, 0, host, d, K);   // padding columns stay zero
       }
       default: c->err = "ttl_set_weight: unknown kind"; return TTL_E_INVALID;
@@ -862,14 +1102,18 @@ int ttl_set_weight(ttl_ctx* c, int32_t layer, int32_t kind, const float* host, i
     case TTL_W_Q_W: case TTL_W_K_W: case TTL_W_V_W: {
       if (!need(static_cast<int64_t>(d) * d)) return TTL_E_SHAPE;
       const int blk = kind == TTL_W_Q_W ? 0 : (kind == TTL_W_K_W ? 1 : 2);
+      if (c->f32) RET_IF(upload_f32(c, w.wqkv_f + static_cast<size_t>(blk) * d * d, host, numel));
       // wqkv rows [blk*d, (blk+1)*d); transpose wqkvT [d, 3d] columns [blk*d, ...)
       return upload_bf16(c, w.wqkv + static_cast<size_t>(blk) * d * d, d, tr ? w.wqkvT : nullptr, 3 * d, blk * d, host, d, d);
     }
     case TTL_W_O_W: if (!need(static_cast<int64_t>(d) * d)) return TTL_E_SHAPE;
+      if (c->f32) RET_IF(upload_f32(c, w.wo_f, host, numel));
       return upload_bf16(c, w.wo, d, tr ? w.woT : nullptr, d, 0, host, d, d);
     case TTL_W_FC1_W: if (!need(static_cast<int64_t>(F) * d)) return TTL_E_SHAPE;
+      if (c->f32) RET_IF(upload_f32(c, w.w1_f, host, numel));
       return upload_bf16(c, w.w1, d, tr ? w.w1T : nullptr, F, 0, host, F, d);     // w1T [d, F]
     case TTL_W_FC2_W: if (!need(static_cast<int64_t>(d) * F)) return TTL_E_SHAPE;
+      if (c->f32) RET_IF(upload_f32(c, w.w2_f, host, numel));
       return upload_bf16(c, w.w2, F, tr ? w.w2T : nullptr, d, 0, host, d, F);     // w2T [F, d]
     default: c->err = "ttl_set_weight: unknown kind"; return TTL_E_INVALID;
   }
@@ -967,6 +1211,18 @@ int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t tr
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->f32) {
+    RET_IF(f32_frozen(c, images_dev, n_views, st));
+    if (train) {
+      RET_IF(f32_tail_train(c, c->XK, n_views, st));
+      launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits, c->entropy, n_views, c->C, c->P, st);
+      c->launches += 2;
+    } else {
+      RET_IF(f32_tail_infer(c, c->XK, n_views, c->feats, c->logits, c->entropy, st));
+    }
+    if (logits_dev) CK(cudaMemcpyAsync(logits_dev, c->logits, sizeof(float) * n_views * c->C, cudaMemcpyDeviceToDevice, st));
+    return check_launch(c, "ttl_forward");
+  }
   if (c->pack_samples != 1) RET_IF(repack(c, 1, st));
   RET_IF(forward_frozen(c, images_dev, n_views, st));
   if (train) {
@@ -983,6 +1239,7 @@ int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t tr
 int ttl_backward(ttl_ctx* c, const float* dlogits_dev, void* stream) {
   if (!c || !dlogits_dev) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
+  if (c->f32) return f32_backward(c, dlogits_dev, c->last_train_views, static_cast<cudaStream_t>(stream));
   return backward(c, dlogits_dev, c->last_train_views, static_cast<cudaStream_t>(stream));
 }
 

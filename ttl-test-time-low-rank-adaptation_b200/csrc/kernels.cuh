@@ -84,4 +84,39 @@ void launch_adamw(float* p, const float* g, float* m, float* v, int n, int step,
 // p[i] <- p0[i % n0], m <- 0, v <- 0   (LoRA_AB.reset + optimizer.load_state_dict(optim_state), ttl.py:338-344; n = S * n0)
 void launch_lora_reset(float* p, const float* p0, float* m, float* v, int n, int n0, cudaStream_t st);
 
+// ---- fp32.cu   fp32 validation mode (ttl_config.precision = TTL_PRECISION_FP32): CUDA-core kernels, fp32 everywhere
+enum SgemmEpi : int {
+  SE_LINEAR = 0,    // out = alpha*acc (+ bias[n]) (+ resid[m,n])
+  SE_GELU = 1,      // z = alpha*acc + bias; out2 (optional) = z; out = z*sigmoid(1.702 z)
+  SE_GELU_BWD = 2,  // out = alpha*acc * dQuickGELU(aux[m,n])
+  SE_PATCH = 3      // patch-embed scatter: row (view, patch) -> token row view*(T+1)+1+patch, + pos[1+patch, n]
+};
+struct SgemmArgs {
+  const float* A = nullptr; int lda = 0;       // [M, K], K contiguous
+  const float* B = nullptr; int ldb = 0;       // b_kn == 0: [N, K] (K contiguous);  b_kn == 1: [K, N] (N contiguous)
+  int b_kn = 0;
+  int M = 0, N = 0, K = 0;
+  float alpha = 1.f;
+  const float* bias = nullptr;
+  const float* resid = nullptr; int ldr = 0;
+  float* out = nullptr; int ldo = 0;
+  float* out2 = nullptr;
+  const float* aux = nullptr;
+  const float* pos = nullptr; int tpv = 0;
+  int epi = SE_LINEAR;
+};
+cudaError_t launch_sgemm(const SgemmArgs& a, cudaStream_t st);
+// qkv fp32 [V*tokens, 3d] -> out fp32 [V*tokens, d], lse (nullable) [V, heads, tokens]
+void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st);
+void launch_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int V,
+                              int tokens, int heads, float scale, cudaStream_t st);
+size_t attention_f32_fwd_smem(int tokens);
+size_t attention_f32_bwd_smem(int tokens);
+void launch_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, int rows, int d, float eps,
+                          cudaStream_t st);
+void launch_im2col_f32(const float* images, float* patches, int V, int S, int p, cudaStream_t st);
+// out[w, j] (or out[j, w] if transpose_out) = scale * sum_m wide[m, w] * narrow[m, j]
+void launch_reduce_tn_f32(const float* wide, int ldw, int nw, const float* narrow, int ldn, int nn, int M, float scale,
+                          float* out, int transpose_out, cudaStream_t st);
+
 }  // namespace ttl

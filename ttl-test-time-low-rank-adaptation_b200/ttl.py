@@ -13,6 +13,7 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
                   the fused per-sample call
   --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
   --concurrent_samples S  adapt S test samples per library call (default 3; 1 = strictly one at a time)
+  --precision fp32  validation mode: every activation/contraction in fp32 (held to 1e-4 against the reference), one sample per call
   --vision_checkpoint F  load the image tower from a checkpoint file (HF or OpenAI format) instead of the local HF cache
   --views_on_device  ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
                   (bit-exact with the reference's PIL/torchvision AugMixAugmenter) instead of 64 fp32 views per sample
@@ -291,7 +292,11 @@ def main_worker(gpu, args):
     from clip.custom_clip import get_coop
     rank, world = args.rank_id, args.world_size
     first = args.test_sets.split("/")[0]
-    extra = {}
+    extra = {"precision": args.precision}
+    if args.precision == "fp32":
+        args.concurrent_samples = 1
+        if args.views_on_device:
+            raise NotImplementedError("--views_on_device feeds the bf16 patch operand; the fp32 validation mode takes fp32 views")
     if args.vision_checkpoint:      # HF safetensors/bin or OpenAI-format .pt (ttl_b200/weights.py); default: local HF cache
         from ttl_b200.weights import load_vision_checkpoint
         extra["weights"] = load_vision_checkpoint(args.vision_checkpoint)
@@ -405,6 +410,8 @@ def build_parser():
     p.add_argument('--views_on_host', action='store_true', default=False)
     p.add_argument('--views_on_device', action='store_true', default=False,
                    help='generate the views on the GPU from the uint8 image (bit-exact with PIL/torchvision)')
+    p.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                   help='bf16 = tensor-core path (default); fp32 = validation mode (fp32 everywhere, one sample per call)')
     p.add_argument('--vision_checkpoint', default=None, type=str,
                    help='CLIP checkpoint file for the image tower: HF model.safetensors / pytorch_model.bin or OpenAI ViT-*.pt')
     p.add_argument('--concurrent_samples', default=3, type=int,

@@ -21,7 +21,7 @@ class TtlConfig(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("proj_dim", C.c_int32), ("max_views", C.c_int32),
                 ("max_classes", C.c_int32), ("lora_rank", C.c_int32), ("lora_alpha", C.c_float),
                 ("lora_layer_lo", C.c_int32), ("lora_layer_hi", C.c_int32), ("ln_eps", C.c_float),
-                ("device", C.c_int32), ("max_samples", C.c_int32)]
+                ("device", C.c_int32), ("max_samples", C.c_int32), ("precision", C.c_int32)]
 
 
 class TtlHparams(C.Structure):
@@ -56,6 +56,7 @@ W_CLASS_EMB, W_PATCH_EMB, W_POS_EMB, W_PRE_LN_G, W_PRE_LN_B, W_POST_LN_G, W_POST
 LORA_A_Q, LORA_B_Q, LORA_A_V, LORA_B_V = range(4)
 LORA_PARAM, LORA_GRAD, LORA_INIT = range(3)
 HEAD_TPT, HEAD_DEYO = 0, 1
+PRECISION_BF16, PRECISION_FP32 = 0, 1
 VIEW_CLEAN, VIEW_CROP = 0, 1
 TW_TOKEN_EMB, TW_POS_EMB, TW_FINAL_LN_G, TW_FINAL_LN_B, TW_TEXT_PROJ = range(5)
 EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_PATCH_F32, EPI_F32, EPI_GELU_BWD = range(6)

@@ -68,7 +68,7 @@ class Pending:
 class Engine:
     def __init__(self, arch: str = "ViT-B/16", max_views: int = 64, max_classes: int = 1000, lora_rank: int = 16,
                  lora_alpha: float = 32.0, layer_range: Sequence[int] = (9, 11), device: int = 0,
-                 geometry: Optional[dict] = None, max_samples: int = 1):
+                 geometry: Optional[dict] = None, max_samples: int = 1, precision: str = "bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("ttl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = L.load()
@@ -82,7 +82,8 @@ class Engine:
         self.n_classes = 0
         cfg = L.TtlConfig(g["image_size"], g["patch"], g["width"], g["layers"], g["heads"], g["mlp_dim"], g["proj_dim"],
                           max_views, max_classes, lora_rank, lora_alpha, self.layer_lo, self.layer_hi, 1e-5, device,
-                          self.max_samples)
+                          self.max_samples, {"bf16": L.PRECISION_BF16, "fp32": L.PRECISION_FP32}[precision])
+        self.precision = precision
         ctx = C.c_void_p()
         L.check(self.lib.ttl_create(C.byref(ctx), C.byref(cfg)))
         self.ctx = ctx
