@@ -128,3 +128,49 @@ def test_fp32_mode_rejects_what_it_does_not_cover():
         Engine("ViT-B/16", max_views=8, max_classes=16, max_samples=2, precision="fp32")      # one sample per call
     with pytest.raises(RuntimeError):
         Engine("ViT-L/14", max_views=8, max_classes=16, layer_range=(21, 23), precision="fp32")   # 257 tokens: smem staging
+
+
+def test_bf16_path_agrees_with_fp32_mode_on_a_synthetic_set(b16_weights):
+    """North-star accuracy parity at the metric's shape (64 views, 1000 classes): adapted top-1 of the bf16 tensor-core path
+    vs the fp32 validation mode (itself within 5e-6 of the reference, above) on 96 synthetic samples, free-running on both
+    sides.  Samples whose fp32 adapted top-1 margin is below 0.5 logit are not counted (bf16 moves a logit by ~0.05)."""
+    import time
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-B/16"]
+    lora0 = O.lora_init(arch, O.LoraSpec(), seed=0)
+    V, n, S, C = 64, 96, 6, 1000
+    text = O.make_text_features(C, arch.proj, seed=3)
+    fast = Engine("ViT-B/16", max_views=V, max_classes=C, layer_range=(9, 11), max_samples=S)
+    slow = Engine("ViT-B/16", max_views=V, max_classes=C, layer_range=(9, 11), precision="fp32")
+    try:
+        for e in (fast, slow):
+            e.load_weights(b16_weights)
+            e.set_lora_init(lora0)
+            e.set_text_features(text, math.log(100.0))
+        hp = Hparams(head="tpt")
+        counted = agree = agree_all = same_sel = 0
+        t_slow = 0.0
+        for b in range(0, n, S):
+            imgs = torch.stack([O.make_synthetic_views(V, arch.image_size, seed=900 + b + j) for j in range(S)]).cuda()
+            got = fast.adapt_predict_batch(imgs, hp, want=("pred_logits", "idx"))
+            for j in range(S):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ref = slow.adapt_predict(imgs[j], hp, want=("pred_logits", "idx"))
+                torch.cuda.synchronize()
+                t_slow += time.perf_counter() - t0
+                rl = ref["pred_logits"].cpu()
+                top2 = rl.topk(2).values
+                same = int(rl.argmax()) == int(got["pred_logits"][j].argmax())
+                agree_all += int(same)
+                same_sel += int(sorted(ref["idx"].cpu().tolist()) == sorted(got["idx"][j].cpu().tolist()))
+                if float(top2[0] - top2[1]) >= 0.5:
+                    counted += 1
+                    agree += int(same)
+        print(f"bf16 vs fp32 mode: adapted top-1 agreement {agree}/{counted} counted, {agree_all}/{n} overall; identical "
+              f"confident-view sets {same_sel}/{n}; fp32 mode {t_slow / n * 1e3:.0f} ms/sample")
+        assert counted >= n // 3, counted
+        assert agree >= math.ceil(0.99 * counted), (agree, counted)
+    finally:
+        fast.close()
+        slow.close()
