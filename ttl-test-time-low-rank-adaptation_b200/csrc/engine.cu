@@ -258,7 +258,11 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   bf16* gb = tp ? tp->g : c->Gb;
   bf16* Tb = tp ? tp->T : c->Tm;
   const bool lora = has_lora(c, layer);
-  launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+  // TTL_DBG_SKIP (development only, results are garbage): 1 = no LayerNorm launches, 2 = no attention launches -- upper
+  // bound of what removing that kernel would buy under the power cap
+  static const char* skip_env = std::getenv("TTL_DBG_SKIP");
+  static const int skip = skip_env ? std::atoi(skip_env) : 0;
+  if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
   c->launches++;
   if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T per sample (needed by dB even while B == 0)
     if (S != c->pack_samples) { c->err = "run_layer: adapter packs were built for another sample count"; return TTL_E_STATE; }
@@ -283,7 +287,7 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.M = M; g.N = 3 * d; g.epi = EPI_BF16; g.bias = w.bqkv; g.out = qkv; g.ldo = 3 * d;
     RET_IF(gemm(c, g, st));
   }
-  launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
+  if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
   c->launches++;
   {
     GemmArgs g;
@@ -292,7 +296,7 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.bo; g.out = x_mid; g.ldo = d; g.resid = x_in; g.ldr = d;
     RET_IF(gemm(c, g, st));
   }
-  launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
+  if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
   c->launches++;
   {
     GemmArgs g;
