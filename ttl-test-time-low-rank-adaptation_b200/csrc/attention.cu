@@ -848,6 +848,316 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 
+// =============================================================================================== tcgen05 forward, two tiles in flight
+// Same arithmetic as attention_fwd_tc_kernel, re-plumbed so the MUFU-bound softmax never waits for loads or for the other
+// tile's MMAs.  One CTA per SM (220 KB smem, all 512 TMEM columns) walks (view, head) units; the two 128-query tiles of a
+// unit are processed CONCURRENTLY by two softmax warpgroups and share one copy of K and V:
+//   warp 0 (one thread)  TMA producer: K + both Q tiles of unit u+1 are (re)loaded as soon as both S MMAs of unit u have
+//                        retired (P has its own smem, so K/Q die early); V is double-buffered across units
+//   warp 1 (one thread)  tcgen05.mma issue: S0 = Q0 K^T -> TMEM [0,208), S1 = Q1 K^T -> TMEM [256,464), then O_t = P_t V block
+//                        by block, alternating tiles as the warpgroups deliver P
+//   warps 2-5 / 6-9      softmax warpgroup of tile 0 / tile 1: one thread per query row, exact two-pass softmax from TMEM,
+//                        bf16 P into the UMMA K-major swizzled layout, O / rowsum -> swizzled smem -> one TMA store per tile
+// K/V are read from L2 once per unit instead of once per tile, and the load latency of unit u+1 hides behind unit u.
+constexpr int PP_THREADS = 320;
+constexpr int PP_PTILE = 3 * 16384 + 4096;     // P of one tile: three 64-key blocks (128 rows x 128 B) + the 16-key tail block
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
+                        int units, int keys, float scale_log2, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_pp_raw[];
+  // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0, per warpgroup: [it][t][stage]
+#define PP_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && wg_tid == 0) dbg[(it * 2 + t) * 8 + (k)] = clock64(); } while (0)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_pp_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = keys * 128;                       // bytes of K (or V): multiple of 1024 (keys % 16 == 0, keys >= 64)
+  uint8_t* sQ = smem;                              // [2 tiles] 16 KB each
+  uint8_t* sK = sQ + 2 * 16384;
+  uint8_t* sV = sK + KB;                           // [2 buffers]
+  uint8_t* sP = sV + 2 * KB;                       // [2 tiles] PP_PTILE each; block 2 doubles as the tile's output stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PP_PTILE);
+  uint64_t* bar_kq = bars;            // K + Q0 + Q1 of the unit landed
+  uint64_t* bar_v = bars + 1;         // [2] V buffer landed
+  uint64_t* bar_vfree = bars + 3;     // [2] every MMA that reads the V buffer has retired
+  uint64_t* bar_s = bars + 5;         // [2] S_t complete in TMEM
+  uint64_t* bar_o = bars + 7;         // [2] O_t complete in TMEM (P_t dead)
+  uint64_t* bar_tfree = bars + 9;     // [2] O_t copied to registers: TMEM region t reusable
+  uint64_t* bar_p = bars + 11;        // [2][4] P block b of tile t written (index 3 = tail block)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * DH;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(bar_kq, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_v[i], 1);
+      mbar_init(&bar_vfree[i], 1);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_tfree[i], 4);
+      for (int b = 0; b < 4; ++b) mbar_init(&bar_p[i * 4 + b], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_trigger();
+  const int n_full = keys / 64, tail = keys - n_full * 64;      // 64-key P blocks + an optional 16-key tail block
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int view = unit / heads, h = unit - view * heads;
+        if (it > 0) mbar_wait(&bar_s[1], (it - 1) & 1);          // both S MMAs of the previous unit retired: K, Q0, Q1 are dead
+        mbar_expect_tx(bar_kq, KB + 2 * 16384);
+        tma_load_3d(&tmKV, bar_kq, sK, d + h * DH, 0, view);
+        tma_load_3d(&tmQ, bar_kq, sQ, h * DH, 0, view);
+        tma_load_3d(&tmQ, bar_kq, sQ + 16384, h * DH, 128, view);
+        const int b = it & 1;
+        if (it >= 2) mbar_wait(&bar_vfree[b], ((it >> 1) - 1) & 1);
+        mbar_expect_tx(&bar_v[b], KB);
+        tma_load_3d(&tmKV, &bar_v[b], sV + b * KB, 2 * d + h * DH, 0, view);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, static_cast<uint32_t>(keys));
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+      const uint32_t v_lbo = static_cast<uint32_t>(KB);
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int b = it & 1;
+        mbar_wait(bar_kq, ph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (it > 0) mbar_wait(&bar_tfree[t], ph ^ 1);           // the previous unit's O_t has left TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + t * 256, umma_desc_k_sw128(qa + t * 16384 + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s,
+                      k != 0 ? 1u : 0u);
+          umma_commit(&bar_s[t]);
+        }
+        mbar_wait(&bar_v[b], (it >> 1) & 1);
+        const uint32_t va = smem_u32(sV + b * KB);
+        int kk = 0;
+        for (int blk = 0; blk < n_full; ++blk) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&bar_p[t * 4 + blk], ph);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(sP + t * PP_PTILE + blk * 16384);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_bf16(tmem + t * 256, umma_desc_k_sw128(pa + j * 32), umma_desc(va + (kk + j) * 2048, 1024, v_lbo, 2), idesc_o,
+                        (kk + j) != 0 ? 1u : 0u);
+            if (!tail && blk == n_full - 1) umma_commit(&bar_o[t]);
+          }
+          kk += 4;
+        }
+        if (tail) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&bar_p[t * 4 + 3], ph);
+            tc_fence_after();
+            umma_bf16(tmem + t * 256, umma_desc(smem_u32(sP + t * PP_PTILE + 3 * 16384), 256, 0, 6),
+                      umma_desc(va + kk * 2048, 1024, v_lbo, 2), idesc_o, kk != 0 ? 1u : 0u);
+            umma_commit(&bar_o[t]);
+          }
+        }
+        umma_commit(&bar_vfree[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warpgroup of tile t
+    const int t = (warp - 2) >> 2;
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const int wg_tid = threadIdx.x - 64 - t * 128;           // 0..127 inside the warpgroup
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + t * 256;
+    const int n32 = keys / 32, rem16 = keys - n32 * 32;
+    uint8_t* myP = sP + t * PP_PTILE;
+    const uint32_t p_blk0 = smem_u32(myP), p_tail = p_blk0 + 3 * 16384;
+    uint8_t* ostage = myP + 2 * 16384;
+    const int r0 = t * 128;
+    const bool active = r0 + quad * 32 < tokens;            // warp-uniform: at least one real query row
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int view = unit / heads, h = unit - view * heads;
+      PP_STAMP(0);
+      mbar_wait(&bar_s[t], ph);
+      PP_STAMP(1);
+      tc_fence_after();
+      float m = -INFINITY, l = 0.f;
+      if (active) {
+        // pass 1: exact row maximum.  Columns >= tokens hold exact zeros (zero-filled K rows): harmless for softmax.
+        for (int c = 0; c < n32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(trow + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        }
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        }
+      }
+      PP_STAMP(2);
+      if (wg_tid == 0) bulk_wait_read<0>();      // the previous unit's output store has finished reading the stage (= P block 2)
+      named_bar_sync(1 + t, 128);
+      PP_STAMP(3);
+      if (active) {
+        // pass 2: p = 2^(s*scale - m*scale), row sum, bf16 P into the UMMA K-major layout, block by block
+        const float ms = m * scale_log2;
+        float l0 = 0.f, l1 = 0.f;
+        for (int c = 0; c < n32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(trow + c * 32, r);
+          tmem_ld_wait();
+          const int blk = c >> 1;
+          const uint32_t base = p_blk0 + blk * 16384 + row * 128;
+          if (c * 32 + 32 <= tokens) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+              l0 += (e[0] + e[1]) + (e[2] + e[3]);
+              l1 += (e[4] + e[5]) + (e[6] + e[7]);
+              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((chunk ^ (row & 7)) << 4)),
+                           "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                           "r"(pack_bf16(e[6], e[7]))
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+                if (c * 32 + q4 * 8 + i >= tokens) v = 0.f;
+                e[i] = v;
+                l0 += v;
+              }
+              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((chunk ^ (row & 7)) << 4)),
+                           "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                           "r"(pack_bf16(e[6], e[7]))
+                           : "memory");
+            }
+          }
+          if (c & 1) {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[t * 4 + blk]);
+          }
+        }
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+          const uint32_t base = p_tail + row * 32;
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v = ex2_approx(fmaf(__uint_as_float(r[q2 * 8 + i]), scale_log2, -ms));
+              if (n32 * 32 + q2 * 8 + i >= tokens) v = 0.f;
+              e[i] = v;
+              l0 += v;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((q2 ^ ((row >> 2) & 1)) << 4)),
+                         "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])), "r"(pack_bf16(e[4], e[5])),
+                         "r"(pack_bf16(e[6], e[7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[t * 4 + 3]);
+        }
+        l = l0 + l1;
+      } else {
+        tc_fence_before();
+        if (lane == 0) {
+          for (int b = 0; b < n_full; ++b) mbar_arrive(&bar_p[t * 4 + b]);
+          if (tail) mbar_arrive(&bar_p[t * 4 + 3]);
+        }
+      }
+      PP_STAMP(4);
+      mbar_wait(&bar_o[t], ph);
+      PP_STAMP(5);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (active) {
+        tmem_ld_32x32b_x32(trow, o0);
+        tmem_ld_32x32b_x32(trow + 32, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tfree[t]);
+      if (active) {
+        const float inv = 1.f / l;
+        const uint32_t obase = smem_u32(ostage) + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const uint32_t* r = q4 < 4 ? o0 + q4 * 8 : o1 + (q4 - 4) * 8;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (row & 7)) << 4)),
+                       "r"(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv))
+                       : "memory");
+        }
+        if (lse != nullptr && r0 + row < tokens)
+          lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + row] = (m * scale_log2 + log2f(l)) * LN2;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(3 + t, 128);
+      if (wg_tid == 0 && r0 < tokens) {
+        tma_store_3d(&tmOut, ostage, h * DH, r0, view);
+        bulk_commit();
+      }
+      PP_STAMP(6);
+    }
+    if (wg_tid == 0) bulk_wait<0>();
+  }
+#undef PP_STAMP
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =============================================================================================== CLS-query attention
 // Last encoder layer in inference: only the CLS token of each view feeds post_layernorm / visual_projection
 // (HF CLIPVisionTransformer.forward: pooled_output = last_hidden_state[:, 0]), so only its query row is needed.
@@ -983,6 +1293,62 @@ static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int 
   return true;
 }
 
+static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                                    cudaStream_t st) {
+  const int keys = (tokens + 15) / 16 * 16;
+  const int tail = keys % 64;
+  if (keys < 128 || keys > 208 || (tail != 0 && tail != 16) || tokens <= 128 || tokens > 256) return false;   // exactly two query tiles
+  const int d = heads * DH;
+  const size_t smem = 2 * 16384 + 3 * static_cast<size_t>(keys) * 128 + 2 * PP_PTILE + 256 + 1024;
+  if (smem > 227 * 1024) return false;
+  CUtensorMap tq, tkv, to;
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+  const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
+  if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
+  const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+  const uint32_t obox[3] = {64, 128, 1};
+  if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
+  const int dv = current_device_slot();
+  static size_t configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[dv];
+  int& num_sms = num_sms_dev[dv];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(attention_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem;
+  }
+  const int units = V * heads;
+  const int grid = units < num_sms ? units : num_sms;
+  static long long* dbg = nullptr;
+  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
+  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
+  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
+  const bool ok = launch_pdl(attention_fwd_pp_kernel, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units,
+                             keys, scale * LOG2E, want_dbg ? dbg : nullptr) == cudaSuccess;
+  if (want_dbg) {
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (units >= 2000 && printed++ == 3) {
+      const char* nm[7] = {"loop top", "S ready", "pass1", "stage free", "pass2", "O ready", "stored"};
+      for (int it = 1; it < 8; ++it)
+        for (int t = 0; t < 2; ++t) {
+          const long long* q = dbg + (it * 2 + t) * 8;
+          std::fprintf(stderr, "unit %d tile %d:", it, t);
+          for (int k = 1; k < 7; ++k) std::fprintf(stderr, " %s +%lld", nm[k], q[k] - q[0]);
+          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 8)[0] - q[0], q[0] - (dbg + it * 2 * 8)[0]);
+        }
+    }
+  }
+  return ok;
+}
+
 static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                                      cudaStream_t st) {
   const int rows_pad = (tokens + 15) / 16 * 16, rows_alloc = (rows_pad + 31) / 32 * 32;
@@ -1029,9 +1395,13 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                           cudaStream_t st) {
   // TTL_ATTN: unset / "tc" = tcgen05 kernel where the geometry allows, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
+  // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
+  // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   static const char* mode = std::getenv("TTL_ATTN");
-  const bool want_tc = mode == nullptr || mode[0] == 't';
+  const bool want_pp = mode == nullptr || mode[0] == 'p';
+  const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';
+  if (want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st)) return;
   if (want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
   if (want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
