@@ -674,10 +674,8 @@ int f32_backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
 
 // bf16 operand packs of the live factors of samples [0, S), K-concatenated
 int repack(ttl_ctx* c, int S, cudaStream_t st) {
-  for (int i = 0; i < c->n_lora; ++i) {
-    launch_lora_pack(c->lp + i * c->lora_per_layer, c->lora_total, c->pk[i], c->d, c->r, c->s, S, st);
-    c->launches++;
-  }
+  launch_lora_pack_layers(c->lp, c->lora_per_layer, c->lora_total, c->pk.data(), c->n_lora, c->d, c->r, c->s, S, st);
+  c->launches += (c->n_lora + 15) / 16;
   c->pack_samples = S;
   return check_launch(c, "lora_pack");
 }
@@ -710,24 +708,19 @@ int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams&
   if (hp.head == TTL_HEAD_TPT) {
     RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, c->logits, c->entropy, st));
     if (hp.tta_steps > 0 && K > 0) {
-      for (int sm = 0; sm < S; ++sm) {
-        launch_select(c->entropy + sm * V, V, K, forced ? c->idx + sm * K : nullptr, c->idx + sm * K, st);
-        launch_gather_views(c->XK + sm * V * view_elems, c->TIN + sm * K * view_elems, c->idx + sm * K, K, 0, c->tokens, c->d, st);
-        c->launches += 2;
-      }
+      // all samples at once: sample s selects among its own V entropies and gathers its own K views
+      launch_select(c->entropy, V, K, forced ? c->idx : nullptr, c->idx, st, S);
+      launch_gather_views(c->XK, c->TIN, c->idx, S * K, 0, c->tokens, c->d, st, V, K);
+      c->launches += 2;
       for (int step = 0; step < hp.tta_steps; ++step) {
         RET_IF(forward_tail_train(c, c->TIN, S * K, S, st));
         if (step > 0) {
           launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, S * K, c->C, c->P, st);
           c->launches += 2;
         }
-        for (int sm = 0; sm < S; ++sm) {
-          if (step == 0) launch_tpt_loss(c->logits + static_cast<size_t>(sm) * V * c->C, c->idx + sm * K, K, c->C, c->loss + sm,
-                                         c->dlogits + static_cast<size_t>(sm) * K * c->C, st);
-          else launch_tpt_loss(c->logits_c + static_cast<size_t>(sm) * K * c->C, nullptr, K, c->C, c->loss + sm,
-                               c->dlogits + static_cast<size_t>(sm) * K * c->C, st);
-          c->launches++;
-        }
+        if (step == 0) launch_tpt_loss(c->logits, c->idx, K, c->C, c->loss, c->dlogits, st, S, static_cast<size_t>(V) * c->C);
+        else launch_tpt_loss(c->logits_c, nullptr, K, c->C, c->loss, c->dlogits, st, S, static_cast<size_t>(K) * c->C);
+        c->launches++;
         RET_IF(backward(c, c->dlogits, S * K, st));
         RET_IF(adamw(c, hp, S, st));
       }

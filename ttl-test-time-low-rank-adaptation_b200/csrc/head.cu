@@ -166,6 +166,9 @@ __global__ void select_kernel(const float* __restrict__ entropy, int V, int K, c
                               int* __restrict__ idx) {
   pdl_wait();
   pdl_trigger();
+  entropy += static_cast<size_t>(blockIdx.x) * V;      // one CTA per test sample
+  idx += static_cast<size_t>(blockIdx.x) * K;
+  if (forced != nullptr) forced += static_cast<size_t>(blockIdx.x) * K;
   if (forced != nullptr) {
     for (int k = threadIdx.x; k < K; k += blockDim.x) idx[k] = forced[k];
     return;
@@ -184,7 +187,7 @@ __global__ void select_kernel(const float* __restrict__ entropy, int V, int K, c
 // single CTA.  a_c = logsumexp_k(lp[k,c]) - ln K ; L = -sum_c a_c e^{a_c} ; dL/dx[k,c] = -(1/K) p[k,c] (a_c - sum_j p[k,j] a_j)
 __global__ void __launch_bounds__(1024)
 tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, int K, int C, float* __restrict__ loss,
-                float* __restrict__ dlogits) {
+                float* __restrict__ dlogits, size_t logits_sstride) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sh[];
@@ -192,6 +195,10 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   float* sk = sh + K;         // [K]  sum_j p[k,j] a_j
   float* red = sh + 2 * K;    // [32]
   float* a = red + 32;        // [C]
+  logits += static_cast<size_t>(blockIdx.x) * logits_sstride;   // one CTA per test sample
+  if (idx != nullptr) idx += static_cast<size_t>(blockIdx.x) * K;
+  loss += blockIdx.x;
+  dlogits += static_cast<size_t>(blockIdx.x) * K * C;
   for (int k = 0; k < K; ++k) {
     const float* x = logits + static_cast<size_t>(idx ? idx[k] : k) * C;
     float mx = -INFINITY;
@@ -359,11 +366,13 @@ void launch_logits_entropy(const float* feats, const float* text, float scale, f
 void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st) {
   launch_pdl(scale_entropy_kernel, dim3(V), dim3(HT), 0, st, nullptr, 1.f, logits, entropy, C, 0);
 }
-void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st) {
-  launch_pdl(select_kernel, dim3(1), dim3(256), 0, st, entropy, V, K, forced_idx, idx);
+void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st, int n_samples) {
+  launch_pdl(select_kernel, dim3(n_samples), dim3(256), 0, st, entropy, V, K, forced_idx, idx);
 }
-void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st) {
-  launch_pdl(tpt_loss_kernel, dim3(1), dim3(1024), (2 * K + 32 + C) * sizeof(float), st, logits, idx, K, C, loss, dlogits);
+void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st,
+                     int n_samples, size_t logits_sstride) {
+  launch_pdl(tpt_loss_kernel, dim3(n_samples), dim3(1024), (2 * K + 32 + C) * sizeof(float), st, logits, idx, K, C, loss, dlogits,
+             logits_sstride);
 }
 void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st) {
   launch_pdl(deyo_loss_kernel, dim3(1), dim3(1024), 3 * V * sizeof(float), st, logits, V, C, margin_e0, loss, dlogits);

@@ -23,8 +23,9 @@ void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* 
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
                           bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st);
 // dst[g*tokens + t, :] = src[v(g)*tokens + t, :],  v(g) = view_idx[g] (device array) or g * view_stride when view_idx == nullptr
+// sample_views > 0 (concurrent samples): n_sel = S*K entries, entry g reads view (g / k_per_sample) * sample_views + view_idx[g]
 void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int view_stride, int tokens, int d,
-                         cudaStream_t st);
+                         cudaStream_t st, int sample_views = 0, int k_per_sample = 1);
 // x bf16 [M, 64*S]: zero every 64-column block except the one of the row's own sample (row / rows_per_sample)
 void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStream_t st);
 
@@ -52,9 +53,12 @@ void launch_logits_entropy(const float* feats, const float* text, float scale, f
 // entropy[v] = H(softmax(logits[v]))  (ttl.py:51 / deyo.py:85-90); logits are read-only in effect (scaled by 1)
 void launch_entropy(float* logits, float* entropy, int V, int C, cudaStream_t st);
 // idx[0..K) = argsort(entropy, stable)[:K]  (ttl.py:52; ties -> lowest index).  forced_idx (nullable) overrides.
-void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st);
+// n_samples > 1: sample s uses entropy + s*V, idx + s*K (forced_idx likewise), one CTA each
+void launch_select(const float* entropy, int V, int K, const int* forced_idx, int* idx, cudaStream_t st, int n_samples = 1);
 // marginal-entropy loss of the K rows logits[idx[k]] (ttl.py:56-61) and its gradient, compact: dlogits[K,C]
-void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st);
+// n_samples > 1: sample s uses logits + s*logits_sstride, idx + s*K, loss + s, dlogits + s*K*C, one CTA each
+void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st,
+                     int n_samples = 1, size_t logits_sstride = 0);
 // weighted-entropy (DeYO, default flags) loss over all V rows and gradient dlogits[V,C]  (deyo.py:97-181)
 void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st);
 // head backward for G compact views: dlogits[G,C] -> dx[G*tokens, d] (fp32, zero except CLS rows) + bf16 copy.
@@ -71,6 +75,9 @@ struct LoraPacked {       // bf16 operands consumed by the GEMM's second operand
 };
 // params: this layer's tensors of sample 0; sample i at params + i * sample_stride.  S samples are K-concatenated.
 void launch_lora_pack(const float* params, int64_t sample_stride, LoraPacked pk, int d, int r, float s, int S, cudaStream_t st);
+// all LoRA layers in one launch: layer i reads params + i*layer_stride and writes pks[i]  (n_layers <= 16 per launch)
+void launch_lora_pack_layers(const float* params, int64_t layer_stride, int64_t sample_stride, const LoraPacked* pks,
+                             int n_layers, int d, int r, float s, int S, cudaStream_t st);
 // out[w, j] (or out[j, w] if transpose_out) = scale * sum_m Wd[m, w] * Nr[m, j];  w < nw (multiple of 64), j < 16 * nj16
 // Deterministic two-pass reduction (partials in workspace `ws`, >= groups*ceil(M/128)*nw*nn floats).
 // groups > 1: group g reduces rows [g*M, (g+1)*M) with the narrow operand shifted by g*narrow_gstride columns and writes

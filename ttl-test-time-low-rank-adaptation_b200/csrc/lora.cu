@@ -10,10 +10,14 @@ namespace ttl {
 namespace {
 
 // params layout per layer: A_q[r,d] | B_q[d,r] | A_v[r,d] | B_v[d,r]   (fp32, contiguous)
-__global__ void lora_pack_kernel(const float* __restrict__ prm0, int64_t sample_stride, LoraPacked pk, int d, int r,
-                                 float s, int S) {
+struct LoraPackedArr { LoraPacked p[16]; };
+
+__global__ void lora_pack_kernel(const float* __restrict__ prm0, int64_t sample_stride, LoraPackedArr pks, int64_t layer_stride,
+                                 int d, int r, float s, int S) {
   pdl_wait();
   pdl_trigger();
+  const LoraPacked pk = pks.p[blockIdx.z];          // one grid plane per LoRA layer
+  prm0 += blockIdx.z * layer_stride;
   const int n_a = 64 * d;          // a_ext / a_ext_t elements of one sample block
   const int n_b = 3 * d * 64;      // b_ext / b_ext_t elements of one sample block
   const int smp = blockIdx.y, kc = 64 * S, c0 = 64 * smp;   // this sample's 64-column block of the K-concatenation
@@ -130,7 +134,22 @@ __global__ void lora_reset_kernel(float* __restrict__ p, const float* __restrict
 
 void launch_lora_pack(const float* params, int64_t sample_stride, LoraPacked pk, int d, int r, float s, int S, cudaStream_t st) {
   const int total = 64 * d + 3 * d * 64;
-  launch_pdl(lora_pack_kernel, dim3(dim3((total + 255) / 256, S)), dim3(256), 0, st, params, sample_stride, pk, d, r, s, S);
+  LoraPackedArr a;
+  a.p[0] = pk;
+  launch_pdl(lora_pack_kernel, dim3((total + 255) / 256, S, 1), dim3(256), 0, st, params, sample_stride, a, static_cast<int64_t>(0), d, r,
+             s, S);
+}
+
+void launch_lora_pack_layers(const float* params, int64_t layer_stride, int64_t sample_stride, const LoraPacked* pks,
+                             int n_layers, int d, int r, float s, int S, cudaStream_t st) {
+  const int total = 64 * d + 3 * d * 64;
+  for (int l0 = 0; l0 < n_layers; l0 += 16) {
+    const int n = n_layers - l0 < 16 ? n_layers - l0 : 16;
+    LoraPackedArr a;
+    for (int i = 0; i < n; ++i) a.p[i] = pks[l0 + i];
+    launch_pdl(lora_pack_kernel, dim3((total + 255) / 256, S, n), dim3(256), 0, st, params + l0 * layer_stride, sample_stride, a,
+               layer_stride, d, r, s, S);
+  }
 }
 
 void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,

@@ -184,11 +184,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 __global__ void gather_views_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
-                                    const int* __restrict__ idx, int n_sel, int view_stride, int per_view4) {
+                                    const int* __restrict__ idx, int n_sel, int view_stride, int per_view4, int sample_views,
+                                    int k_per_sample) {
   pdl_wait();
   pdl_trigger();
   const int g = blockIdx.y;
-  const float4* s = src + static_cast<size_t>(idx != nullptr ? idx[g] : g * view_stride) * per_view4;
+  const int view = idx != nullptr ? (g / k_per_sample) * sample_views + idx[g] : g * view_stride;
+  const float4* s = src + static_cast<size_t>(view) * per_view4;
   float4* o = dst + static_cast<size_t>(g) * per_view4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_view4; i += gridDim.x * blockDim.x) o[i] = s[i];
 }
@@ -236,11 +238,11 @@ void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, c
 }
 
 void launch_gather_views(const float* src, float* dst, const int* view_idx, int n_sel, int view_stride, int tokens, int d,
-                         cudaStream_t st) {
+                         cudaStream_t st, int sample_views, int k_per_sample) {
   const int per_view4 = tokens * d / 4;
   dim3 grid((per_view4 + 255) / 256 < 32 ? (per_view4 + 255) / 256 : 32, n_sel);
   launch_pdl(gather_views_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst),
-                                            view_idx, n_sel, view_stride, per_view4);
+                                            view_idx, n_sel, view_stride, per_view4, sample_views, k_per_sample);
 }
 
 void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStream_t st) {
