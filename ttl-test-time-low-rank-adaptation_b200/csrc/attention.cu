@@ -860,6 +860,21 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 //                        bf16 P into the UMMA K-major swizzled layout, O / rowsum -> swizzled smem -> one TMA store per tile
 // K/V are read from L2 once per unit instead of once per tile, and the load latency of unit u+1 hides behind unit u.
 constexpr int PP_THREADS = 320;
+// Pass 2 is MUFU-bound (16 ex2 per clock and SM): PP_POLY_MASK picks the elements of every group of 8 whose 2^x is evaluated on
+// the FMA pipe instead (Cody-Waite split with the 1.5 * 2^23 trick + cubic on [-0.5, 0.5], max relative error 7.5e-5, far
+// below the bf16 rounding of P).  x <= 0 here (the row maximum has been subtracted).
+#ifndef PP_POLY_MASK
+#define PP_POLY_MASK 0x88
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xf = x + 12582912.f;                 // integer part (round to nearest) lands in the low mantissa bits
+  const float fr = x - (xf - 12582912.f);          // [-0.5, 0.5]
+  float p = fmaf(fr, 0.0551716685f, 0.2426111251f);
+  p = fmaf(p, fr, 0.6932609677f);
+  p = fmaf(p, fr, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
 constexpr int PP_PTILE = 3 * 16384 + 4096;     // P of one tile: three 64-key blocks (128 rows x 128 B) + the 16-key tail block
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
@@ -1009,12 +1024,20 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       float m = -INFINITY, l = 0.f;
       if (active) {
         // pass 1: exact row maximum.  Columns >= tokens hold exact zeros (zero-filled K rows): harmless for softmax.
-        for (int c = 0; c < n32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(trow + c * 32, r);
+        // Two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is reduced.
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(trow, ra);
+        for (int c = 0; c < n32; c += 2) {
           tmem_ld_wait();
+          if (c + 1 < n32) tmem_ld_32x32b_x32(trow + (c + 1) * 32, rb);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          if (c + 1 < n32) {
+            tmem_ld_wait();
+            if (c + 2 < n32) tmem_ld_32x32b_x32(trow + (c + 2) * 32, ra);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+          }
         }
         if (rem16) {
           uint32_t r[16];
@@ -1043,7 +1066,10 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             for (int q4 = 0; q4 < 4; ++q4) {
               float e[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+              for (int i = 0; i < 8; ++i) {
+                const float x = fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms);
+                e[i] = ((PP_POLY_MASK >> i) & 1) ? ex2_poly(x) : ex2_approx(x);
+              }
               l0 += (e[0] + e[1]) + (e[2] + e[3]);
               l1 += (e[4] + e[5]) + (e[6] + e[7]);
               const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
