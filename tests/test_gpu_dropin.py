@@ -202,3 +202,11 @@ def test_cli_deyo_optional_branches_run_in_compat_mode(extra):
     import ttl
     res = ttl.main(['--synthetic', '2', '--test_sets', 'A', '--gpu', '0', '--workers', '0', '--print_freq', '100'] + extra)
     assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+
+
+def test_cli_fp32_validation_mode():
+    """--precision fp32 routes the whole CLI through the fp32 validation mode (one sample per call)."""
+    import ttl
+    res = ttl.main(['--synthetic', '2', '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0',
+                    '--print_freq', '100', '--precision', 'fp32'])
+    assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0

@@ -129,3 +129,25 @@ def test_adapt_from_images_equals_adapt_from_views():
         assert torch.equal(c["pred_logits"], a["pred_logits"])
     finally:
         eng.close()
+
+
+def test_adapt_from_images_vit_l14_patch_layout():
+    """ViT-L/14 (BASELINE config 4 geometry): patch 14 -> 588 patch columns padded to 640 in the GEMM operand; the view
+    generator's fused im2col must write the same operand the fp32-view path builds."""
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features
+    import math
+    eng = Engine("ViT-L/14", max_views=8, max_classes=16, layer_range=(21, 23), max_samples=1)
+    try:
+        eng.load_weights(synthetic_vit_weights("ViT-L/14", seed=1234))
+        eng.set_text_features(synthetic_text_features(10, 768, seed=11), math.log(100.0))
+        eng.set_lora_init(synthetic_lora_init("ViT-L/14", rank=16, layers=(21, 23), seed=0))
+        hp = Hparams(head="tpt", selection_p=0.25)
+        img = _img(333, 500, 77)
+        specs = _specs(333, 500, _boxes(333, 500, 7, 5))
+        a = eng.adapt_predict_images([img], [specs], hp, want=("pred_logits", "entropy"))
+        b = eng.adapt_predict_batch(eng.make_views([img], [specs]), hp, want=("pred_logits", "entropy"))
+        assert torch.equal(a["entropy"].cpu(), b["entropy"].cpu())
+        assert torch.equal(a["pred_logits"].cpu(), b["pred_logits"].cpu())
+    finally:
+        eng.close()
