@@ -1,0 +1,46 @@
+"""Small end-to-end exercise of the ViT-B/16 paths for `compute-sanitizer --tool memcheck`: bf16 path (eager, capture,
+replay; 2 concurrent samples; images path), fp32 validation mode, text tower."""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "ttl-test-time-low-rank-adaptation_b200")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from ttl_b200 import Engine, Hparams  # noqa: E402
+from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features  # noqa: E402
+from ttl_b200.views import ViewSpecSampler  # noqa: E402
+
+V = 16
+w = synthetic_vit_weights("ViT-B/16", seed=1234)
+text = synthetic_text_features(100, 512, seed=11)
+lora = synthetic_lora_init("ViT-B/16", rank=16, layers=(9, 11), seed=0)
+for prec, S in (("bf16", 2), ("fp32", 1)):
+    eng = Engine("ViT-B/16", max_views=V, max_classes=128, max_samples=S, precision=prec)
+    eng.load_weights(w)
+    eng.set_text_features(text, math.log(100.0))
+    eng.set_lora_init(lora)
+    for head in ("tpt", "deyo"):
+        hp = Hparams(head=head, selection_p=0.25, tta_steps=2 if head == "tpt" else 1)
+        x = torch.randn(S, V, 3, 224, 224, device="cuda")
+        for _ in range(3 if prec == "bf16" else 1):
+            out = eng.adapt_predict_batch(x, hp, want=("pred_logits", "idx", "loss"))
+        print(prec, head, out["pred_logits"].float().abs().mean().item())
+    if prec == "bf16":
+        rng = np.random.default_rng(0)
+        imgs = [rng.integers(0, 256, size=(200 + 50 * i, 300, 3), dtype=np.uint8) for i in range(S)]
+        torch.manual_seed(0)
+        specs = [ViewSpecSampler(V - 1)(im)[1] for im in imgs]
+        print("images", eng.adapt_predict_images(imgs, specs, Hparams(selection_p=0.25))["pred_logits"].abs().mean().item())
+    eng.close()
+from ttl_b200.text import TextEncoder  # noqa: E402
+sys.path.insert(0, ROOT)
+from oracle import text_oracle as TO  # noqa: E402
+a = TO.TEXT_ARCHS["tiny"]
+enc = TextEncoder("tiny", max_prompts=4)
+enc.load_weights(TO.make_synthetic_text_weights(a, 5))
+print("text", enc.encode(TO.make_synthetic_tokens(6, a, 3)).shape)
+enc.close()
+torch.cuda.synchronize()
+print("done")

@@ -374,8 +374,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tma_prefetch_desc(&tmB2);
     }
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], CL == 4 ? 3 : 2);   // one arrival per CTA's producer (+ the peer's B forwarder), leader's copy is used
-      mbar_init(&empty[s], CL == 4 ? 2 : 1);  // multicast tcgen05.commit of every pair in the cluster
+      mbar_init(&full[s], CL > 2 ? 3 : 2);    // one arrival per CTA's producer (+ the peer's B forwarder), leader's copy is used
+      mbar_init(&empty[s], CL / 2);           // multicast tcgen05.commit of every pair in the cluster
       mbar_init(&fullB[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -411,26 +411,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full0 = mapa_u32(smem_u32(&full[0]), lead_rank);   // the pair LEADER's full barriers
-      const uint16_t bmask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));   // CL == 4: same parity, both pairs
+      uint16_t bmask = 0;                                      // CL > 2: the CTAs of the same parity in every pair
+      for (int q = 0; q < PAIRS; ++q) bmask |= static_cast<uint16_t>(1u << (rank + 2 * q));
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
         const int a_row = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128;
-        const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) +
-                          (CL == 4 ? static_cast<int>(pair) * (BLOCK_N / 4) : 0);
+        const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) + static_cast<int>(pair) * (BLOCK_N / CL);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t fb = full0 + stage * 8;
-          if (leader) mbar_expect_tx(&full[stage], (p.dbg & 4) ? 0 : 2 * C::A_BYTES + (CL == 4 ? 1 : 2) * C::B_BYTES);
+          if (leader) mbar_expect_tx(&full[stage], (p.dbg & 4) ? 0 : 2 * C::A_BYTES + (CL > 2 ? 1 : 2) * C::B_BYTES);
           else mbar_arrive_cluster(fb);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
-          uint8_t* b_dst = sB + stage * C::B_BYTES + (CL == 4 ? pair * (C::B_BYTES / 2) : 0);
+          uint8_t* b_dst = sB + stage * C::B_BYTES + pair * (C::B_BYTES / PAIRS);
           const void* tA = kb < p.kb1 ? static_cast<const void*>(&tmA1) : static_cast<const void*>(&tmA2);
           const void* tB = kb < p.kb1 ? static_cast<const void*>(&tmB1) : static_cast<const void*>(&tmB2);
           const int kc = (kb < p.kb1 ? kb : kb - p.kb1) * BLOCK_K;
           if (p.dbg & 4) {
           } else {
             tma_load_2d_cg2(tA, fb, a_dst, kc, a_row);
-            if (CL == 4) tma_load_2d_mc(tB, leader ? &full[stage] : &fullB[stage], b_dst, kc, b_row, bmask);
+            if (CL > 2) tma_load_2d_mc(tB, leader ? &full[stage] : &fullB[stage], b_dst, kc, b_row, bmask);
             else tma_load_2d_cg2(tB, fb, b_dst, kc, b_row);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -461,7 +461,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             umma_bf16_cg2(d_tmem, umma_desc_k_sw128(a_addr + k * UMMA_K * 2), umma_desc_k_sw128(b_addr + k * UMMA_K * 2),
                           idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_mc2(&empty[stage], CL == 4 ? 0xF : 3);   // frees the slot in every CTA that loads into it
+          umma_commit_mc2(&empty[stage], static_cast<uint16_t>((1u << CL) - 1));   // frees the slot in every CTA that loads into it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_mc2(&tfull[as], pair_mask);   // accumulator complete -> both CTAs' epilogues
@@ -474,7 +474,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
-    } else if (CL == 4 && !leader && lane == 0 && !(p.dbg & 4)) {
+    } else if (CL > 2 && !leader && lane == 0 && !(p.dbg & 4)) {
       // B forwarder of the non-leader CTA: its half of the B tile arrives as two multicast quarters on the local fullB
       // barrier; one remote arrival per stage tells the leader's MMA thread that this CTA's operands are complete.
       int stage = 0;
@@ -818,9 +818,14 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   {
     // force_block_n: 0 = heuristic; 64/128/256 = 1-CTA kernel; 1000 + {128,192,256} = CTA-pair kernel;
     // 2256 = 4-CTA cluster (two pairs, multicast B tiles), BLOCK_N = 256
+    // 3192 = 6-CTA cluster (three pairs), BLOCK_N = 192
     if (bn == 2256) {
       if (g.N % 256 != 0 || g.out2 != nullptr) { set_err("gemm_launch: 4-CTA cluster kernel needs N % 256 == 0, no out2"); return cudaErrorInvalidValue; }
       return launch2_n<256, 4>(g, stream, num_sms);
+    }
+    if (bn == 3192) {
+      if (g.N % 192 != 0 || g.out2 != nullptr) { set_err("gemm_launch: 6-CTA cluster kernel needs N % 192 == 0, no out2"); return cudaErrorInvalidValue; }
+      return launch2_n<192, 6>(g, stream, num_sms);
     }
     int bn2 = bn >= 1000 ? bn - 1000 : (bn == 0 ? pick_pair_block_n(g, num_sms) : 0);
     static const char* env = std::getenv("TTL_GEMM_PAIR");
@@ -837,6 +842,7 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
       static const char* cl_env = std::getenv("TTL_GEMM_CLUSTER");
       static const int cl = cl_env ? std::atoi(cl_env) : 2;
       if (cl == 4 && bn2 == 256 && g.M > 2048) return launch2_n<256, 4>(g, stream, num_sms);
+      if (cl == 6 && g.N % 192 == 0 && g.M > 2048) return launch2_n<192, 6>(g, stream, num_sms);
       switch (bn2) {
         case 256: return launch2_n<256>(g, stream, num_sms);
         case 192: return launch2_n<192>(g, stream, num_sms);
