@@ -32,8 +32,25 @@ for p in (ROOT, PKG):
 
 METRIC = "adapted samples/s, ViT-B/16 64-view TTL"
 UNIT = "samples/s"
-F_ALG_TFLOP = 2.342   # algorithmic TFLOP per adapted sample, north-star head (SURVEY.md §8d / BASELINE.md §3)
-F_ALG_TFLOP_DEYO = 2.876
+
+
+def f_alg_tflop(geo: dict, classes: int, views: int, head: str, tta_steps: int, selection_p: float = 0.1, r: int = 16,
+                n_lora: int = 3) -> float:
+    """Algorithmic TFLOP per adapted sample: 2mnk per GEMM, no text tower, no recompute, backward only for the
+    G gradient-carrying views; later steps re-forward only those G views through the adapted layers.  ViT-B/16, 1000 classes,
+    64 views: 2.342 (north-star head, 1 step), 2.876 (DeYO head), 2.666 (4 steps); ViT-L/14: 10.67 / 11.90."""
+    n = (geo["image_size"] // geo["patch"]) ** 2 + 1
+    d, layers, proj, patch = geo["width"], geo["layers"], geo["proj_dim"], geo["patch"]
+    lin_tok, attn_view, head_f = 24 * d * d, 4 * n * n * d, 2 * proj * classes
+    fwd = 2 * (n - 1) * d * 3 * patch * patch + layers * (lin_tok * n + attn_view) + n_lora * 8 * d * r * n + 2 * d * proj
+    bwd = n_lora * (lin_tok * n + 2 * attn_view + 16 * d * r * n) + 2 * d * proj
+    fwd_tail = n_lora * (lin_tok * n + attn_view + 8 * d * r * n) + 2 * d * proj
+    if head == "tpt":
+        g, t = int(views * selection_p), tta_steps
+    else:                       # DeYO head: every view carries gradient, tta_steps^2 optimiser steps (SURVEY.md Q2)
+        g, t = views, tta_steps * tta_steps
+    total = views * (fwd + head_f) + t * g * (bwd + head_f) + max(t - 1, 0) * g * (fwd_tail + head_f) + (fwd + head_f)
+    return total / 1e12
 
 
 def parse_args():
@@ -47,6 +64,8 @@ def parse_args():
                     help="ViT-B/16 is the metric's configuration; ViT-L/14 (BASELINE config 4, layers 21-23) is informational")
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--views", type=int, default=64)
+    ap.add_argument("--tta-steps", type=int, default=1,
+                    help="optimiser steps per sample (the metric is quoted at 1; 4 = BASELINE config 5, informational)")
     ap.add_argument("--ring", type=int, default=4, help="distinct pre-staged batches (ring * S * 38.5 MB > L2)")
     ap.add_argument("--concurrent", type=int, default=6,
                     help="test samples adapted concurrently per step (BASELINE config 5); every multiple of 3 x 64 x 197 rows = 147.75 "
@@ -143,7 +162,7 @@ def synth_sample_gpu(torch, gen, views: int, size: int = 224):
     return torch.cat(out).contiguous()
 
 
-def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, threads: int):
+def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, threads: int, tta_steps: int = 1):
     """The reference algorithm (oracle port, fp32, autograd) on the host cores; returns (seconds_per_sample list)."""
     import torch
     from oracle import ttl_oracle as O
@@ -156,7 +175,7 @@ def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, thre
     for i in range(n_samples):
         imgs = O.make_synthetic_views(views, arch.image_size, seed=100 + i)
         t0 = time.perf_counter()
-        O.adapt_and_predict(arch, w, imgs, text, math.log(100.0), lora0, spec, head=head)
+        O.adapt_and_predict(arch, w, imgs, text, math.log(100.0), lora0, spec, head=head, tta_steps=tta_steps)
         times.append(time.perf_counter() - t0)
     return times
 
@@ -176,7 +195,7 @@ def run_reference_arm(args):
     bounded = total > 24
     if bounded:   # keep the run within a few minutes: fewer views per step, scaled back to 64-view samples
         views = max(10, min(args.views, int(1500 / total)))
-    times = cpu_reference_pass(total, args.classes, views, args.head, cores)
+    times = cpu_reference_pass(total, args.classes, views, args.head, cores, args.tta_steps)
     timed = times[warm:]
     per_step = sum(timed) / len(timed)
     value = (views / args.views) / per_step
@@ -187,7 +206,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3 * (args.views / views), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head)",
+            "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, {args.tta_steps} step"
+                                   f"{'s' if args.tta_steps != 1 else ''} ({args.head} head)",
                        "device": "host CPU"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -231,7 +251,7 @@ def main():
     eng.load_weights(synthetic_vit_weights(args.arch, seed=1234))
     eng.set_text_features(synthetic_text_features(args.classes, geo["proj_dim"], seed=11), math.log(100.0))
     eng.set_lora_init(synthetic_lora_init(args.arch, rank=16, layers=lora_layers, seed=0))
-    hp = Hparams(head=args.head)
+    hp = Hparams(head=args.head, tta_steps=args.tta_steps)
 
     # ---- data: this rank's shard of a seeded synthetic evaluation set, pre-staged in HBM (ring > L2)
     gen = torch.Generator(device="cuda").manual_seed(7 + 1000 * rank)
@@ -366,26 +386,24 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_pass(args.cpu_baseline_samples, args.classes, args.views, args.head, cores)
+        times = cpu_reference_pass(args.cpu_baseline_samples, args.classes, args.views, args.head, cores, args.tta_steps)
         per = sum(times) / len(times)
         cpu_base = {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{len(times)} samples of the same workload, oracle port (fp32 PyTorch CPU, autograd) of "
                               f"ttl.py:338-352 with cached class features, {per:.2f} s/sample"}
 
     if rank == 0:
-        f_alg = F_ALG_TFLOP if args.head == "tpt" else F_ALG_TFLOP_DEYO
-        if args.arch == "ViT-L/14":
-            f_alg = 10.67 if args.head == "tpt" else 11.90
+        f_alg = f_alg_tflop(geo, args.classes, args.views, args.head, args.tta_steps)
         per_gpu_tflops = value / world * f_alg
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"TTL {args.arch}, {args.classes} classes, {args.views} views, r=16, 1 step ({args.head} head), "
-                                       f"random-init weights", "samples_per_rank": args.steps * S,
+                "config": {"workload": f"TTL {args.arch}, {args.classes} classes, {args.views} views, r=16, {args.tta_steps} step{'s' if args.tta_steps != 1 else ''} "
+                                       f"({args.head} head), random-init weights", "samples_per_rank": args.steps * S,
                            "concurrent_samples_per_step": S,
                            "l2": f"inputs larger than L2: ring of {args.ring} pre-staged batches x {ring[0].numel() * 4 / 1e6:.1f} MB",
                            "parallelism": f"sample-sharded x{world}"},
-                "tflops_per_gpu_alg": per_gpu_tflops,
+                "tflops_per_gpu_alg": per_gpu_tflops, "f_alg_tflop_per_sample": f_alg,
                 "frac_of_bf16_peak": {"sustained_measured": per_gpu_tflops / peaks["tf_sus"],
                                       "burst_measured": per_gpu_tflops / peaks["tf_burst"], "spec_2250": per_gpu_tflops / 2250.0,
                                       "peaks": peaks["src"]},

@@ -301,3 +301,27 @@ def test_vit_l14_geometry_forward_and_adapt():
         assert _rel(out["pred_logits"].cpu().numpy(), out["logits0"][0].cpu().numpy()) > 1e-4   # the adapter moved it
     finally:
         eng.close()
+
+
+def test_zigzag_walk_is_bit_identical(b16_weights, monkeypatch):
+    """The frozen pass walks rows / (view, head) units in alternating directions from kernel to kernel (L2 reuse, engine.cu
+    run_layer); TTL_ZIGZAG=0 walks everything ascending.  Same arithmetic per tile, so the outputs must be bit-identical."""
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-B/16"]
+    S, V = 2, 64
+    eng = Engine("ViT-B/16", max_views=V, max_classes=64, layer_range=(9, 11), max_samples=S)
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(O.lora_init(arch, O.LoraSpec(), seed=0))
+        eng.set_text_features(O.make_text_features(37, arch.proj), math.log(100.0))
+        eng.set_graphs(False)
+        imgs = torch.stack([O.make_synthetic_views(V, arch.image_size, seed=31 + i) for i in range(S)]).cuda()
+        res = {}
+        for zz in ("0", "1"):
+            monkeypatch.setenv("TTL_ZIGZAG", zz)
+            out = eng.adapt_predict_batch(imgs, Hparams(head="tpt"), want=("logits0", "pred_logits", "idx", "loss"))
+            res[zz] = {k: v.cpu().numpy().copy() for k, v in out.items()}
+        for k in res["0"]:
+            assert np.array_equal(res["0"][k], res["1"][k]), k
+    finally:
+        eng.close()

@@ -880,7 +880,7 @@ constexpr int PP_PTILE = 3 * 16384 + 4096;     // P of one tile: three 64-key bl
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
-                        int units, int keys, float scale_log2, long long* __restrict__ dbg) {
+                        int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev) {
   extern __shared__ uint8_t smem_pp_raw[];
   // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0, per warpgroup: [it][t][stage]
 #define PP_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && wg_tid == 0) dbg[(it * 2 + t) * 8 + (k)] = clock64(); } while (0)
@@ -935,7 +935,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
-        const int view = unit / heads, h = unit - view * heads;
+        const int u2 = rev ? units - 1 - unit : unit;            // descending walk: see g_rows_descending
+        const int view = u2 / heads, h = u2 - view * heads;
         if (it > 0) mbar_wait(&bar_s[1], (it - 1) & 1);          // both S MMAs of the previous unit retired: K, Q0, Q1 are dead
         mbar_expect_tx(bar_kq, KB + 2 * 16384);
         tma_load_3d(&tmKV, bar_kq, sK, d + h * DH, 0, view);
@@ -1016,7 +1017,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     int it = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const int view = unit / heads, h = unit - view * heads;
+      const int u2 = rev ? units - 1 - unit : unit;
+      const int view = u2 / heads, h = u2 - view * heads;
       PP_STAMP(0);
       mbar_wait(&bar_s[t], ph);
       PP_STAMP(1);
@@ -1357,7 +1359,7 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
   if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
   const bool ok = launch_pdl(attention_fwd_pp_kernel, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units,
-                             keys, scale * LOG2E, want_dbg ? dbg : nullptr) == cudaSuccess;
+                             keys, scale * LOG2E, want_dbg ? dbg : nullptr, g_rows_descending) == cudaSuccess;
   if (want_dbg) {
     cudaStreamSynchronize(st);
     static int printed = 0;

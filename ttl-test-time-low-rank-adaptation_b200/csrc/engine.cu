@@ -121,6 +121,7 @@ struct ttl_ctx {
   int last_train_views = 0, last_train_samples = 1;   // total views / samples of the last train-mode forward
   const float* last_train_in = nullptr;
   int pack_samples = 1;                                // K-concatenation width (in samples) of the current bf16 packs
+  int zz_dir = 0;                                      // direction of the last zigzag kernel (run_layer)
 
   // fp32 validation mode (cfg.precision == TTL_PRECISION_FP32): fp32 twins of every bf16 buffer
   bool f32 = false;
@@ -262,7 +263,16 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   // bound of what removing that kernel would buy under the power cap
   static const char* skip_env = std::getenv("TTL_DBG_SKIP");
   static const int skip = skip_env ? std::atoi(skip_env) : 0;
+  // Zigzag (default; TTL_ZIGZAG=0 disables): consecutive streaming kernels of the frozen pass walk the rows in alternating
+  // directions, so each starts on the part of its input the previous kernel wrote last (still in the 126 MB L2).  Same
+  // arithmetic per row / tile, so results are bit-identical; measured +0.5..1 % per adapted sample (gpurun s84).
+  const char* zz_env = std::getenv("TTL_ZIGZAG");       // read per call: the tests toggle it
+  const bool zz_on = zz_env == nullptr || std::atoi(zz_env) != 0;
+  const bool zz = zz_on && tp == nullptr && M >= 8192;
+  auto next_dir = [&]() -> int { if (!zz) return 0; c->zz_dir ^= 1; return c->zz_dir; };
+  g_rows_descending = next_dir();
   if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+  g_rows_descending = 0;
   c->launches++;
   if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T per sample (needed by dB even while B == 0)
     if (S != c->pack_samples) { c->err = "run_layer: adapter packs were built for another sample count"; return TTL_E_STATE; }
@@ -285,24 +295,31 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
       g.b2 = opnd(c->pk[layer - c->lo].b_ext, 3 * d, kc, kc);
     }
     g.M = M; g.N = 3 * d; g.epi = EPI_BF16; g.bias = w.bqkv; g.out = qkv; g.ldo = 3 * d;
+    g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
+  g_rows_descending = next_dir();
   if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
+  g_rows_descending = 0;
   c->launches++;
   {
     GemmArgs g;
     g.a1 = opnd(ao, M, d, d);
     g.b1 = opnd(w.wo, d, d, d);
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.bo; g.out = x_mid; g.ldo = d; g.resid = x_in; g.ldr = d;
+    g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
+  g_rows_descending = next_dir();
   if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
+  g_rows_descending = 0;
   c->launches++;
   {
     GemmArgs g;
     g.a1 = opnd(h2, M, d, d);
     g.b1 = opnd(w.w1, F, d, d);
     g.M = M; g.N = F; g.epi = EPI_GELU; g.bias = w.b1; g.out = gb; g.ldo = F; g.out2 = tp ? tp->z : nullptr;
+    g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
   {
@@ -310,6 +327,7 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.a1 = opnd(gb, M, F, F);
     g.b1 = opnd(w.w2, d, F, F);
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.b2; g.out = x_out; g.ldo = d; g.resid = x_mid; g.ldr = d;
+    g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
   return check_launch(c, "run_layer");

@@ -328,6 +328,7 @@ struct Epi2Params {
   int kb1, kb2;
   const float* bias;
   int dbg;   // TTL_GEMM_DBG bits (development only): 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
+  int rev;   // tiles walked from the last row block to the first
 };
 
 // CL = 2: one CTA pair per cluster (above).  CL = 4: two pairs stacked along M share every B tile: each CTA loads a QUARTER of
@@ -414,7 +415,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       uint16_t bmask = 0;                                      // CL > 2: the CTAs of the same parity in every pair
       for (int q = 0; q < PAIRS; ++q) bmask |= static_cast<uint16_t>(1u << (rank + 2 * q));
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+        const int t2 = p.rev ? num_tiles - 1 - tile : tile;
+        const int m_pair = t2 / n_tiles, n_blk = t2 - m_pair * n_tiles;
         const int a_row = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) + static_cast<int>(pair) * (BLOCK_N / CL);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -502,7 +504,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     uint32_t aphase = 0;
     uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int t2 = p.rev ? num_tiles - 1 - tile : tile;
+      const int m_pair = t2 / n_tiles, n_blk = t2 - m_pair * n_tiles;
       const int row0 = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
       const bool live = row0 < p.M;     // warp-uniform
@@ -668,6 +671,7 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   p.bias = g.bias;
   static const char* dbg_env = std::getenv("TTL_GEMM_DBG");
   p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  p.rev = g.descending;
   auto kern = gemm2_kernel<BLOCK_N, EPI, CL>;
   const int dv = current_device_slot();
   static bool attr_done[MAX_DEVICES] = {};  // per instantiation and device

@@ -40,6 +40,7 @@ struct GemmArgs {
   const float* pos = nullptr;          // EPI_PATCH_F32: [T+1, N]
   int tokens_per_view = 0;             // EPI_PATCH_F32: T (patches per view)
   int force_block_n = 0;               // 0 = heuristic
+  int descending = 0;                  // CTA-pair kernel: walk the row blocks from the last to the first (engine.cu zigzag)
 };
 
 // Generic tiled tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point), shared with the

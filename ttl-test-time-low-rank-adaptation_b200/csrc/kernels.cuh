@@ -16,6 +16,10 @@ void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cuda
 // x[V*tokens, d] holds patch rows = conv + pos (GEMM epilogue); writes CLS rows = cls + pos[0], then pre-LN in place.
 void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
                         int tokens, int d, float eps, cudaStream_t st);
+// Walk direction of the big streaming kernels (layernorm_kernel, attention_fwd_pp_kernel; the GEMM takes GemmArgs::descending):
+// 1 = last rows / units first, so a consumer starts on what its producer wrote last and still sits in L2 (engine.cu zigzag).
+// Plain global read by the launchers at launch time (one context per process and device, calls are not thread-safe anyway).
+extern int g_rows_descending;
 // y(bf16) = LN(x) * gamma + beta, one warp per row, fp32 statistics.
 void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
                       cudaStream_t st);

@@ -104,10 +104,11 @@ embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const f
 
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int rows, int d, float eps) {
+                 const float* __restrict__ beta, int rows, int d, float eps, int rev) {
   pdl_wait();
   pdl_trigger();
-  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int blk = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int row = blk * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nv = d / 128;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
@@ -225,10 +226,12 @@ void launch_embed_preln(float* x, const float* cls, const float* pos, const floa
       x, cls, pos, gamma, beta, rows, tokens, d, eps);
 }
 
+int g_rows_descending = 0;
+
 void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
                       cudaStream_t st) {
   launch_pdl(layernorm_kernel, dim3((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, st, x, y, gamma, beta,
-                                                                                                rows, d, eps);
+                                                                                                rows, d, eps, g_rows_descending);
 }
 
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
