@@ -12,7 +12,7 @@ from ttl_b200 import Engine, Hparams  # noqa: E402
 from ttl_b200.synthetic import synthetic_vit_weights, synthetic_lora_init, synthetic_text_features  # noqa: E402
 from ttl_b200.views import ViewSpecSampler  # noqa: E402
 
-V = 16
+V = 22          # 2 samples x 22 views x 197 tokens = 8668 rows: the zigzag walk of the frozen pass is active (M >= 8192)
 w = synthetic_vit_weights("ViT-B/16", seed=1234)
 text = synthetic_text_features(100, 512, seed=11)
 lora = synthetic_lora_init("ViT-B/16", rank=16, layers=(9, 11), seed=0)

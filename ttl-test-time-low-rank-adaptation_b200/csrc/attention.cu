@@ -935,7 +935,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
-        const int u2 = rev ? units - 1 - unit : unit;            // descending walk: see g_rows_descending
+        const int u2 = rev ? units - 1 - unit : unit;            // descending walk (kernels.cuh)
         const int view = u2 / heads, h = u2 - view * heads;
         if (it > 0) mbar_wait(&bar_s[1], (it - 1) & 1);          // both S MMAs of the previous unit retired: K, Q0, Q1 are dead
         mbar_expect_tx(bar_kq, KB + 2 * 16384);
@@ -1322,7 +1322,7 @@ static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int 
 }
 
 static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, int descending) {
   const int keys = (tokens + 15) / 16 * 16;
   const int tail = keys % 64;
   if (keys < 128 || keys > 208 || (tail != 0 && tail != 16) || tokens <= 128 || tokens > 256) return false;   // exactly two query tiles
@@ -1359,7 +1359,7 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
   if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
   const bool ok = launch_pdl(attention_fwd_pp_kernel, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units,
-                             keys, scale * LOG2E, want_dbg ? dbg : nullptr, g_rows_descending) == cudaSuccess;
+                             keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending) == cudaSuccess;
   if (want_dbg) {
     cudaStreamSynchronize(st);
     static int printed = 0;
@@ -1421,7 +1421,7 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
 }
 
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
-                          cudaStream_t st) {
+                          cudaStream_t st, int descending) {   // only the default kernel honours `descending`
   // TTL_ATTN: unset / "tc" = tcgen05 kernel where the geometry allows, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
   // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
@@ -1429,7 +1429,7 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   const bool want_pp = mode == nullptr || mode[0] == 'p';
   const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';
-  if (want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st)) return;
+  if (want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
   if (want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
   if (want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;

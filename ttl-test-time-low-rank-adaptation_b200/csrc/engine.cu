@@ -270,9 +270,8 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   const bool zz_on = zz_env == nullptr || std::atoi(zz_env) != 0;
   const bool zz = zz_on && tp == nullptr && M >= 8192;
   auto next_dir = [&]() -> int { if (!zz) return 0; c->zz_dir ^= 1; return c->zz_dir; };
-  g_rows_descending = next_dir();
-  if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
-  g_rows_descending = 0;
+  const int dir_ln1 = next_dir();
+  if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st, dir_ln1);
   c->launches++;
   if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T per sample (needed by dB even while B == 0)
     if (S != c->pack_samples) { c->err = "run_layer: adapter packs were built for another sample count"; return TTL_E_STATE; }
@@ -298,9 +297,8 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
-  g_rows_descending = next_dir();
-  if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
-  g_rows_descending = 0;
+  const int dir_attn = next_dir();
+  if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st, dir_attn);
   c->launches++;
   {
     GemmArgs g;
@@ -310,9 +308,8 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.descending = next_dir();
     RET_IF(gemm(c, g, st));
   }
-  g_rows_descending = next_dir();
-  if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
-  g_rows_descending = 0;
+  const int dir_ln2 = next_dir();
+  if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st, dir_ln2);
   c->launches++;
   {
     GemmArgs g;

@@ -16,13 +16,11 @@ void launch_im2col(const float* images, bf16* patches, int V, int S, int p, cuda
 // x[V*tokens, d] holds patch rows = conv + pos (GEMM epilogue); writes CLS rows = cls + pos[0], then pre-LN in place.
 void launch_embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int V,
                         int tokens, int d, float eps, cudaStream_t st);
-// Walk direction of the big streaming kernels (layernorm_kernel, attention_fwd_pp_kernel; the GEMM takes GemmArgs::descending):
-// 1 = last rows / units first, so a consumer starts on what its producer wrote last and still sits in L2 (engine.cu zigzag).
-// Plain global read by the launchers at launch time (one context per process and device, calls are not thread-safe anyway).
-extern int g_rows_descending;
+// `descending` (here, launch_attention_fwd, GemmArgs::descending): walk the rows / units from the last to the first, so a consumer
+// starts on what its producer wrote last and still sits in L2 (engine.cu zigzag).  Same arithmetic per row, same result.
 // y(bf16) = LN(x) * gamma + beta, one warp per row, fp32 statistics.
 void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
-                      cudaStream_t st);
+                      cudaStream_t st, int descending = 0);
 // dx = dres + LN'(x)^T (dy * gamma); statistics recomputed from x.  dres nullable.  dx_bf16 nullable.
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
                           bf16* dx_bf16, int rows, int d, float eps, cudaStream_t st);
@@ -36,7 +34,7 @@ void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStrea
 // ---- attention.cu   qkv bf16 [V*tokens, 3d] (q | k | v, heads concatenated, 64 per head)
 // out bf16 [V*tokens, d]; lse (nullable) fp32 [V, heads, tokens] natural-log softmax normaliser of scale*q.k
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
-                          cudaStream_t st);
+                          cudaStream_t st, int descending = 0);
 // dqkv bf16 [V*tokens, 3d]  from dout bf16 [V*tokens, d], qkv, out, lse
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
                           int tokens, int heads, float scale, cudaStream_t st);

@@ -226,12 +226,10 @@ void launch_embed_preln(float* x, const float* cls, const float* pos, const floa
       x, cls, pos, gamma, beta, rows, tokens, d, eps);
 }
 
-int g_rows_descending = 0;
-
 void launch_layernorm(const float* x, bf16* y, const float* gamma, const float* beta, int rows, int d, float eps,
-                      cudaStream_t st) {
+                      cudaStream_t st, int descending) {
   launch_pdl(layernorm_kernel, dim3((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, st, x, y, gamma, beta,
-                                                                                                rows, d, eps, g_rows_descending);
+                                                                                                rows, d, eps, descending);
 }
 
 void launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* dres, float* dx,
