@@ -1513,7 +1513,8 @@ int ttl_op_gemm(const void* a, const void* b, const void* a2, const void* b2, in
     g.b2 = opnd(static_cast<const bf16*>(b2), N, K2, K2);
   }
   g.M = M; g.N = N; g.epi = epi; g.bias = bias; g.out = out; g.ldo = N; g.out2 = out2; g.resid = resid; g.ldr = N;
-  g.aux = static_cast<const bf16*>(aux); g.pos = pos; g.tokens_per_view = tokens_per_view; g.force_block_n = block_n;
+  g.aux = static_cast<const bf16*>(aux); g.pos = pos; g.tokens_per_view = tokens_per_view;
+  g.force_block_n = block_n % 100000; g.max_clusters = block_n / 100000;   // block_n = 100000 * (grid cap in clusters) + tile code
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

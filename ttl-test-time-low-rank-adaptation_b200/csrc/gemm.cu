@@ -702,7 +702,9 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
     if (std::getenv("TTL_DEBUG")) std::fprintf(stderr, "ttl: gemm2<%d,%d,%d> co-resident clusters: %d (SMs %d)\n", BLOCK_N, EPI, CL, n, num_sms);
   }
   const int tiles = (((g.M + 255) / 256 + CL / 2 - 1) / (CL / 2)) * (g.N / BLOCK_N);
-  const int grid = CL * (tiles < max_pairs ? tiles : max_pairs);
+  int clusters = tiles < max_pairs ? tiles : max_pairs;
+  if (g.max_clusters > 0 && g.max_clusters < clusters) clusters = g.max_clusters;
+  const int grid = CL * clusters;
   return launch_pdl(kern, dim3(grid), dim3(G2_THREADS), C::SMEM_BYTES, stream, tA1, tB1, tA2, tB2, tOut, tRes, p);
 }
 

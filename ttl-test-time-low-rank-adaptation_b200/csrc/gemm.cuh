@@ -40,6 +40,7 @@ struct GemmArgs {
   const float* pos = nullptr;          // EPI_PATCH_F32: [T+1, N]
   int tokens_per_view = 0;             // EPI_PATCH_F32: T (patches per view)
   int force_block_n = 0;               // 0 = heuristic
+  int max_clusters = 0;                // CTA-pair / cluster kernels: cap on the persistent grid (0 = every co-resident cluster)
   int descending = 0;                  // CTA-pair kernel: walk the row blocks from the last to the first (engine.cu zigzag)
 };
 
