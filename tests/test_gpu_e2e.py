@@ -325,3 +325,40 @@ def test_zigzag_walk_is_bit_identical(b16_weights, monkeypatch):
             assert np.array_equal(res["0"][k], res["1"][k]), k
     finally:
         eng.close()
+
+
+def test_edge_cases_few_views_few_classes():
+    """Edge cases of ttl.py:50-54 on the tiny geometry: fewer than 10 views select nothing (int(8 * 0.1) == 0: the library leaves
+    the adapter at its reset state instead of the reference's NaN loss), a ragged batch (fewer views than max_views), and
+    fewer than 5 classes."""
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-tiny"]
+    spec = O.LoraSpec(rank=16, alpha=32.0, layer_lo=2, layer_hi=3)
+    w = O.make_synthetic_weights(arch, 5)
+    lora0 = O.lora_init(arch, spec, 1)
+    eng = Engine("ViT-tiny", max_views=32, max_classes=16, layer_range=(2, 3))
+    try:
+        eng.load_weights(w)
+        eng.set_lora_init(lora0)
+        text = O.make_text_features(3, arch.proj, seed=2)                       # 3 classes (< 5)
+        eng.set_text_features(text, math.log(100.0))
+        for graphs in (False, True):
+            eng.set_graphs(graphs)
+            # 8 views: K = 0, no optimiser step, prediction = the un-adapted model's
+            imgs8 = O.make_synthetic_views(8, arch.image_size, 9).cuda()
+            out = eng.adapt_predict(imgs8, Hparams(head="tpt"), want=("logits0", "pred_logits", "idx"))
+            assert out["idx"].numel() == 0 and out["logits0"].shape == (8, 3)
+            assert torch.isfinite(out["pred_logits"]).all()
+            eng.lora_reset()
+            plain = eng.forward(imgs8[:1])
+            assert _rel(out["pred_logits"].cpu().numpy(), plain[0].cpu().numpy()) < 1e-6
+            # 10 of max 32 views: K = 1, one selected view, the adapter moves
+            imgs10 = O.make_synthetic_views(10, arch.image_size, 10)
+            ref = O.adapt_and_predict(arch, w, imgs10, text, math.log(100.0), lora0, spec, head="tpt")
+            out = eng.adapt_predict(imgs10.cuda(), Hparams(head="tpt"), forced_idx=ref.idx,
+                                    want=("logits0", "pred_logits", "idx", "loss"))
+            assert out["idx"].numel() == 1
+            assert _rel(out["logits0"].cpu().numpy(), ref.logits0.numpy()) < 1e-2
+            assert _rel(out["pred_logits"].cpu().numpy(), ref.pred_logits[0].numpy()) < 5e-2
+    finally:
+        eng.close()
