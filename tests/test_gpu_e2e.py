@@ -362,3 +362,34 @@ def test_edge_cases_few_views_few_classes():
             assert _rel(out["pred_logits"].cpu().numpy(), ref.pred_logits[0].numpy()) < 5e-2
     finally:
         eng.close()
+
+
+def test_outlier_channels_robustness(b16_weights):
+    """Pretrained CLIP towers carry a few 'massive activation' channels in the residual stream (tens of sigmas) and LayerNorm
+    gains far from 1.  The synthetic weights do not, so plant some: three residual channels get a large constant through the
+    position embedding and the pre-LN bias, and some LayerNorm gains are scaled by 8.  fp32 statistics, fp32 residual stream and
+    the exact two-pass softmax must keep the bf16 path within the usual tolerance of the fp32 oracle."""
+    from ttl_b200 import Engine
+    arch = O.ARCHS["ViT-B/16"]
+    w = {k: v.clone() for k, v in b16_weights.items()}
+    pre = "vision_model."
+    w[pre + "pre_layrnorm.bias"][[5, 300, 701]] += torch.tensor([40.0, -25.0, 60.0])
+    w[pre + "embeddings.position_embedding.weight"][:, 17] += 3.0
+    for i in (0, 4, 9, 11):
+        w[f"{pre}encoder.layers.{i}.layer_norm1.weight"][::7] *= 8.0
+        w[f"{pre}encoder.layers.{i}.layer_norm2.weight"][3::11] *= 8.0
+    imgs = O.make_synthetic_views(6, arch.image_size, seed=12)
+    text = O.make_text_features(10, arch.proj, seed=3)
+    ref = O.clip_logits(O.vision_forward(arch, w, imgs), text, math.log(100.0)).detach().numpy()
+    eng = Engine("ViT-B/16", max_views=8, max_classes=16, layer_range=(9, 11))
+    try:
+        eng.load_weights(w)
+        eng.set_lora_init(O.lora_init(arch, O.LoraSpec(), seed=0))
+        eng.set_text_features(text, math.log(100.0))
+        eng.lora_reset()
+        got = eng.forward(imgs.cuda()).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert _rel(got, ref) < 1.5e-2, _rel(got, ref)
+        assert (got.argmax(1) == ref.argmax(1)).mean() >= 5 / 6
+    finally:
+        eng.close()
