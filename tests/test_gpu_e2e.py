@@ -299,6 +299,17 @@ def test_vit_l14_geometry_forward_and_adapt():
         out = eng.adapt_predict(imgs.cuda(), Hparams(head="tpt", selection_p=0.3), want=("logits0", "pred_logits", "idx", "loss"))
         assert torch.isfinite(out["pred_logits"]).all() and out["idx"].numel() == 3
         assert _rel(out["pred_logits"].cpu().numpy(), out["logits0"][0].cpu().numpy()) > 1e-4   # the adapter moved it
+        # full adapt step against the fp32 oracle on the same selection: loss, LoRA gradients of the three adapted layers, prediction
+        from ttl_b200 import _lib as L
+        ref_a = O.adapt_and_predict(arch, w, imgs, text, math.log(100.0), lora0, spec, head="tpt", selection_p=0.3)
+        eng.set_graphs(False)
+        out = eng.adapt_predict(imgs.cuda(), Hparams(head="tpt", selection_p=0.3), forced_idx=ref_a.idx,
+                                want=("logits0", "pred_logits", "loss"))
+        assert abs(float(out["loss"]) - ref_a.loss) < 2e-2 * max(1.0, abs(ref_a.loss))
+        for i in spec.layers():
+            for j in (1, 3):            # B_q, B_v (dA == 0 at step 1)
+                assert _rel(eng.lora_get(i, j, L.LORA_GRAD), ref_a.grads[i][j].numpy()) < 3e-2, (i, j)
+        assert _rel(out["pred_logits"].cpu().numpy(), ref_a.pred_logits[0].numpy()) < 3e-2
     finally:
         eng.close()
 
