@@ -864,7 +864,7 @@ constexpr int PP_THREADS = 320;
 // the FMA pipe instead (Cody-Waite split with the 1.5 * 2^23 trick + cubic on [-0.5, 0.5], max relative error 7.5e-5, far
 // below the bf16 rounding of P).  x <= 0 here (the row maximum has been subtracted).
 #ifndef PP_POLY_MASK
-#define PP_POLY_MASK 0x88
+#define PP_POLY_MASK 0x80      // 1 of 8: 77.1-77.8 us per layer at S=3 against 78.0-79.1 with 0x88 and 80.9-81.2 with 0 (gpurun s108)
 #endif
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.f);
