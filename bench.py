@@ -67,7 +67,7 @@ def parse_args():
     ap.add_argument("--tta-steps", type=int, default=1,
                     help="optimiser steps per sample (the metric is quoted at 1; 4 = BASELINE config 5, informational)")
     ap.add_argument("--ring", type=int, default=4, help="distinct pre-staged batches (ring * S * 38.5 MB > L2)")
-    ap.add_argument("--concurrent", type=int, default=6,
+    ap.add_argument("--concurrent", type=int, default=9,
                     help="test samples adapted concurrently per step (BASELINE config 5); every multiple of 3 x 64 x 197 rows = 147.75 "
                          "tiles of 256 rows, one full wave of the 74 CTA pairs per 256-column block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
