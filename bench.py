@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- adapted samples/s of the TTL per-sample loop (BASELINE.json metric) on N B200s of one node.
 
-A "step" is one pass of the hot path over one test sample: reset -> 64-view forward with rank-16 LoRA -> confidence
-selection -> marginal-entropy loss -> backward into the LoRA factors -> AdamW -> predict on view 0 (ttl.py:338-352).
+A "step" is one pass of the hot path over one batch of S independent test samples (--concurrent, default 9), each going through
+reset -> 64-view forward with rank-16 LoRA -> confidence selection -> marginal-entropy loss -> backward into its own LoRA
+factors -> AdamW -> predict on view 0 (ttl.py:338-352); `value` counts samples, not steps.
 Workload = BASELINE.json configs[1]: ViT-B/16, 1000 classes, 64 views, r=16, 1 TTA step, bf16, synthetic data,
 random-init weights.  Test samples are independent, so ranks shard them with no data-path collective (weak scaling);
 the only collective is the final all-reduce of the accuracy counters.
