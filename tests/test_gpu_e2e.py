@@ -277,7 +277,7 @@ def test_adapted_top1_agreement_with_oracle(b16_weights):
 def test_vit_l14_geometry_forward_and_adapt():
     """BASELINE config 4 geometry (ViT-L/14 @224: 257 tokens, d=1024, 24 layers, 16 heads, proj 768; adapters on the last
     three layers): first-forward logits against the fp32 oracle on 4 views, then one fused adapt+predict runs and moves
-    the prediction.  (257 tokens exceed the tcgen05 attention tile plan; the mma.sync kernel serves this geometry.)"""
+    the prediction.  (257 tokens: tcgen05 attention with 256 keys in TMEM and key / query 256 handled on the side, csrc/attention.cu.)"""
     from ttl_b200 import Engine, Hparams
     arch = O.ARCHS["ViT-L/14"]
     spec = O.LoraSpec(rank=16, alpha=32.0, layer_lo=21, layer_hi=23)

@@ -877,10 +877,17 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 constexpr int PP_PTILE = 3 * 16384 + 4096;     // P of one tile: three 64-key blocks (128 rows x 128 B) + the 16-key tail block
 
+template <bool XK>     // XK: the 257-token form (one extra key, four 64-key P blocks, one V buffer); false: 129..208 tokens
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
-                        int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev) {
+                        int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev, int ptile_rt, int vbufs_rt,
+                        int xkey_rt, const bf16* __restrict__ qkv) {
+  // compile-time constants in the classic form, so that its code is what it was before the 257-token form existed
+  const int ptile = XK ? ptile_rt : PP_PTILE, vbufs = XK ? vbufs_rt : 2, xkey = XK ? xkey_rt : -1;
+  // ptile: bytes of one tile's P (PP_PTILE, or four 64-key blocks); vbufs: V buffers (2, or 1 when shared memory is short);
+  // xkey >= 0: ONE extra key / value row (index xkey = keys) that the MMAs do not cover -- 257 tokens = 256 keys in TMEM
+  // (2 tiles x 256 columns = all 512) + key 256 folded in by the softmax threads from global memory (qkv).
   extern __shared__ uint8_t smem_pp_raw[];
   // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0, per warpgroup: [it][t][stage]
 #define PP_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && wg_tid == 0) dbg[(it * 2 + t) * 8 + (k)] = clock64(); } while (0)
@@ -889,8 +896,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* sQ = smem;                              // [2 tiles] 16 KB each
   uint8_t* sK = sQ + 2 * 16384;
   uint8_t* sV = sK + KB;                           // [2 buffers]
-  uint8_t* sP = sV + 2 * KB;                       // [2 tiles] PP_PTILE each; block 2 doubles as the tile's output stage
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PP_PTILE);
+  uint8_t* sP = sV + vbufs * KB;                   // [2 tiles] ptile bytes each; block 2 doubles as the tile's output stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ptile);
   uint64_t* bar_kq = bars;            // K + Q0 + Q1 of the unit landed
   uint64_t* bar_v = bars + 1;         // [2] V buffer landed
   uint64_t* bar_vfree = bars + 3;     // [2] every MMA that reads the V buffer has retired
@@ -942,8 +949,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(&tmKV, bar_kq, sK, d + h * DH, 0, view);
         tma_load_3d(&tmQ, bar_kq, sQ, h * DH, 0, view);
         tma_load_3d(&tmQ, bar_kq, sQ + 16384, h * DH, 128, view);
-        const int b = it & 1;
-        if (it >= 2) mbar_wait(&bar_vfree[b], ((it >> 1) - 1) & 1);
+        const int b = vbufs == 2 ? (it & 1) : 0, use = vbufs == 2 ? (it >> 1) : it;     // buffer and how often it has been used
+        if (use >= 1) mbar_wait(&bar_vfree[b], (use - 1) & 1);
         mbar_expect_tx(&bar_v[b], KB);
         tma_load_3d(&tmKV, &bar_v[b], sV + b * KB, 2 * d + h * DH, 0, view);
       }
@@ -959,7 +966,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
-        const int b = it & 1;
+        const int b = vbufs == 2 ? (it & 1) : 0, use = vbufs == 2 ? (it >> 1) : it;
         mbar_wait(bar_kq, ph);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -971,7 +978,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                       k != 0 ? 1u : 0u);
           umma_commit(&bar_s[t]);
         }
-        mbar_wait(&bar_v[b], (it >> 1) & 1);
+        mbar_wait(&bar_v[b], use & 1);
         const uint32_t va = smem_u32(sV + b * KB);
         int kk = 0;
         for (int blk = 0; blk < n_full; ++blk) {
@@ -979,7 +986,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int t = 0; t < 2; ++t) {
             mbar_wait(&bar_p[t * 4 + blk], ph);
             tc_fence_after();
-            const uint32_t pa = smem_u32(sP + t * PP_PTILE + blk * 16384);
+            const uint32_t pa = smem_u32(sP + t * ptile + blk * 16384);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               umma_bf16(tmem + t * 256, umma_desc_k_sw128(pa + j * 32), umma_desc(va + (kk + j) * 2048, 1024, v_lbo, 2), idesc_o,
@@ -993,7 +1000,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int t = 0; t < 2; ++t) {
             mbar_wait(&bar_p[t * 4 + 3], ph);
             tc_fence_after();
-            umma_bf16(tmem + t * 256, umma_desc(smem_u32(sP + t * PP_PTILE + 3 * 16384), 256, 0, 6),
+            umma_bf16(tmem + t * 256, umma_desc(smem_u32(sP + t * ptile + 3 * 16384), 256, 0, 6),
                       umma_desc(va + kk * 2048, 1024, v_lbo, 2), idesc_o, kk != 0 ? 1u : 0u);
             umma_commit(&bar_o[t]);
           }
@@ -1009,7 +1016,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int wg_tid = threadIdx.x - 64 - t * 128;           // 0..127 inside the warpgroup
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + t * 256;
     const int n32 = keys / 32, rem16 = keys - n32 * 32;
-    uint8_t* myP = sP + t * PP_PTILE;
+    uint8_t* myP = sP + t * ptile;
     const uint32_t p_blk0 = smem_u32(myP), p_tail = p_blk0 + 3 * 16384;
     uint8_t* ostage = myP + 2 * 16384;
     const int r0 = t * 128;
@@ -1020,6 +1027,25 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int u2 = rev ? units - 1 - unit : unit;
       const int view = u2 / heads, h = u2 - view * heads;
       PP_STAMP(0);
+      // extra key (xkey >= 0): its score q_i . k_x from global memory while the S MMAs run; every query row r0 + row is real here
+      float sx = 0.f, px = 0.f;
+      if (xkey >= 0 && active) {
+        const size_t ld = static_cast<size_t>(3) * d;
+        const uint4* qrow = reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(view) * tokens + r0 + row) * ld + h * DH);
+        const uint4* krow = reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(view) * tokens + xkey) * ld + d + h * DH);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 a = __ldg(qrow + c8), b = __ldg(krow + c8);
+          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(a2[j]), fb = __bfloat1622float2(b2[j]);
+            sx = fmaf(fa.x, fb.x, sx);
+            sx = fmaf(fa.y, fb.y, sx);
+          }
+        }
+      }
       mbar_wait(&bar_s[t], ph);
       PP_STAMP(1);
       tc_fence_after();
@@ -1049,6 +1075,7 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
         }
       }
+      if (xkey >= 0) m = fmaxf(m, sx);
       PP_STAMP(2);
       if (wg_tid == 0) bulk_wait_read<0>();      // the previous unit's output store has finished reading the stage (= P block 2)
       named_bar_sync(1 + t, 128);
@@ -1130,7 +1157,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[t * 4 + 3]);
         }
-        l = l0 + l1;
+        if (xkey >= 0) px = ex2_approx(fmaf(sx, scale_log2, -ms));
+        l = l0 + l1 + px;
       } else {
         tc_fence_before();
         if (lane == 0) {
@@ -1151,6 +1179,22 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tfree[t]);
+      if (xkey >= 0 && active) {            // O_i += p_x v_x
+        const uint4* vrow = reinterpret_cast<const uint4*>(qkv + (static_cast<size_t>(view) * tokens + xkey) * (3 * static_cast<size_t>(d)) +
+                                                           2 * d + h * DH);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint4 vv = __ldg(vrow + c8);
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+          uint32_t* o = c8 < 4 ? o0 + c8 * 8 : o1 + (c8 - 4) * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fv = __bfloat1622float2(v2[j]);
+            o[2 * j] = __float_as_uint(fmaf(px, fv.x, __uint_as_float(o[2 * j])));
+            o[2 * j + 1] = __float_as_uint(fmaf(px, fv.y, __uint_as_float(o[2 * j + 1])));
+          }
+        }
+      }
       if (active) {
         const float inv = 1.f / l;
         const uint32_t obase = smem_u32(ostage) + row * 128;
@@ -1192,8 +1236,10 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // One CTA per (head, view): phase 1 one thread per key (q . k_j, fp32), block softmax, phase 2 one thread per output
 // dimension (sum_j p_j v_j[d], coalesced over d).  q comes from a compact [V, d] tensor, K/V from the usual qkv rows.
 __global__ void __launch_bounds__(128)
-attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qkv, bf16* __restrict__ out_cls, int tokens,
-                     int heads, float scale_log2) {
+attention_cls_kernel(const bf16* __restrict__ q_cls, size_t q_view_stride, const bf16* __restrict__ qkv, bf16* __restrict__ out_cls,
+                     size_t out_view_stride, float* __restrict__ lse, int lse_row, int tokens, int heads, float scale_log2) {
+  // General single-query-row form: q row of view v at q_cls + v * q_view_stride, output row at out_cls + v * out_view_stride
+  // (compact [V, d] tensors for the CLS path; the last token row of qkv / out for the 257-token path, which also wants lse).
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sh_cls[];
@@ -1202,7 +1248,7 @@ attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qk
   __shared__ float red[8];
   const int h = blockIdx.x, view = blockIdx.y, d = heads * DH, ld = 3 * d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < DH) sq[tid] = __bfloat162float(q_cls[static_cast<size_t>(view) * d + h * DH + tid]);
+  if (tid < DH) sq[tid] = __bfloat162float(q_cls[static_cast<size_t>(view) * q_view_stride + h * DH + tid]);
   __syncthreads();
   const bf16* kbase = qkv + static_cast<size_t>(view) * tokens * ld + d + h * DH;
   float mx = -INFINITY;
@@ -1236,7 +1282,9 @@ attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qk
   sum = warp_sum(sum);
   if (lane == 0) red[4 + warp] = sum;
   __syncthreads();
-  const float inv = 1.f / (red[4] + red[5] + red[6] + red[7]);
+  const float tot = red[4] + red[5] + red[6] + red[7];
+  const float inv = 1.f / tot;
+  if (lse != nullptr && tid == 0) lse[(static_cast<size_t>(view) * heads + h) * tokens + lse_row] = (mx + log2f(tot)) * LN2;
   // phase 2: threads 0..63 take the even keys, 64..127 the odd keys of output dimension tid & 63
   const int dd = tid & 63, half = tid >> 6;
   const bf16* vbase = qkv + static_cast<size_t>(view) * tokens * ld + 2 * d + h * DH + dd;
@@ -1245,7 +1293,7 @@ attention_cls_kernel(const bf16* __restrict__ q_cls, const bf16* __restrict__ qk
   __syncthreads();
   if (half == 1) sq[dd] = o;
   __syncthreads();
-  if (half == 0) out_cls[static_cast<size_t>(view) * d + h * DH + dd] = __float2bfloat16((o + sq[dd]) * inv);
+  if (half == 0) out_cls[static_cast<size_t>(view) * out_view_stride + h * DH + dd] = __float2bfloat16((o + sq[dd]) * inv);
 }
 
 inline int pick_warps(int tiles) {
@@ -1323,11 +1371,21 @@ static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int 
 
 static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                                     cudaStream_t st, int descending) {
-  const int keys = (tokens + 15) / 16 * 16;
+  // 257 tokens (ViT-L/14): 256 keys / queries through the MMAs (2 tiles x 256 TMEM columns), key 256 folded in by the softmax
+  // threads, query 256 by the single-row kernel below
+  const int xkey = tokens == 257 ? 256 : -1;
+  const int keys = xkey >= 0 ? 256 : (tokens + 15) / 16 * 16;
   const int tail = keys % 64;
-  if (keys < 128 || keys > 208 || (tail != 0 && tail != 16) || tokens <= 128 || tokens > 256) return false;   // exactly two query tiles
+  if (xkey < 0 && (keys < 128 || keys > 208 || (tail != 0 && tail != 16) || tokens <= 128 || tokens > 256)) return false;   // exactly two query tiles
   const int d = heads * DH;
-  const size_t smem = 2 * 16384 + 3 * static_cast<size_t>(keys) * 128 + 2 * PP_PTILE + 256 + 1024;
+  const int n_full = keys / 64;
+  const int ptile = n_full * 16384 + (tail ? 4096 : 0) > PP_PTILE ? n_full * 16384 + (tail ? 4096 : 0) : PP_PTILE;
+  int vbufs = 2;
+  size_t smem = 2 * 16384 + static_cast<size_t>(1 + vbufs) * keys * 128 + 2 * static_cast<size_t>(ptile) + 256 + 1024;
+  if (smem > 227 * 1024) {
+    vbufs = 1;
+    smem = 2 * 16384 + static_cast<size_t>(1 + vbufs) * keys * 128 + 2 * static_cast<size_t>(ptile) + 256 + 1024;
+  }
   if (smem > 227 * 1024) return false;
   CUtensorMap tq, tkv, to;
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
@@ -1340,13 +1398,17 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   const uint32_t obox[3] = {64, 128, 1};
   if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
   const int dv = current_device_slot();
-  static size_t configured_dev[MAX_DEVICES] = {};
+  static size_t configured_dev[2][MAX_DEVICES] = {};      // per instantiation and device
   static int num_sms_dev[MAX_DEVICES] = {};
-  size_t& configured = configured_dev[dv];
+  size_t& configured = configured_dev[xkey >= 0 ? 1 : 0][dv];
   int& num_sms = num_sms_dev[dv];
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
   if (smem > configured) {
-    if (cudaFuncSetAttribute(attention_fwd_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+    const cudaError_t ea = xkey >= 0 ? cudaFuncSetAttribute(attention_fwd_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            static_cast<int>(smem))
+                                     : cudaFuncSetAttribute(attention_fwd_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                            static_cast<int>(smem));
+    if (ea != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
@@ -1358,8 +1420,17 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
   if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
   if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
-  const bool ok = launch_pdl(attention_fwd_pp_kernel, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units,
-                             keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending) == cudaSuccess;
+  const bool ok = (xkey >= 0 ? launch_pdl(attention_fwd_pp_kernel<true>, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens,
+                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv)
+                             : launch_pdl(attention_fwd_pp_kernel<false>, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens,
+                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv)) ==
+                  cudaSuccess;
+  if (ok && xkey >= 0) {       // query row 256 of every (view, head): q from the qkv row itself, output + lse row 256
+    const size_t ld = static_cast<size_t>(3) * d;
+    launch_pdl(attention_cls_kernel, dim3(heads, V), dim3(128), (64 + tokens) * sizeof(float), st, qkv + static_cast<size_t>(xkey) * ld,
+               static_cast<size_t>(tokens) * ld, qkv, out + static_cast<size_t>(xkey) * d, static_cast<size_t>(tokens) * d, lse, xkey,
+               tokens, heads, scale * LOG2E);
+  }
   if (want_dbg) {
     cudaStreamSynchronize(st);
     static int printed = 0;
@@ -1446,8 +1517,9 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
 
 void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
                           cudaStream_t st) {
-  launch_pdl(attention_cls_kernel, dim3(heads, V), dim3(128), (64 + tokens) * sizeof(float), st, q_cls, qkv, out_cls, tokens,
-             heads, scale * LOG2E);
+  const size_t dd = static_cast<size_t>(heads) * DH;
+  launch_pdl(attention_cls_kernel, dim3(heads, V), dim3(128), (64 + tokens) * sizeof(float), st, q_cls, dd, qkv, out_cls, dd,
+             static_cast<float*>(nullptr), 0, tokens, heads, scale * LOG2E);
 }
 
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
