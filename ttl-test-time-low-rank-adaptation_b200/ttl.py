@@ -12,7 +12,7 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
   --compat        drive the module through autograd + torch.optim.AdamW (the reference's control flow) instead of
                   the fused per-sample call
   --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
-  --concurrent_samples S  adapt S test samples per library call (default 3; 1 = strictly one at a time)
+  --concurrent_samples S  adapt S test samples per library call (default 9; 1 = strictly one at a time)
   --precision fp32  validation mode: every activation/contraction in fp32 (held to 1e-4 against the reference), one sample per call
   --vision_checkpoint F  load the image tower from a checkpoint file (HF or OpenAI format) instead of the local HF cache
   --views_on_device  ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
@@ -414,7 +414,7 @@ def build_parser():
                    help='bf16 = tensor-core path (default); fp32 = validation mode (fp32 everywhere, one sample per call)')
     p.add_argument('--vision_checkpoint', default=None, type=str,
                    help='CLIP checkpoint file for the image tower: HF model.safetensors / pytorch_model.bin or OpenAI ViT-*.pt')
-    p.add_argument('--concurrent_samples', default=3, type=int,
+    p.add_argument('--concurrent_samples', default=9, type=int,
                    help='test samples adapted concurrently per library call (each keeps its own adapter/optimiser state)')
     return p
 
