@@ -877,12 +877,13 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 constexpr int PP_PTILE = 3 * 16384 + 4096;     // P of one tile: three 64-key blocks (128 rows x 128 B) + the 16-key tail block
 
-template <bool XK>     // XK: the 257-token form (one extra key, four 64-key P blocks, one V buffer); false: 129..208 tokens
-__global__ void __launch_bounds__(PP_THREADS, 1)
+constexpr int PP_THREADS_XK = PP_THREADS + 64;    // + two warps for the extra query row
+template <bool XK>     // XK: the 257-token form (one extra key and query, four 64-key P blocks, one V buffer); false: 129..208 tokens
+__global__ void __launch_bounds__(XK ? PP_THREADS_XK : PP_THREADS, 1)
 attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
                         int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev, int ptile_rt, int vbufs_rt,
-                        int xkey_rt, const bf16* __restrict__ qkv) {
+                        int xkey_rt, const bf16* __restrict__ qkv, bf16* __restrict__ out_x) {
   // compile-time constants in the classic form, so that its code is what it was before the 257-token form existed
   const int ptile = XK ? ptile_rt : PP_PTILE, vbufs = XK ? vbufs_rt : 2, xkey = XK ? xkey_rt : -1;
   // ptile: bytes of one tile's P (PP_PTILE, or four 64-key blocks); vbufs: V buffers (2, or 1 when shared memory is short);
@@ -906,6 +907,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* bar_tfree = bars + 9;     // [2] O_t copied to registers: TMEM region t reusable
   uint64_t* bar_p = bars + 11;        // [2][4] P block b of tile t written (index 3 = tail block)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* bar_xk = bars + 20;       // XK: the extra-query warps have read K of the unit (2 arrivals)
+  uint64_t* bar_xv = bars + 21;       // XK: ... and V
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * DH;
@@ -914,6 +917,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmKV);
     tma_prefetch_desc(&tmOut);
     mbar_init(bar_kq, 1);
+    mbar_init(bar_xk, 2);
+    mbar_init(bar_xv, 2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_v[i], 1);
       mbar_init(&bar_vfree[i], 1);
@@ -945,12 +950,14 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int u2 = rev ? units - 1 - unit : unit;            // descending walk (kernels.cuh)
         const int view = u2 / heads, h = u2 - view * heads;
         if (it > 0) mbar_wait(&bar_s[1], (it - 1) & 1);          // both S MMAs of the previous unit retired: K, Q0, Q1 are dead
+        if (XK && it > 0) mbar_wait(bar_xk, (it - 1) & 1);       // ... and the extra-query warps are done with K
         mbar_expect_tx(bar_kq, KB + 2 * 16384);
         tma_load_3d(&tmKV, bar_kq, sK, d + h * DH, 0, view);
         tma_load_3d(&tmQ, bar_kq, sQ, h * DH, 0, view);
         tma_load_3d(&tmQ, bar_kq, sQ + 16384, h * DH, 128, view);
         const int b = vbufs == 2 ? (it & 1) : 0, use = vbufs == 2 ? (it >> 1) : it;     // buffer and how often it has been used
         if (use >= 1) mbar_wait(&bar_vfree[b], (use - 1) & 1);
+        if (XK && it > 0) mbar_wait(bar_xv, (it - 1) & 1);       // one V buffer in this form: the extra-query warps are done with it
         mbar_expect_tx(&bar_v[b], KB);
         tma_load_3d(&tmKV, &bar_v[b], sV + b * KB, 2 * d + h * DH, 0, view);
       }
@@ -1009,7 +1016,98 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
     __syncwarp();
-  } else {
+  } else if (XK && warp >= 10) {
+    // ------------------------------------------------------------------ query row xkey (XK): two warps, CUDA cores, K / V from the
+    // tiles the unit has in shared memory anyway (a separate kernel would read all K and V a second time).
+    // Scores: thread x takes keys x, x+64, x+128, x+192 (+ key xkey, redundantly, from global memory); softmax over the 257
+    // scores through shuffles + a 64-thread named barrier; P V: thread x = output dimension x.
+    const int x = threadIdx.x - PP_THREADS;
+    float* xP = reinterpret_cast<float*>(bars + 32);     // [256] probabilities of the keys in shared memory
+    float* xR = xP + 256;                                // [2] partial maxima, [2] partial sums
+    const size_t ld = static_cast<size_t>(3) * d;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int u2 = rev ? units - 1 - unit : unit;
+      const int view = u2 / heads, h = u2 - view * heads;
+      const bf16* rowx = qkv + (static_cast<size_t>(view) * tokens + xkey) * ld + h * DH;     // q | k | v of token xkey, this head
+      float q[64];
+      float sxx = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(rowx) + c8), b = __ldg(reinterpret_cast<const uint4*>(rowx + d) + c8);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = __bfloat1622float2(a2[j]), fb = __bfloat1622float2(b2[j]);
+          q[c8 * 8 + 2 * j] = fa.x;
+          q[c8 * 8 + 2 * j + 1] = fa.y;
+          sxx = fmaf(fa.x, fb.x, sxx);
+          sxx = fmaf(fa.y, fb.y, sxx);
+        }
+      }
+      mbar_wait(bar_kq, ph);                     // K of the unit has landed (TMA, 128-byte swizzle: chunk c of row j at (c ^ (j & 7)) * 16)
+      float sc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = x + 64 * i;
+        const uint32_t rowa = smem_u32(sK) + j * 128;
+        float acc = 0.f;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 kk;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(kk.x), "=r"(kk.y), "=r"(kk.z), "=r"(kk.w)
+                       : "r"(rowa + ((static_cast<uint32_t>(c8) ^ (j & 7)) << 4)));
+          const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fk = __bfloat1622float2(k2[e]);
+            acc = fmaf(q[c8 * 8 + 2 * e], fk.x, acc);
+            acc = fmaf(q[c8 * 8 + 2 * e + 1], fk.y, acc);
+          }
+        }
+        sc[i] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_xk);        // K may be overwritten
+      float m = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), sxx);
+      m = warp_max(m);
+      if (lane == 0) xR[warp - 10] = m;
+      named_bar_sync(7, 64);
+      m = fmaxf(xR[0], xR[1]);
+      const float ms = m * scale_log2;
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pv = ex2_approx(fmaf(sc[i], scale_log2, -ms));
+        xP[x + 64 * i] = pv;
+        lsum += pv;
+      }
+      const float pxx = ex2_approx(fmaf(sxx, scale_log2, -ms));
+      if (x == 0) lsum += pxx;
+      lsum = warp_sum(lsum);
+      if (lane == 0) xR[2 + warp - 10] = lsum;
+      named_bar_sync(7, 64);                     // partial sums and all of xP visible
+      const float l = xR[2] + xR[3];
+      mbar_wait(&bar_v[0], it & 1);              // V of the unit (one buffer in this form)
+      const uint32_t vcol = smem_u32(sV) + (x & 7) * 2;
+      const uint32_t vch = static_cast<uint32_t>(x >> 3);
+      float acc = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 256; ++j) {
+        uint16_t raw;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(raw) : "r"(vcol + j * 128 + ((vch ^ (j & 7)) << 4)));
+        acc = fmaf(xP[j], __uint_as_float(static_cast<uint32_t>(raw) << 16), acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_xv);        // V may be overwritten
+      acc = fmaf(pxx, __bfloat162float(rowx[2 * d + x]), acc);
+      out_x[(static_cast<size_t>(view) * tokens + xkey) * d + h * DH + x] = __float2bfloat16(acc / l);
+      if (x == 0 && lse != nullptr) lse[(static_cast<size_t>(view) * heads + h) * tokens + xkey] = (ms + log2f(l)) * LN2;
+      named_bar_sync(7, 64);                     // xP / xR are rewritten in the next unit
+    }
+  } else if (warp < 10) {
     // ------------------------------------------------------------------ softmax + epilogue warpgroup of tile t
     const int t = (warp - 2) >> 2;
     const int quad = warp & 3, row = quad * 32 + lane;
@@ -1386,6 +1484,10 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
     vbufs = 1;
     smem = 2 * 16384 + static_cast<size_t>(1 + vbufs) * keys * 128 + 2 * static_cast<size_t>(ptile) + 256 + 1024;
   }
+  if (xkey >= 0) {
+    if (vbufs != 1) return false;          // the extra-query warps' barriers assume the single V buffer of this form
+    smem += 1280;                          // probabilities + partials of the extra query row
+  }
   if (smem > 227 * 1024) return false;
   CUtensorMap tq, tkv, to;
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
@@ -1420,17 +1522,11 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
   if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
   if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
-  const bool ok = (xkey >= 0 ? launch_pdl(attention_fwd_pp_kernel<true>, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens,
-                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv)
+  const bool ok = (xkey >= 0 ? launch_pdl(attention_fwd_pp_kernel<true>, dim3(grid), dim3(PP_THREADS_XK), smem, st, tq, tkv, to, lse, tokens,
+                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv, out)
                              : launch_pdl(attention_fwd_pp_kernel<false>, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens,
-                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv)) ==
+                                          heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv, out)) ==
                   cudaSuccess;
-  if (ok && xkey >= 0) {       // query row 256 of every (view, head): q from the qkv row itself, output + lse row 256
-    const size_t ld = static_cast<size_t>(3) * d;
-    launch_pdl(attention_cls_kernel, dim3(heads, V), dim3(128), (64 + tokens) * sizeof(float), st, qkv + static_cast<size_t>(xkey) * ld,
-               static_cast<size_t>(tokens) * ld, qkv, out + static_cast<size_t>(xkey) * d, static_cast<size_t>(tokens) * d, lse, xkey,
-               tokens, heads, scale * LOG2E);
-  }
   if (want_dbg) {
     cudaStreamSynchronize(st);
     static int printed = 0;
