@@ -209,22 +209,42 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
                                      bf16* __restrict__ dqkv, int tokens, int heads, float scale, int tiles, int nkp) {
   pdl_wait();
   pdl_trigger();
+  // Shared memory per CTA: the two matrices the phase uses as B operands in full (phase A: K, V; phase B: Q, dO), the row
+  // statistics, and per warp a 2 x 16-row staging area for the A-operand rows of the tile it is working on (phase A: Q, dO rows;
+  // phase B: K, V rows).  Half of what keeping all four matrices resident took: two CTAs per SM at 197 tokens.
   extern __shared__ __align__(16) uint8_t smem_att[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_att);
-  bf16* sK = sQ + nkp * LDS;
-  bf16* sV = sK + nkp * LDS;
-  bf16* sDO = sV + nkp * LDS;
-  float* sD = reinterpret_cast<float*>(sDO + nkp * LDS);  // rowsum(dO * O)
+  const bool phase_a = blockIdx.z == 0;
+  bf16* sF0 = reinterpret_cast<bf16*>(smem_att);          // phase A: K      phase B: Q
+  bf16* sF1 = sF0 + nkp * LDS;                            // phase A: V      phase B: dO
+  float* sD = reinterpret_cast<float*>(sF1 + nkp * LDS);  // rowsum(dO * O)
   float* sL = sD + nkp;                                    // lse in log2 units
   const int h = blockIdx.x, view = blockIdx.y, d = heads * DH, ld = 3 * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  bf16* sW0 = reinterpret_cast<bf16*>(sL + nkp) + warp * (2 * 16 * LDS);
+  bf16* sW1 = sW0 + 16 * LDS;
   const bf16* base = qkv + static_cast<size_t>(view) * tokens * ld + h * DH;
   const bf16* gO = out + static_cast<size_t>(view) * tokens * d + h * DH;
   const bf16* gDO = dout + static_cast<size_t>(view) * tokens * d + h * DH;
-  load_head_tile(sQ, base, ld, tokens, nkp);
-  load_head_tile(sK, base + d, ld, tokens, nkp);
-  load_head_tile(sV, base + 2 * d, ld, tokens, nkp);
-  load_head_tile(sDO, gDO, d, tokens, nkp);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  bf16 *sQ, *sK, *sV, *sDO;
+  if (phase_a) {
+    sK = sF0; sV = sF1; sQ = nullptr; sDO = nullptr;
+    load_head_tile(sK, base + d, ld, tokens, nkp);
+    load_head_tile(sV, base + 2 * d, ld, tokens, nkp);
+  } else {
+    sQ = sF0; sDO = sF1; sK = nullptr; sV = nullptr;
+    load_head_tile(sQ, base, ld, tokens, nkp);
+    load_head_tile(sDO, gDO, d, tokens, nkp);
+  }
+  // 16 rows x 64 columns of a global matrix into the warp's staging area (rows >= tokens zero)
+  auto stage16 = [&](bf16* dst, const bf16* g, int g_ld, int row0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = lane + u * 32, r = i >> 3, c = (i & 7) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row0 + r < tokens) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(row0 + r) * g_ld + c);
+      *reinterpret_cast<uint4*>(dst + r * LDS + c) = v;
+    }
+  };
   const float* L = lse + (static_cast<size_t>(view) * heads + h) * tokens;
   // D[r] = rowsum(dO[r,:] * O[r,:]) and the log-sum-exp in log2 units: one thread per row, eight independent 16-byte loads
   for (int r = threadIdx.x; r < nkp; r += blockDim.x) {
@@ -254,16 +274,19 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   const float scale_log2 = scale * LOG2E;
   bf16* gdq = dqkv + static_cast<size_t>(view) * tokens * ld + h * DH;
 
-  // The two phases are independent given Q/K/V/dO/D in smem: blockIdx.z picks one, which doubles the number of CTAs of
-  // the (small: G <= 18 views) backward launches and halves the serial work per CTA.
-  const bool do_a = gridDim.z == 1 || blockIdx.z == 0, do_b = gridDim.z == 1 || blockIdx.z == 1;
+  // The two phases are independent: blockIdx.z picks one (gridDim.z == 2).
+  const bool do_a = phase_a, do_b = !phase_a;
   // ---------------- phase A: dQ for 16-query tiles
   for (int qt = warp; do_a && qt < tiles; qt += nwarps) {
     uint32_t aq[4][4], ado[4][4];
+    __syncwarp();
+    stage16(sW0, base, ld, qt * 16);
+    stage16(sW1, gDO, d, qt * 16);
+    __syncwarp();
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      load_a(sQ, qt * 16, ks * 16, lane, aq[ks]);
-      load_a(sDO, qt * 16, ks * 16, lane, ado[ks]);
+      load_a(sW0, 0, ks * 16, lane, aq[ks]);
+      load_a(sW1, 0, ks * 16, lane, ado[ks]);
     }
     const int r0 = qt * 16 + (lane >> 2), r1 = r0 + 8;
     const float L0 = sL[r0], L1 = sL[r1], D0 = sD[r0], D1 = sD[r1];
@@ -281,7 +304,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const bool ok = key + (e & 1) < tokens;
-          const float p = ok ? exp2f(s[nt][e] * scale_log2 - (e < 2 ? L0 : L1)) : 0.f;
+          const float p = ok ? ex2_approx(s[nt][e] * scale_log2 - (e < 2 ? L0 : L1)) : 0.f;
           s[nt][e] = p * (dp[nt][e] - (e < 2 ? D0 : D1)) * scale;   // dS
         }
       }
@@ -301,10 +324,14 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   // ---------------- phase B: dK, dV for 16-key tiles (transposed problem: rows = keys, columns = queries)
   for (int kt = warp; do_b && kt < tiles; kt += nwarps) {
     uint32_t ak[4][4], av[4][4];
+    __syncwarp();
+    stage16(sW0, base + d, ld, kt * 16);
+    stage16(sW1, base + 2 * d, ld, kt * 16);
+    __syncwarp();
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      load_a(sK, kt * 16, ks * 16, lane, ak[ks]);
-      load_a(sV, kt * 16, ks * 16, lane, av[ks]);
+      load_a(sW0, 0, ks * 16, lane, ak[ks]);
+      load_a(sW1, 0, ks * 16, lane, av[ks]);
     }
     float dk[8][4], dv[8][4];
     zero_acc(dk);
@@ -321,7 +348,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
         const float La = sL[q], Lb = sL[q + 1], Da = sD[q], Db = sD[q + 1];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p = exp2f(st[nt][e] * scale_log2 - ((e & 1) ? Lb : La));   // 0 for padded queries (L = +inf)
+          const float p = ex2_approx(st[nt][e] * scale_log2 - ((e & 1) ? Lb : La));   // 0 for padded queries (L = +inf)
           dpt[nt][e] = p * (dpt[nt][e] - ((e & 1) ? Db : Da)) * scale;           // dS^T
           st[nt][e] = p;                                                         // P^T
         }
@@ -1405,9 +1432,10 @@ size_t attention_fwd_smem(int tokens) {
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   return static_cast<size_t>(q_tiles * 16 + 2 * nkp) * LDS * sizeof(bf16);
 }
-size_t attention_bwd_smem(int tokens) {
-  const int nkp = (tokens + 63) / 64 * 64;
-  return static_cast<size_t>(4 * nkp) * LDS * sizeof(bf16) + 2 * nkp * sizeof(float);
+size_t attention_bwd_smem(int tokens) {      // two full matrices + row statistics + per-warp staging (see the kernel)
+  const int nkp = (tokens + 63) / 64 * 64, tiles = (tokens + 15) / 16;
+  return static_cast<size_t>(2 * nkp) * LDS * sizeof(bf16) + 2 * nkp * sizeof(float) +
+         static_cast<size_t>(pick_warps(tiles)) * 2 * 16 * LDS * sizeof(bf16);
 }
 
 static bool launch_attention_fwd_tc(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
@@ -1628,7 +1656,7 @@ void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, co
     cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  launch_pdl(attention_bwd_kernel, dim3(heads, V, 2), dim3(pick_warps(tiles) * 32), smem, st, qkv, out, dout, lse, dqkv, tokens,
+  launch_pdl(attention_bwd_kernel, dim3(heads, V, 2), dim3(pick_warps(tiles) * 32), smem, st, qkv, out, dout, lse, dqkv, tokens,   // z: phase
              heads, scale, tiles, nkp);
 }
 
