@@ -90,6 +90,57 @@ skinny_partial_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __rest
   for (int j = 0; j < JPT; ++j) o[j] = acc[j];
 }
 
+// The same partial products on the tensor cores (narrow width 16): out[64 w x 16 j] = W^T [64 x 128 rows] . N [128 rows x 16] per CTA,
+// four warps, one m16 tile of w each, mma.sync.m16n8k16 with both operands taken transposed out of the row-major staging
+// (ldmatrix.trans).  The scalar kernel above needed 3.5 instructions per MAC: 198 us per launch at 64 views x 9 samples (DeYO head).
+__global__ void __launch_bounds__(128)
+skinny_partial_mma_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __restrict__ narrow, int ldn, int M, int nw,
+                          float* __restrict__ ws, int narrow_gstride) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int NN = 16;
+  __shared__ __align__(16) bf16 sW[SR_MC][64 + 8];
+  __shared__ __align__(16) bf16 sN[SR_MC][NN + 8];
+  const int w0 = blockIdx.x * 64, m0 = blockIdx.y * SR_MC, grp = blockIdx.z;
+  wide += static_cast<size_t>(grp) * M * ldw;
+  narrow += static_cast<size_t>(grp) * M * ldn + grp * narrow_gstride;
+  ws += static_cast<size_t>(grp) * gridDim.y * nw * NN;
+  for (int i = threadIdx.x; i < SR_MC * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m0 + r < M) v = *reinterpret_cast<const uint4*>(wide + static_cast<size_t>(m0 + r) * ldw + w0 + c);
+    *reinterpret_cast<uint4*>(&sW[r][c]) = v;
+  }
+  for (int i = threadIdx.x; i < SR_MC * (NN / 8); i += blockDim.x) {
+    const int r = i / (NN / 8), c = (i % (NN / 8)) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m0 + r < M) v = *reinterpret_cast<const uint4*>(narrow + static_cast<size_t>(m0 + r) * ldn + c);
+    *reinterpret_cast<uint4*>(&sN[r][c]) = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mi = lane >> 3;
+  const int wt = warp * 16;                      // this warp's 16 columns of `wide` = rows of the output tile
+  float acc[2][4] = {};
+#pragma unroll
+  for (int k0 = 0; k0 < SR_MC; k0 += 16) {
+    uint32_t a[4], b[4];
+    // A = W^T (16 w x 16 rows): 8x8 blocks (w 0-7 | 8-15) x (rows 0-7 | 8-15), stored row-major by rows -> .trans
+    ldsm_x4_t(smem_u32(&sW[k0 + (mi >> 1) * 8 + (lane & 7)][wt + (mi & 1) * 8]), a[0], a[1], a[2], a[3]);
+    // B = N (16 rows x 16 j) stored [rows][j] -> .trans; (b0, b1): j 0-7, (b2, b3): j 8-15
+    ldsm_x4_t(smem_u32(&sN[k0 + (mi & 1) * 8 + (lane & 7)][(mi >> 1) * 8]), b[0], b[1], b[2], b[3]);
+    mma_bf16_16816(acc[0], a, b[0], b[1]);
+    mma_bf16_16816(acc[1], a, b[2], b[3]);
+  }
+  const int r0 = wt + (lane >> 2), c0 = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    float* o0 = ws + (static_cast<size_t>(blockIdx.y) * nw + w0 + r0) * NN + nt * 8 + c0;
+    float* o1 = o0 + 8 * NN;
+    *reinterpret_cast<float2*>(o0) = make_float2(acc[nt][0], acc[nt][1]);
+    *reinterpret_cast<float2*>(o1) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+}
+
 __global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, int nw, int nn, float scale,
                                     float* __restrict__ out, int transpose_out, int64_t out_gstride) {
   pdl_wait();
@@ -157,7 +208,10 @@ void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow,
                           cudaStream_t st) {
   const int chunks = (M + SR_MC - 1) / SR_MC;
   dim3 grid(nw / 64, chunks, groups);
-  if (nn == 16) launch_pdl(skinny_partial_kernel<16>, dim3(grid), dim3(256), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  static const char* sk_env = std::getenv("TTL_SKINNY");      // "scalar": the CUDA-core kernel (A/B reference)
+  static const bool scalar = sk_env != nullptr && sk_env[0] == 's';
+  if (nn == 16 && !scalar) launch_pdl(skinny_partial_mma_kernel, dim3(grid), dim3(128), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
+  else if (nn == 16) launch_pdl(skinny_partial_kernel<16>, dim3(grid), dim3(256), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
   else launch_pdl(skinny_partial_kernel<32>, dim3(grid), dim3(256), 0, st, wide, ldw, narrow, ldn, M, nw, ws, narrow_gstride);
   launch_pdl(skinny_final_kernel, dim3(dim3((nw * nn + 255) / 256, groups)), dim3(256), 0, st, ws, chunks, nw, nn, scale, out, transpose_out,
                                                                            out_gstride);
