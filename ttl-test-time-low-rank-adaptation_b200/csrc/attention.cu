@@ -7,6 +7,8 @@
 //   forward : O = softmax(scale * Q K^T) V, optional LSE for the backward
 //   backward: phase A per 16-query tile -> dQ ; phase B per 16-key tile (transposed problem) -> dK, dV.
 //             No atomics, deterministic.
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -46,12 +48,14 @@ __device__ __forceinline__ void load_b_kn(const bf16* s, int k0, int n0, int lan
 }
 
 // acc[16 x 64] += A[16 x 64(k = head dim)] * B[n0..n0+63][k]^T          (scores: Q K^T, dO V^T, K Q^T, V dO^T)
+// NV (compile time): only the first NV 16-wide groups of the 64 columns hold real rows of B; the rest (padding) is skipped
+template <int NV = 4>
 __device__ __forceinline__ void mma_rows_nk(float (&acc)[8][4], const uint32_t (&a)[4][4], const bf16* sB, int n0,
                                             int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
+    for (int np = 0; np < NV; ++np) {
       uint32_t b[4];
       load_b_nk(sB, n0 + np * 16, ks * 16, lane, b);
       mma_bf16_16816(acc[2 * np], a[ks], b[0], b[1]);
@@ -60,10 +64,12 @@ __device__ __forceinline__ void mma_rows_nk(float (&acc)[8][4], const uint32_t (
   }
 }
 // acc[16 x 64(n = head dim)] += P[16 x 64(k)] * B[k0..k0+63][n]              (P V, dS K, P^T dO, dS^T Q)
+// NV (compile time): only the first NV 16-deep k-steps of P are non-zero
+template <int NV = 4>
 __device__ __forceinline__ void mma_rows_kn(float (&acc)[8][4], const uint32_t (&p)[4][4], const bf16* sB, int k0,
                                             int lane) {
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < NV; ++ks) {
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t b[4];
@@ -272,6 +278,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   }
   __syncthreads();
   const float scale_log2 = scale * LOG2E;
+  const int tok16 = (tokens + 15) & ~15;
   bf16* gdq = dqkv + static_cast<size_t>(view) * tokens * ld + h * DH;
 
   // The two phases are independent: blockIdx.z picks one (gridDim.z == 2).
@@ -292,14 +299,16 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
     const float L0 = sL[r0], L1 = sL[r1], D0 = sD[r0], D1 = sD[r1];
     float dq[8][4];
     zero_acc(dq);
-    for (int kc = 0; kc < nkp; kc += 64) {
+    // one 64-key chunk; NV = real 16-key groups in it (4 except for the last chunk: 197 tokens -> 1), a compile-time constant
+    auto chunk_a = [&](const int kc, auto nvc) {
+      constexpr int NV = decltype(nvc)::value;
       float s[8][4], dp[8][4];
       zero_acc(s);
       zero_acc(dp);
-      mma_rows_nk(s, aq, sK, kc, lane);
-      mma_rows_nk(dp, ado, sV, kc, lane);
+      mma_rows_nk<NV>(s, aq, sK, kc, lane);
+      mma_rows_nk<NV>(dp, ado, sV, kc, lane);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 2 * NV; ++nt) {
         const int key = kc + nt * 8 + (lane & 3) * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -310,7 +319,15 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
       }
       uint32_t ds[4][4];
       acc_to_afrag(s, ds);
-      mma_rows_kn(dq, ds, sK, kc, lane);
+      mma_rows_kn<NV>(dq, ds, sK, kc, lane);
+    };
+    int kc = 0;
+    for (; kc + 64 <= tok16; kc += 64) chunk_a(kc, std::integral_constant<int, 4>{});
+    switch ((tok16 - kc) >> 4) {
+      case 1: chunk_a(kc, std::integral_constant<int, 1>{}); break;
+      case 2: chunk_a(kc, std::integral_constant<int, 2>{}); break;
+      case 3: chunk_a(kc, std::integral_constant<int, 3>{}); break;
+      default: break;
     }
     // stage through global directly (Q rows in smem are still needed by phase B of other warps)
 #pragma unroll
@@ -336,14 +353,15 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
     float dk[8][4], dv[8][4];
     zero_acc(dk);
     zero_acc(dv);
-    for (int qc = 0; qc < nkp; qc += 64) {
+    auto chunk_b = [&](const int qc, auto nvc) {
+      constexpr int NV = decltype(nvc)::value;
       float st[8][4], dpt[8][4];
       zero_acc(st);
       zero_acc(dpt);
-      mma_rows_nk(st, ak, sQ, qc, lane);     // S^T = K_t Q^T
-      mma_rows_nk(dpt, av, sDO, qc, lane);   // dP^T = V_t dO^T
+      mma_rows_nk<NV>(st, ak, sQ, qc, lane);     // S^T = K_t Q^T
+      mma_rows_nk<NV>(dpt, av, sDO, qc, lane);   // dP^T = V_t dO^T
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < 2 * NV; ++nt) {
         const int q = qc + nt * 8 + (lane & 3) * 2;
         const float La = sL[q], Lb = sL[q + 1], Da = sD[q], Db = sD[q + 1];
 #pragma unroll
@@ -356,8 +374,16 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
       uint32_t pt[4][4], dst[4][4];
       acc_to_afrag(st, pt);
       acc_to_afrag(dpt, dst);
-      mma_rows_kn(dv, pt, sDO, qc, lane);    // dV += P^T dO
-      mma_rows_kn(dk, dst, sQ, qc, lane);    // dK += dS^T Q
+      mma_rows_kn<NV>(dv, pt, sDO, qc, lane);    // dV += P^T dO
+      mma_rows_kn<NV>(dk, dst, sQ, qc, lane);    // dK += dS^T Q
+    };
+    int qc = 0;
+    for (; qc + 64 <= tok16; qc += 64) chunk_b(qc, std::integral_constant<int, 4>{});
+    switch ((tok16 - qc) >> 4) {
+      case 1: chunk_b(qc, std::integral_constant<int, 1>{}); break;
+      case 2: chunk_b(qc, std::integral_constant<int, 2>{}); break;
+      case 3: chunk_b(qc, std::integral_constant<int, 3>{}); break;
+      default: break;
     }
     const int r0 = kt * 16 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
