@@ -50,14 +50,21 @@ def test_gemm_cta_pair_kernel(G, M, N, K, bn):
     acc = a.float() @ b.float().t()
     out, _ = gu.gemm(a, b, L.EPI_BF16, bias=bias, block_n=1000 + bn)
     assert gu.rel_err(out, acc + bias) < 4e-3 and torch.isfinite(out.float()).all()
-    out, _ = gu.gemm(a, b, L.EPI_GELU, bias=bias, block_n=1000 + bn)
+    out, z2 = gu.gemm(a, b, L.EPI_GELU, bias=bias, block_n=1000 + bn, want_out2=True)     # + pre-activation copy for the backward
     z = acc + bias
     assert gu.rel_err(out, z * torch.sigmoid(1.702 * z)) < 6e-3
+    assert gu.rel_err(z2, z) < 4e-3
     resid = torch.randn(M, N, device="cuda")
     out, _ = gu.gemm(a, b, L.EPI_RESID_F32, bias=bias, resid=resid, block_n=1000 + bn)
     assert gu.rel_err(out, resid + acc + bias) < 1e-5
     out, _ = gu.gemm(a, b, L.EPI_F32, block_n=1000 + bn)
     assert gu.rel_err(out, acc) < 1e-5
+    # dQuickGELU epilogue (pre-activations read straight from global memory, 64 bytes per lane and chunk)
+    zb = _bf(M, N, seed=13)
+    out, _ = gu.gemm(a, b, L.EPI_GELU_BWD, aux=zb, block_n=1000 + bn)
+    zf = zb.float()
+    sg = torch.sigmoid(1.702 * zf)
+    assert gu.rel_err(out, acc * sg * (1 + 1.702 * zf * (1 - sg))) < 6e-3
 
 
 def test_gemm_cta_pair_lora_pair_and_guard_rows(G):

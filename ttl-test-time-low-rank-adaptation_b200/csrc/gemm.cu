@@ -329,6 +329,9 @@ struct Epi2Params {
   const float* bias;
   int dbg;   // TTL_GEMM_DBG bits (development only): 1 = no epilogue stores, 2 = no MMA, 4 = no TMA loads
   int rev;   // tiles walked from the last row block to the first
+  const __nv_bfloat16* aux;   // EPI_GELU_BWD: z [M, N] bf16, row pitch ldaux
+  int ldaux;
+  __nv_bfloat16* out2;        // EPI_GELU: optional copy of the pre-activation z = acc + bias (bf16, row pitch ldaux), for the backward
 };
 
 // CL = 2: one CTA pair per cluster (above).  CL = 4: two pairs stacked along M share every B tile: each CTA loads a QUARTER of
@@ -524,6 +527,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       for (int c = 0; c < C::CHUNKS; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * 256 + half * (BLOCK_N / 2) + c * 32, r);
+        uint4 zq[4];      // EPI_GELU_BWD: this lane's 32 pre-activations (64 contiguous bytes), in flight with the TMEM load
+        if (EPI == EPI_GELU_BWD) {
+          const int zrow = row0 + lane < p.M ? row0 + lane : p.M - 1;
+          const uint4* zp = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(zrow) * p.ldaux + col_base + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) zq[i] = __ldg(zp + i);
+        }
         tmem_ld_wait();
         if (c == C::CHUNKS - 1) {       // accumulator fully read: hand the TMEM stage back before the stores
           tc_fence_before();
@@ -565,8 +575,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
             if (EPI == EPI_GELU) {
+              if (p.out2 != nullptr && row0 + lane < p.M) {      // pre-activation copy: 16 of this lane's 64 contiguous bytes
+                uint4 zz;
+                zz.x = pack_bf16(v[0], v[1]); zz.y = pack_bf16(v[2], v[3]); zz.z = pack_bf16(v[4], v[5]); zz.w = pack_bf16(v[6], v[7]);
+                reinterpret_cast<uint4*>(p.out2 + static_cast<size_t>(row0 + lane) * p.ldaux + col)[i] = zz;
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = v[j] * (0.5f + 0.5f * tanh_approx(0.851f * v[j]));   // z * sigmoid(1.702 z)
+            }
+            if (EPI == EPI_GELU_BWD) {     // dz = dg * sigma(1.702 z) (1 + 1.702 z (1 - sigma(1.702 z)))
+              const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zq[i]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 z = __bfloat1622float2(z2[j]);
+                const float s0 = 0.5f + 0.5f * tanh_approx(0.851f * z.x), s1 = 0.5f + 0.5f * tanh_approx(0.851f * z.y);   // sigma(1.702 z), one MUFU op
+                v[2 * j] *= s0 * (1.0f + 1.702f * z.x * (1.0f - s0));
+                v[2 * j + 1] *= s1 * (1.0f + 1.702f * z.y * (1.0f - s1));
+              }
             }
             uint4 o;
             o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
@@ -672,6 +697,10 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   static const char* dbg_env = std::getenv("TTL_GEMM_DBG");
   p.dbg = dbg_env ? std::atoi(dbg_env) : 0;
   p.rev = g.descending;
+  p.aux = g.aux; p.ldaux = g.ldo;
+  p.out2 = EPI == EPI_GELU ? static_cast<__nv_bfloat16*>(g.out2) : nullptr;
+  if (g.out2 != nullptr && EPI != EPI_GELU) { set_err("gemm2: out2 only with the QuickGELU epilogue"); return cudaErrorInvalidValue; }
+  if (EPI == EPI_GELU_BWD && (g.aux == nullptr || g.ldo % 8 != 0)) { set_err("gemm2: EPI_GELU_BWD needs aux (z), ld % 8 == 0"); return cudaErrorInvalidValue; }
   auto kern = gemm2_kernel<BLOCK_N, EPI, CL>;
   const int dv = current_device_slot();
   static bool attr_done[MAX_DEVICES] = {};  // per instantiation and device
@@ -715,6 +744,7 @@ cudaError_t launch2_n(const GemmArgs& g, cudaStream_t s, int sms) {
     case EPI_GELU: return launch2_t<BLOCK_N, EPI_GELU, CL>(g, s, sms);
     case EPI_RESID_F32: return launch2_t<BLOCK_N, EPI_RESID_F32, CL>(g, s, sms);
     case EPI_F32: return launch2_t<BLOCK_N, EPI_F32, CL>(g, s, sms);
+    case EPI_GELU_BWD: return launch2_t<BLOCK_N, EPI_GELU_BWD, CL>(g, s, sms);
     default: set_err("gemm2: epilogue not supported by the CTA-pair kernel"); return cudaErrorInvalidValue;
   }
 }
@@ -722,8 +752,8 @@ cudaError_t launch2_n(const GemmArgs& g, cudaStream_t s, int sms) {
 // The CTA-pair kernel covers the plain epilogues (no second output, no scatter); BLOCK_N by a per-k-block cost model:
 // rounds of the persistent schedule x bytes a pair pulls from L2 per k-block (the kernel is L2->SM bound).
 int pick_pair_block_n(const GemmArgs& g, int num_sms) {
-  if (g.out2 != nullptr || g.M < 1024) return 0;
-  if (g.epi != EPI_BF16 && g.epi != EPI_GELU && g.epi != EPI_RESID_F32 && g.epi != EPI_F32) return 0;
+  if ((g.out2 != nullptr && g.epi != EPI_GELU) || g.M < 1024) return 0;
+  if (g.epi != EPI_BF16 && g.epi != EPI_GELU && g.epi != EPI_RESID_F32 && g.epi != EPI_F32 && g.epi != EPI_GELU_BWD) return 0;
   if (g.ldo % 4 != 0 || (g.epi == EPI_RESID_F32 && (g.resid == nullptr || g.ldr % 4 != 0))) return 0;
   const int pairs = g_pairs_hint > 0 ? g_pairs_hint : num_sms / 2, m_pairs = (g.M + 255) / 256;
   int best = 0;
@@ -841,7 +871,7 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
       else if (v > 1 && bn2 != 0 && g.N % v == 0) bn2 = v;
     }
     if (bn2 != 0) {
-      if (g.N % bn2 != 0 || g.out2 != nullptr) { set_err("gemm_launch: CTA-pair kernel: bad BLOCK_N / out2"); return cudaErrorInvalidValue; }
+      if (g.N % bn2 != 0 || (g.out2 != nullptr && g.epi != EPI_GELU)) { set_err("gemm_launch: CTA-pair kernel: bad BLOCK_N / out2"); return cudaErrorInvalidValue; }
       // 4-CTA clusters with multicast B tiles: TTL_GEMM_CLUSTER=4 (BLOCK_N = 256, at least two row blocks of 256).  Opt-in:
       // measured on B200 (gpurun s59/s60) only 33 clusters of 4 are co-resident (132 of 148 SMs): +6-7 % per SM from the
       // smaller L2->SM operand traffic, but -4 % per kernel and -2 % per adapted sample with 16 SMs stranded.
