@@ -912,6 +912,11 @@ attention_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 //   warps 2-5 / 6-9      softmax warpgroup of tile 0 / tile 1: one thread per query row, exact two-pass softmax from TMEM,
 //                        bf16 P into the UMMA K-major swizzled layout, O / rowsum -> swizzled smem -> one TMA store per tile
 // K/V are read from L2 once per unit instead of once per tile, and the load latency of unit u+1 hides behind unit u.
+// XK = true is the 257-token form (ViT-L/14): 256 keys and queries go through the MMAs (S0 / S1 fill all 512 TMEM columns, four
+// 64-key P blocks per tile, ONE V buffer, 226 KB smem); key 256 is folded in by the softmax threads (q_i . k_256 from global
+// memory while the S MMAs run, p_256 v_256 added to O in the epilogue) and query 256 is computed by
+//   warps 10-11 (XK)     on the CUDA cores from the K / V tiles in shared memory; the producer waits for their bar_xk / bar_xv
+//                        arrivals before it overwrites K / V.
 constexpr int PP_THREADS = 320;
 // Pass 2 is MUFU-bound (16 ex2 per clock and SM): PP_POLY_MASK picks the elements of every group of 8 whose 2^x is evaluated on
 // the FMA pipe instead (Cody-Waite split with the 1.5 * 2^23 trick + cubic on [-0.5, 0.5], max relative error 7.5e-5, far
