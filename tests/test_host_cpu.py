@@ -132,3 +132,18 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_algorithmic_flop_formula():
+    """bench.f_alg_tflop must reproduce SURVEY.md 8d's figures (the fraction-of-peak numbers hang on it)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from ttl_b200 import ARCH_GEOMETRY as G
+    b16, l14 = G["ViT-B/16"], G["ViT-L/14"]
+    assert abs(bench.f_alg_tflop(b16, 1000, 64, "tpt", 1) - 2.342) < 1e-3          # north-star head, 1 step
+    assert abs(bench.f_alg_tflop(b16, 1000, 64, "deyo", 1) - 2.876) < 1e-3         # all 64 views carry gradient
+    assert abs(bench.f_alg_tflop(b16, 1000, 64, "tpt", 4) - 2.666) < 5e-3          # 4 steps: only the 6 selected views re-forwarded
+    assert abs(bench.f_alg_tflop(l14, 1000, 64, "tpt", 1) - 10.67) < 1e-2
+    assert abs(bench.f_alg_tflop(l14, 1000, 64, "deyo", 1) - 11.90) < 1e-2
