@@ -136,7 +136,7 @@ def test_bf16_path_agrees_with_fp32_mode_on_a_synthetic_set(b16_weights):
     """North-star accuracy parity at the metric's shape (64 views, 1000 classes): adapted top-1 of the bf16 tensor-core path
     vs the fp32 validation mode (itself within 5e-6 of the reference, above) on 96 synthetic samples, free-running on both
     sides.  Samples whose fp32 adapted top-1 margin is below 0.5 logit are not counted (bf16 moves a logit by ~0.05).
-    TTL_AGREEMENT_SAMPLES=<n> runs a larger set (81 ms per sample in the fp32 mode); TTL_AGREEMENT_JSON=<path> records it."""
+    TTL_AGREEMENT_SAMPLES=<n> runs a larger set (81 ms per sample in the fp32 mode), TTL_AGREEMENT_HEAD=deyo the other head; TTL_AGREEMENT_JSON=<path> records it."""
     import json
     import os
     import time
@@ -153,7 +153,8 @@ def test_bf16_path_agrees_with_fp32_mode_on_a_synthetic_set(b16_weights):
             e.load_weights(b16_weights)
             e.set_lora_init(lora0)
             e.set_text_features(text, math.log(100.0))
-        hp = Hparams(head="tpt")
+        head = os.environ.get("TTL_AGREEMENT_HEAD", "tpt")
+        hp = Hparams(head=head)
         counted = agree = agree_all = same_sel = 0
         t_slow = 0.0
         for b in range(0, n, S):
@@ -177,7 +178,7 @@ def test_bf16_path_agrees_with_fp32_mode_on_a_synthetic_set(b16_weights):
               f"confident-view sets {same_sel}/{n}; fp32 mode {t_slow / n * 1e3:.0f} ms/sample")
         if os.environ.get("TTL_AGREEMENT_JSON"):
             with open(os.environ["TTL_AGREEMENT_JSON"], "w") as f:
-                json.dump({"samples": n, "views": V, "classes": C, "head": "tpt", "margin_threshold_logits": 0.5,
+                json.dump({"samples": n, "views": V, "classes": C, "head": head, "margin_threshold_logits": 0.5,
                            "counted": counted, "agree_counted": agree, "agree_overall": agree_all,
                            "identical_confident_view_sets": same_sel, "fp32_mode_ms_per_sample": t_slow / n * 1e3}, f)
         assert counted >= n // 3, counted
