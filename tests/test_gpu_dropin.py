@@ -193,6 +193,26 @@ def test_cli_views_on_device():
     assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
 
 
+def test_cli_real_image_folder_both_input_routes(tmp_path):
+    """Real-image route without the reference's data package: a folder-per-class test set under the reference's directory
+    convention (ttl_b200/datasets.py), host views (HostViews in the DataLoader) and --views_on_device (uint8 image + crop
+    specs, views resampled on the GPU).  Class names come from the folder names; 6 classes so that top-5 is defined (Q11)."""
+    import numpy as np
+    from PIL import Image
+    import ttl
+    from ttl_b200 import datasets as D
+    g = np.random.default_rng(5)
+    for c in range(6):
+        d = tmp_path / D.SET_DIRS["A"] / f"class_{c}"
+        d.mkdir(parents=True)
+        Image.fromarray(g.integers(0, 256, size=(240 + 8 * c, 300, 3), dtype=np.uint8)).save(d / "img.png")
+    common = [str(tmp_path), '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0', '--print_freq', '100']
+    host = ttl.main(common)
+    dev = ttl.main(common + ['--views_on_device'])
+    for res in (host, dev):
+        assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+
+
 @pytest.mark.parametrize("extra", [["--filter_ent", "1"], ["--filter_plpd", "1", "--aug_type", "occ", "--plpd_threshold", "-1"],
                                    ["--filter_plpd", "1", "--aug_type", "patch", "--plpd_threshold", "-1"]])
 def test_cli_deyo_optional_branches_run_in_compat_mode(extra):

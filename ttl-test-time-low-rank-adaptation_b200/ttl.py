@@ -263,7 +263,16 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
     return [100.0 * tot[0] / n, 100.0 * tot[1] / n]
 
 
-def _classnames_for(set_id, args):
+def _build_dataset(set_id, transform, args):
+    """The reference's data package when it is importable (same tree and class tables), else ttl_b200/datasets.py."""
+    try:
+        from data.datautils import build_dataset
+    except ImportError:
+        from ttl_b200.datasets import build_dataset
+    return build_dataset(set_id=set_id, transform=transform, args=args)
+
+
+def _classnames_for(set_id, args, dataset=None):
     try:   # class lists live in the reference's data/ package (inputs to the path, not vendored here)
         from data.imagnet_prompts import imagenet_classes
         from data.imagenet_variants import imagenet_a_mask, imagenet_r_mask, imagenet_v_mask  # noqa: F401
@@ -277,6 +286,9 @@ def _classnames_for(set_id, args):
             return [imagenet_classes[i] for i, m in enumerate(imagenet_r_mask) if m]
         return imagenet_classes
     except Exception:
+        if dataset is not None and hasattr(dataset, "classes"):    # folder-per-class test set: names from its own folders
+            from ttl_b200.datasets import classnames_for_folders
+            return classnames_for_folders(dataset.root, dataset.classes)
         n = {'A': 200, 'R': 200}.get(set_id, 1000)
         return [f"class {i}" for i in range(n)]
 
@@ -322,23 +334,21 @@ def main_worker(gpu, args):
     scaler = torch.amp.GradScaler("cuda", init_scale=1000, enabled=False)   # bf16 path: no loss scaling
     results = {}
     for set_id in args.test_sets.split("/"):
-        classnames = _classnames_for(set_id, args)
+        ds = None
+        if args.synthetic <= 0 and args.views_on_device:
+            ds = _build_dataset(set_id, _ImageSpecTransform(args.batch_size - 1), args)
+        elif args.synthetic <= 0:
+            # [clean view] + (batch_size - 1) x (RandomResizedCrop + flip), normalised: data/datautils.py:98-157, ttl.py:226-241
+            from ttl_b200.datasets import default_host_views
+            ds = _build_dataset(set_id, default_host_views(args.batch_size - 1, args.resolution), args)
+        classnames = _classnames_for(set_id, args, ds)
+        if ds is not None and hasattr(ds, "classes") and len(ds.classes) != len(classnames):
+            raise RuntimeError(f"test set {set_id}: {len(ds.classes)} class folders but {len(classnames)} class names")
         model.reset_classnames(classnames, args.arch)
         if args.synthetic > 0 and args.views_on_device:
             ds = SyntheticImages(args.synthetic, args.batch_size, len(classnames), seed=args.seed)
         elif args.synthetic > 0:
             ds = SyntheticViews(args.synthetic, args.batch_size, args.resolution, len(classnames), seed=args.seed)
-        elif args.views_on_device:
-            from data.datautils import build_dataset   # the reference's dataset tree (not vendored)
-            ds = build_dataset(set_id=set_id, transform=_ImageSpecTransform(args.batch_size - 1), args=args)
-        else:
-            from data.datautils import AugMixAugmenter, build_dataset   # the reference's data pipeline (not vendored)
-            import torchvision.transforms as T
-            norm = T.Normalize(mean=[0.48145466, 0.4578275, 0.40821073], std=[0.26862954, 0.26130258, 0.27577711])
-            base = T.Compose([T.Resize(args.resolution, interpolation=T.InterpolationMode.BICUBIC, antialias=True),
-                              T.CenterCrop(args.resolution)])
-            tf = AugMixAugmenter(base, T.Compose([T.ToTensor(), norm]), n_views=args.batch_size - 1, augmix=len(set_id) > 1)
-            ds = build_dataset(set_id=set_id, transform=tf, args=args)
         # sample-sharding: rank r evaluates samples r, r+W, ... of the seeded order
         g = torch.Generator().manual_seed(args.seed)
         order = torch.randperm(len(ds), generator=g).tolist()

@@ -33,6 +33,8 @@ class ViewSpecSampler:
         arr = np.asarray(img.convert("RGB") if hasattr(img, "convert") else img, dtype=np.uint8)
         if arr.ndim != 3 or arr.shape[2] != 3:
             raise ValueError("expected an RGB image [H,W,3]")
+        if not arr.flags.writeable:      # a PIL image exposes a read-only buffer; torch.from_numpy wants a writable one
+            arr = arr.copy()
         h, w = int(arr.shape[0]), int(arr.shape[1])
         probe = torch.empty(3, h, w, dtype=torch.uint8, device="meta")   # get_params only reads the size
         specs = np.zeros((1 + self.n_views, SPEC_FIELDS), dtype=np.int32)
