@@ -147,3 +147,21 @@ def test_bench_algorithmic_flop_formula():
     assert abs(bench.f_alg_tflop(b16, 1000, 64, "tpt", 4) - 2.666) < 5e-3          # 4 steps: only the 6 selected views re-forwarded
     assert abs(bench.f_alg_tflop(l14, 1000, 64, "tpt", 1) - 10.67) < 1e-2
     assert abs(bench.f_alg_tflop(l14, 1000, 64, "deyo", 1) - 11.90) < 1e-2
+
+
+def test_launcher_script_flags_parse():
+    """scripts/test_ttl.sh keeps the reference launcher's parameter block; every flag it passes must parse (incl. --b)."""
+    import ttl
+    path = os.path.join(PKG, "scripts", "test_ttl.sh")
+    subprocess.run(["bash", "-n", path], check=True)
+    flags = sorted(set(re.findall(r"(--[a-z_]+)", re.search(r"ARGS=\((.*?)\)\n", open(path).read(), flags=re.S).group(1))))
+    assert "--b" in flags and "--deyo_selection" in flags and "--views_on_device" in flags
+    argv = ["/data"]
+    values = {"--test_sets": "A/R", "--dataset_mode": "test", "--arch": "ViT-B/16", "--b": "64", "--ctx_init": "a_photo_of_a",
+              "--lr": "5e-3", "--tta_steps": "1", "--print_freq": "200", "--selection_p": "0.1", "--layer_range": "9,11",
+              "--init_method": "xavier", "--lora_encoder": "image", "--rank": "16", "--deyo_selection": ""}
+    for f in flags:
+        argv += [f] + ([values[f]] if f in values else [])
+    a = ttl.build_parser().parse_args(argv)
+    assert a.data == "/data" and a.batch_size == 64 and not a.deyo_selection and a.views_on_device
+    assert list(a.layer_range) == [9, 11] and a.test_sets == "A/R"
