@@ -163,12 +163,14 @@ def synth_sample_gpu(torch, gen, views: int, size: int = 224):
     return torch.cat(out).contiguous()
 
 
-def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, threads: int, tta_steps: int = 1):
+def cpu_reference_pass(n_samples: int, classes: int, views: int, head: str, threads: int, tta_steps: int = 1,
+                       arch_name: str = "ViT-B/16"):
     """The reference algorithm (oracle port, fp32, autograd) on the host cores; returns (seconds_per_sample list)."""
     import torch
     from oracle import ttl_oracle as O
     torch.set_num_threads(threads)
-    arch, spec = O.ARCHS["ViT-B/16"], O.LoraSpec()
+    arch = O.ARCHS[arch_name]
+    spec = O.LoraSpec(layer_lo=arch.layers - 3, layer_hi=arch.layers - 1)     # the last three layers: 9..11 / 21..23
     w = O.make_synthetic_weights(arch, 1234)
     lora0 = O.lora_init(arch, spec, 0)
     text = O.make_text_features(classes, arch.proj)
@@ -196,7 +198,7 @@ def run_reference_arm(args):
     bounded = total > 24
     if bounded:   # keep the run within a few minutes: fewer views per step, scaled back to 64-view samples
         views = max(10, min(args.views, int(1500 / total)))
-    times = cpu_reference_pass(total, args.classes, views, args.head, cores, args.tta_steps)
+    times = cpu_reference_pass(total, args.classes, views, args.head, cores, args.tta_steps, args.arch)
     timed = times[warm:]
     per_step = sum(timed) / len(timed)
     value = (views / args.views) / per_step
@@ -204,10 +206,10 @@ def run_reference_arm(args):
               f"features cached (the reference re-runs its text tower twice per sample on top of this)"
               + (f"; bounded: scaled by {views}/{args.views} views" if bounded else "")
               + (f"; {steps} of the requested {args.steps} steps timed" if steps != args.steps else ""))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC.replace("ViT-B/16", args.arch), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3 * (args.views / views), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"TTL ViT-B/16, {args.classes} classes, {args.views} views, r=16, {args.tta_steps} step"
+            "config": {"workload": f"TTL {args.arch}, {args.classes} classes, {args.views} views, r=16, {args.tta_steps} step"
                                    f"{'s' if args.tta_steps != 1 else ''} ({args.head} head)",
                        "device": "host CPU"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -387,7 +389,8 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_reference_pass(args.cpu_baseline_samples, args.classes, args.views, args.head, cores, args.tta_steps)
+        times = cpu_reference_pass(args.cpu_baseline_samples, args.classes, args.views, args.head, cores, args.tta_steps,
+                                   args.arch)
         per = sum(times) / len(times)
         cpu_base = {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{len(times)} samples of the same workload, oracle port (fp32 PyTorch CPU, autograd) of "
@@ -396,7 +399,7 @@ def main():
     if rank == 0:
         f_alg = f_alg_tflop(geo, args.classes, args.views, args.head, args.tta_steps)
         per_gpu_tflops = value / world * f_alg
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC.replace("ViT-B/16", args.arch), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"TTL {args.arch}, {args.classes} classes, {args.views} views, r=16, {args.tta_steps} step{'s' if args.tta_steps != 1 else ''} "
