@@ -1,5 +1,7 @@
 """Small end-to-end exercise of the ViT-B/16 paths for `compute-sanitizer --tool memcheck`: bf16 path (eager, capture,
-replay; 2 concurrent samples; images path), fp32 validation mode, text tower."""
+replay; 2 concurrent samples; images path), fp32 validation mode, text tower.  Not collected by pytest (no test_ prefix); lives
+under tests/ because it borrows the text oracle's synthetic weight generator (oracle/ is test infrastructure only):
+    compute-sanitizer --tool memcheck python tests/sanitizer_driver_b16.py"""
 import math
 import os
 import sys
