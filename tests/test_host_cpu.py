@@ -165,3 +165,20 @@ def test_launcher_script_flags_parse():
     a = ttl.build_parser().parse_args(argv)
     assert a.data == "/data" and a.batch_size == 64 and not a.deyo_selection and a.views_on_device
     assert list(a.layer_range) == [9, 11] and a.test_sets == "A/R"
+
+
+def test_oracle_is_imported_by_test_infrastructure_only():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke()/build() and bench.py's CPU arms may import it; the product
+    package and the tools must not (a product path through the oracle would void every parity claim)."""
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for top in (PKG, os.path.join(ROOT, "tools")):
+        for d, _, files in os.walk(top):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(d, f)).read()):
+                    offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert not offenders, offenders
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in pat.finditer(src)]
+    body = src[src.index("def cpu_reference_pass"):src.index("def run_reference_arm")]
+    assert len(uses) == 1 and pat.search(body)          # bench.py: inside cpu_reference_pass only
