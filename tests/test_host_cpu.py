@@ -134,6 +134,22 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
+def test_bench_reference_arm_under_torchrun_world2():
+    """Launched as the driver launches N > 1 (torchrun, one process per GPU): rank 0 alone runs the CPU arm and prints the one
+    line; the other rank exits 0 without work or output."""
+    import json
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--gpus", "2", "--steps", "1", "--warmup", "0", "--views", "10", "--classes", "10"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0 and line["gpu_launches"] == 0
+
+
 def test_bench_algorithmic_flop_formula():
     """bench.f_alg_tflop must reproduce SURVEY.md 8d's figures (the fraction-of-peak numbers hang on it)."""
     import importlib.util
