@@ -198,3 +198,36 @@ def test_oracle_is_imported_by_test_infrastructure_only():
     uses = [m.start() for m in pat.finditer(src)]
     body = src[src.index("def cpu_reference_pass"):src.index("def run_reference_arm")]
     assert len(uses) == 1 and pat.search(body)          # bench.py: inside cpu_reference_pass only
+
+
+def test_accuracy_and_meter_semantics():
+    """accuracy()/AverageMeter (utils/tools.py:26-63,88-102): percentages of rows whose target is within the top-k, running
+    average weighted by n.  Checked against brute force and, when the reference tree is present (dev container), against the
+    reference's own functions loaded from their file."""
+    import importlib.util
+    import ttl
+    g = torch.Generator().manual_seed(0)
+    out = torch.randn(37, 12, generator=g)
+    tgt = torch.randint(0, 12, (37,), generator=g)
+    a1, a5 = ttl.accuracy(out, tgt, topk=(1, 5))
+    order = out.argsort(dim=1, descending=True)
+    want1 = 100.0 * sum(int(order[i, 0] == tgt[i]) for i in range(37)) / 37
+    want5 = 100.0 * sum(int(tgt[i] in order[i, :5]) for i in range(37)) / 37
+    assert abs(float(a1) - want1) < 1e-4 and abs(float(a5) - want5) < 1e-4
+    m = ttl.AverageMeter("Acc@1", ":6.2f")
+    m.update(100.0, 1), m.update(0.0, 3)
+    assert m.avg == 25.0 and m.count == 4 and "Acc@1" in str(m)
+    assert float(ttl.accuracy(out[:, :3], tgt.clamp(max=2), topk=(1, 5))[1]) == 100.0     # fewer than 5 classes: k clamps to C
+    ref_path = "/root/reference/utils/tools.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_tools", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(ref)
+        except Exception as e:     # its other imports are not part of the path
+            pytest.skip(f"reference utils/tools.py not importable here: {e}")
+        r1, r5 = ref.accuracy(out, tgt, topk=(1, 5))
+        assert torch.equal(a1, r1) and torch.equal(a5, r5)
+        rm = ref.AverageMeter("Acc@1", ":6.2f")
+        rm.update(100.0, 1), rm.update(0.0, 3)
+        assert rm.avg == m.avg and str(rm) == str(m)
