@@ -749,11 +749,8 @@ int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams&
       float* en = step == 0 ? c->entropy : c->entropy_c;
       launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, lg, en, VV, c->C, c->P, st);
       c->launches += 2;
-      for (int sm = 0; sm < S; ++sm) {
-        launch_deyo_loss(lg + static_cast<size_t>(sm) * V * c->C, V, c->C, hp.deyo_margin_e0, c->loss + sm,
-                         c->dlogits + static_cast<size_t>(sm) * V * c->C, st);
-        c->launches++;
-      }
+      launch_deyo_loss(lg, V, c->C, hp.deyo_margin_e0, c->loss, c->dlogits, st, S);   // one CTA per sample
+      c->launches++;
       RET_IF(backward(c, c->dlogits, VV, st));
       RET_IF(adamw(c, hp, S, st));
     }

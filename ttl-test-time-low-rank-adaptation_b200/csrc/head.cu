@@ -240,13 +240,16 @@ tpt_loss_kernel(const float* __restrict__ logits, const int* __restrict__ idx, i
   }
 }
 
-// single CTA (V <= 1024 views).  H_v; keep H_v <= ln 1000; w_v = exp(-(H_v - e0)); L = mean_kept(w H);
+// one CTA per test sample (V <= 1024 views).  H_v; keep H_v <= ln 1000; w_v = exp(-(H_v - e0)); L = mean_kept(w H);
 // dL/dx[v,c] = -(w_v / n) p (log p + H_v)
 __global__ void __launch_bounds__(1024)
 deyo_loss_kernel(const float* __restrict__ logits, int V, int C, float e0, float* __restrict__ loss,
                  float* __restrict__ dlogits) {
   pdl_wait();
   pdl_trigger();
+  logits += static_cast<size_t>(blockIdx.x) * V * C;     // samples are sample-major: [S][V][C] logits, [S] losses
+  dlogits += static_cast<size_t>(blockIdx.x) * V * C;
+  loss += blockIdx.x;
   extern __shared__ float sh[];
   float* lse = sh;          // [V]
   float* H = sh + V;        // [V]
@@ -374,8 +377,9 @@ void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* l
   launch_pdl(tpt_loss_kernel, dim3(n_samples), dim3(1024), (2 * K + 32 + C) * sizeof(float), st, logits, idx, K, C, loss, dlogits,
              logits_sstride);
 }
-void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st) {
-  launch_pdl(deyo_loss_kernel, dim3(1), dim3(1024), 3 * V * sizeof(float), st, logits, V, C, margin_e0, loss, dlogits);
+void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st,
+                      int n_samples) {
+  launch_pdl(deyo_loss_kernel, dim3(n_samples), dim3(1024), 3 * V * sizeof(float), st, logits, V, C, margin_e0, loss, dlogits);
 }
 void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
                      const float* x, const float* gamma, float* dfh, float* dpool, float* dx, bf16* dx_bf16, int G, int C,

@@ -62,7 +62,8 @@ void launch_select(const float* entropy, int V, int K, const int* forced_idx, in
 void launch_tpt_loss(const float* logits, const int* idx, int K, int C, float* loss, float* dlogits, cudaStream_t st,
                      int n_samples = 1, size_t logits_sstride = 0);
 // weighted-entropy (DeYO, default flags) loss over all V rows and gradient dlogits[V,C]  (deyo.py:97-181)
-void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st);
+void launch_deyo_loss(const float* logits, int V, int C, float margin_e0, float* loss, float* dlogits, cudaStream_t st,
+                      int n_samples = 1);
 // head backward for G compact views: dlogits[G,C] -> dx[G*tokens, d] (fp32, zero except CLS rows) + bf16 copy.
 void launch_head_bwd(const float* dlogits, const float* text, float scale, const float* feats, const float* Wp,
                      const float* x, const float* gamma, float* dfh, float* dpool, float* dx, bf16* dx_bf16, int G, int C,
