@@ -206,21 +206,32 @@ def default_args(**over) -> types.SimpleNamespace:
     return types.SimpleNamespace(**a)
 
 
-def build_reference_model(vision_weights, classnames: List[str], lora_seed: int = 0, layer_range=(9, 11)):
-    """get_coop(...) -> requires_grad filter (ttl.py:151-163) -> AdamW param groups (ttl.py:189-220)."""
+def _lora_layers(model, lora_encoder: str):
+    """The layer list ttl.py:190-193 walks for the optimizer groups."""
+    if lora_encoder == "text":
+        return model.text_encoder.text_model.encoder.layers
+    return model.image_encoder.vision_model.encoder.layers
+
+
+def build_reference_model(vision_weights, classnames: List[str], lora_seed: int = 0, layer_range=(9, 11),
+                          lora_encoder: str = "image"):
+    """get_coop(...) -> requires_grad filter (ttl.py:151-163) -> AdamW param groups (ttl.py:189-220).
+    `vision_weights` may also carry `text_model.*` / `text_projection.weight` entries (same CLIPModel state dict);
+    `lora_encoder='text'` builds the reference's text-tower variant (clip/custom_clip.py:602-606, ttl.py:146-147,190-191)."""
     from copy import deepcopy
     ttl_ref, clip_pkg = install(vision_weights)
     from clip.custom_clip import get_coop
     torch.manual_seed(lora_seed)
     model = get_coop("ViT-B/16", "A", "cpu", 4, "a_photo_of_a", layer_range=list(layer_range),
-                     init_method="xavier", lora_encoder="image", rank=16)
+                     init_method="xavier", lora_encoder=lora_encoder, rank=16)
     model.reset_classnames(classnames, "ViT-B/16")
+    enc_name = "text_encoder" if lora_encoder == "text" else "image_encoder"
     for name, p in model.named_parameters():
-        ok = ("image_encoder" in name and ("lora_A" in name or "lora_B" in name)
+        ok = (enc_name in name and ("lora_A" in name or "lora_B" in name)
               and any(f"layers.{i}." in name for i in range(layer_range[0], layer_range[1] + 1)))
         p.requires_grad_(ok)
     groups = []
-    for i, layer in enumerate(model.image_encoder.vision_model.encoder.layers):
+    for i, layer in enumerate(_lora_layers(model, lora_encoder)):
         if layer_range[0] <= i <= layer_range[1]:
             groups.extend([{"params": layer.self_attn.q_proj.lora_A.parameters()},
                            {"params": layer.self_attn.q_proj.lora_B.parameters()},
@@ -233,9 +244,9 @@ def build_reference_model(vision_weights, classnames: List[str], lora_seed: int 
     return ttl_ref, model, opt, optim_state, scaler
 
 
-def set_lora(model, lora: Dict[int, List[torch.Tensor]]) -> None:
+def set_lora(model, lora: Dict[int, List[torch.Tensor]], lora_encoder: str = "image") -> None:
     """Overwrite the reference model's LoRA factors AND its reset snapshot with given tensors."""
-    layers = model.image_encoder.vision_model.encoder.layers
+    layers = _lora_layers(model, lora_encoder)
     with torch.no_grad():
         for i, (a_q, b_q, a_v, b_v) in lora.items():
             sa = layers[i].self_attn
@@ -246,8 +257,8 @@ def set_lora(model, lora: Dict[int, List[torch.Tensor]]) -> None:
             model.LoRA_AB.init_weights[i] = (a_q.clone(), b_q.clone(), a_v.clone(), b_v.clone())
 
 
-def get_lora(model, layers_range) -> Dict[int, List[torch.Tensor]]:
-    layers = model.image_encoder.vision_model.encoder.layers
+def get_lora(model, layers_range, lora_encoder: str = "image") -> Dict[int, List[torch.Tensor]]:
+    layers = _lora_layers(model, lora_encoder)
     out = {}
     for i in layers_range:
         sa = layers[i].self_attn
