@@ -11,7 +11,6 @@ plpd_threshold is placed in the widest gap of the reference's own PLPD values ne
 device cannot flip a view across it; the chosen value is stored and passed back through args in the test."""
 from __future__ import annotations
 
-import math
 import os
 import sys
 

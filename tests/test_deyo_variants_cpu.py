@@ -3,7 +3,6 @@ against golden fixtures produced by the UNMODIFIED reference (oracle/make_golden
 `filter_plpd` with the deterministic occlusion and with the seeded patch shuffle.  The model under the head is the fp32
 CPU oracle (the checker), so the branch logic is compared at fp32 precision -- the PLPD values of a random-init model sit
 within +-8e-3, far below bf16 noise, so the device path cannot be held to a threshold decision on this fixture."""
-import math
 import os
 import types
 

@@ -5,7 +5,6 @@ PyTorch is used for device memory and streams only; all arithmetic of the path r
 from __future__ import annotations
 
 import ctypes as C
-import math
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 

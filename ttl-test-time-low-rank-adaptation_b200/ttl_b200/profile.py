@@ -9,7 +9,6 @@ import ctypes as C
 from collections import defaultdict
 from typing import Dict, List
 
-import torch
 
 from . import _lib as L
 
