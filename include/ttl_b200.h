@@ -90,7 +90,7 @@ enum ttl_head {
 typedef struct ttl_hparams {
   int32_t head;        /* enum ttl_head */
   int32_t tta_steps;   /* --tta_steps; the DeYO head performs tta_steps^2 optimiser steps like the reference */
-  float selection_p;   /* --selection_p 0.1  -> K = (int)(V * p) */
+  double selection_p;  /* --selection_p 0.1  -> K = (int)(V * p), evaluated in double like Python's int(V * top) at ttl.py:52 */
   float lr;            /* 5e-3 */
   float beta1, beta2;  /* 0.9, 0.999 */
   float eps;           /* 1e-8 */
@@ -128,6 +128,10 @@ int ttl_lora_set_init(ttl_ctx* ctx, int32_t layer, int32_t which, const float* h
 int ttl_lora_reset(ttl_ctx* ctx, void* stream);
 /* Synchronising getter: what = param | grad | init. */
 int ttl_lora_get(ttl_ctx* ctx, int32_t layer, int32_t which, int32_t what, float* host_out, int64_t numel);
+/* The same for sample `sample` of the last ttl_adapt_predict_batch* call (each concurrent sample owns its factors,
+ * gradients and AdamW moments until the next call resets them; ttl.py:338-344 per sample). */
+int ttl_lora_get_sample(ttl_ctx* ctx, int32_t sample, int32_t layer, int32_t which, int32_t what, float* host_out,
+                        int64_t numel);
 /* Device aliases of one tensor so a host framework can wrap them as parameters/gradients
  * (the names ttl.py:159-160,197-201 walk).  After writing through them call ttl_lora_touch(). */
 int ttl_lora_device_ptr(ttl_ctx* ctx, int32_t layer, int32_t which, int32_t what, float** dev_ptr, int64_t* numel);

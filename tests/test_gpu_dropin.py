@@ -178,7 +178,7 @@ def test_kernel_backed_head_functions():
 def test_cli_synthetic_fused_and_compat():
     import ttl
     common = ['--synthetic', '6', '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0', '--print_freq', '100']
-    fused = ttl.main(common)
+    fused = ttl.main(common + ['--views_on_host'])     # same 64 fp32 host views per sample as the compat route below
     compat = ttl.main(common + ['--compat'])
     assert set(fused) == {'A'} and len(fused['A']) == 2
     assert fused['A'] == compat['A']      # same per-sample predictions -> same accuracy counters
@@ -193,24 +193,122 @@ def test_cli_views_on_device():
     assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
 
 
-def test_cli_real_image_folder_both_input_routes(tmp_path):
+def _write_synthetic_clip_checkpoint(dirpath, openai_format=False):
+    """One CLIP checkpoint file (HF names, safetensors) with seeded random-init image AND text towers + logit_scale, and a
+    small BPE merge table next to it: what `CLIPModel.from_pretrained` hands the reference (clip/custom_clip.py:581,619)."""
+    from safetensors.torch import save_file
+    from oracle import text_oracle as TO
+    from ttl_b200.synthetic import synthetic_vit_weights
+    sd = dict(synthetic_vit_weights("ViT-B/16", seed=1234))
+    sd.update(TO.make_synthetic_text_weights(TO.TEXT_ARCHS["ViT-B/16"], seed=5))
+    sd["logit_scale"] = torch.tensor(3.9)                 # not ln(100): the run must pick it up from the file
+    path = os.path.join(dirpath, "model.safetensors")
+    save_file({k: v.contiguous() for k, v in sd.items()}, path)
+    merges = ["#version: 0.2", "c l", "cl a", "cla s", "clas s</w>", "p h", "o t", "ph ot", "phot o</w>", "o f</w>", "a</w> x"]
+    with open(os.path.join(dirpath, "merges.txt"), "w") as f:
+        f.write("\n".join(merges) + "\n")
+    return path, sd
+
+
+def test_checkpoint_file_builds_class_features_with_its_own_text_tower(tmp_path):
+    """--vision_checkpoint route: the file's text tower builds the class features (not random vectors), its
+    logit_scale is used, and a checkpoint without a text tower is an error unless random init was asked for."""
+    from clip.custom_clip import get_coop
+    from oracle import text_oracle as TO
+    from ttl_b200.tokenizer import SimpleTokenizer
+    from ttl_b200.weights import load_clip_checkpoint
+    path, sd = _write_synthetic_clip_checkpoint(str(tmp_path))
+    ck = load_clip_checkpoint(path)
+    assert ck.text is not None and abs(ck.logit_scale - 3.9) < 1e-6 and ck.bpe_path.endswith("merges.txt")
+    names = ["class 0", "photo class", "of a"]
+    m = get_coop("ViT-B/16", "A", 0, 4, "a_photo_of_a", layer_range=[9, 11], init_method="xavier", lora_encoder="image",
+                 rank=16, classnames=names, weights=ck.vision, text_weights=ck.text, logit_scale=ck.logit_scale,
+                 bpe_path=ck.bpe_path, max_views=4)
+    try:
+        tok = SimpleTokenizer(ck.bpe_path)
+        tokens = tok([f"a photo of a {n}." for n in names])
+        assert torch.equal(m.prompt_learner.tokenized_prompts.cpu(), tokens)
+        ref = TO.text_forward(TO.TEXT_ARCHS["ViT-B/16"], {k: v for k, v in sd.items() if k.startswith("text_") }, tokens)
+        got = m.get_text_features().cpu()
+        assert _rel(got.numpy(), ref.numpy()) < 1e-2
+        assert abs(float(m.logit_scale) - 3.9) < 1e-6
+        imgs = O.make_synthetic_views(2, 224, seed=3)
+        want = O.clip_logits(O.vision_forward(O.ARCHS["ViT-B/16"], ck.vision, imgs), ref, 3.9).detach().numpy()
+        assert _rel(m(imgs.cuda()).detach().cpu().numpy(), want) < 1e-2
+    finally:
+        m.engine.close()
+    with pytest.raises(RuntimeError, match="text"):       # no text tower, no class features, no --random_init
+        get_coop("ViT-B/16", "A", 0, 4, "a_photo_of_a", layer_range=[9, 11], lora_encoder="image", classnames=names,
+                 weights=ck.vision, max_views=4)
+
+
+def test_cli_real_image_folder_from_checkpoint_file_both_input_routes(tmp_path):
     """Real-image route without the reference's data package: a folder-per-class test set under the reference's directory
-    convention (ttl_b200/datasets.py), host views (HostViews in the DataLoader) and --views_on_device (uint8 image + crop
-    specs, views resampled on the GPU).  Class names come from the folder names; 6 classes so that top-5 is defined (Q11)."""
-    import numpy as np
+    convention (ttl_b200/datasets.py), weights + text tower + logit_scale from one checkpoint file (--vision_checkpoint, merge
+    table found next to it), default input route (uint8 image + crop specs, views resampled on the GPU) and --views_on_host
+    (HostViews in the DataLoader).  Class names come from the folder names; 6 classes so that top-5 is defined (Q11)."""
     from PIL import Image
     import ttl
     from ttl_b200 import datasets as D
     g = np.random.default_rng(5)
     for c in range(6):
-        d = tmp_path / D.SET_DIRS["A"] / f"class_{c}"
+        d = tmp_path / "data" / D.SET_DIRS["A"] / f"class_{c}"
         d.mkdir(parents=True)
         Image.fromarray(g.integers(0, 256, size=(240 + 8 * c, 300, 3), dtype=np.uint8)).save(d / "img.png")
-    common = [str(tmp_path), '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0', '--print_freq', '100']
-    host = ttl.main(common)
-    dev = ttl.main(common + ['--views_on_device'])
+    ckdir = tmp_path / "ck"
+    ckdir.mkdir()
+    path, _ = _write_synthetic_clip_checkpoint(str(ckdir))
+    common = [str(tmp_path / "data"), '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '0', '--print_freq', '100',
+              '--vision_checkpoint', path]
+    dev = ttl.main(common)
+    host = ttl.main(common + ['--views_on_host'])
     for res in (host, dev):
         assert set(res) == {'A'} and len(res['A']) == 2 and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+    # same seed -> the same crop boxes on both routes (ViewSpecSampler == torchvision's draws), views bit-exact -> same accuracy
+    assert host['A'] == dev['A']
+    with pytest.raises(RuntimeError, match="checkpoint"):            # no checkpoint, no --random_init: fail like the reference
+        ttl.main(common[:-2])
+
+
+def test_cli_throughput_matches_the_engine_loop():
+    """The drop-in CLI must be as fast as the loop bench.py times: `python ttl.py --synthetic N --deyo_selection ''` (default
+    route: uint8 images + crop boxes from DataLoader workers, S = 9 samples per fused call, depth-2 pipeline) against the same
+    items pushed straight through Engine.adapt_predict_images(sync=False) -- bench.py's `e2e` loop."""
+    import time
+    import ttl
+    n = 45 * 9
+    args = ['--synthetic', str(n), '--test_sets', 'A', '--deyo_selection', '', '--gpu', '0', '--workers', '8', '--print_freq', '100000']
+    ttl.main(args)
+    cli = ttl.test_time_adapt_eval.last_stats
+    assert cli["fused"] and cli["concurrent_samples"] == 9 and cli["samples"] == n
+    # engine-direct loop over pre-built items of the same dataset
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200.synthetic import synthetic_lora_init, synthetic_text_features, synthetic_vit_weights
+    ds = ttl.SyntheticImages(36, 64, 200, seed=0)
+    items = [ds[i] for i in range(36)]
+    eng = Engine("ViT-B/16", max_views=64, max_classes=1000, max_samples=9)
+    try:
+        eng.load_weights(synthetic_vit_weights("ViT-B/16", seed=1234))
+        eng.set_text_features(synthetic_text_features(200, 512), math.log(100.0))
+        eng.set_lora_init(synthetic_lora_init("ViT-B/16"))
+        batches = [([it[0].numpy() for it in items[b:b + 9]], [it[1].numpy() for it in items[b:b + 9]]) for b in range(0, 36, 9)]
+        hp = Hparams(head="tpt")
+        for i in range(3):
+            eng.adapt_predict_images(*batches[i % 4], hp)
+        torch.cuda.synchronize()
+        t0, pending, steps = time.perf_counter(), None, 30
+        for i in range(steps):
+            cur = eng.adapt_predict_images(*batches[i % 4], hp, sync=False)
+            if pending is not None:
+                pending.wait()
+            pending = cur
+        pending.wait()
+        direct = steps * 9 / (time.perf_counter() - t0)
+    finally:
+        eng.close()
+    print(f"CLI steady state {cli['steady_samples_per_s']:.1f} samples/s (whole loop {cli['samples_per_s']:.1f}), "
+          f"engine-direct loop {direct:.1f} samples/s")
+    assert cli["steady_samples_per_s"] >= 0.9 * direct, (cli, direct)
 
 
 @pytest.mark.parametrize("extra", [["--filter_ent", "1"], ["--filter_plpd", "1", "--aug_type", "occ", "--plpd_threshold", "-1"],

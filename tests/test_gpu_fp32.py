@@ -28,18 +28,20 @@ def _rel(a, b):
 @pytest.fixture(scope="module")
 def b16_fp32_engine(b16_weights):
     from ttl_b200 import Engine
-    eng = Engine("ViT-B/16", max_views=64, max_classes=16, layer_range=(9, 11), precision="fp32")
+    eng = Engine("ViT-B/16", max_views=64, max_classes=1000, layer_range=(9, 11), precision="fp32")
     eng.load_weights(b16_weights)
     eng.set_lora_init(O.lora_init(O.ARCHS["ViT-B/16"], O.LoraSpec(), seed=0))
     yield eng
     eng.close()
 
 
-@pytest.mark.parametrize("case", ["tpt", "deyo", "tpt2"])
+@pytest.mark.parametrize("case", ["c10_tpt", "c10_deyo", "c10_tpt2", "c1000_tpt", "c200_tpt", "c200_deyo"])
 def test_fp32_mode_vs_reference(b16_fp32_engine, b16_views, case):
+    """BASELINE configs[0] (10 classes, both heads, two steps) and the class counts of configs[1] / [2] (1000 / 200 ImageNet
+    prompts through the reference's own text tower)."""
     from ttl_b200 import Hparams
     from ttl_b200 import _lib as L
-    g = np.load(os.path.join(GOLD, f"ref_b16_c10_{case}.npz"))
+    g = np.load(os.path.join(GOLD, f"ref_b16_{case}.npz"))
     eng = b16_fp32_engine
     eng.set_text_features(g["text_features"], float(g["logit_scale"]))
     hp = Hparams(head=str(g["head"]), tta_steps=int(g["tta_steps"]))

@@ -41,6 +41,32 @@ def test_oracle_reproduces_reference(case, b16_weights, b16_views):
             np.testing.assert_allclose(res.lora[i][j].numpy(), g[f"lora_{i}_{nm}"], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("case", ["ref_b16_c1000_tpt", "ref_b16_c200_tpt", "ref_b16_c200_deyo", "ref_b16_c10_tpt4",
+                                  "ref_b16_c10_deyo2"])
+def test_oracle_reproduces_reference_at_benched_configs(case, b16_weights, b16_views):
+    """BASELINE.json configs[1], [2] and [4] (1000 / 200 classes through the reference's own prompt builder + text tower;
+    4 TTA steps; 2 x 2 DeYO steps): fixtures from the unmodified reference (oracle/make_golden_configs.py), per-step losses
+    included.  Same bar as above: fp32 CPU against fp32 CPU."""
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    arch, spec = O.ARCHS["ViT-B/16"], O.LoraSpec()
+    lora0 = O.lora_init(arch, spec, seed=int(g["lora_seed"]))
+    text = torch.from_numpy(g["text_features"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = O.adapt_and_predict(arch, b16_weights, b16_views, text, float(g["logit_scale"]), lora0, spec,
+                              head=str(g["head"]), tta_steps=int(g["tta_steps"]))
+    np.testing.assert_allclose(res.logits0.numpy(), g["logits0"], rtol=0, atol=5e-5)
+    if str(g["head"]) == "tpt":
+        assert res.idx.tolist() == g["idx"].tolist()                      # argsort order too, not only the set
+        np.testing.assert_allclose(np.asarray(res.losses), g["losses"], rtol=2e-4, atol=2e-6)
+    multi = int(g["tta_steps"]) > 1     # later steps sit on sign-like first-step updates: fp32 summation order shows (1e-3)
+    np.testing.assert_allclose(res.pred_logits.numpy(), g["pred_logits"], rtol=0, atol=2e-3 if multi else 5e-5)
+    for i in spec.layers():
+        for j, nm in enumerate(NAMES):
+            ref_g, got_g = g[f"grad_{i}_{nm}"], res.grads[i][j].numpy()
+            denom = max(np.linalg.norm(ref_g), 1e-30)
+            assert np.linalg.norm(got_g - ref_g) / denom < (2e-2 if multi else 1e-4) or np.abs(ref_g).max() == 0, (i, nm)
+
+
 def test_golden_structural_facts():
     """at step 1 dA == 0 exactly and B == -lr*g/(|g|+eps); at step 2 dA != 0."""
     g = _load("tpt")

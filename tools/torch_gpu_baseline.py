@@ -74,23 +74,20 @@ class Vit(nn.Module):
         return self.proj(self.post(x[:, 0]))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--samples", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--classes", type=int, default=1000)
-    ap.add_argument("--views", type=int, default=64)
-    a = ap.parse_args()
+def run(samples: int = 24, warmup: int = 4, classes: int = 1000, views: int = 64, geo: dict | None = None) -> dict:
+    """Time `samples` adapted samples of the stock-PyTorch loop on the current CUDA device; returns the JSON-able record."""
+    a = argparse.Namespace(samples=samples, warmup=warmup, classes=classes, views=views)
+    rng_state = torch.random.get_rng_state()
     torch.manual_seed(0)
     dev = "cuda"
-    m = Vit().to(dev).eval()
+    m = Vit(**(geo or {})).to(dev).eval()
     for p in m.parameters():
         p.requires_grad_(False)
     lora = [p for l in m.layers for mod in (l.q, l.v) if isinstance(mod, LoraLinear) for p in (mod.A.weight, mod.B.weight)]
     for p in lora:
         p.requires_grad_(True)
     init = [p.detach().clone() for p in lora]
-    text = F.normalize(torch.randn(a.classes, 512, device=dev), dim=-1)
+    text = F.normalize(torch.randn(a.classes, m.proj.out_features, device=dev), dim=-1)
     opt = torch.optim.AdamW(lora, lr=5e-3)
     opt_state = copy.deepcopy(opt.state_dict())
     ring = [torch.randn(a.views, 3, 224, 224, device=dev) for _ in range(8)]      # 8 x 38.5 MB > L2
@@ -128,10 +125,23 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"what": "stock PyTorch bf16-autocast TTL loop on this GPU (autograd through all 64 views, SDPA, AdamW; "
-                              "class features cached)", "value": a.samples / (ms * 1e-3), "unit": "samples/s",
-                      "ms_per_sample": ms / a.samples, "samples": a.samples, "torch": torch.__version__,
-                      "gpu": torch.cuda.get_device_name(0)}))
+    torch.random.set_rng_state(rng_state)
+    del m, opt, ring
+    torch.cuda.empty_cache()
+    return {"what": "stock PyTorch bf16-autocast TTL loop on this GPU (nn.Linear / SDPA / autograd through all 64 views / "
+                    "torch.optim.AdamW; class features cached, so faster than the real reference would be)",
+            "value": a.samples / (ms * 1e-3), "unit": "samples/s", "ms_per_sample": ms / a.samples, "samples": a.samples,
+            "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--views", type=int, default=64)
+    a = ap.parse_args()
+    print(json.dumps(run(a.samples, a.warmup, a.classes, a.views)))
 
 
 if __name__ == "__main__":

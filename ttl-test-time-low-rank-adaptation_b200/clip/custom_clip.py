@@ -189,9 +189,15 @@ class ClipTestTimeTuning(nn.Module):
     def __init__(self, device, classnames, batch_size, criterion="cosine", arch="ViT-B/16", n_ctx=16, ctx_init=None,
                  ctx_position="end", learned_cls=False, layer_range=[9, 11], init_method=None, lora_encoder="text",
                  rank=16, max_views: int = 64, weights: Optional[dict] = None, text_features: Optional[torch.Tensor] = None,
-                 logit_scale: float = math.log(100.0), max_samples: int = 1, text_weights: Optional[dict] = None,
-                 bpe_path: Optional[str] = None, tokenizer=None, precision: str = "bf16"):
+                 logit_scale: Optional[float] = None, max_samples: int = 1, text_weights: Optional[dict] = None,
+                 bpe_path: Optional[str] = None, tokenizer=None, precision: str = "bf16", allow_synthetic: bool = False):
+        """`weights` / `text_weights` / `logit_scale`: what CLIPModel.from_pretrained hands the reference
+        (clip/custom_clip.py:581,619); when `weights` is None the local HF cache is read.  `allow_synthetic` (CLI:
+        --synthetic / --random_init, or TTL_SYNTHETIC_WEIGHTS=1) permits seeded random-init towers and prompt-keyed random
+        class features when no checkpoint exists; without it a missing checkpoint or text tower raises, as the
+        reference's from_pretrained would."""
         super().__init__()
+        self.allow_synthetic = bool(allow_synthetic) or os.environ.get("TTL_SYNTHETIC_WEIGHTS", "0") == "1"
         if lora_encoder != "image":
             raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
                                       "'text' and 'prompt' are out of scope (SURVEY.md §8f N4)")
@@ -207,9 +213,17 @@ class ClipTestTimeTuning(nn.Module):
                              lora_alpha=32.0, layer_range=self.layer_range, device=dev_index,
                              max_samples=1 if precision == "fp32" else max_samples, precision=precision)
         self._text_weights, self._bpe_path, self._text_encoder, self._tokenizer = text_weights, bpe_path, None, tokenizer
-        self.engine.load_weights(weights if weights is not None else self._load_vision_weights(arch))
-        if self._text_weights is None and weights is None:
-            self._text_weights = getattr(ClipTestTimeTuning, "_hf_text_weights", None)
+        hf = None
+        if weights is None:
+            weights, hf = self._load_vision_weights(arch, self.allow_synthetic)
+        self.engine.load_weights(weights)
+        if hf is not None:        # the HF checkpoint also carries the text tower and logit_scale (clip/custom_clip.py:619)
+            if self._text_weights is None:
+                self._text_weights = hf["text"]
+            if logit_scale is None:
+                logit_scale = hf["logit_scale"]
+        if logit_scale is None:
+            logit_scale = math.log(100.0)       # CLIP's trained value; random-init runs use it too
 
         # LoRA module tree.  Trainable-range tensors alias the library's device buffers.
         layers: List[_Layer] = []
@@ -242,22 +256,23 @@ class ClipTestTimeTuning(nn.Module):
 
     # ---- frozen inputs ------------------------------------------------------------------------------
     @staticmethod
-    def _load_vision_weights(arch):
-        """HF checkpoint from the local cache when present (clip/custom_clip.py:581), else seeded random init
-        (set TTL_SYNTHETIC_WEIGHTS=0 to forbid the fallback to random weights)."""
+    def _load_vision_weights(arch, allow_synthetic: bool):
+        """CLIPModel.from_pretrained from the local HF cache (clip/custom_clip.py:581) -> (vision tensors, {text tower,
+        logit_scale}).  Without a checkpoint this raises like the reference does, unless random init was asked for."""
         try:
             from transformers import CLIPModel
             m = CLIPModel.from_pretrained(_HF_NAME[arch], local_files_only=True)
-            sd = {k: v for k, v in m.state_dict().items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
-            ClipTestTimeTuning._hf_logit_scale = float(m.logit_scale)
-            ClipTestTimeTuning._hf_text_weights = {k: v for k, v in m.state_dict().items()
-                                                   if k.startswith("text_model.") or k == "text_projection.weight"}
-            return sd
-        except Exception:
-            if os.environ.get("TTL_SYNTHETIC_WEIGHTS", "1") == "0":
-                raise
-            print("ttl_b200: no local CLIP checkpoint; using seeded random-init ViT weights (synthetic mode)")
-            return synthetic_vit_weights(arch, seed=1234)
+        except Exception as e:
+            if not allow_synthetic:
+                raise RuntimeError(
+                    f"no CLIP checkpoint for {arch}: {_HF_NAME.get(arch, arch)} is not in the local HF cache ({type(e).__name__}). "
+                    "Pass --vision_checkpoint FILE, or --synthetic N / --random_init for seeded random-init weights") from e
+            print("ttl_b200: no local CLIP checkpoint; using seeded random-init ViT weights (random init was requested)")
+            return synthetic_vit_weights(arch, seed=1234), None
+        sd = m.state_dict()
+        vision = {k: v for k, v in sd.items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
+        text = {k: v for k, v in sd.items() if k.startswith("text_model.") or k == "text_projection.weight"}
+        return vision, {"text": text, "logit_scale": float(m.logit_scale)}
 
     def _refresh_text_features(self):
         """Once per class-name set (the reference recomputes the text tower in every forward, custom_clip.py:667-671)."""
@@ -278,7 +293,10 @@ class ClipTestTimeTuning(nn.Module):
             self.tokenized_prompts = self.prompt_learner.tokenized_prompts
             t = self._text_encoder.encode(self.prompt_learner.tokenized_prompts)
         else:
-            # synthetic mode (no text-tower weights given): deterministic unit vectors keyed by the prompt text
+            if not self.allow_synthetic:
+                raise RuntimeError("no text tower and no class features: the checkpoint has no text_model.* tensors and no "
+                                   "text_features= were given (random class features need --synthetic / --random_init)")
+            # random-init mode (no text-tower weights given): deterministic unit vectors keyed by the prompt text
             rows = []
             for p in self.prompt_learner.prompts:
                 g = torch.Generator().manual_seed(zlib.crc32(p.encode()))

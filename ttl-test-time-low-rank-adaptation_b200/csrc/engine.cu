@@ -18,6 +18,8 @@
 #include "kernels.cuh"
 #include "views.cuh"
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +32,13 @@ using namespace ttl;
 namespace {
 
 thread_local std::string g_create_err;
+
+// NVTX range per phase of the per-sample body (reset / frozen pass / head / train forward / backward / AdamW / predict):
+// host-side markers, so they bracket the enqueue of a phase; inside a captured graph they mark the capture.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 inline uint16_t f2bf(float f) {  // round-to-nearest-even, matches __float2bfloat16 for finite values
   uint32_t u;
@@ -227,6 +236,10 @@ GemmOperand opnd(const bf16* p, int rows, int k, int ld) {
   return o;
 }
 
+// K = int(V * top) of select_confident_samples (ttl.py:52): the product is taken in double, as Python does, so the count
+// (and the size of the caller's idx buffer) agrees with the host for every (V, p)
+inline int select_count(int V, double p) { return static_cast<int>(static_cast<double>(V) * p); }
+
 bool has_lora(const ttl_ctx* c, int layer) { return layer >= c->lo && layer <= c->hi; }
 
 // ---------------------------------------------------------------------------------------------- forward pieces
@@ -332,6 +345,7 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
 
 // layers [0, lo) on all views: images -> XK
 int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
+  NvtxRange nv("ttl:frozen_forward(layers<lo)");
   RET_IF(embed(c, images, V, c->XK, st));
   for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, c->XK, c->XB, c->XK, V, 1, false, nullptr, st));
   return TTL_OK;
@@ -413,6 +427,7 @@ int run_last_layer_cls(ttl_ctx* c, int layer, const float* x_in, int V, int S, b
 // layers [lo, L) in inference mode from x_in (V views of S samples) -> feats/logits/entropy written to the given buffers
 int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats, float* logits, float* entropy,
                        cudaStream_t st) {
+  NvtxRange nv("ttl:tail_infer(layers>=lo)+logits");
   const float* cur = x_in;
   const int last = c->L - 1;
   const bool shortcut = c->cls_shortcut && last >= c->lo;
@@ -434,6 +449,7 @@ int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats
 
 // layers [lo, L) in train mode from x_in (G views of S samples): tape + feats_c
 int forward_tail_train(ttl_ctx* c, const float* x_in, int G, int S, cudaStream_t st) {
+  NvtxRange nv("ttl:tail_train(tape)");
   const float* cur = x_in;
   for (int l = c->lo; l < c->L; ++l) {
     Tape& tp = c->tape[l - c->lo];
@@ -450,6 +466,7 @@ int forward_tail_train(ttl_ctx* c, const float* x_in, int G, int S, cudaStream_t
 
 // dlogits_c [G,C] (G views of S samples, sample-major) -> LoRA gradients of every sample (overwrites c->lg)
 int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
+  NvtxRange nv("ttl:backward(LoRA grads)");
   if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
   const int S = c->last_train_samples;
   const int Mg = G * c->tokens, Ms = Mg / S, d = c->d, F = c->F, r = c->r;
@@ -696,6 +713,7 @@ int repack(ttl_ctx* c, int S, cudaStream_t st) {
 }
 
 int lora_reset(ttl_ctx* c, int S, cudaStream_t st) {
+  NvtxRange nv("ttl:lora_reset");
   launch_lora_reset(c->lp, c->l0, c->lm, c->lv, static_cast<int>(c->lora_total) * S, static_cast<int>(c->lora_total), st);
   c->launches++;
   c->opt_step = 0;
@@ -704,6 +722,7 @@ int lora_reset(ttl_ctx* c, int S, cudaStream_t st) {
 }
 
 int adamw(ttl_ctx* c, const ttl_hparams& hp, int S, cudaStream_t st) {
+  NvtxRange nv("ttl:adamw+repack");
   c->opt_step++;
   launch_adamw(c->lp, c->lg, c->lm, c->lv, static_cast<int>(c->lora_total) * S, c->opt_step, hp.lr, hp.beta1, hp.beta2,
                hp.eps, hp.weight_decay, st);
@@ -718,7 +737,7 @@ int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams&
   const int VV = S * V;
   RET_IF(lora_reset(c, S, st));
   RET_IF(forward_frozen(c, images, VV, st));
-  const int K = static_cast<int>(V * hp.selection_p);
+  const int K = select_count(V, hp.selection_p);
   const size_t view_elems = static_cast<size_t>(c->tokens) * c->d;
   if (hp.head == TTL_HEAD_TPT) {
     RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, c->logits, c->entropy, st));
@@ -770,7 +789,7 @@ int adapt_body(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams&
 int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
   RET_IF(lora_reset(c, 1, st));
   RET_IF(f32_frozen(c, images, V, st));
-  const int K = static_cast<int>(V * hp.selection_p);
+  const int K = select_count(V, hp.selection_p);
   const size_t view_elems = static_cast<size_t>(c->tokens) * c->d;
   if (hp.head == TTL_HEAD_TPT) {
     RET_IF(f32_tail_infer(c, c->XK, V, c->feats, c->logits, c->entropy, st));
@@ -811,7 +830,7 @@ int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp
 
 int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int S, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
   if (!o) return TTL_OK;
-  const int K = static_cast<int>(V * hp.selection_p);
+  const int K = select_count(V, hp.selection_p);
   if (o->logits0) CK(cudaMemcpyAsync(o->logits0, c->logits, sizeof(float) * S * V * c->C, kind, st));
   if (o->entropy) CK(cudaMemcpyAsync(o->entropy, c->entropy, sizeof(float) * S * V, kind, st));
   if (o->idx && K > 0) CK(cudaMemcpyAsync(o->idx, c->idx, sizeof(int) * S * K, kind, st));
@@ -827,12 +846,13 @@ int validate_run(ttl_ctx* c, int S, int V, const ttl_hparams* hp) {
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
   if (hp->head != TTL_HEAD_TPT && hp->head != TTL_HEAD_DEYO) { c->err = "unknown head"; return TTL_E_INVALID; }
   if (hp->tta_steps < 0 || hp->tta_steps > 64) { c->err = "tta_steps out of range"; return TTL_E_INVALID; }
-  if (hp->selection_p < 0.f || hp->selection_p > 1.f) { c->err = "selection_p out of range"; return TTL_E_INVALID; }
+  if (!(hp->selection_p >= 0.0 && hp->selection_p <= 1.0)) { c->err = "selection_p out of range"; return TTL_E_INVALID; }
   return TTL_OK;
 }
 
 // images_dev == nullptr: the bf16 patch matrix c->patches is already in place (view generator).
 int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const ttl_hparams* hp, bool forced, cudaStream_t st) {
+  NvtxRange nv("ttl:adapt_predict");
   const int64_t before = c->launches;
   if (c->f32) {
     if (S != 1 || images_dev == nullptr) { c->err = "fp32 validation mode: one sample per call, fp32 views as input"; return TTL_E_SHAPE; }
@@ -1134,12 +1154,13 @@ int ttl_set_text_features(ttl_ctx* c, const float* host_text, int32_t n_classes,
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
   RET_IF(upload_f32(c, c->text, host_text, static_cast<int64_t>(n_classes) * proj_dim));
-  if (n_classes != c->C) {   // C is baked into captured graphs
+  const float scale_exp = std::exp(logit_scale);
+  if (n_classes != c->C || scale_exp != c->logit_scale_exp) {   // C and exp(logit_scale) are baked into captured graphs
     for (auto& e : c->gcache) if (e.exec) cudaGraphExecDestroy(e.exec);
     c->gcache.clear();
   }
   c->C = n_classes;
-  c->logit_scale_exp = std::exp(logit_scale);
+  c->logit_scale_exp = scale_exp;
   return TTL_OK;
 }
 
@@ -1185,6 +1206,20 @@ int ttl_lora_get(ttl_ctx* c, int32_t layer, int32_t which, int32_t what, float* 
   RET_IF(lora_slot(c, layer, which, &off, &n));
   if (numel != n) { c->err = "lora_get: wrong numel"; return TTL_E_SHAPE; }
   const float* src = what == TTL_LORA_PARAM ? c->lp : (what == TTL_LORA_GRAD ? c->lg : c->l0);
+  cudaSetDevice(c->cfg.device);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host_out, src + off, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return TTL_OK;
+}
+
+int ttl_lora_get_sample(ttl_ctx* c, int32_t sample, int32_t layer, int32_t which, int32_t what, float* host_out, int64_t numel) {
+  if (!c || !host_out) return TTL_E_INVALID;
+  if (sample < 0 || sample >= c->Sm) { c->err = "lora_get_sample: sample out of range (ttl_config.max_samples)"; return TTL_E_INVALID; }
+  int64_t off, n;
+  RET_IF(lora_slot(c, layer, which, &off, &n));
+  if (numel != n) { c->err = "lora_get_sample: wrong numel"; return TTL_E_SHAPE; }
+  const float* src = what == TTL_LORA_PARAM ? c->lp : (what == TTL_LORA_GRAD ? c->lg : c->l0);
+  if (what != TTL_LORA_INIT) off += static_cast<int64_t>(sample) * c->lora_total;   // one shared reset snapshot
   cudaSetDevice(c->cfg.device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host_out, src + off, sizeof(float) * n, cudaMemcpyDeviceToHost));
@@ -1258,7 +1293,7 @@ int ttl_adapt_predict_batch(ttl_ctx* c, const float* images_dev, int32_t n_sampl
   if (!images_dev) return TTL_E_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int K = static_cast<int>(n_views * hp->selection_p);
+  const int K = select_count(n_views, hp->selection_p);
   const bool forced = forced_idx_dev != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
   if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K * n_samples, cudaMemcpyDeviceToDevice, st));
   RET_IF(adapt_predict_impl(c, images_dev, n_samples, n_views, hp, forced, st));
@@ -1286,7 +1321,7 @@ int ttl_adapt_predict_batch_host_async(ttl_ctx* c, const float* images_host, int
   CK(cudaMemcpyAsync(c->stage[b], images_host, img_bytes, cudaMemcpyHostToDevice, c->copy_stream));
   CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
   CK(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
-  const int K = static_cast<int>(n_views * hp->selection_p);
+  const int K = select_count(n_views, hp->selection_p);
   const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
   if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K * n_samples, cudaMemcpyHostToDevice, st));
   RET_IF(adapt_predict_impl(c, c->stage[b], n_samples, n_views, hp, forced, st));
@@ -1422,7 +1457,7 @@ int ttl_adapt_predict_images_async(ttl_ctx* c, const uint8_t* const* images_host
   RET_IF(vg_stage(c, images_host, heights, widths, n_samples, specs_host, n_views, b, c->copy_stream, &max_h));
   CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
   CK(cudaStreamWaitEvent(st, c->ev_copied[b], 0));
-  const int K = static_cast<int>(n_views * hp->selection_p);
+  const int K = select_count(n_views, hp->selection_p);
   const bool forced = forced_idx_host != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
   if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_host, sizeof(int) * K * n_samples, cudaMemcpyHostToDevice, st));
   launch_views(c->vg_img[b], c->vg_desc[b], n_samples * n_views, max_h, c->vg_coef, c->vg_tmp, nullptr, c->patches,

@@ -2,11 +2,11 @@
 # Launcher with the reference's parameter block (scripts/test_ttl.sh), for the B200 path.
 #   bash scripts/test_ttl.sh A/R            # one GPU
 #   NGPU=8 bash scripts/test_ttl.sh A/R     # one process per GPU, test samples sharded by index, one final all-reduce
-# Two deliberate differences from the reference's script:
-#   * the data root is passed as the positional DIR argument; the reference's `--data $DATA_ROOT` is parsed by argparse as an
-#     abbreviation of --dataset_mode and the root silently stays at its default;
-#   * DEYO_SELECTION='' selects the confidence-selection + marginal-entropy head the paper describes; any non-empty string
-#     (the reference's default "True", but also "False") selects the weighted-entropy head, as in the reference.
+# One deliberate difference from the reference's script: the data root is passed as the positional DIR
+# argument; the reference's `--data $DATA_ROOT` is parsed by argparse as an abbreviation of --dataset_mode and the root
+# silently stays at its default.
+# DEYO_SELECTION defaults to True like the reference's script (weighted-entropy head, deyo.py); DEYO_SELECTION='' selects the
+# confidence-selection + marginal-entropy head the paper describes.  Any non-empty string ("False" too) is truthy (Q1).
 set -euo pipefail
 cd "$(dirname "$0")/.."
 
@@ -25,7 +25,7 @@ LAYER_RANGE=${LAYER_RANGE:-9,11}
 INIT_METHOD='xavier'
 LORA_ENCODER='image'
 RANK=16
-DEYO_SELECTION=${DEYO_SELECTION-}
+DEYO_SELECTION=${DEYO_SELECTION-True}
 NGPU=${NGPU:-1}
 
 ARGS=("$DATA_ROOT" --test_sets "$TEST_SETS" --dataset_mode "$MODE" --arch "$ARCH" --b "$BS" --ctx_init "$CTX_INIT"

@@ -11,11 +11,15 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
   --synthetic N   evaluate on N seeded synthetic samples instead of a dataset on disk
   --compat        drive the module through autograd + torch.optim.AdamW (the reference's control flow) instead of
                   the fused per-sample call
-  --views_on_host keep the synthetic views in pinned host memory (exercises the H2D path)
+  --views_on_host the reference's input route: the DataLoader workers produce 64 fp32 views per sample (host -> device copy
+                  of 38.5 MB per sample) instead of the default uint8 image + crop boxes
   --concurrent_samples S  adapt S test samples per library call (default 9; 1 = strictly one at a time)
   --precision fp32  validation mode: every activation/contraction in fp32 (held to 1e-4 against the reference), one sample per call
-  --vision_checkpoint F  load the image tower from a checkpoint file (HF or OpenAI format) instead of the local HF cache
-  --views_on_device  ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
+  --vision_checkpoint F  load image tower + text tower + logit_scale from one CLIP checkpoint file (HF or OpenAI format)
+                  instead of the local HF cache
+  --random_init   allow seeded random-init weights / random class features when no checkpoint exists (implied by --synthetic)
+  --merges F      CLIP BPE merge table for the class prompts
+  --views_on_device  (default) ship the decoded uint8 image + the drawn crop boxes and generate the 64 views on the GPU
                   (bit-exact with the reference's PIL/torchvision AugMixAugmenter) instead of 64 fp32 views per sample
 """
 from __future__ import annotations
@@ -174,10 +178,49 @@ class _ImageSpecTransform:
         return torch.from_numpy(arr), torch.from_numpy(specs)
 
 
+def _collate_samples(items):
+    """DataLoader collate for the fused route: keep the S dataset items of a batch as a list (images of a batch differ in size)."""
+    return list(items)
+
+
+def _iter_samples(val_loader):
+    """(payload, target[1]) per test sample from either loader flavour: the reference's (batch_size=1, default collate: a list of
+    64 tensors [1,3,S,S] + target [1], ttl.py:274-279,322-336) or this file's (batch_size=S, `_collate_samples`).
+    payload = fp32 views [V,3,S,S]  |  (uint8 image [H,W,3], int32 view specs [V,6])."""
+    for item in val_loader:
+        for it in (item if isinstance(item, list) and item and isinstance(item[0], tuple) else [item]):
+            if len(it) == 3:                                   # SyntheticImages: image, specs, label
+                images, target = (it[0], it[1]), it[2]
+            else:
+                images, target = it
+            if isinstance(images, (list, tuple)) and len(images) == 2 and torch.is_tensor(images[0]) and images[0].dtype == torch.uint8:
+                im, sp = images                                # build_dataset(transform=_ImageSpecTransform)
+                images = (im[0] if im.dim() == 4 else im, sp[0] if sp.dim() == 3 else sp)
+            elif isinstance(images, (list, tuple)):
+                images = torch.cat([v if v.dim() == 4 else v[None] for v in images], dim=0)
+            elif images.dim() > 4:
+                images = images.squeeze(0)
+            yield images, torch.as_tensor(target).view(-1)[:1]
+
+
+class _Ready:
+    """Device-resident results behind the same .wait() as ttl_b200.engine.Pending."""
+
+    def __init__(self, outs):
+        self.outs = outs
+
+    def wait(self):
+        return {k: v.cpu() for k, v in self.outs.items()}
+
+
 @torch.enable_grad()
 def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state, scaler, args):
-    """ttl.py:300-363.  With default flags each sample is ONE fused library call (reset -> adapt -> predict); `--compat`
-    keeps the reference's explicit sequence LoRA_reset / load_state_dict / test_time_tuning / model(image)."""
+    """ttl.py:300-363.  With default flags S test samples are ONE fused library call (each: reset -> adapt -> predict,
+    ttl.py:338-352) submitted without synchronising: the host->device copy and the view generation of batch i+1 overlap the
+    kernels of batch i and the predictions of batch i are scored while batch i+1 runs (depth-2 pipeline, the role of the
+    reference's pin_memory + non_blocking loader).  `--compat` keeps the reference's explicit per-sample sequence
+    LoRA_reset / load_state_dict / test_time_tuning / model(image)."""
+    from collections import deque
     batch_time = AverageMeter('Time', ':6.3f')
     top1 = AverageMeter('Acc@1', ':6.2f')
     top5 = AverageMeter('Acc@5', ':6.2f')
@@ -186,60 +229,67 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
         model.LoRA_reset()
     fused = (not getattr(args, "compat", False)) and model.fast_path_ok(args)
     rank, world = getattr(args, "rank_id", 0), getattr(args, "world_size", 1)
-    counts = torch.zeros(3, dtype=torch.int64, device=model.device)
-    end = time.time()
+    tally = [0, 0, 0]                       # top-1 hits, top-5 hits, n  (utils/tools.py:40-44 semantics: sums, not averages)
     S = max(1, int(getattr(args, "concurrent_samples", 1))) if fused else 1
-    pend_imgs, pend_tgt, seen = [], [], 0
+    n_total = len(val_loader.dataset) if hasattr(val_loader, "dataset") else None
+    t_start = end = time.time()
+    done_at = []                            # (wall time, samples scored so far) after every scored batch
 
     def score(output, target):
+        output, target = output.float().cpu(), target.cpu()
         acc1, acc5 = accuracy(output, target, topk=(1, 5))
         n = target.numel()
         top1.update(float(acc1[0]), n)
         top5.update(float(acc5[0]), n)
-        k1 = torch.round(acc1[0] * n / 100.0).long()
-        k5 = torch.round(acc5[0] * n / 100.0).long()
-        counts.add_(torch.stack([k1, k5, torch.full_like(k1, n)]).to(counts.device))
+        tally[0] += int(round(float(acc1[0]) * n / 100.0))
+        tally[1] += int(round(float(acc5[0]) * n / 100.0))
+        tally[2] += n
 
-    def flush():
-        """one fused library call for the pending samples (each: reset -> adapt -> predict, ttl.py:338-352)"""
-        nonlocal pend_imgs, pend_tgt
-        if not pend_imgs:
-            return
-        if isinstance(pend_imgs[0], tuple):     # --views_on_device: (uint8 image, view specs) per sample
-            out = model.adapt_and_predict_images([im.numpy() for im, _ in pend_imgs], [sp.numpy() for _, sp in pend_imgs],
-                                                 args)["pred_logits"].to(model.device)
-            score(out, torch.cat(pend_tgt))
-            pend_imgs, pend_tgt = [], []
-            return
-        batch = torch.stack(pend_imgs)
-        if not batch.is_cuda and not getattr(args, "views_on_host", False):
-            batch = batch.to(model.device, non_blocking=True)
-        out = model.adapt_and_predict_batch(batch, args)["pred_logits"].to(model.device)
-        score(out, torch.cat(pend_tgt))
-        pend_imgs, pend_tgt = [], []
+    inflight = deque()
+    staging = {}                            # two pinned fp32 staging batches for host-resident views
 
-    for i, item in enumerate(val_loader):
-        if len(item) == 3:                      # --views_on_device: uint8 image [1,H,W,3], specs [1,V,6], label
-            if not fused:
-                raise NotImplementedError("--views_on_device needs the fused path (default flags, no --compat)")
-            images, target = (item[0][0], item[1][0]), item[2]
-        else:
-            images, target = item
-            if isinstance(images, (list, tuple)) and len(images) == 2 and images[0].dtype == torch.uint8:
-                images = (images[0][0], images[1][0])   # build_dataset(transform=_ImageSpecTransform) item
-        if isinstance(images, tuple):
-            pass
-        elif isinstance(images, list):
-            images = torch.cat([im if im.dim() == 4 else im[None] for im in images], dim=0)
-        elif images.dim() > 4:
-            images = images.squeeze(0)
-        target = torch.as_tensor(target).view(-1)[:1].to(model.device)
+    def retire(k):
+        nonlocal end
+        while len(inflight) > k:
+            pending, targets = inflight.popleft()
+            score(pending.wait()["pred_logits"], torch.cat(targets))
+            now = time.time()
+            done_at.append((now, tally[2]))
+            batch_time.update((now - end) / len(targets), len(targets))
+            end = now
+            if rank == 0 and (tally[2] // args.print_freq) != ((tally[2] - len(targets)) // args.print_freq):
+                print(f"Test: [{tally[2]}/{n_total if n_total is not None else '?'}]\t{batch_time}\t{top1}\t{top5}")
+
+    def submit(payloads, targets, seq):
+        if isinstance(payloads[0], tuple):      # uint8 image + view specs per sample: views are generated on the device
+            pend = model.adapt_and_predict_images([im.numpy() for im, _ in payloads], [sp.numpy() for _, sp in payloads],
+                                                  args, sync=False)
+        elif payloads[0].is_cuda:
+            pend = _Ready(model.adapt_and_predict_batch(torch.stack(payloads), args))
+        else:                                   # fp32 views from the loader: stage in pinned memory, copy asynchronously
+            shape = (S,) + tuple(payloads[0].shape)
+            if staging.get("shape") != shape:
+                staging["shape"] = shape
+                staging["buf"] = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+            buf = staging["buf"][seq % 2]
+            for j, pl in enumerate(payloads):
+                buf[j].copy_(pl)
+            pend = model.adapt_and_predict_batch(buf[:len(payloads)], args, sync=False)
+        inflight.append((pend, targets))
+        retire(1)                               # keep one batch in flight behind the one just submitted
+
+    pend_p, pend_t, seq = [], [], 0
+    for images, target in _iter_samples(val_loader):
         if fused:
-            pend_imgs.append(images)
-            pend_tgt.append(target)
-            if len(pend_imgs) == S:
-                flush()
+            pend_p.append(images)
+            pend_t.append(target)
+            if len(pend_p) == S:
+                submit(pend_p, pend_t, seq)
+                pend_p, pend_t, seq = [], [], seq + 1
         else:
+            if isinstance(images, tuple):
+                raise NotImplementedError("device-generated views need the fused path (default flags, no --compat): "
+                                          "pass --views_on_host")
             images = images.to(model.device, non_blocking=True)
             image = images[:1]
             if args.tta_steps > 0:
@@ -249,17 +299,27 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
             test_time_tuning(model, images, optimizer, scaler, args)
             with torch.no_grad():
                 output = model(image)
-            score(output, target)
-        seen += 1
-        batch_time.update(time.time() - end)
-        end = time.time()
-        if (i + 1) % args.print_freq == 0 and rank == 0:
-            print(f"Test: [{i + 1}/{len(val_loader)}]\t{batch_time}\t{top1}\t{top5}")
-    flush()
+            inflight.append((_Ready({"pred_logits": output}), [target]))
+            retire(0)
+    if pend_p:
+        submit(pend_p, pend_t, seq)
+    retire(0)
+    counts = torch.tensor(tally, dtype=torch.int64, device=model.device)
     tot = tdist.reduce_counts(counts, world)   # the only collective of the path: 3 int64 (utils/tools.py:40-44 semantics)
     n = max(tot[2], 1)
+    # throughput of this rank's loop: whole loop, and steady state (after the first two batches: eager pass + graph capture)
+    elapsed = max(time.time() - t_start, 1e-9)
+    stats = {"samples": tally[2], "seconds": elapsed, "samples_per_s": tally[2] / elapsed, "steady_samples_per_s": None,
+             "concurrent_samples": S, "fused": fused}
+    if len(done_at) > 3:
+        (t0, n0), (t1, n1) = done_at[1], done_at[-1]
+        stats["steady_samples_per_s"] = (n1 - n0) / max(t1 - t0, 1e-9)
+    test_time_adapt_eval.last_stats = stats
     if rank == 0:
+        steady = stats["steady_samples_per_s"]
         print(f" *  Acc@1 {100.0 * tot[0] / n:.3f} Acc@5 {100.0 * tot[1] / n:.3f}  (n={tot[2]}, {world} rank(s))")
+        print(f" *  {stats['samples_per_s']:.1f} adapted samples/s on this rank over the whole loop"
+              + (f", {steady:.1f} in steady state (after the first two batches)" if steady else ""))
     return [100.0 * tot[0] / n, 100.0 * tot[1] / n]
 
 
@@ -307,11 +367,29 @@ def main_worker(gpu, args):
     extra = {"precision": args.precision}
     if args.precision == "fp32":
         args.concurrent_samples = 1
-        if args.views_on_device:
-            raise NotImplementedError("--views_on_device feeds the bf16 patch operand; the fp32 validation mode takes fp32 views")
+    # Input route.  Default: the host ships the decoded uint8 image + the drawn crop boxes and the 64 views are generated on
+    # the GPU, bit-exactly as the reference's PIL/torchvision pipeline would (csrc/views.cu).  --views_on_host, --compat and
+    # --precision fp32 take the reference's route: 64 fp32 views per sample from the DataLoader workers (ttl.py:232-241).
+    args.views_on_device = not (args.views_on_host or args.compat or args.precision == "fp32")
+    extra["allow_synthetic"] = args.synthetic > 0 or args.random_init
     if args.vision_checkpoint:      # HF safetensors/bin or OpenAI-format .pt (ttl_b200/weights.py); default: local HF cache
-        from ttl_b200.weights import load_vision_checkpoint
-        extra["weights"] = load_vision_checkpoint(args.vision_checkpoint)
+        # one file = what CLIPModel.from_pretrained yields (clip/custom_clip.py:581,619): image tower, the text tower that
+        # builds the class features, logit_scale
+        from ttl_b200.weights import load_clip_checkpoint
+        ck = load_clip_checkpoint(args.vision_checkpoint)
+        extra["weights"] = ck.vision
+        if ck.text is not None:
+            extra["text_weights"] = ck.text
+        elif not extra["allow_synthetic"]:
+            raise RuntimeError(f"{args.vision_checkpoint} has no text tower: class features cannot be built "
+                               "(give a full CLIP checkpoint, or --random_init for random class features)")
+        if ck.logit_scale is not None:
+            extra["logit_scale"] = ck.logit_scale
+        bpe = args.bpe_path or ck.bpe_path
+        if bpe:
+            extra["bpe_path"] = bpe
+    elif args.bpe_path:
+        extra["bpe_path"] = args.bpe_path
     model = get_coop(args.arch, args.test_sets, args.gpu, args.n_ctx, args.ctx_init, layer_range=args.layer_range,
                      init_method=args.init_method, lora_encoder=args.lora_encoder, rank=args.rank,
                      classnames=_classnames_for(first, args), max_views=args.batch_size,
@@ -333,6 +411,8 @@ def main_worker(gpu, args):
     optim_state = deepcopy(optimizer.state_dict())
     scaler = torch.amp.GradScaler("cuda", init_scale=1000, enabled=False)   # bf16 path: no loss scaling
     results = {}
+    fused = (not args.compat) and model.fast_path_ok(args)
+    args.views_on_device = args.views_on_device and fused
     for set_id in args.test_sets.split("/"):
         ds = None
         if args.synthetic <= 0 and args.views_on_device:
@@ -353,8 +433,13 @@ def main_worker(gpu, args):
         g = torch.Generator().manual_seed(args.seed)
         order = torch.randperm(len(ds), generator=g).tolist()
         shard = [order[j] for j in tdist.shard_indices(len(order), rank, world)]
-        loader = torch.utils.data.DataLoader(torch.utils.data.Subset(ds, shard), batch_size=1, shuffle=False,
-                                             num_workers=args.workers, pin_memory=True)
+        if fused:   # S samples per item, kept as a list (image sizes differ); pinning happens in the staging buffers
+            loader = torch.utils.data.DataLoader(torch.utils.data.Subset(ds, shard), batch_size=max(1, args.concurrent_samples),
+                                                 shuffle=False, num_workers=args.workers, collate_fn=_collate_samples,
+                                                 persistent_workers=False, prefetch_factor=4 if args.workers > 0 else None)
+        else:
+            loader = torch.utils.data.DataLoader(torch.utils.data.Subset(ds, shard), batch_size=1, shuffle=False,
+                                                 num_workers=args.workers, pin_memory=True)
         t0 = time.time()
         results[set_id] = test_time_adapt_eval(loader, model, None, optimizer, optim_state, scaler, args)
         if rank == 0:
@@ -417,13 +502,21 @@ def build_parser():
     # additions of this implementation (none starts with --data / --b)
     p.add_argument('--synthetic', default=0, type=int, help='evaluate on N seeded synthetic samples')
     p.add_argument('--compat', action='store_true', default=False, help='autograd + torch.optim.AdamW control flow')
-    p.add_argument('--views_on_host', action='store_true', default=False)
+    p.add_argument('--views_on_host', action='store_true', default=False,
+                   help="the reference's input route: 64 fp32 views per sample from the DataLoader workers, copied host->device")
     p.add_argument('--views_on_device', action='store_true', default=False,
-                   help='generate the views on the GPU from the uint8 image (bit-exact with PIL/torchvision)')
+                   help='(default on the fused path) generate the views on the GPU from the uint8 image, bit-exact with '
+                        'PIL/torchvision; kept as an explicit flag for older command lines')
     p.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                    help='bf16 = tensor-core path (default); fp32 = validation mode (fp32 everywhere, one sample per call)')
     p.add_argument('--vision_checkpoint', default=None, type=str,
                    help='CLIP checkpoint file for the image tower: HF model.safetensors / pytorch_model.bin or OpenAI ViT-*.pt')
+    p.add_argument('--random_init', action='store_true', default=False,
+                   help='allow seeded random-init towers / random class features when no checkpoint is available '
+                        '(implied by --synthetic); without it a missing checkpoint is an error, as in the reference')
+    p.add_argument('--merges', dest='bpe_path', default=None, type=str,
+                   help='CLIP BPE merge table (bpe_simple_vocab_16e6.txt.gz or HF merges.txt); default: next to the '
+                        'checkpoint, else $TTL_BPE_PATH')
     p.add_argument('--concurrent_samples', default=9, type=int,
                    help='test samples adapted concurrently per library call (each keeps its own adapter/optimiser state)')
     return p

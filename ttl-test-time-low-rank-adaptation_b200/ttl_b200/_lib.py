@@ -25,7 +25,7 @@ class TtlConfig(C.Structure):
 
 
 class TtlHparams(C.Structure):
-    _fields_ = [("head", C.c_int32), ("tta_steps", C.c_int32), ("selection_p", C.c_float), ("lr", C.c_float),
+    _fields_ = [("head", C.c_int32), ("tta_steps", C.c_int32), ("selection_p", C.c_double), ("lr", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("deyo_margin_e0", C.c_float)]
 
@@ -71,6 +71,7 @@ _SIGS = {
     "ttl_lora_set_init": (C.c_int, [vp, C.c_int32, C.c_int32, vp, C.c_int64]),
     "ttl_lora_reset": (C.c_int, [vp, vp]),
     "ttl_lora_get": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64]),
+    "ttl_lora_get_sample": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int64]),
     "ttl_lora_device_ptr": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_int64)]),
     "ttl_lora_touch": (C.c_int, [vp, vp]),
     "ttl_adamw_step": (C.c_int, [vp, C.POINTER(TtlHparams), vp]),

@@ -148,11 +148,13 @@ class Engine:
         L.check(self.lib.ttl_lora_reset(self.ctx, self._st()), self.ctx)
         self._sync_out()
 
-    def lora_get(self, layer: int, which: int, what: int = L.LORA_PARAM) -> np.ndarray:
+    def lora_get(self, layer: int, which: int, what: int = L.LORA_PARAM, sample: int = 0) -> np.ndarray:
+        """Factor / gradient / snapshot of one LoRA tensor; `sample` = position in the last concurrent-sample call."""
         d, r = self.geom["width"], self.rank
         shape = (r, d) if which in (L.LORA_A_Q, L.LORA_A_V) else (d, r)
         out = np.empty(shape, dtype=np.float32)
-        L.check(self.lib.ttl_lora_get(self.ctx, layer, which, what, out.ctypes.data_as(C.c_void_p), out.size), self.ctx)
+        L.check(self.lib.ttl_lora_get_sample(self.ctx, sample, layer, which, what, out.ctypes.data_as(C.c_void_p), out.size),
+                self.ctx)
         return out
 
     def lora_alias(self, layer: int, which: int, what: int = L.LORA_PARAM) -> torch.Tensor:

@@ -61,9 +61,10 @@ def _clean(text: str) -> str:
 class SimpleTokenizer:
     def __init__(self, bpe_path: str | None = None):
         path = bpe_path or default_bpe_path()
-        with gzip.open(path, "rt", encoding="utf-8") as f:
+        # the OpenAI release gzips the table; HF checkpoints carry the same lines as plain `merges.txt`
+        with (gzip.open(path, "rt", encoding="utf-8") if path.endswith(".gz") else open(path, "rt", encoding="utf-8")) as f:
             lines = f.read().split("\n")
-        merges: List[Tuple[str, str]] = [tuple(l.split()) for l in lines[1:1 + N_MERGES]]   # line 0 is a header
+        merges: List[Tuple[str, str]] = [tuple(l.split()) for l in lines[1:1 + N_MERGES] if l.strip()]   # line 0 is a header
         alphabet = list(byte_alphabet().values())
         # GPT-2 orders its alphabet "printable bytes first (in byte order), then the shifted ones"
         printable = [c for c in alphabet if ord(c) < 256]

@@ -6,8 +6,9 @@ clip/model.py `VisionTransformer` / `build_model`:428-467): `openai_to_hf_vision
 layout, `load_vision_checkpoint` reads a .safetensors / .pt / .bin file of either format.  Host-side, once per run."""
 from __future__ import annotations
 
+import os
 import re
-from typing import Dict
+from typing import Dict, NamedTuple, Optional
 
 import torch
 
@@ -64,9 +65,7 @@ def hf_vision_subset(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return {k: v.detach().float() for k, v in sd.items() if k.startswith("vision_model.") or k == "visual_projection.weight"}
 
 
-def load_vision_checkpoint(path: str) -> Dict[str, torch.Tensor]:
-    """Read a CLIP checkpoint file (HF `model.safetensors` / `pytorch_model.bin`, or an OpenAI `ViT-B-16.pt` -- a TorchScript
-    archive or a plain state dict) and return the HF-named vision tensors `Engine.load_weights` takes."""
+def _read_state_dict(path: str) -> Dict[str, torch.Tensor]:
     if path.endswith(".safetensors"):
         from safetensors.torch import load_file
         sd = load_file(path)
@@ -77,4 +76,38 @@ def load_vision_checkpoint(path: str) -> Dict[str, torch.Tensor]:
             sd = torch.load(path, map_location="cpu", weights_only=True)
             if isinstance(sd, dict) and "state_dict" in sd:
                 sd = sd["state_dict"]
+    return sd
+
+
+def load_vision_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """Read a CLIP checkpoint file (HF `model.safetensors` / `pytorch_model.bin`, or an OpenAI `ViT-B-16.pt` -- a TorchScript
+    archive or a plain state dict) and return the HF-named vision tensors `Engine.load_weights` takes."""
+    sd = _read_state_dict(path)
     return openai_to_hf_vision(sd) if is_openai_format(sd) else hf_vision_subset(sd)
+
+
+class ClipCheckpoint(NamedTuple):
+    vision: Dict[str, torch.Tensor]            # HF names: vision_model.*, visual_projection.weight
+    text: Optional[Dict[str, torch.Tensor]]    # HF names: text_model.*, text_projection.weight; None if the file has no text tower
+    logit_scale: Optional[float]               # log domain, as CLIPModel.logit_scale (clip/custom_clip.py:619)
+    bpe_path: Optional[str]                    # merge table found next to the file (HF `merges.txt` or the OpenAI .txt.gz)
+
+
+def load_clip_checkpoint(path: str) -> ClipCheckpoint:
+    """Everything the TTL path needs from one CLIP checkpoint file: the image tower, the text tower that turns the class
+    prompts into the cached class features (clip/custom_clip.py:651-663) and `logit_scale` (:619) -- what
+    `CLIPModel.from_pretrained` (clip/custom_clip.py:581) hands the reference in one object."""
+    from .text import openai_to_hf_text
+    sd = _read_state_dict(path)
+    if is_openai_format(sd):
+        vision = openai_to_hf_vision(sd)
+        text = openai_to_hf_text(sd) if "token_embedding.weight" in sd else None
+    else:
+        vision = hf_vision_subset(sd)
+        text = {k: v.detach().float() for k, v in sd.items() if k.startswith("text_model.") or k == "text_projection.weight"}
+        text = text if "text_projection.weight" in text else None
+    scale = float(sd["logit_scale"]) if "logit_scale" in sd else None
+    here = os.path.dirname(os.path.abspath(path))
+    bpe = next((os.path.join(here, n) for n in ("merges.txt", "bpe_simple_vocab_16e6.txt.gz")
+                if os.path.exists(os.path.join(here, n))), None)
+    return ClipCheckpoint(vision, text, scale, bpe)
