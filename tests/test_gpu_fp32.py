@@ -51,7 +51,7 @@ def test_fp32_mode_vs_reference(b16_fp32_engine, b16_views, case):
     assert float(np.abs(out["entropy"].cpu().numpy() - g["entropies"]).max()) < 1e-4
     if str(g["head"]) == "tpt":
         assert sorted(out["idx"].cpu().tolist()) == g["idx_sorted"].tolist()      # free-running selection, bit-exact
-    assert _rel(out["pred_logits"].cpu().numpy(), g["pred_logits"][0]) < TOL
+    e_pred = _rel(out["pred_logits"].cpu().numpy(), g["pred_logits"][0])
     worst_g = worst_p = 0.0
     for i in (9, 10, 11):
         for j, nm in enumerate(NAMES):
@@ -70,6 +70,11 @@ def test_fp32_mode_vs_reference(b16_fp32_engine, b16_views, case):
     # whose first gradient sits at the eps scale (measured 1.01e-4; the bf16 path needs 1e-1 for this case).
     tol = TOL if int(g["tta_steps"]) == 1 else 5e-4
     assert worst_g < tol and worst_p < tol
+    # The adapted prediction sits behind Adam's first step, lr * g / (|g| + eps): the 0.1 % of the gradient elements below
+    # 1e-7 (fixture statistics, C = 1000 / 200) get an update of order lr whose size depends on fp32 summation order, which
+    # moves the 1000-class prediction by 3.9e-4 (measured) although gradients and masked factors agree to 1e-4.
+    print(f"[fp32 {case}] adapted prediction rel err {e_pred:.2e}")
+    assert e_pred < (TOL if case.startswith("c10_") else 1e-3)
 
 
 @pytest.mark.parametrize("head,steps", [("tpt", 1), ("deyo", 1), ("tpt", 2)])

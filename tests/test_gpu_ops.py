@@ -197,7 +197,10 @@ def _attn_ref(qkv, V, tokens, heads):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("V,tokens,heads", [(3, 197, 12), (2, 257, 16), (4, 17, 2), (1, 64, 1), (64, 197, 12), (5, 50, 3)])
+# 129..208 tokens: tcgen05 backward (two query tiles x two key halves; 129 / 144 / 145 / 176 / 208 walk the 16..80-key second half
+# and the partial last query tile; 200 views x 12 heads = 2400 units > 148 CTAs wrap the mbarrier phases many times)
+@pytest.mark.parametrize("V,tokens,heads", [(3, 197, 12), (2, 257, 16), (4, 17, 2), (1, 64, 1), (64, 197, 12), (5, 50, 3),
+                                            (2, 129, 2), (2, 144, 3), (3, 145, 2), (7, 176, 4), (2, 208, 2), (200, 197, 12)])
 def test_attention_fwd_bwd(G, V, tokens, heads):
     gu, L = G
     d = heads * 64

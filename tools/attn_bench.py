@@ -28,7 +28,7 @@ for (V, tokens, heads) in ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197,
     by = V * tokens * d * 2 * 4
     print(f"attention fwd V={V} tokens={tokens} heads={heads}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
 
-for (V, tokens, heads) in ((18, 197, 12), (6, 197, 12), (64, 197, 12)):
+for (V, tokens, heads) in ((18, 197, 12), (6, 197, 12), (54, 197, 12), (64, 197, 12), (576, 197, 12)):
     d = heads * 64
     qkv = (torch.randn(V * tokens, 3 * d, device="cuda") * 1.5).bfloat16()
     out = torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16)

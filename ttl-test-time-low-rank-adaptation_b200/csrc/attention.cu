@@ -1452,6 +1452,375 @@ attention_cls_kernel(const bf16* __restrict__ q_cls, size_t q_view_stride, const
   if (half == 0) out_cls[static_cast<size_t>(view) * out_view_stride + h * DH + dd] = __float2bfloat16((o + sq[dd]) * inv);
 }
 
+// =============================================================================================== tcgen05 backward
+// Attention backward on the 5th-gen tensor cores, one persistent CTA per SM walking (view, head) units of 129..208 tokens.
+// All five contractions of a unit run as tcgen05.mma with fp32 accumulators in TMEM; nothing of size tokens x tokens leaves
+// the SM.  With P = exp(scale S - lse), dP = dO V^T, Delta_q = sum_d dO_qd O_qd, dS = scale P o (dP - Delta):
+//     dQ = dS K        dK = dS^T Q        dV = P^T dO
+// The unit is walked as (key half kh) x (query tile t): keys [0,128) then [128, keys), queries [0,128) then [128,256)
+// (rows >= tokens are zero-filled by the TMA).  TMEM (all 512 columns):
+//     [  0,128) S = Q_t K_kh^T      [128,256) dP = dO_t V_kh^T        (overwritten every sub-step)
+//     [256,320) dQ_0   [320,384) dQ_1   (accumulate over both key halves)
+//     [384,448) dV_kh  [448,512) dK_kh  (accumulate over both query tiles, drained after t = 1)
+// Shared memory: K, V (keys x 64), both Q tiles, both dO tiles (TMA, 128B swizzle), and one P and one dS tile
+// [128 queries][128 keys] bf16 written by the softmax threads as two 64-key blocks in the UMMA K-major 128B-swizzle layout.
+// That same tile is the A operand twice: K-major for dQ = dS K (M = queries, K = keys) and -- through an MN-major
+// descriptor (instruction-descriptor bit 15) -- transposed for dV = P^T dO and dK = dS^T Q (M = keys, K = queries): the 8-row
+// x 128-byte swizzle atom is the same physical layout under both readings, so no transposed copy is ever written.
+// K / Q_t / dO_t are B operands as they sit in memory (MN-major, like V in the forward's P V).
+//   warp 0 (one thread): TMA loads, all MMAs, commits.
+//   warps 1-8: two threads per query row (each takes 64 of the 128 key columns of a sub-step): tcgen05.ld of S and dP,
+//              P / dS in fp32, bf16 tiles to smem; then the drains: dV / dK rows (one key per TMEM lane) and dQ rows.
+// Keys >= tokens need no mask: their K / V rows are zero, so S = dP = 0, P and dS stay finite, and every product they enter
+// is with a zero K row (dQ) or lands in a dK / dV row that is not stored.
+constexpr int BT_THREADS = 288;
+
+// 8 scores + 8 dP values -> 4 packed bf16 pairs of P and of dS (registers; written to smem once the tiles are free)
+__device__ __forceinline__ void bt_group8(const uint32_t* s8, const uint32_t* dp8, float scale_log2, float lse2, float delta,
+                                          float scale, uint32_t* p4, uint32_t* ds4) {
+  float p[8], ds[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    p[i] = ex2_approx(fmaf(__uint_as_float(s8[i]), scale_log2, -lse2));
+    ds[i] = p[i] * (__uint_as_float(dp8[i]) - delta) * scale;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    p4[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+    ds4[i] = pack_bf16(ds[2 * i], ds[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ void bt_st16(uint32_t addr, const uint32_t* v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+// 64 fp32 accumulator columns of this thread's TMEM lane -> one bf16 row of the 128B-swizzled staging tile [128][64]
+__device__ __forceinline__ void bt_stage_row(const uint32_t (&a)[32], const uint32_t (&b)[32], uint32_t row_addr, uint32_t sw) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t* r = q < 4 ? a + q * 8 : b + (q - 4) * 8;
+    const uint32_t v[4] = {pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])),
+                           pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5])), pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]))};
+    bt_st16(row_addr + ((static_cast<uint32_t>(q) ^ sw) << 4), v);
+  }
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmO,
+                        const __grid_constant__ CUtensorMap tmDst, const float* __restrict__ lse, int tokens, int heads, int units,
+                        int keys, float scale, long long* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_bt_raw[];
+  // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0; slots 0..31 = MMA thread, 32..63 = softmax warp 1
+#define BT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && local_u < 6) dbg[local_u * 64 + (k)] = clock64(); } while (0)
+  int local_u = 0;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_bt_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = keys * 128;                     // bytes of K (or V): keys rows of 128 bytes, a multiple of 2048
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KB;
+  uint8_t* sQ = sV + KB;                         // 2 x 16 KB  [128 q][64 dh]
+  uint8_t* sdO = sQ + 32768;                     // 2 x 16 KB
+  uint8_t* sP = sdO + 32768;                     // 2 x 16 KB  blocks of 64 keys: [128 q][64 keys]
+  uint8_t* sdS = sP + 32768;                     // 2 x 16 KB
+  uint8_t* sOut = sdS + 32768;                   // 2 x 16 KB  output staging, one tile per softmax warpgroup
+  float* sDelta = reinterpret_cast<float*>(sOut + 32768);   // [256] Delta_q of the unit
+  float* sLse2 = sDelta + 256;                              // [256] lse_q * log2(e), +inf for rows >= tokens
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLse2 + 256);
+  uint64_t* bar_load0 = bars;       // K, V, Q0, dO0 of the unit landed
+  uint64_t* bar_load1 = bars + 1;   // Q1, dO1 landed
+  uint64_t* bar_sdp = bars + 2;     // S and dP of a sub-step complete in TMEM
+  uint64_t* bar_pds = bars + 3;     // P and dS tiles of a sub-step written, its S / dP drained (8 softmax warps)
+  uint64_t* bar_s2 = bars + 4;      // dQ / dV / dK MMAs of a sub-step complete: the P / dS tiles may be overwritten
+  uint64_t* bar_kv = bars + 5;      // every MMA up to and including the t = 1 sub-step of a key half has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * DH;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmDst);
+    mbar_init(bar_load0, 1);
+    mbar_init(bar_load1, 1);
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, 8);
+    mbar_init(bar_s2, 1);
+    mbar_init(bar_kv, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_trigger();
+  const int nh1 = keys - 128;                                   // keys of the second half (16..80)
+  const int nq1 = (tokens - 128 + 15) / 16;                     // 16-row k-steps that hold real queries in tile 1
+  const float scale_log2 = scale * LOG2E;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, static_cast<uint32_t>(nh1));
+      const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 1);                  // A K-major, B MN-major
+      const uint32_t idesc_tr = umma_idesc_bf16(128, 64, 1) | (1u << 15);     // A MN-major (transposed read), B MN-major
+      // Base descriptors once; per MMA only the 16-byte-granular start address moves (one 64-bit add): the issue loop of
+      // the first version rebuilt both descriptors per MMA and needed ~115 cycles per tcgen05.mma, more than the MMA itself.
+      const uint64_t kQ = umma_desc_k_sw128(smem_u32(sQ)), kK = umma_desc_k_sw128(smem_u32(sK)), kdO = umma_desc_k_sw128(smem_u32(sdO)),
+                     kV = umma_desc_k_sw128(smem_u32(sV)), kdS = umma_desc_k_sw128(smem_u32(sdS));
+      const uint64_t mK = umma_desc(smem_u32(sK), 1024, 16384, 2), mP = umma_desc(smem_u32(sP), 1024, 16384, 2),
+                     mdS = umma_desc(smem_u32(sdS), 1024, 16384, 2), mdO = umma_desc(smem_u32(sdO), 1024, 16384, 2),
+                     mQ = umma_desc(smem_u32(sQ), 1024, 16384, 2);
+      // Consecutive tcgen05.mma into the SAME accumulator are a dependent chain (~115 cycles per link measured here, against a
+      // 32 / 64 cycle issue floor at N = 64 / 128): the first version, chain after chain, spent 3.7 k cycles per sub-step in the
+      // tensor pipe.  So the five chains that are ready together -- S and dP of the NEXT sub-step, dQ / dV / dK of this one --
+      // are issued round-robin, one k-step of each per round.  Every round is a switch over the set of chains still running:
+      // straight-line, unpredicated MMAs per case (an unrolled `if (j < n) mma` form was compiled to predicated UTCHMMA with
+      // wrong uniform descriptor registers and faulted with out-of-range shared addresses).
+      auto mma_S = [&](int sub, int k) {
+        const int kh = sub >> 1, t = sub & 1;
+        umma_bf16(tmem, kQ + static_cast<uint64_t>(t * 1024 + 2 * k), kK + static_cast<uint64_t>(kh * 1024 + 2 * k),
+                  kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
+      };
+      auto mma_dP = [&](int sub, int k) {
+        const int kh = sub >> 1, t = sub & 1;
+        umma_bf16(tmem + 128, kdO + static_cast<uint64_t>(t * 1024 + 2 * k), kV + static_cast<uint64_t>(kh * 1024 + 2 * k),
+                  kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
+      };
+      auto mma_dQ = [&](int sub, int j) {     // dQ_t (+)= dS K_kh : A = dS tile (K-major), B = K rows as they sit (MN-major)
+        const int kh = sub >> 1, t = sub & 1;
+        umma_bf16(tmem + 256 + 64 * t, kdS + static_cast<uint64_t>((j >> 2) * 1024 + (j & 3) * 2),
+                  mK + static_cast<uint64_t>(kh * 1024 + j * 128), idesc_dq, (kh | j) != 0 ? 1u : 0u);
+      };
+      auto mma_dV = [&](int sub, int ks) {    // dV_kh (+)= P^T dO_t : A = P tile read MN-major (M = keys, K = queries)
+        const int t = sub & 1;
+        umma_bf16(tmem + 384, mP + static_cast<uint64_t>(ks * 128), mdO + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+                  (t | ks) != 0 ? 1u : 0u);
+      };
+      auto mma_dK = [&](int sub, int ks) {    // dK_kh (+)= dS^T Q_t
+        const int t = sub & 1;
+        umma_bf16(tmem + 448, mdS + static_cast<uint64_t>(ks * 128), mQ + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+                  (t | ks) != 0 ? 1u : 0u);
+      };
+      uint32_t n_sub = 0, n_load = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local_u) {
+        const int view = unit / heads, h = unit - view * heads;
+        BT_STAMP(0);
+        // O_0 / O_1 ride in the (dead) P tile: the softmax threads take Delta = rowsum(dO o O) from shared memory before the
+        // first P is written there (global row loads for Delta cost ~10 k cycles per unit behind the TMA traffic)
+        mbar_expect_tx(bar_load0, 2 * KB + 3 * 16384);
+        tma_load_3d(&tmKV, bar_load0, sK, d + h * DH, 0, view);
+        tma_load_3d(&tmQ, bar_load0, sQ, h * DH, 0, view);
+        tma_load_3d(&tmKV, bar_load0, sV, 2 * d + h * DH, 0, view);
+        tma_load_3d(&tmdO, bar_load0, sdO, h * DH, 0, view);
+        tma_load_3d(&tmO, bar_load0, sP, h * DH, 0, view);
+        mbar_expect_tx(bar_load1, 3 * 16384);
+        tma_load_3d(&tmQ, bar_load1, sQ + 16384, h * DH, 128, view);
+        tma_load_3d(&tmdO, bar_load1, sdO + 16384, h * DH, 128, view);
+        tma_load_3d(&tmO, bar_load1, sP + 16384, h * DH, 128, view);
+        mbar_wait(bar_load0, n_load & 1);
+        BT_STAMP(1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) { mma_S(0, k); mma_dP(0, k); }
+        umma_commit(bar_sdp);
+        if (unit + static_cast<int>(gridDim.x) < units) {      // the next unit's operands: HBM -> L2 behind this unit's compute
+          const int nu = unit + gridDim.x, nv = nu / heads, nhd = nu - nv * heads;
+          tma_prefetch_l2_3d(&tmKV, d + nhd * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmKV, 2 * d + nhd * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmQ, nhd * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmQ, nhd * DH, 128, nv);
+          tma_prefetch_l2_3d(&tmdO, nhd * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmdO, nhd * DH, 128, nv);
+          tma_prefetch_l2_3d(&tmO, nhd * DH, 0, nv);
+          tma_prefetch_l2_3d(&tmO, nhd * DH, 128, nv);
+        }
+        for (int sub = 0; sub < 4; ++sub) {
+          const int kh = sub >> 1, t = sub & 1;
+          const int nk = (kh == 0 ? 128 : nh1) >> 4;     // 16-key k-steps of dQ
+          const int nq = t == 0 ? 8 : nq1;                // 16-query k-steps of dV / dK
+          mbar_wait(bar_pds, n_sub & 1);      // P / dS of this sub-step are in smem, its S / dP have left TMEM
+          ++n_sub;
+          BT_STAMP(2 + 2 * sub);
+          tc_fence_after();
+          if (sub == 0) { mbar_wait(bar_load1, n_load & 1); tc_fence_after(); }
+          if (sub < 3) {      // S / dP of the NEXT sub-step first (two chains): the softmax threads start on them at once
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) { mma_S(sub + 1, k); mma_dP(sub + 1, k); }
+            umma_commit(bar_sdp);
+          }
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {       // dQ / dV / dK of this sub-step: three chains, round-robin
+            switch ((i < nk ? 1 : 0) | (i < nq ? 2 : 0)) {
+              case 3: mma_dQ(sub, i); mma_dV(sub, i); mma_dK(sub, i); break;
+              case 2: mma_dV(sub, i); mma_dK(sub, i); break;
+              case 1: mma_dQ(sub, i); break;
+              default: break;
+            }
+          }
+          umma_commit(bar_s2);
+          if (t == 1) umma_commit(bar_kv);
+          BT_STAMP(3 + 2 * sub);
+        }
+        ++n_load;
+        mbar_wait(bar_kv, 1);       // second commit of the unit: every MMA has completed, the smem operands may be reloaded
+        BT_STAMP(10);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;                  // TMEM lane quadrant a warp may access = warp index % 4
+    const int half = (warp - 1) >> 2;           // warps 1-4: key columns [0,64) of a sub-step; warps 5-8: [64,128)
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    // this thread's 64 key columns = one 64-key block of the tiles: block `half`, row `row`
+    const uint32_t p_row = smem_u32(sP) + half * 16384 + row * 128, ds_row = smem_u32(sdS) + half * 16384 + row * 128;
+    uint8_t* my_out = sOut + half * 16384;       // staging tile of this warpgroup (half 0: dV then dQ_0; half 1: dK then dQ_1)
+    const uint32_t out_row = smem_u32(my_out) + row * 128;
+    const bool issuer = quad == 1 && lane == 0;  // warps 1 and 5: the TMA-store thread of each warpgroup
+    const bool st = threadIdx.x == 32;
+    uint32_t n_sub = 0;             // sub-steps seen (parity of bar_sdp; bar_s2 of sub-step n - 1 has parity (n - 1) & 1)
+    uint32_t n_unit = 0;            // units seen (parity of the load barriers)
+
+    // one accumulator tile (64 TMEM columns at `col`, lane = row) -> bf16 staging tile -> one TMA store; rows >= tokens clipped
+    auto drain_tile = [&](uint32_t col, int c0, int r0, int view) {
+      uint32_t a[32], b[32];
+      tmem_ld_32x32b_x32(trow + col, a);
+      tmem_ld_32x32b_x32(trow + col + 32, b);
+      tmem_ld_wait();
+      if (issuer) bulk_wait_read<0>();         // the previous store of this warpgroup has finished reading the staging tile
+      named_bar_sync(1 + half, 128);
+      bt_stage_row(a, b, out_row, sw);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (issuer) {
+        tma_store_3d(&tmDst, my_out, c0, r0, view);
+        bulk_commit();
+      }
+    };
+
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local_u) {
+      const int view = unit / heads, h = unit - view * heads;
+      if (st) BT_STAMP(32);
+      // Delta_q = sum_d dO_qd O_qd of the unit's 256 query rows: warpgroup `half` takes tile `half`, one row per thread, O from
+      // the P tile (TMA-loaded there while it is dead) and dO from its own tile, both 128B-swizzled (conflict-free 16-byte
+      // reads); rows >= tokens are zero-filled.  lse_q comes from global memory; rows >= tokens get +inf: P = 2^(-inf) = 0 and
+      // dS = 0 without a branch in the inner loop.  Both are exchanged through smem (every thread needs both tiles' values).
+      {
+        const int q = half * 128 + row;
+        const float l = q < tokens ? __ldg(lse + (static_cast<size_t>(view) * heads + h) * tokens + q) * LOG2E : INFINITY;
+        mbar_wait(half == 0 ? bar_load0 : bar_load1, n_unit & 1);
+        const uint32_t o_row = smem_u32(sP) + half * 16384 + row * 128, do_row = smem_u32(sdO) + half * 16384 + row * 128;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t uo[4], ud[4];
+          const uint32_t o16 = (static_cast<uint32_t>(c) ^ sw) << 4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(uo[0]), "=r"(uo[1]), "=r"(uo[2]), "=r"(uo[3]) : "r"(o_row + o16));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ud[0]), "=r"(ud[1]), "=r"(ud[2]), "=r"(ud[3]) : "r"(do_row + o16));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uo[e]));
+            const float2 fd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ud[e]));
+            acc = fmaf(fo.x, fd.x, acc);
+            acc = fmaf(fo.y, fd.y, acc);
+          }
+        }
+        sDelta[q] = acc;
+        sLse2[q] = l;
+      }
+      ++n_unit;
+      if (st) BT_STAMP(53);
+      named_bar_sync(3, 256);
+      const float delta0 = sDelta[row], delta1 = sDelta[128 + row], lse20 = sLse2[row], lse21 = sLse2[128 + row];
+      if (st) BT_STAMP(33);
+      for (int sub = 0; sub < 4; ++sub) {
+        const int kh = sub >> 1, t = sub & 1;
+        const int nh = kh == 0 ? 128 : nh1;
+        const int ncol = nh - half * 64 < 64 ? nh - half * 64 : 64;   // this thread's key columns in this sub-step: 64/48/32/16/<=0
+        mbar_wait(bar_sdp, n_sub & 1);
+        if (st) BT_STAMP(34 + 4 * sub);
+        tc_fence_after();
+        const bool warp_active = t * 128 + quad * 32 < tokens;        // warp-uniform: at least one real query row
+        uint32_t pk[32], dk[32];                                      // packed bf16 pairs of P and dS: up to 64 columns
+        if (warp_active) {
+          const float l2 = t == 0 ? lse20 : lse21, dl = t == 0 ? delta0 : delta1;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 64 + cc * 32;
+            if (cc * 32 + 32 <= ncol) {
+              uint32_t s[32], dp[32];
+              tmem_ld_32x32b_x32(trow + c, s);
+              tmem_ld_32x32b_x32(trow + 128 + c, dp);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                bt_group8(s + q4 * 8, dp + q4 * 8, scale_log2, l2, dl, scale, pk + cc * 16 + q4 * 4, dk + cc * 16 + q4 * 4);
+            } else if (cc * 32 < ncol) {
+              uint32_t s[16], dp[16];
+              tmem_ld_32x32b_x16(trow + c, s);
+              tmem_ld_32x32b_x16(trow + 128 + c, dp);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q4 = 0; q4 < 2; ++q4)
+                bt_group8(s + q4 * 8, dp + q4 * 8, scale_log2, l2, dl, scale, pk + cc * 16 + q4 * 4, dk + cc * 16 + q4 * 4);
+            }
+          }
+        }
+        tc_fence_before();            // this warp's tcgen05.ld of S / dP have completed
+        if (st) BT_STAMP(35 + 4 * sub);
+        // The tiles are still being read by the dQ / dV / dK MMAs of the previous sub-step (they were issued behind this
+        // sub-step's S / dP): wait for them, and drain what they completed, before overwriting the tiles.
+        if (n_sub > 0) mbar_wait(bar_s2, (n_sub - 1) & 1);
+        if (sub == 2) {               // the first key half is complete: dV_0 (warpgroup 0) / dK_0 (warpgroup 1), TMEM lane = key
+          tc_fence_after();
+          drain_tile(384 + 64 * half, (2 - half) * d + h * DH, 0, view);
+          tc_fence_before();
+        }
+        ++n_sub;
+        if (st) BT_STAMP(36 + 4 * sub);
+        if (warp_active) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 8 < ncol) {
+              const uint32_t o16 = (static_cast<uint32_t>(g) ^ sw) << 4;
+              bt_st16(p_row + o16, pk + g * 4);
+              bt_st16(ds_row + o16, dk + g * 4);
+            }
+          }
+        }
+        fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pds);
+        if (st) BT_STAMP(37 + 4 * sub);
+      }
+      // end of the unit: dV_1 / dK_1 (TMEM lane = key 128 + row) and dQ_0 / dQ_1 (TMEM lane = query of tile `half`)
+      mbar_wait(bar_kv, 1);
+      if (st) BT_STAMP(50);
+      tc_fence_after();
+      drain_tile(384 + 64 * half, (2 - half) * d + h * DH, 128, view);
+      drain_tile(256 + 64 * half, h * DH, half * 128, view);
+      tc_fence_before();
+      if (st) BT_STAMP(51);
+    }
+    if (issuer) bulk_wait<0>();
+  }
+#undef BT_STAMP
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 inline int pick_warps(int tiles) {
   const int rounds = (tiles + 7) / 8;
   return (tiles + rounds - 1) / rounds;
@@ -1677,8 +2046,68 @@ void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int
              static_cast<float*>(nullptr), 0, tokens, heads, scale * LOG2E);
 }
 
+static bool launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
+                                    int tokens, int heads, float scale, cudaStream_t st) {
+  if (tokens < 129 || tokens > 208) return false;       // two 128-query tiles, keys split 128 + (16..80)
+  const int keys = (tokens + 15) / 16 * 16;
+  const int d = heads * DH;
+  const size_t smem = 2 * static_cast<size_t>(keys) * 128 + 5 * 32768 + 2048 + 256 + 1024;
+  CUtensorMap tq, tkv, tdo;
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+  const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
+  if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
+  const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+  if (!encode_tiled_map(&tdo, 0, dout, 3, odims, ostrides, boxq, 128)) return false;
+  CUtensorMap tdst, to;
+  if (!encode_tiled_map(&tdst, 0, dqkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, boxq, 128)) return false;
+  const int dv = current_device_slot();
+  static size_t configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  if (num_sms_dev[dv] == 0) cudaDeviceGetAttribute(&num_sms_dev[dv], cudaDevAttrMultiProcessorCount, dv);
+  if (smem > configured_dev[dv]) {
+    if (cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured_dev[dv] = smem;
+  }
+  const int units = V * heads;
+  const int grid = units < num_sms_dev[dv] ? units : num_sms_dev[dv];
+  static long long* dbg = nullptr;
+  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
+  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 6 * 64 * sizeof(long long));
+  if (want_dbg) { cudaStreamSynchronize(st); std::memset(dbg, 0, 6 * 64 * sizeof(long long)); }
+  launch_pdl(attention_bwd_tc_kernel, dim3(grid), dim3(BT_THREADS), smem, st, tq, tkv, tdo, to, tdst, lse, tokens, heads, units, keys,
+             scale, want_dbg ? dbg : nullptr);
+  if (want_dbg) {   // per-stage clock64 deltas of units 1..3 of CTA 0
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (units >= 2000 && printed++ == 2) {
+      for (int u = 1; u < 4; ++u) {
+        const long long* t = dbg + u * 64;
+        std::fprintf(stderr, "bwd unit %d MMA thread: landed +%lld", u, t[1] - t[0]);
+        for (int sb = 0; sb < 4; ++sb) std::fprintf(stderr, " | pds%d +%lld issued +%lld", sb, t[2 + 2 * sb] - t[0], t[3 + 2 * sb] - t[0]);
+        std::fprintf(stderr, " | all done +%lld | next unit +%lld\n", t[10] - t[0], (dbg + (u + 1) * 64)[0] - t[0]);
+        std::fprintf(stderr, "bwd unit %d softmax warp: start %+lld delta +%lld prologue +%lld", u, t[32] - t[0], t[53] - t[0], t[33] - t[0]);
+        for (int sb = 0; sb < 4; ++sb)
+          std::fprintf(stderr, " | sdp%d +%lld computed +%lld tiles free +%lld stored +%lld", sb, t[34 + 4 * sb] - t[0], t[35 + 4 * sb] - t[0],
+                       t[36 + 4 * sb] - t[0], t[37 + 4 * sb] - t[0]);
+        std::fprintf(stderr, " | kv +%lld drained +%lld\n", t[50] - t[0], t[51] - t[0]);
+      }
+    }
+  }
+  return true;
+}
+
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
                           int tokens, int heads, float scale, cudaStream_t st) {
+  // TTL_ATTN_BWD: unset / "tc" = tcgen05 kernel where the geometry allows (129..208 tokens), "mma" = the mma.sync kernel
+  static const char* mode = std::getenv("TTL_ATTN_BWD");
+  if ((mode == nullptr || mode[0] == 't') && launch_attention_bwd_tc(qkv, out, dout, lse, dqkv, V, tokens, heads, scale, st)) return;
   const int tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_bwd_smem(tokens);
   static size_t configured_dev[MAX_DEVICES] = {};
