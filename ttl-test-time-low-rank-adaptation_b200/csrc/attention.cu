@@ -1512,7 +1512,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         int keys, float scale, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_bt_raw[];
   // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0; slots 0..31 = MMA thread, 32..63 = softmax warp 1
-#define BT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && local_u < 6) dbg[local_u * 64 + (k)] = clock64(); } while (0)
+#define if (lane == 0) BT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && local_u < 6) dbg[local_u * 64 + (k)] = clock64(); } while (0)
   int local_u = 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_bt_raw) + 1023) & ~uintptr_t(1023));
   const int KB = keys * 128;                     // bytes of K (or V): keys rows of 128 bytes, a multiple of 2048
@@ -1532,7 +1532,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* bar_pds = bars + 3;     // P and dS tiles of a sub-step written, its S / dP drained (8 softmax warps)
   uint64_t* bar_s2 = bars + 4;      // dQ / dV / dK MMAs of a sub-step complete: the P / dS tiles may be overwritten
   uint64_t* bar_kv = bars + 5;      // every MMA up to and including the t = 1 sub-step of a key half has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_drn = bars + 6;     // S / dP of a sub-step have been read out of TMEM (8 softmax warps): the next S / dP may be issued
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * DH;
@@ -1548,6 +1549,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(bar_pds, 8);
     mbar_init(bar_s2, 1);
     mbar_init(bar_kv, 1);
+    mbar_init(bar_drn, 8);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
@@ -1566,7 +1568,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const float scale_log2 = scale * LOG2E;
 
   if (warp == 0) {
-    if (elect_one()) {
+    // The whole warp runs this control flow with warp-uniform values (descriptors stay in uniform registers); only the
+    // tcgen05.mma / commit / TMA instructions themselves are issued by one elected lane.  With the loop inside a
+    // single-lane branch every MMA cost ~7 R2UR moves and ~80 issue cycles, more than twice its execution time.
+    {
       const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, static_cast<uint32_t>(nh1));
       const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 1);                  // A K-major, B MN-major
       const uint32_t idesc_tr = umma_idesc_bf16(128, 64, 1) | (1u << 15);     // A MN-major (transposed read), B MN-major
@@ -1585,33 +1590,34 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // wrong uniform descriptor registers and faulted with out-of-range shared addresses).
       auto mma_S = [&](int sub, int k) {
         const int kh = sub >> 1, t = sub & 1;
-        umma_bf16(tmem, kQ + static_cast<uint64_t>(t * 1024 + 2 * k), kK + static_cast<uint64_t>(kh * 1024 + 2 * k),
+        if (elect_one()) umma_bf16(tmem, kQ + static_cast<uint64_t>(t * 1024 + 2 * k), kK + static_cast<uint64_t>(kh * 1024 + 2 * k),
                   kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
       };
       auto mma_dP = [&](int sub, int k) {
         const int kh = sub >> 1, t = sub & 1;
-        umma_bf16(tmem + 128, kdO + static_cast<uint64_t>(t * 1024 + 2 * k), kV + static_cast<uint64_t>(kh * 1024 + 2 * k),
+        if (elect_one()) umma_bf16(tmem + 128, kdO + static_cast<uint64_t>(t * 1024 + 2 * k), kV + static_cast<uint64_t>(kh * 1024 + 2 * k),
                   kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
       };
       auto mma_dQ = [&](int sub, int j) {     // dQ_t (+)= dS K_kh : A = dS tile (K-major), B = K rows as they sit (MN-major)
         const int kh = sub >> 1, t = sub & 1;
-        umma_bf16(tmem + 256 + 64 * t, kdS + static_cast<uint64_t>((j >> 2) * 1024 + (j & 3) * 2),
+        if (elect_one()) umma_bf16(tmem + 256 + 64 * t, kdS + static_cast<uint64_t>((j >> 2) * 1024 + (j & 3) * 2),
                   mK + static_cast<uint64_t>(kh * 1024 + j * 128), idesc_dq, (kh | j) != 0 ? 1u : 0u);
       };
       auto mma_dV = [&](int sub, int ks) {    // dV_kh (+)= P^T dO_t : A = P tile read MN-major (M = keys, K = queries)
         const int t = sub & 1;
-        umma_bf16(tmem + 384, mP + static_cast<uint64_t>(ks * 128), mdO + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+        if (elect_one()) umma_bf16(tmem + 384, mP + static_cast<uint64_t>(ks * 128), mdO + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
                   (t | ks) != 0 ? 1u : 0u);
       };
       auto mma_dK = [&](int sub, int ks) {    // dK_kh (+)= dS^T Q_t
         const int t = sub & 1;
-        umma_bf16(tmem + 448, mdS + static_cast<uint64_t>(ks * 128), mQ + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+        if (elect_one()) umma_bf16(tmem + 448, mdS + static_cast<uint64_t>(ks * 128), mQ + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
                   (t | ks) != 0 ? 1u : 0u);
       };
       uint32_t n_sub = 0, n_load = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local_u) {
         const int view = unit / heads, h = unit - view * heads;
-        BT_STAMP(0);
+        if (lane == 0) BT_STAMP(0);
+        if (elect_one()) {
         // O_0 / O_1 ride in the (dead) P tile: the softmax threads take Delta = rowsum(dO o O) from shared memory before the
         // first P is written there (global row loads for Delta cost ~10 k cycles per unit behind the TMA traffic)
         mbar_expect_tx(bar_load0, 2 * KB + 3 * 16384);
@@ -1624,13 +1630,14 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(&tmQ, bar_load1, sQ + 16384, h * DH, 128, view);
         tma_load_3d(&tmdO, bar_load1, sdO + 16384, h * DH, 128, view);
         tma_load_3d(&tmO, bar_load1, sP + 16384, h * DH, 128, view);
+        }
         mbar_wait(bar_load0, n_load & 1);
-        BT_STAMP(1);
+        if (lane == 0) BT_STAMP(1);
         tc_fence_after();
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) { mma_S(0, k); mma_dP(0, k); }
-        umma_commit(bar_sdp);
-        if (unit + static_cast<int>(gridDim.x) < units) {      // the next unit's operands: HBM -> L2 behind this unit's compute
+        if (elect_one()) umma_commit(bar_sdp);
+        if (unit + static_cast<int>(gridDim.x) < units && elect_one()) {      // the next unit's operands: HBM -> L2 behind this unit's compute
           const int nu = unit + gridDim.x, nv = nu / heads, nhd = nu - nv * heads;
           tma_prefetch_l2_3d(&tmKV, d + nhd * DH, 0, nv);
           tma_prefetch_l2_3d(&tmKV, 2 * d + nhd * DH, 0, nv);
@@ -1645,16 +1652,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           const int kh = sub >> 1, t = sub & 1;
           const int nk = (kh == 0 ? 128 : nh1) >> 4;     // 16-key k-steps of dQ
           const int nq = t == 0 ? 8 : nq1;                // 16-query k-steps of dV / dK
-          mbar_wait(bar_pds, n_sub & 1);      // P / dS of this sub-step are in smem, its S / dP have left TMEM
-          ++n_sub;
-          BT_STAMP(2 + 2 * sub);
+          // S / dP of the NEXT sub-step as soon as this sub-step's S / dP have left TMEM (the softmax threads are still writing
+          // the tiles then): they are complete by the time the tiles are handed over, so the threads start on them at once
+          mbar_wait(bar_drn, n_sub & 1);
           tc_fence_after();
           if (sub == 0) { mbar_wait(bar_load1, n_load & 1); tc_fence_after(); }
-          if (sub < 3) {      // S / dP of the NEXT sub-step first (two chains): the softmax threads start on them at once
+          if (sub < 3) {
 #pragma unroll 1
             for (int k = 0; k < 4; ++k) { mma_S(sub + 1, k); mma_dP(sub + 1, k); }
-            umma_commit(bar_sdp);
+            if (elect_one()) umma_commit(bar_sdp);
           }
+          mbar_wait(bar_pds, n_sub & 1);      // P / dS of this sub-step are in smem
+          ++n_sub;
+          if (lane == 0) BT_STAMP(2 + 2 * sub);
+          tc_fence_after();
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {       // dQ / dV / dK of this sub-step: three chains, round-robin
             switch ((i < nk ? 1 : 0) | (i < nq ? 2 : 0)) {
@@ -1664,13 +1675,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               default: break;
             }
           }
-          umma_commit(bar_s2);
-          if (t == 1) umma_commit(bar_kv);
-          BT_STAMP(3 + 2 * sub);
+          if (elect_one()) {
+            umma_commit(bar_s2);
+            if (t == 1) umma_commit(bar_kv);
+          }
+          if (lane == 0) BT_STAMP(3 + 2 * sub);
         }
         ++n_load;
         mbar_wait(bar_kv, 1);       // second commit of the unit: every MMA has completed, the smem operands may be reloaded
-        BT_STAMP(10);
+        if (lane == 0) BT_STAMP(10);
       }
     }
     __syncwarp();
@@ -1706,6 +1719,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     };
 
+    float lse_next = INFINITY;
+    if (static_cast<int>(blockIdx.x) < units && half * 128 + row < tokens) {
+      const int v0 = blockIdx.x / heads, h0 = blockIdx.x - v0 * heads;
+      lse_next = __ldg(lse + (static_cast<size_t>(v0) * heads + h0) * tokens + half * 128 + row) * LOG2E;
+    }
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local_u) {
       const int view = unit / heads, h = unit - view * heads;
       if (st) BT_STAMP(32);
@@ -1715,7 +1733,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // dS = 0 without a branch in the inner loop.  Both are exchanged through smem (every thread needs both tiles' values).
       {
         const int q = half * 128 + row;
-        const float l = q < tokens ? __ldg(lse + (static_cast<size_t>(view) * heads + h) * tokens + q) * LOG2E : INFINITY;
+        const float l = lse_next;      // loaded one unit ahead (a global load here waits ~2 k cycles behind the TMA traffic)
+        {
+          const int nu = unit + gridDim.x, nv = nu / heads, nhd = nu - nv * heads;
+          lse_next = nu < units && q < tokens ? __ldg(lse + (static_cast<size_t>(nv) * heads + nhd) * tokens + q) * LOG2E : INFINITY;
+        }
         mbar_wait(half == 0 ? bar_load0 : bar_load1, n_unit & 1);
         const uint32_t o_row = smem_u32(sP) + half * 16384 + row * 128, do_row = smem_u32(sdO) + half * 16384 + row * 128;
         float acc = 0.f;
@@ -1738,6 +1760,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       ++n_unit;
       if (st) BT_STAMP(53);
+      if (issuer) bulk_wait_read<0>();   // the previous unit's last stores have finished reading the dS tile (used as staging)
       named_bar_sync(3, 256);
       const float delta0 = sDelta[row], delta1 = sDelta[128 + row], lse20 = sLse2[row], lse21 = sLse2[128 + row];
       if (st) BT_STAMP(33);
@@ -1775,6 +1798,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           }
         }
         tc_fence_before();            // this warp's tcgen05.ld of S / dP have completed
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_drn);
         if (st) BT_STAMP(35 + 4 * sub);
         // The tiles are still being read by the dQ / dV / dK MMAs of the previous sub-step (they were issued behind this
         // sub-step's S / dP): wait for them, and drain what they completed, before overwriting the tiles.
@@ -1805,8 +1830,26 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(bar_kv, 1);
       if (st) BT_STAMP(50);
       tc_fence_after();
-      drain_tile(384 + 64 * half, (2 - half) * d + h * DH, 128, view);
-      drain_tile(256 + 64 * half, h * DH, half * 128, view);
+      {   // dV_1 / dK_1 -> this warpgroup's staging tile, dQ_half -> its (dead) 64-key block of the dS tile; one hand-over for both
+        uint32_t a[32], b[32];
+        tmem_ld_32x32b_x32(trow + 384 + 64 * half, a);
+        tmem_ld_32x32b_x32(trow + 384 + 64 * half + 32, b);
+        tmem_ld_wait();
+        if (issuer) bulk_wait_read<0>();         // the mid-unit store has finished reading the staging tile
+        named_bar_sync(1 + half, 128);
+        bt_stage_row(a, b, out_row, sw);
+        tmem_ld_32x32b_x32(trow + 256 + 64 * half, a);
+        tmem_ld_32x32b_x32(trow + 256 + 64 * half + 32, b);
+        tmem_ld_wait();
+        bt_stage_row(a, b, ds_row, sw);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          tma_store_3d(&tmDst, my_out, (2 - half) * d + h * DH, 128, view);
+          tma_store_3d(&tmDst, sdS + half * 16384, h * DH, half * 128, view);
+          bulk_commit();
+        }
+      }
       tc_fence_before();
       if (st) BT_STAMP(51);
     }
