@@ -167,6 +167,34 @@ int ttl_adapt_predict_batch_host(ttl_ctx* ctx, const float* images_host, int32_t
 int ttl_adapt_predict_batch_host_async(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
                                        const ttl_hparams* hp, const int32_t* forced_idx_host,
                                        const ttl_outputs* out_host, void* stream);
+/* ---- optional branches of the weighted-entropy head ----------------------------------------
+ * deyo.py:103-151 behind the flags of ttl.py:410-424, for n_samples concurrent test samples, fused like ttl_adapt_predict_batch:
+ *   filter_ent    keep the int(V * selection_p) lowest-entropy views instead of every view with H <= ln 1000 (deyo.py:103-108)
+ *   filter_plpd   second forward on x' = the kept views with their structure destroyed (--aug_type occ | patch | pixel,
+ *                 deyo.py:115-136); keep the views whose top-class probability drops by more than plpd_threshold (:137-148)
+ *   reweight_ent / reweight_plpd   deyo.py:159-179: coefficient reweight_ent * exp(-(H - margin)) when either is set, else 1
+ * A sample whose views are all filtered out takes no optimiser step (deyo.py:184).  The head runs tta_steps^2 times like the
+ * default one.  The random draws stay on the host (the torch seed decides, as in the reference): for aug_type patch,
+ * perm_host = int32 [n_samples][tta_steps^2][n_kept][patch_len^2], row = torch.argsort(torch.rand(patch_len^2)) (deyo.py:127),
+ * n_kept = filter_ent ? int(V * selection_p) : V; for pixel, int32 [n_samples][tta_steps^2][image_size^2] = torch.randperm;
+ * NULL for occ.  Runs eagerly (no graph replay).  out_dev->idx receives the kept views of the first step when filter_ent. */
+enum ttl_aug_type { TTL_AUG_OCC = 0, TTL_AUG_PATCH = 1, TTL_AUG_PIXEL = 2 };
+typedef struct ttl_deyo_options {
+  int32_t filter_ent, filter_plpd, reweight_ent, reweight_plpd;
+  float plpd_threshold;     /* --plpd_threshold 0.2 */
+  int32_t aug_type;         /* enum ttl_aug_type */
+  int32_t occlusion_size, row_start, column_start, patch_len;   /* 112, 56, 56, 6 */
+  const int32_t* perm_host;
+  int64_t perm_numel;
+  const int32_t* forced_keep_host;  /* nullable, for parity tests: [n_samples][n_kept] 0/1 flags that replace the outcome of the
+                                       PLPD filter (PLPD is still computed and reported); the analogue of forced_idx for the
+                                       selection, needed because a threshold inside the bf16 noise of the PLPD values flips views */
+} ttl_deyo_options;
+int ttl_adapt_predict_batch_deyo(ttl_ctx* ctx, const float* images_dev, int32_t n_samples, int32_t n_views,
+                                 const ttl_hparams* hp, const ttl_deyo_options* opt, const ttl_outputs* out_dev, void* stream);
+/* PLPD values [n_samples * n_kept] and kept-view counts [n_samples] of the last optimiser step of that call (synchronises). */
+int ttl_deyo_last_plpd(ttl_ctx* ctx, float* plpd_host, int32_t* n_final_host, int32_t n_samples, int32_t n_kept);
+
 /* ---- view generator on the device ------------------------------------------------------
  * Stands in for the host-side AugMixAugmenter the reference's DataLoader workers run per test image
  * (data/datautils.py:98-157 with the empty augmentation list; ttl.py:232-241): the caller ships the decoded uint8 RGB

@@ -15,10 +15,11 @@ HEADER = os.path.join(ROOT, "include", "ttl_b200.h")
 
 # C struct -> ctypes mirror
 STRUCTS = {"ttl_config": "TtlConfig", "ttl_hparams": "TtlHparams", "ttl_outputs": "TtlOutputs",
-           "ttl_view_spec": "TtlViewSpec", "ttl_text_config": "TtlTextConfig", "ttl_gemm_record": "TtlGemmRecord"}
+           "ttl_view_spec": "TtlViewSpec", "ttl_text_config": "TtlTextConfig", "ttl_gemm_record": "TtlGemmRecord",
+           "ttl_deyo_options": "TtlDeyoOptions"}
 # C enumerator prefix -> prefix of the Python constant
 ENUM_PREFIXES = {"TTL_W_": "W_", "TTL_LORA_": "LORA_", "TTL_HEAD_": "HEAD_", "TTL_PRECISION_": "PRECISION_",
-                 "TTL_VIEW_": "VIEW_", "TTL_TW_": "TW_"}
+                 "TTL_VIEW_": "VIEW_", "TTL_TW_": "TW_", "TTL_AUG_": "AUG_"}
 
 
 def _header_text():
@@ -32,8 +33,8 @@ def _struct_fields(text, name):
         decl = decl.strip()
         if not decl:
             continue
-        names = decl.replace("*", " ").split(None, 1)[1]       # drop the type
-        fields += [n.strip() for n in names.split(",")]
+        # "const int32_t* a" / "int32_t a, b": the field name is the last identifier of every comma-separated part
+        fields += [part.replace("*", " ").split()[-1] for part in decl.split(",")]
     return fields
 
 

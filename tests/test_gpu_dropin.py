@@ -313,13 +313,19 @@ def test_cli_throughput_matches_the_engine_loop():
 
 @pytest.mark.parametrize("extra", [["--filter_ent", "1"], ["--filter_plpd", "1", "--aug_type", "occ", "--plpd_threshold", "-1"],
                                    ["--filter_plpd", "1", "--aug_type", "patch", "--plpd_threshold", "-1"]])
-def test_cli_deyo_optional_branches_run_in_compat_mode(extra):
-    """filter_ent / filter_plpd (deyo.py:103-151) are not covered by the fused call: the CLI must route them through
-    compat mode (library forward/backward under the reference's control flow) and still adapt + predict.  The branch logic
-    itself is pinned to the reference in tests/test_deyo_variants_cpu.py."""
+def test_cli_deyo_optional_branches_fused_and_compat(extra):
+    """filter_ent / filter_plpd (deyo.py:103-151) through the CLI: the fused route (ttl_adapt_predict_batch_deyo, parity in
+    tests/test_gpu_deyo_variants.py) and --compat (library forward/backward under the reference's control flow) both adapt +
+    predict, one sample per call so that both consume the torch RNG in the same order."""
     import ttl
-    res = ttl.main(['--synthetic', '2', '--test_sets', 'A', '--gpu', '0', '--workers', '0', '--print_freq', '100'] + extra)
-    assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+    common = ['--synthetic', '3', '--test_sets', 'A', '--gpu', '0', '--workers', '0', '--print_freq', '100', '--concurrent_samples', '1']
+    fused = ttl.main(common + extra)
+    assert ttl.test_time_adapt_eval.last_stats["fused"]
+    compat = ttl.main(common + extra + ['--compat'])
+    assert not ttl.test_time_adapt_eval.last_stats["fused"]
+    for res in (fused, compat):
+        assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
+    assert fused['A'] == compat['A']
 
 
 def test_cli_fp32_validation_mode():

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "ttl_b200", "libttl_b200.so")
-SOURCES = ["gemm.cu", "rowops.cu", "attention.cu", "head.cu", "lora.cu", "views.cu", "text.cu", "fp32.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "rowops.cu", "attention.cu", "head.cu", "lora.cu", "views.cu", "text.cu", "fp32.cu", "deyo.cu", "engine.cu"]
 HEADERS = ["ptx.cuh", "gemm.cuh", "kernels.cuh", "views.cuh", os.path.join("..", "..", "include", "ttl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]

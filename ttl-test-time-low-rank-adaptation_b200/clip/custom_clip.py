@@ -353,16 +353,29 @@ class ClipTestTimeTuning(nn.Module):
         return Hparams(head="deyo" if deyo else "tpt", tta_steps=int(args.tta_steps), selection_p=float(args.selection_p),
                        lr=float(args.lr), deyo_margin_e0=float(getattr(args, "deyo_margin_e0", 0.4)))
 
+    @staticmethod
+    def deyo_general(args) -> bool:
+        """True when the weighted-entropy head runs with any of its optional branches (deyo.py:103-151) switched on."""
+        deyo = bool(getattr(args, "deyo_selection", True)) and getattr(args, "lora_encoder", "image") != "prompt"
+        return deyo and bool(getattr(args, "filter_ent", 0) or getattr(args, "filter_plpd", 0) or getattr(args, "reweight_plpd", 0)
+                             or getattr(args, "reweight_ent", 1) != 1)
+
     def fast_path_ok(self, args) -> bool:
-        """The fused call covers the default flag set; anything else goes through compat mode."""
-        return (not getattr(args, "cocoop", False) and getattr(args, "filter_ent", 0) == 0
-                and getattr(args, "filter_plpd", 0) == 0 and getattr(args, "reweight_ent", 1) == 1
-                and getattr(args, "reweight_plpd", 0) == 0)
+        """Whether one fused library call per batch of samples covers these flags (else: compat mode, the reference's control
+        flow over the autograd bridge).  The optional DeYO branches are fused too (ttl_adapt_predict_batch_deyo), on the
+        bf16 path; without filter_ent they need C <= 1000 (the ln 1000 filter of deyo.py:107 is then a no-op)."""
+        if getattr(args, "cocoop", False):
+            return False
+        if self.deyo_general(args):
+            return self.engine.precision == "bf16" and (bool(getattr(args, "filter_ent", 0)) or self.engine.n_classes <= 1000)
+        return True
 
     def adapt_and_predict(self, images: torch.Tensor, args=None, hparams: Optional[Hparams] = None,
                           want=("pred_logits",)):
         """reset -> test_time_tuning -> model(image)  (ttl.py:338-352) as ONE library call.  `images` [V,3,S,S], on the
         device or in pinned host memory.  Returns a dict with `pred_logits` [C] (+ anything else in `want`)."""
+        if args is not None and hparams is None and self.deyo_general(args):
+            return {k: v[0] for k, v in self.adapt_and_predict_batch(images.unsqueeze(0), args, want=want).items()}
         hp = hparams or self.hparams_from_args(args)
         return self.engine.adapt_predict(images, hp, want=want)
 
@@ -371,6 +384,13 @@ class ClipTestTimeTuning(nn.Module):
         """The same for S test samples adapted concurrently, each with its own adapter and optimiser state: `images`
         [S,V,3,size,size] (S <= max_samples) -> per-sample results with leading dimension S."""
         hp = hparams or self.hparams_from_args(args)
+        if args is not None and hparams is None and self.deyo_general(args):
+            return self.engine.adapt_predict_batch_deyo(
+                images, hp, filter_ent=int(getattr(args, "filter_ent", 0)), filter_plpd=int(getattr(args, "filter_plpd", 0)),
+                reweight_ent=int(getattr(args, "reweight_ent", 1)), reweight_plpd=int(getattr(args, "reweight_plpd", 0)),
+                plpd_threshold=float(getattr(args, "plpd_threshold", 0.2)), aug_type=str(getattr(args, "aug_type", "patch")),
+                occlusion_size=int(getattr(args, "occlusion_size", 112)), row_start=int(getattr(args, "row_start", 56)),
+                column_start=int(getattr(args, "column_start", 56)), patch_len=int(getattr(args, "patch_len", 6)), want=want)
         return self.engine.adapt_predict_batch(images, hp, want=want, sync=sync)
 
 

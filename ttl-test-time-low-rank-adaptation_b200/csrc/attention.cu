@@ -1512,7 +1512,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         int keys, float scale, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_bt_raw[];
   // development aid (TTL_ATTN_DBG): clock64 stamps of the first units of CTA 0; slots 0..31 = MMA thread, 32..63 = softmax warp 1
-#define if (lane == 0) BT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && local_u < 6) dbg[local_u * 64 + (k)] = clock64(); } while (0)
+#define BT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && local_u < 6) dbg[local_u * 64 + (k)] = clock64(); } while (0)
   int local_u = 0;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_bt_raw) + 1023) & ~uintptr_t(1023));
   const int KB = keys * 128;                     // bytes of K (or V): keys rows of 128 bytes, a multiple of 2048
@@ -1568,10 +1568,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const float scale_log2 = scale * LOG2E;
 
   if (warp == 0) {
-    // The whole warp runs this control flow with warp-uniform values (descriptors stay in uniform registers); only the
-    // tcgen05.mma / commit / TMA instructions themselves are issued by one elected lane.  With the loop inside a
-    // single-lane branch every MMA cost ~7 R2UR moves and ~80 issue cycles, more than twice its execution time.
-    {
+    // One elected lane runs the whole loop (elect.sync, not `lane == 0`: ptxas then issues the tcgen05.mma of a case back to
+    // back instead of wrapping each in an ELECT / BRA.U.ANY retry loop).  The other form -- the whole warp in the loop, each
+    // instruction behind its own elect.sync -- was measured slower (644 vs 444 us at 576 views: ~130 issue cycles per MMA).
+    if (elect_one()) {
       const uint32_t idesc_s0 = umma_idesc_bf16(128, 128), idesc_s1 = umma_idesc_bf16(128, static_cast<uint32_t>(nh1));
       const uint32_t idesc_dq = umma_idesc_bf16(128, 64, 1);                  // A K-major, B MN-major
       const uint32_t idesc_tr = umma_idesc_bf16(128, 64, 1) | (1u << 15);     // A MN-major (transposed read), B MN-major
@@ -1590,34 +1590,33 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // wrong uniform descriptor registers and faulted with out-of-range shared addresses).
       auto mma_S = [&](int sub, int k) {
         const int kh = sub >> 1, t = sub & 1;
-        if (elect_one()) umma_bf16(tmem, kQ + static_cast<uint64_t>(t * 1024 + 2 * k), kK + static_cast<uint64_t>(kh * 1024 + 2 * k),
+        umma_bf16(tmem, kQ + static_cast<uint64_t>(t * 1024 + 2 * k), kK + static_cast<uint64_t>(kh * 1024 + 2 * k),
                   kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
       };
       auto mma_dP = [&](int sub, int k) {
         const int kh = sub >> 1, t = sub & 1;
-        if (elect_one()) umma_bf16(tmem + 128, kdO + static_cast<uint64_t>(t * 1024 + 2 * k), kV + static_cast<uint64_t>(kh * 1024 + 2 * k),
+        umma_bf16(tmem + 128, kdO + static_cast<uint64_t>(t * 1024 + 2 * k), kV + static_cast<uint64_t>(kh * 1024 + 2 * k),
                   kh == 0 ? idesc_s0 : idesc_s1, k != 0 ? 1u : 0u);
       };
       auto mma_dQ = [&](int sub, int j) {     // dQ_t (+)= dS K_kh : A = dS tile (K-major), B = K rows as they sit (MN-major)
         const int kh = sub >> 1, t = sub & 1;
-        if (elect_one()) umma_bf16(tmem + 256 + 64 * t, kdS + static_cast<uint64_t>((j >> 2) * 1024 + (j & 3) * 2),
+        umma_bf16(tmem + 256 + 64 * t, kdS + static_cast<uint64_t>((j >> 2) * 1024 + (j & 3) * 2),
                   mK + static_cast<uint64_t>(kh * 1024 + j * 128), idesc_dq, (kh | j) != 0 ? 1u : 0u);
       };
       auto mma_dV = [&](int sub, int ks) {    // dV_kh (+)= P^T dO_t : A = P tile read MN-major (M = keys, K = queries)
         const int t = sub & 1;
-        if (elect_one()) umma_bf16(tmem + 384, mP + static_cast<uint64_t>(ks * 128), mdO + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+        umma_bf16(tmem + 384, mP + static_cast<uint64_t>(ks * 128), mdO + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
                   (t | ks) != 0 ? 1u : 0u);
       };
       auto mma_dK = [&](int sub, int ks) {    // dK_kh (+)= dS^T Q_t
         const int t = sub & 1;
-        if (elect_one()) umma_bf16(tmem + 448, mdS + static_cast<uint64_t>(ks * 128), mQ + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
+        umma_bf16(tmem + 448, mdS + static_cast<uint64_t>(ks * 128), mQ + static_cast<uint64_t>(t * 1024 + ks * 128), idesc_tr,
                   (t | ks) != 0 ? 1u : 0u);
       };
       uint32_t n_sub = 0, n_load = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++local_u) {
         const int view = unit / heads, h = unit - view * heads;
-        if (lane == 0) BT_STAMP(0);
-        if (elect_one()) {
+        BT_STAMP(0);
         // O_0 / O_1 ride in the (dead) P tile: the softmax threads take Delta = rowsum(dO o O) from shared memory before the
         // first P is written there (global row loads for Delta cost ~10 k cycles per unit behind the TMA traffic)
         mbar_expect_tx(bar_load0, 2 * KB + 3 * 16384);
@@ -1630,14 +1629,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_load_3d(&tmQ, bar_load1, sQ + 16384, h * DH, 128, view);
         tma_load_3d(&tmdO, bar_load1, sdO + 16384, h * DH, 128, view);
         tma_load_3d(&tmO, bar_load1, sP + 16384, h * DH, 128, view);
-        }
         mbar_wait(bar_load0, n_load & 1);
-        if (lane == 0) BT_STAMP(1);
+        BT_STAMP(1);
         tc_fence_after();
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) { mma_S(0, k); mma_dP(0, k); }
-        if (elect_one()) umma_commit(bar_sdp);
-        if (unit + static_cast<int>(gridDim.x) < units && elect_one()) {      // the next unit's operands: HBM -> L2 behind this unit's compute
+        umma_commit(bar_sdp);
+        if (unit + static_cast<int>(gridDim.x) < units) {      // the next unit's operands: HBM -> L2 behind this unit's compute
           const int nu = unit + gridDim.x, nv = nu / heads, nhd = nu - nv * heads;
           tma_prefetch_l2_3d(&tmKV, d + nhd * DH, 0, nv);
           tma_prefetch_l2_3d(&tmKV, 2 * d + nhd * DH, 0, nv);
@@ -1660,11 +1658,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (sub < 3) {
 #pragma unroll 1
             for (int k = 0; k < 4; ++k) { mma_S(sub + 1, k); mma_dP(sub + 1, k); }
-            if (elect_one()) umma_commit(bar_sdp);
+            umma_commit(bar_sdp);
           }
           mbar_wait(bar_pds, n_sub & 1);      // P / dS of this sub-step are in smem
           ++n_sub;
-          if (lane == 0) BT_STAMP(2 + 2 * sub);
+          BT_STAMP(2 + 2 * sub);
           tc_fence_after();
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {       // dQ / dV / dK of this sub-step: three chains, round-robin
@@ -1675,15 +1673,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
               default: break;
             }
           }
-          if (elect_one()) {
-            umma_commit(bar_s2);
-            if (t == 1) umma_commit(bar_kv);
-          }
-          if (lane == 0) BT_STAMP(3 + 2 * sub);
+          umma_commit(bar_s2);
+          if (t == 1) umma_commit(bar_kv);
+          BT_STAMP(3 + 2 * sub);
         }
         ++n_load;
         mbar_wait(bar_kv, 1);       // second commit of the unit: every MMA has completed, the smem operands may be reloaded
-        if (lane == 0) BT_STAMP(10);
+        BT_STAMP(10);
       }
     }
     __syncwarp();

@@ -163,6 +163,12 @@ struct ttl_ctx {
   float pix_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // ttl.py:226-227
   float pix_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
+  // optional DeYO branches (filter_ent / filter_plpd; deyo.cu): allocated on first use
+  float *xprime = nullptr, *xscratch = nullptr, *XK2 = nullptr, *feats2 = nullptr, *logits2 = nullptr, *entropy2 = nullptr,
+        *logits_s = nullptr, *entropy_s = nullptr, *plpd = nullptr;
+  int *keep = nullptr, *dg_active = nullptr, *dg_steps = nullptr, *dg_nkept = nullptr, *perm_dev = nullptr;
+  size_t perm_cap = 0;
+
   // graphs
   bool graphs = true;
   std::vector<GraphEntry> gcache;
@@ -344,10 +350,11 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
 }
 
 // layers [0, lo) on all views: images -> XK
-int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st) {
+int forward_frozen(ttl_ctx* c, const float* images, int V, cudaStream_t st, float* xk = nullptr) {
   NvtxRange nv("ttl:frozen_forward(layers<lo)");
-  RET_IF(embed(c, images, V, c->XK, st));
-  for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, c->XK, c->XB, c->XK, V, 1, false, nullptr, st));
+  if (xk == nullptr) xk = c->XK;
+  RET_IF(embed(c, images, V, xk, st));
+  for (int l = 0; l < c->lo; ++l) RET_IF(run_layer(c, l, xk, c->XB, xk, V, 1, false, nullptr, st));
   return TTL_OK;
 }
 
@@ -828,6 +835,91 @@ int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp
   return f32_tail_infer(c, c->XK, 1, c->pred_feats, c->pred, c->pred_entropy, st);   // view 0 with the adapted factors
 }
 
+// ---- optional branches of the weighted-entropy head (deyo.py:103-151): filter_ent, filter_plpd, reweight switches
+int ensure_deyo_general(ttl_ctx* c) {
+  if (c->keep != nullptr) return TTL_OK;
+  const size_t VV = c->VVm, px = static_cast<size_t>(3) * c->cfg.image_size * c->cfg.image_size;
+  int rc = TTL_OK;
+#define A(p, n) if (rc == TTL_OK) rc = dalloc(c, &(p), static_cast<size_t>(n))
+  A(c->xprime, VV * px); A(c->xscratch, VV * px); A(c->XK2, static_cast<size_t>(c->Mm) * c->d);
+  A(c->feats2, VV * c->P); A(c->logits2, VV * c->Cm); A(c->entropy2, VV); A(c->logits_s, VV * c->Cm); A(c->entropy_s, VV);
+  A(c->plpd, VV); A(c->dg_active, c->Sm + 4); A(c->dg_steps, c->Sm + 4); A(c->dg_nkept, c->Sm + 4); A(c->keep, VV);
+#undef A
+  return rc;
+}
+
+// S concurrent samples of V views each; eager (the kept sets and the per-sample step decisions are data dependent).
+int adapt_body_deyo_general(ttl_ctx* c, const float* images, int S, int V, const ttl_hparams& hp, const ttl_deyo_options& o,
+                            cudaStream_t st) {
+  NvtxRange nv("ttl:adapt_predict(deyo, optional branches)");
+  const int VV = S * V, size = c->cfg.image_size;
+  const int nsteps = hp.tta_steps * hp.tta_steps;              // deyo.DeYO loops `steps` times inside the tta_steps loop (Q2)
+  const int n1 = o.filter_ent ? select_count(V, hp.selection_p) : V, G = S * n1;
+  const int reweight = (o.reweight_ent != 0 || o.reweight_plpd != 0) ? 1 : 0;
+  RET_IF(lora_reset(c, S, st));
+  RET_IF(forward_frozen(c, images, VV, st));
+  CK(cudaMemsetAsync(c->dg_steps, 0, sizeof(int) * S, st));
+  if (nsteps == 0 || n1 == 0) RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, c->logits, c->entropy, st));
+  for (int step = 0; step < nsteps && n1 > 0; ++step) {
+    const float* train_in = c->XK;
+    const int* idx = nullptr;
+    if (o.filter_ent) {   // entropies of all views with the current factors -> the n1 lowest per sample, in argsort order
+      float* lg = step == 0 ? c->logits : c->logits_s;
+      float* en = step == 0 ? c->entropy : c->entropy_s;
+      RET_IF(forward_tail_infer(c, c->XK, VV, S, c->feats, lg, en, st));
+      launch_select(en, V, n1, nullptr, c->idx, st, S);
+      launch_gather_views(c->XK, c->TIN, c->idx, G, 0, c->tokens, c->d, st, V, n1);
+      c->launches += 2;
+      train_in = c->TIN;
+      idx = c->idx;
+    }
+    RET_IF(forward_tail_train(c, train_in, G, S, st));
+    launch_logits_entropy(c->feats_c, c->text, c->logit_scale_exp, c->logits_c, c->entropy_c, G, c->C, c->P, st);
+    c->launches += 2;
+    if (!o.filter_ent && step == 0) {   // first-forward logits / entropies of every view are outputs of the call
+      CK(cudaMemcpyAsync(c->logits, c->logits_c, sizeof(float) * VV * c->C, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c->entropy, c->entropy_c, sizeof(float) * VV, cudaMemcpyDeviceToDevice, st));
+    }
+    const int* keep = nullptr;
+    if (o.filter_plpd) {
+      // x' of the kept views (deyo.py:116-136), second forward with the current factors (no tape), PLPD filter
+      const size_t per_step = o.aug_type == TTL_AUG_PATCH ? static_cast<size_t>(n1) * o.patch_len * o.patch_len
+                                                          : static_cast<size_t>(size) * size;
+      // host layout [S][nsteps][per_step]: this step's rows of all samples were packed to the front of perm_dev + step * S * per_step
+      const int* pm = c->perm_dev != nullptr ? c->perm_dev + static_cast<size_t>(step) * S * per_step : nullptr;
+      if (o.aug_type == TTL_AUG_OCC) launch_destroy_occ(images, idx, c->xprime, S, V, n1, size, o.occlusion_size, o.row_start, o.column_start, st);
+      else if (o.aug_type == TTL_AUG_PIXEL) launch_destroy_pixel(images, idx, pm, c->xprime, S, V, n1, size, st);
+      else launch_destroy_patch(images, idx, pm, c->xscratch, c->xprime, S, V, n1, size, o.patch_len, st);
+      c->launches += 2;
+      RET_IF(forward_frozen(c, c->xprime, G, st, c->XK2));
+      RET_IF(forward_tail_infer(c, c->XK2, G, S, c->feats2, c->logits2, c->entropy2, st));
+      launch_plpd(c->logits_c, c->logits2, G, c->C, o.plpd_threshold, c->keep, c->plpd, st);
+      c->launches++;
+      if (o.forced_keep_host != nullptr) CK(cudaMemcpyAsync(c->keep, o.forced_keep_host, sizeof(int) * G, cudaMemcpyHostToDevice, st));
+      keep = c->keep;
+    }
+    launch_deyo_general_loss(c->logits_c, keep, n1, c->C, hp.deyo_margin_e0, o.filter_ent, reweight, static_cast<float>(o.reweight_ent),
+                             c->loss, c->dlogits, c->dg_active, c->dg_steps, c->dg_nkept, S, st);
+    c->launches++;
+    RET_IF(backward(c, c->dlogits, G, st));
+    // AdamW only for the samples that kept at least one view (deyo.py:184), each with its own step count
+    launch_adamw_masked(c->lp, c->lg, c->lm, c->lv, static_cast<int>(c->lora_total), S, c->dg_active, c->dg_steps, hp.lr, hp.beta1,
+                        hp.beta2, hp.eps, hp.weight_decay, st);
+    c->launches++;
+    c->opt_step++;
+    c->b_zero = false;
+    RET_IF(repack(c, S, st));
+  }
+  const float* pin = c->XK;
+  if (S > 1) {
+    launch_gather_views(c->XK, c->PIN, nullptr, S, V, c->tokens, c->d, st);
+    c->launches++;
+    pin = c->PIN;
+  }
+  RET_IF(forward_tail_infer(c, pin, S, S, c->pred_feats, c->pred, c->pred_entropy, st));
+  return check_launch(c, "adapt_body_deyo_general");
+}
+
 int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int S, int V, const ttl_hparams& hp, cudaMemcpyKind kind, cudaStream_t st) {
   if (!o) return TTL_OK;
   const int K = select_count(V, hp.selection_p);
@@ -1062,6 +1154,7 @@ void ttl_destroy(ttl_ctx* c) {
     if (c->vg_desc[i]) cudaFree(c->vg_desc[i]);
     if (c->vg_desc_host[i]) cudaFreeHost(c->vg_desc_host[i]);
   }
+  if (c->perm_dev) cudaFree(c->perm_dev);
   if (c->vg_coef) cudaFree(c->vg_coef);
   if (c->vg_tmp) cudaFree(c->vg_tmp);
   for (void* p : c->allocs) cudaFree(p);
@@ -1298,6 +1391,74 @@ int ttl_adapt_predict_batch(ttl_ctx* c, const float* images_dev, int32_t n_sampl
   if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K * n_samples, cudaMemcpyDeviceToDevice, st));
   RET_IF(adapt_predict_impl(c, images_dev, n_samples, n_views, hp, forced, st));
   return copy_outputs(c, out_dev, n_samples, n_views, *hp, cudaMemcpyDeviceToDevice, st);
+}
+
+int ttl_adapt_predict_batch_deyo(ttl_ctx* c, const float* images_dev, int32_t n_samples, int32_t n_views, const ttl_hparams* hp,
+                                 const ttl_deyo_options* opt, const ttl_outputs* out_dev, void* stream) {
+  RET_IF(validate_run(c, n_samples, n_views, hp));
+  if (!images_dev || !opt) return TTL_E_INVALID;
+  if (c->f32) { c->err = "the optional DeYO branches run on the bf16 path (the fp32 validation mode covers the default flags)"; return TTL_E_STATE; }
+  if (hp->head != TTL_HEAD_DEYO) { c->err = "ttl_adapt_predict_batch_deyo: head must be TTL_HEAD_DEYO"; return TTL_E_INVALID; }
+  if (!opt->filter_ent && c->C > 1000) { c->err = "without filter_ent the H <= ln 1000 filter of deyo.py:107 can drop views when C > 1000: use the compat route"; return TTL_E_SHAPE; }
+  const int size = c->cfg.image_size;
+  if (opt->filter_plpd) {
+    if (opt->aug_type < TTL_AUG_OCC || opt->aug_type > TTL_AUG_PIXEL) { c->err = "unknown aug_type"; return TTL_E_INVALID; }
+    if (opt->aug_type == TTL_AUG_OCC && (opt->occlusion_size <= 0 || opt->row_start < 0 || opt->column_start < 0 ||
+                                         opt->row_start + opt->occlusion_size > size || opt->column_start + opt->occlusion_size > size)) {
+      c->err = "occlusion window outside the view"; return TTL_E_SHAPE;
+    }
+    if (opt->aug_type == TTL_AUG_PATCH && (opt->patch_len <= 0 || opt->patch_len > size)) { c->err = "bad patch_len"; return TTL_E_SHAPE; }
+  }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET_IF(ensure_deyo_general(c));
+  const int nsteps = hp->tta_steps * hp->tta_steps;
+  const int n1 = opt->filter_ent ? select_count(n_views, hp->selection_p) : n_views;
+  if (opt->filter_plpd && opt->aug_type != TTL_AUG_OCC && nsteps > 0 && n1 > 0) {
+    const size_t per_step = opt->aug_type == TTL_AUG_PATCH ? static_cast<size_t>(n1) * opt->patch_len * opt->patch_len
+                                                           : static_cast<size_t>(size) * size;
+    const size_t need = static_cast<size_t>(n_samples) * nsteps * per_step;
+    if (!opt->perm_host || opt->perm_numel != static_cast<int64_t>(need)) { c->err = "perm_host: expected [n_samples][tta_steps^2][per-step] int32"; return TTL_E_SHAPE; }
+    const int lim = opt->aug_type == TTL_AUG_PATCH ? opt->patch_len * opt->patch_len : size * size;
+    for (size_t i = 0; i < need; ++i)
+      if (opt->perm_host[i] < 0 || opt->perm_host[i] >= lim) { c->err = "perm_host: index out of range"; return TTL_E_INVALID; }
+    if (need > c->perm_cap) {
+      CK(cudaStreamSynchronize(st));
+      if (c->perm_dev) cudaFree(c->perm_dev);
+      c->perm_dev = nullptr; c->perm_cap = 0;
+      if (cudaMalloc(reinterpret_cast<void**>(&c->perm_dev), need * sizeof(int)) != cudaSuccess) { cudaGetLastError(); c->err = "perm: cudaMalloc failed"; return TTL_E_NOMEM; }
+      c->perm_cap = need;
+    }
+    // host order [sample][step][...] (the order the reference draws in, one sample after the other) -> device [step][sample][...]
+    for (int s = 0; s < n_samples; ++s)
+      for (int k = 0; k < nsteps; ++k)
+        CK(cudaMemcpyAsync(c->perm_dev + (static_cast<size_t>(k) * n_samples + s) * per_step,
+                           opt->perm_host + (static_cast<size_t>(s) * nsteps + k) * per_step, per_step * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  const int64_t before = c->launches;
+  int r = adapt_body_deyo_general(c, images_dev, n_samples, n_views, *hp, *opt, st);
+  c->last_launches = c->launches - before;
+  if (r != TTL_OK) return r;
+  if (out_dev) {
+    const int K = n1;
+    if (out_dev->logits0) CK(cudaMemcpyAsync(out_dev->logits0, c->logits, sizeof(float) * n_samples * n_views * c->C, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->entropy) CK(cudaMemcpyAsync(out_dev->entropy, c->entropy, sizeof(float) * n_samples * n_views, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->idx && opt->filter_ent && K > 0) CK(cudaMemcpyAsync(out_dev->idx, c->idx, sizeof(int) * n_samples * K, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->loss) CK(cudaMemcpyAsync(out_dev->loss, c->loss, sizeof(float) * n_samples, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->pred_logits) CK(cudaMemcpyAsync(out_dev->pred_logits, c->pred, sizeof(float) * n_samples * c->C, cudaMemcpyDeviceToDevice, st));
+  }
+  return TTL_OK;
+}
+
+int ttl_deyo_last_plpd(ttl_ctx* c, float* plpd_host, int32_t* n_final_host, int32_t n_samples, int32_t n_kept) {
+  if (!c) return TTL_E_INVALID;
+  if (c->keep == nullptr) { c->err = "no ttl_adapt_predict_batch_deyo call yet"; return TTL_E_STATE; }
+  if (n_samples <= 0 || n_samples > c->Sm || n_kept < 0 || n_samples * n_kept > c->VVm) { c->err = "ttl_deyo_last_plpd: bad sizes"; return TTL_E_SHAPE; }
+  cudaSetDevice(c->cfg.device);
+  CK(cudaDeviceSynchronize());
+  if (plpd_host && n_kept > 0) CK(cudaMemcpy(plpd_host, c->plpd, sizeof(float) * n_samples * n_kept, cudaMemcpyDeviceToHost));
+  if (n_final_host) CK(cudaMemcpy(n_final_host, c->dg_nkept, sizeof(int) * n_samples, cudaMemcpyDeviceToHost));
+  return TTL_OK;
 }
 
 int ttl_adapt_predict(ttl_ctx* c, const float* images_dev, int32_t n_views, const ttl_hparams* hp,

@@ -129,4 +129,19 @@ void launch_im2col_f32(const float* images, float* patches, int V, int S, int p,
 void launch_reduce_tn_f32(const float* wide, int ldw, int nw, const float* narrow, int ldn, int nn, int M, float scale,
                           float* out, int transpose_out, cudaStream_t st);
 
+// ---- deyo.cu   optional branches of the weighted-entropy head (deyo.py:103-151).  Kept entry b of sample s is view
+// s * V + idx[s * n1 + b] (idx == nullptr: b); x' fp32 [S * n1, 3, size, size]
+void launch_destroy_occ(const float* images, const int* idx, float* xprime, int S, int V, int n1, int size, int occ, int r0, int c0,
+                        cudaStream_t st);
+void launch_destroy_pixel(const float* images, const int* idx, const int* perm, float* xprime, int S, int V, int n1, int size,
+                          cudaStream_t st);
+void launch_destroy_patch(const float* images, const int* idx, const int* perm, float* scratch, float* xprime, int S, int V, int n1,
+                          int size, int patch_len, cudaStream_t st);
+void launch_plpd(const float* logits, const float* logits_prime, int G, int C, float thr, int* keep, float* plpd_out, cudaStream_t st);
+void launch_deyo_general_loss(const float* logits, const int* keep, int n1, int C, float e0, int filter_ent, int reweight,
+                              float reweight_ent, float* loss, float* dlogits, int* active, int* steps, int* n_kept, int S,
+                              cudaStream_t st);
+void launch_adamw_masked(float* p, const float* g, float* m, float* v, int n_per_sample, int S, const int* active, const int* steps,
+                         float lr, float b1, float b2, float eps, float wd, cudaStream_t st);
+
 }  // namespace ttl

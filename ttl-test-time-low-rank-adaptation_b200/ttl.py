@@ -264,8 +264,8 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
         if isinstance(payloads[0], tuple):      # uint8 image + view specs per sample: views are generated on the device
             pend = model.adapt_and_predict_images([im.numpy() for im, _ in payloads], [sp.numpy() for _, sp in payloads],
                                                   args, sync=False)
-        elif payloads[0].is_cuda:
-            pend = _Ready(model.adapt_and_predict_batch(torch.stack(payloads), args))
+        elif payloads[0].is_cuda or model.deyo_general(args):      # the optional DeYO branches build x' from device-resident views
+            pend = _Ready(model.adapt_and_predict_batch(torch.stack(payloads).to(model.device, non_blocking=True), args))
         else:                                   # fp32 views from the loader: stage in pinned memory, copy asynchronously
             shape = (S,) + tuple(payloads[0].shape)
             if staging.get("shape") != shape:
@@ -371,6 +371,8 @@ def main_worker(gpu, args):
     # the GPU, bit-exactly as the reference's PIL/torchvision pipeline would (csrc/views.cu).  --views_on_host, --compat and
     # --precision fp32 take the reference's route: 64 fp32 views per sample from the DataLoader workers (ttl.py:232-241).
     args.views_on_device = not (args.views_on_host or args.compat or args.precision == "fp32")
+    if args.deyo_selection and (args.filter_ent or args.filter_plpd or args.reweight_plpd or args.reweight_ent != 1):
+        args.views_on_device = False      # filter_plpd destroys the structure of the fp32 views (deyo.py:116-136): they must exist
     extra["allow_synthetic"] = args.synthetic > 0 or args.random_init
     if args.vision_checkpoint:      # HF safetensors/bin or OpenAI-format .pt (ttl_b200/weights.py); default: local HF cache
         # one file = what CLIPModel.from_pretrained yields (clip/custom_clip.py:581,619): image tower, the text tower that

@@ -45,6 +45,13 @@ class TtlTextConfig(C.Structure):
                 ("ln_eps", C.c_float), ("device", C.c_int32)]
 
 
+class TtlDeyoOptions(C.Structure):
+    _fields_ = [("filter_ent", C.c_int32), ("filter_plpd", C.c_int32), ("reweight_ent", C.c_int32), ("reweight_plpd", C.c_int32),
+                ("plpd_threshold", C.c_float), ("aug_type", C.c_int32), ("occlusion_size", C.c_int32), ("row_start", C.c_int32),
+                ("column_start", C.c_int32), ("patch_len", C.c_int32), ("perm_host", vp), ("perm_numel", C.c_int64),
+                ("forced_keep_host", vp)]
+
+
 class TtlOutputs(C.Structure):
     _fields_ = [("logits0", vp), ("entropy", vp), ("idx", vp), ("loss", vp), ("pred_logits", vp)]
 
@@ -58,6 +65,7 @@ LORA_PARAM, LORA_GRAD, LORA_INIT = range(3)
 HEAD_TPT, HEAD_DEYO = 0, 1
 PRECISION_BF16, PRECISION_FP32 = 0, 1
 VIEW_CLEAN, VIEW_CROP = 0, 1
+AUG_OCC, AUG_PATCH, AUG_PIXEL = 0, 1, 2
 TW_TOKEN_EMB, TW_POS_EMB, TW_FINAL_LN_G, TW_FINAL_LN_B, TW_TEXT_PROJ = range(5)
 EPI_BF16, EPI_GELU, EPI_RESID_F32, EPI_PATCH_F32, EPI_F32, EPI_GELU_BWD = range(6)
 
@@ -80,6 +88,9 @@ _SIGS = {
     "ttl_adapt_predict": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_host": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_batch": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
+    "ttl_adapt_predict_batch_deyo": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), C.POINTER(TtlDeyoOptions),
+                                               C.POINTER(TtlOutputs), vp]),
+    "ttl_deyo_last_plpd": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32]),
     "ttl_adapt_predict_batch_host": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs),
                                                vp]),
     "ttl_adapt_predict_batch_host_async": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp,

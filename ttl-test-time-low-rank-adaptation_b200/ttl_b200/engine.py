@@ -260,6 +260,78 @@ class Engine:
             outs["idx"] = outs["idx"][:, :K]
         return outs
 
+    # ------------------------------------------------------------------ optional branches of the weighted-entropy head
+    @staticmethod
+    def draw_deyo_perms(n_samples: int, n_steps: int, n_kept: int, aug_type: str, patch_len: int, image_size: int):
+        """The random draws of deyo.py:127 / :133 from the (CPU) torch RNG, in the order the reference consumes it: one test
+        sample after the other, one draw per optimiser step.  patch: argsort(rand(n_kept, patch_len^2)) -> int32
+        [S, steps, n_kept, patch_len^2]; pixel: randperm(image_size^2) -> [S, steps, image_size^2]; occ: None."""
+        if aug_type == "occ" or n_steps == 0 or n_kept == 0:
+            return None
+        rows = []
+        for _ in range(n_samples):
+            for _ in range(n_steps):
+                if aug_type == "patch":
+                    rows.append(torch.argsort(torch.rand(n_kept, patch_len * patch_len), dim=-1))
+                else:
+                    rows.append(torch.randperm(image_size * image_size))
+        return torch.stack(rows).reshape(n_samples, n_steps, *rows[0].shape).to(torch.int32).contiguous()
+
+    def adapt_predict_batch_deyo(self, images: torch.Tensor, hp: Hparams, filter_ent: int = 0, filter_plpd: int = 0,
+                                 reweight_ent: int = 1, reweight_plpd: int = 0, plpd_threshold: float = 0.2,
+                                 aug_type: str = "patch", occlusion_size: int = 112, row_start: int = 56, column_start: int = 56,
+                                 patch_len: int = 6, perm: Optional[torch.Tensor] = None,
+                                 want: Sequence[str] = ("pred_logits",), forced_keep=None) -> Dict[str, torch.Tensor]:
+        """adapt_predict_batch with the optional branches of the reference's weighted-entropy head (deyo.py:103-151; flags
+        ttl.py:410-424): `images` [S,V,3,size,size] fp32 on the device (x' is built from them).  `perm`: draws for
+        aug_type patch / pixel (draw_deyo_perms); drawn here from the torch RNG when omitted.  `forced_keep` [S, n_kept] 0/1
+        (parity tests only): teacher-forces the outcome of the PLPD filter."""
+        if hp.head != "deyo":
+            raise ValueError("the optional DeYO branches belong to head='deyo'")
+        S, V = int(images.shape[0]), int(images.shape[1])
+        if S > self.max_samples:
+            raise ValueError(f"{S} samples > max_samples={self.max_samples}")
+        images = images.to(self.device, torch.float32).contiguous()
+        n_kept = int(V * hp.selection_p) if filter_ent else V
+        n_steps = hp.tta_steps * hp.tta_steps
+        aug = {"occ": L.AUG_OCC, "patch": L.AUG_PATCH, "pixel": L.AUG_PIXEL}[aug_type]
+        if filter_plpd and perm is None:
+            perm = self.draw_deyo_perms(S, n_steps, n_kept, aug_type, patch_len, self.geom["image_size"])
+        perm_np = None if (perm is None or not filter_plpd) else np.ascontiguousarray(perm.cpu().numpy(), dtype=np.int32)
+        fk = None if forced_keep is None else np.ascontiguousarray(np.asarray(forced_keep), dtype=np.int32).reshape(S, n_kept)
+        opt = L.TtlDeyoOptions(int(filter_ent), int(filter_plpd), int(reweight_ent), int(reweight_plpd), float(plpd_threshold), aug,
+                               int(occlusion_size), int(row_start), int(column_start), int(patch_len),
+                               perm_np.ctypes.data if perm_np is not None else None, perm_np.size if perm_np is not None else 0,
+                               fk.ctypes.data if fk is not None else None)
+        outs: Dict[str, torch.Tensor] = {}
+        o = L.TtlOutputs()
+        shapes = {"logits0": ((S, V, self.n_classes), torch.float32), "entropy": ((S, V), torch.float32),
+                  "idx": ((S, max(n_kept, 1)), torch.int32), "loss": ((S,), torch.float32),
+                  "pred_logits": ((S, self.n_classes), torch.float32)}
+        for name in want:
+            shp, dt = shapes[name]
+            t = torch.empty(shp, dtype=dt, device=self.device)
+            outs[name] = t
+            setattr(o, name, t.data_ptr())
+        h = hp.to_c()
+        self._sync_in()
+        L.check(self.lib.ttl_adapt_predict_batch_deyo(self.ctx, images.data_ptr(), S, V, C.byref(h), C.byref(opt), C.byref(o),
+                                                      self._st()), self.ctx)
+        self._sync_out()
+        images.record_stream(self.stream)
+        if "idx" in outs:
+            outs["idx"] = outs["idx"][:, :n_kept] if filter_ent else outs["idx"][:, :0]
+        self._last_deyo = (S, n_kept)
+        return outs
+
+    def deyo_last_plpd(self):
+        """(PLPD values [S, n_kept], final kept-view counts [S]) of the last optimiser step of adapt_predict_batch_deyo."""
+        S, n_kept = self._last_deyo
+        plpd = np.zeros((S, max(n_kept, 1)), dtype=np.float32)
+        n = np.zeros(S, dtype=np.int32)
+        L.check(self.lib.ttl_deyo_last_plpd(self.ctx, plpd.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), S, n_kept), self.ctx)
+        return plpd[:, :n_kept], n
+
     # ------------------------------------------------------------------ views generated on the device (views.cu)
     @staticmethod
     def _image_table(images):
