@@ -56,6 +56,12 @@ typedef struct ttl_config {
   int32_t precision;     /* enum ttl_precision: 0 = bf16 operands / fp32 accumulation on the tensor cores (the product);
                             1 = fp32 validation mode: every activation and contraction in fp32 on the CUDA cores, one sample
                             per call, no graphs -- held to the fp32 tolerance (1e-4) against the reference's fp32 CPU run */
+  int32_t text_mode;     /* 1 = this context is the CLIP TEXT tower carrying the adapter (--lora_encoder text, ttl.py:145-149,
+                            190-191; clip/custom_clip.py:602-606): width/layers/heads/mlp_dim/proj_dim describe the text tower,
+                            max_views bounds the class prompts, max_classes the image views per test sample; image_size / patch
+                            are ignored.  0 = image tower (the TTL configuration) */
+  int32_t context;       /* text mode: tokens per prompt (77) */
+  int32_t vocab;         /* text mode: 49408 */
 } ttl_config;
 enum ttl_precision { TTL_PRECISION_BF16 = 0, TTL_PRECISION_FP32 = 1 };
 
@@ -68,6 +74,9 @@ enum ttl_weight_kind {
   TTL_W_PRE_LN_G = 3, TTL_W_PRE_LN_B = 4,   /* vision_model.pre_layrnorm                  */
   TTL_W_POST_LN_G = 5, TTL_W_POST_LN_B = 6, /* vision_model.post_layernorm                */
   TTL_W_VIS_PROJ = 7,  /* visual_projection.weight [P,d]                                  */
+  TTL_W_TOKEN_EMB = 8, /* text mode: text_model.embeddings.token_embedding.weight [vocab,d]; in text mode POS_EMB is
+                          text_model.embeddings.position_embedding.weight [context,d], POST_LN_* the final_layer_norm and VIS_PROJ
+                          text_projection.weight [P,d]; the per-layer slots below take text_model.encoder.layers.{i}.* */
   /* per encoder layer (layer index argument) */
   TTL_W_LN1_G = 16, TTL_W_LN1_B = 17,
   TTL_W_Q_W = 18, TTL_W_Q_B = 19, TTL_W_K_W = 20, TTL_W_K_B = 21, TTL_W_V_W = 22, TTL_W_V_B = 23,
@@ -167,6 +176,25 @@ int ttl_adapt_predict_batch_host(ttl_ctx* ctx, const float* images_host, int32_t
 int ttl_adapt_predict_batch_host_async(ttl_ctx* ctx, const float* images_host, int32_t n_samples, int32_t n_views,
                                        const ttl_hparams* hp, const int32_t* forced_idx_host,
                                        const ttl_outputs* out_host, void* stream);
+/* ---- adapter on the text tower: `--lora_encoder text` ---------------------------------------------
+ * Reference: ttl.py:145-149 (requires-grad filter on text_encoder), :190-191 (optimizer groups over
+ * text_encoder.text_model.encoder.layers), clip/custom_clip.py:602-606 (peft on the text tower), :672-678 (image features
+ * under no_grad, class features with gradient).  Two contexts: an image-tower context (adapter unused) that yields the frozen
+ * image features of the views, and a text-mode context (ttl_config.text_mode = 1) that owns the adapter. */
+/* Image-tower context: images fp32 [n_views,3,S,S] on the device -> raw image features fp32 [n_views, P] on the device
+ * (VisionEncoder.forward, clip/custom_clip.py:62-71; normalisation happens where they are used). */
+int ttl_image_features(ttl_ctx* ctx, const float* images_dev, int32_t n_views, float* feats_dev, void* stream);
+/* Text-mode context: the tokenised class prompts int32 [n_prompts, context] (clip.tokenize layout) and logit_scale (log
+ * domain); runs the layers below the adapter once (reset_classnames, clip/custom_clip.py:343-372). */
+int ttl_text_set_prompts(ttl_ctx* ctx, const int32_t* tokens_host, int32_t n_prompts, float logit_scale, void* stream);
+/* L2-normalised class features fp32 [n_prompts, P] with the current factors (get_text_features, :651-663); synchronises. */
+int ttl_text_features(ttl_ctx* ctx, float* feats_host, void* stream);
+/* One test sample (ttl.py:338-352 with lora_encoder == 'text'): reset -> tta steps over the class features -> prediction for
+ * view 0.  img_feats_dev: what ttl_image_features returned for the sample's views.  Outputs as ttl_adapt_predict with S = 1,
+ * C = n_prompts.  The ttl_lora_* entry points address the text-tower factors of this context. */
+int ttl_text_adapt_predict(ttl_ctx* ctx, const float* img_feats_dev, int32_t n_views, const ttl_hparams* hp,
+                           const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream);
+
 /* ---- optional branches of the weighted-entropy head ----------------------------------------
  * deyo.py:103-151 behind the flags of ttl.py:410-424, for n_samples concurrent test samples, fused like ttl_adapt_predict_batch:
  *   filter_ent    keep the int(V * selection_p) lowest-entropy views instead of every view with H <= ln 1000 (deyo.py:103-108)

@@ -86,11 +86,21 @@ class VisionEncoder(nn.Module):
         self.dtype = torch.float32
 
 
-class PromptEncoder(nn.Module):
-    """Frozen text side (clip/custom_clip.py:73-82): holds the cached, L2-normalised class features."""
-
-    def __init__(self):
+class _TextModel(nn.Module):
+    def __init__(self, enc: _Encoder):
         super().__init__()
+        self.encoder = enc
+
+
+class PromptEncoder(nn.Module):
+    """Text side (clip/custom_clip.py:73-82).  --lora_encoder image: frozen, holds the cached class features.
+    --lora_encoder text: carries the adapter module tree `text_model.encoder.layers.{i}.self_attn.{q,v}_proj.lora_{A,B}`
+    (ttl.py:146-147,190-191 walk it), aliasing the text-mode engine's factors."""
+
+    def __init__(self, tm: Optional[_TextModel] = None):
+        super().__init__()
+        if tm is not None:
+            self.text_model = tm
         self.dtype = torch.float32
 
 
@@ -139,9 +149,7 @@ class LoRA_AB:
             fn = None
         else:
             raise ValueError(f"Unsupported init_method: {self.init_method}")
-        if self.lora_encoder != "image":
-            raise NotImplementedError("only --lora_encoder image is on the B200 path")
-        for layer in self.model.vision_model.encoder.layers:
+        for layer in self._layers():
             self.initialize_layer_weights(layer, fn)
 
     def initialize_layer_weights(self, layer, fn):
@@ -153,8 +161,16 @@ class LoRA_AB:
                 fn(ws[2])
         self.init_weights.append(tuple(w.detach().clone() for w in ws))
 
+    def _layers(self):
+        """clip/custom_clip.py:163-174: the vision tower's layers, or the text tower's with lora_encoder == 'text'."""
+        if self.lora_encoder == "text":
+            return self.model.text_model.encoder.layers
+        if self.lora_encoder == "image":
+            return self.model.vision_model.encoder.layers
+        raise NotImplementedError("--lora_encoder prompt (prompt tuning) is outside the TTL path")
+
     def reset(self):
-        layers = self.model.vision_model.encoder.layers
+        layers = self._layers()
         with torch.no_grad():
             for i, layer in enumerate(layers):
                 if i in range(self.layer_range[0], self.layer_range[1] + 1):
@@ -198,9 +214,9 @@ class ClipTestTimeTuning(nn.Module):
         reference's from_pretrained would."""
         super().__init__()
         self.allow_synthetic = bool(allow_synthetic) or os.environ.get("TTL_SYNTHETIC_WEIGHTS", "0") == "1"
-        if lora_encoder != "image":
-            raise NotImplementedError("the B200 path implements --lora_encoder image (the TTL configuration); "
-                                      "'text' and 'prompt' are out of scope (SURVEY.md §8f N4)")
+        if lora_encoder not in ("image", "text"):
+            raise NotImplementedError("--lora_encoder prompt (CoOp/TPT prompt tuning) does not run in the reference either "
+                                      "(clip/custom_clip.py:680: image_features unbound); the B200 path implements image and text")
         dev_index = device if isinstance(device, int) else (torch.device(device).index or 0)
         self.device = torch.device("cuda", dev_index)
         self.lora_encoder = lora_encoder
@@ -226,28 +242,54 @@ class ClipTestTimeTuning(nn.Module):
             logit_scale = math.log(100.0)       # CLIP's trained value; random-init runs use it too
 
         # LoRA module tree.  Trainable-range tensors alias the library's device buffers.
-        layers: List[_Layer] = []
         self._param_aliases, self._grad_aliases = [], []
-        for i in range(n_layers):
-            in_range = self.layer_range[0] <= i <= self.layer_range[1]
-            ts = []
-            for which in range(4):
-                if in_range:
-                    t = self.engine.lora_alias(i, which, L.LORA_PARAM)
-                    self._param_aliases.append(t)
-                    self._grad_aliases.append(self.engine.lora_alias(i, which, L.LORA_GRAD))
-                else:
-                    shape = (rank, d) if which in (0, 2) else (d, rank)
-                    t = torch.zeros(shape, device=self.device)
-                ts.append(t)
-            layers.append(_Layer(_SelfAttn(_LoraProj(ts[0], ts[1], in_range), _LoraProj(ts[2], ts[3], in_range))))
-        self.image_encoder = VisionEncoder(_VisionModel(_Encoder(layers)))
-        self.text_encoder = PromptEncoder()
-        self.LoRA_AB = LoRA_AB(self.image_encoder, layer_range=self.layer_range, init_method=init_method,
-                               lora_encoder=lora_encoder)
+
+        def build_layers(eng, n_lyr, width, live):
+            out: List[_Layer] = []
+            for i in range(n_lyr):
+                in_range = live and self.layer_range[0] <= i <= self.layer_range[1]
+                ts = []
+                for which in range(4):
+                    if in_range:
+                        t = eng.lora_alias(i, which, L.LORA_PARAM)
+                        self._param_aliases.append(t)
+                        self._grad_aliases.append(eng.lora_alias(i, which, L.LORA_GRAD))
+                    else:
+                        shape = (rank, width) if which in (0, 2) else (width, rank)
+                        t = torch.zeros(shape, device=self.device)
+                    ts.append(t)
+                out.append(_Layer(_SelfAttn(_LoraProj(ts[0], ts[1], in_range), _LoraProj(ts[2], ts[3], in_range))))
+            return out
+
+        self.text_engine = None
+        if lora_encoder == "text":
+            # peft wraps the TEXT tower only (clip/custom_clip.py:602-606): a text-mode engine owns the adapter, the image-tower
+            # engine above yields the frozen image features of the views
+            from ttl_b200.engine import TEXT_TOWER_GEOMETRY
+            from ttl_b200.synthetic import HashTokenizer, synthetic_text_weights
+            tgeo = TEXT_TOWER_GEOMETRY[arch]
+            if self._text_weights is None:
+                if not self.allow_synthetic:
+                    raise RuntimeError("--lora_encoder text needs the text tower's weights (checkpoint with text_model.* tensors), "
+                                       "or --synthetic / --random_init for a seeded random-init tower")
+                self._text_weights = synthetic_text_weights(arch, seed=4321)
+                if self._tokenizer is None and self._bpe_path is None and not os.environ.get("TTL_BPE_PATH"):
+                    self._tokenizer = HashTokenizer(tgeo["vocab"], tgeo["context"])
+            self.text_engine = Engine(arch, max_views=max(16, len(classnames)), max_classes=max_views, lora_rank=rank, lora_alpha=32.0,
+                                      layer_range=self.layer_range, device=dev_index, text_mode=True)
+            self.text_engine.load_text_weights(self._text_weights)
+            self.image_encoder = VisionEncoder(_VisionModel(_Encoder(build_layers(self.engine, n_layers, d, False))))
+            self.text_encoder = PromptEncoder(_TextModel(_Encoder(build_layers(self.text_engine, tgeo["layers"], tgeo["width"], True))))
+            self.LoRA_AB = LoRA_AB(self.text_encoder, layer_range=self.layer_range, init_method=init_method, lora_encoder="text")
+        else:
+            self.image_encoder = VisionEncoder(_VisionModel(_Encoder(build_layers(self.engine, n_layers, d, True))))
+            self.text_encoder = PromptEncoder()
+            self.LoRA_AB = LoRA_AB(self.image_encoder, layer_range=self.layer_range, init_method=init_method,
+                                   lora_encoder=lora_encoder)
         # snapshot -> library (p0 for the fused reset) ; the live factors already hold it through the aliases
+        lora_engine = self.text_engine if lora_encoder == "text" else self.engine
         for i in range(self.layer_range[0], self.layer_range[1] + 1):
-            self.engine.set_lora_init({i: [t.cpu() for t in self.LoRA_AB.init_weights[i]]})
+            lora_engine.set_lora_init({i: [t.cpu() for t in self.LoRA_AB.init_weights[i]]})
         self.logit_scale = torch.tensor(float(logit_scale), device=self.device)
         self._given_text = text_features
         self.prompt_learner = _PromptState(self, classnames, ctx_init)
@@ -278,6 +320,19 @@ class ClipTestTimeTuning(nn.Module):
         """Once per class-name set (the reference recomputes the text tower in every forward, custom_clip.py:667-671)."""
         names = self.prompt_learner.classnames
         P = ARCH_GEOMETRY[self.arch]["proj_dim"]
+        if self.lora_encoder == "text":
+            # the class features are a function of the adapter: tokenise, run the layers below the adapter once, keep the rest live
+            from ttl_b200.tokenizer import SimpleTokenizer
+            if self._tokenizer is None:
+                self._tokenizer = SimpleTokenizer(self._bpe_path)
+            if len(names) > self.text_engine.max_views:
+                raise RuntimeError(f"{len(names)} class prompts > {self.text_engine.max_views} the text engine was sized for")
+            self.prompt_learner.tokenized_prompts = self._tokenizer(self.prompt_learner.prompts).to(self.device)
+            self.tokenized_prompts = self.prompt_learner.tokenized_prompts
+            self.text_engine.set_prompts(self.prompt_learner.tokenized_prompts, float(self.logit_scale))
+            self.text_engine.lora_reset()
+            self.text_features = self.text_engine.text_features().to(self.device)
+            return
         if self._given_text is not None and self._given_text.shape[0] == len(names):
             t = self._given_text.detach().float().cpu()
         elif self._text_weights is not None:
@@ -328,6 +383,9 @@ class ClipTestTimeTuning(nn.Module):
         self.prompt_learner.reset_classnames(classnames, arch)
 
     def get_text_features(self):
+        if self.lora_encoder == "text":       # a function of the current adapter state (clip/custom_clip.py:651-663)
+            self.text_engine.lora_touch()
+            return self.text_engine.text_features().to(self.device)
         return self.text_features
 
     def _trainable(self):
@@ -340,6 +398,12 @@ class ClipTestTimeTuning(nn.Module):
         image = image.to(self.device, torch.float32)
         params = self._trainable()
         train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if self.lora_encoder == "text":
+            if train:
+                raise NotImplementedError("--lora_encoder text runs on the fused route (adapt_and_predict); --compat needs "
+                                          "autograd through the text tower, which the library does not expose")
+            f = torch.nn.functional.normalize(self.engine.image_features(image), dim=-1)
+            return float(self.logit_scale.exp()) * f @ self.get_text_features().t()
         return _TtlLogits.apply(image, self, train, *params)
 
     def forward(self, input, label=None, coeff=None):
@@ -366,6 +430,10 @@ class ClipTestTimeTuning(nn.Module):
         bf16 path; without filter_ent they need C <= 1000 (the ln 1000 filter of deyo.py:107 is then a no-op)."""
         if getattr(args, "cocoop", False):
             return False
+        if self.lora_encoder == "text":
+            if self.deyo_general(args):
+                raise NotImplementedError("--lora_encoder text with the optional DeYO branches (filter_ent / filter_plpd) is not built")
+            return True
         if self.deyo_general(args):
             return self.engine.precision == "bf16" and (bool(getattr(args, "filter_ent", 0)) or self.engine.n_classes <= 1000)
         return True
@@ -374,8 +442,8 @@ class ClipTestTimeTuning(nn.Module):
                           want=("pred_logits",)):
         """reset -> test_time_tuning -> model(image)  (ttl.py:338-352) as ONE library call.  `images` [V,3,S,S], on the
         device or in pinned host memory.  Returns a dict with `pred_logits` [C] (+ anything else in `want`)."""
-        if args is not None and hparams is None and self.deyo_general(args):
-            return {k: v[0] for k, v in self.adapt_and_predict_batch(images.unsqueeze(0), args, want=want).items()}
+        if self.lora_encoder == "text" or (args is not None and hparams is None and self.deyo_general(args)):
+            return {k: v[0] for k, v in self.adapt_and_predict_batch(images.unsqueeze(0), args, hparams, want=want).items()}
         hp = hparams or self.hparams_from_args(args)
         return self.engine.adapt_predict(images, hp, want=want)
 
@@ -384,6 +452,14 @@ class ClipTestTimeTuning(nn.Module):
         """The same for S test samples adapted concurrently, each with its own adapter and optimiser state: `images`
         [S,V,3,size,size] (S <= max_samples) -> per-sample results with leading dimension S."""
         hp = hparams or self.hparams_from_args(args)
+        if self.lora_encoder == "text":
+            # ttl.py:338-352 with the adapter on the text tower: frozen image features of the views, then reset -> adapt ->
+            # predict over the class features, one test sample after the other (the class features are per-sample state)
+            per = []
+            for s_i in range(int(images.shape[0])):
+                feats = self.engine.image_features(images[s_i].to(self.device, non_blocking=True))
+                per.append(self.text_engine.adapt_predict_text(feats, hp, want=want))
+            return {k: torch.stack([p_[k] for p_ in per]) for k in want}
         if args is not None and hparams is None and self.deyo_general(args):
             return self.engine.adapt_predict_batch_deyo(
                 images, hp, filter_ent=int(getattr(args, "filter_ent", 0)), filter_plpd=int(getattr(args, "filter_plpd", 0)),

@@ -136,8 +136,10 @@ __device__ __forceinline__ void store_tile(bf16* stage, const float (&acc)[8][4]
   __syncwarp();
 }
 
+// causal != 0: key j contributes to query i only when j <= i (the text tower of `--lora_encoder text`, HF CLIPTextTransformer's
+// causal mask); here and in attention_bwd_kernel below.
 __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
-                                     int tokens, int heads, float scale_log2, int q_tiles, int nkp) {
+                                     int tokens, int heads, float scale_log2, int q_tiles, int nkp, int causal) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) uint8_t smem_att[];
@@ -164,12 +166,15 @@ __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restr
       zero_acc(s);
       mma_rows_nk(s, aq, sK, kc, lane);
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      const int qr0 = qt * 16 + (lane >> 2), qr1 = qr0 + 8;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int key = kc + nt * 8 + (lane & 3) * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float v = (key + (e & 1) < tokens) ? s[nt][e] * scale_log2 : -INFINITY;
+          const int kk = key + (e & 1);
+          const bool ok = kk < tokens && (!causal || kk <= (e < 2 ? qr0 : qr1));
+          const float v = ok ? s[nt][e] * scale_log2 : -INFINITY;
           s[nt][e] = v;
           if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
         }
@@ -212,7 +217,8 @@ __global__ void attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restr
 
 __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                      const bf16* __restrict__ dout, const float* __restrict__ lse,
-                                     bf16* __restrict__ dqkv, int tokens, int heads, float scale, int tiles, int nkp) {
+                                     bf16* __restrict__ dqkv, int tokens, int heads, float scale, int tiles, int nkp, int causal,
+                                     const float* __restrict__ delta) {
   pdl_wait();
   pdl_trigger();
   // Shared memory per CTA: the two matrices the phase uses as B operands in full (phase A: K, V; phase B: Q, dO), the row
@@ -253,9 +259,13 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   };
   const float* L = lse + (static_cast<size_t>(view) * heads + h) * tokens;
   // D[r] = rowsum(dO[r,:] * O[r,:]) and the log-sum-exp in log2 units: one thread per row, eight independent 16-byte loads
+  // delta != nullptr: rowsum(P o dP) computed exactly by attention_delta_kernel (text tower, see there)
+  const float* Dg = delta != nullptr ? delta + (static_cast<size_t>(view) * heads + h) * tokens : nullptr;
   for (int r = threadIdx.x; r < nkp; r += blockDim.x) {
     float acc = 0.f;
-    if (r < tokens) {
+    if (r < tokens && Dg != nullptr) {
+      acc = Dg[r];
+    } else if (r < tokens) {
       uint4 a[8], b[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -312,7 +322,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
         const int key = kc + nt * 8 + (lane & 3) * 2;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const bool ok = key + (e & 1) < tokens;
+          const bool ok = key + (e & 1) < tokens && (!causal || key + (e & 1) <= (e < 2 ? r0 : r1));
           const float p = ok ? ex2_approx(s[nt][e] * scale_log2 - (e < 2 ? L0 : L1)) : 0.f;
           s[nt][e] = p * (dp[nt][e] - (e < 2 ? D0 : D1)) * scale;   // dS
         }
@@ -353,6 +363,7 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
     float dk[8][4], dv[8][4];
     zero_acc(dk);
     zero_acc(dv);
+    const int kr0 = kt * 16 + (lane >> 2), kr1 = kr0 + 8;     // the key rows of this thread's accumulator elements
     auto chunk_b = [&](const int qc, auto nvc) {
       constexpr int NV = decltype(nvc)::value;
       float st[8][4], dpt[8][4];
@@ -366,7 +377,8 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
         const float La = sL[q], Lb = sL[q + 1], Da = sD[q], Db = sD[q + 1];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p = ex2_approx(st[nt][e] * scale_log2 - ((e & 1) ? Lb : La));   // 0 for padded queries (L = +inf)
+          float p = ex2_approx(st[nt][e] * scale_log2 - ((e & 1) ? Lb : La));   // 0 for padded queries (L = +inf)
+          if (causal && (e < 2 ? kr0 : kr1) > q + (e & 1)) p = 0.f;
           dpt[nt][e] = p * (dpt[nt][e] - ((e & 1) ? Db : Da)) * scale;           // dS^T
           st[nt][e] = p;                                                         // P^T
         }
@@ -401,6 +413,58 @@ __global__ void attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* _
   }
 }
 
+
+// Delta_i = sum_j P_ij dP_ij (= dO_i . O_i in exact arithmetic) for the backward, in fp32 from Q, K, V, dO and the forward's lse.
+// The backward kernels normally take Delta as rowsum(dO o O) with the bf16 O of the tape: dS = P o (dP - Delta) then carries
+// |Delta| * 2^-9 of rounding noise.  In the image tower that is harmless; in the text tower of `--lora_encoder text` the V rows
+// of a prompt are nearly identical (shared prompt prefix), dP_ij barely depends on j, |Delta| is ~25 x |dP - Delta| and the
+// noise reaches 10-17 % of dQ (measured against the reference).  One CTA per (head, sequence), one warp per query row; K / V
+// staged in smem as fp32 (tokens <= 128).
+__global__ void __launch_bounds__(256)
+attention_delta_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                       float* __restrict__ delta, int tokens, int heads, float scale, int causal) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sm_delta[];
+  const int ldk = DH + 1;
+  float* sK = sm_delta;                         // [tokens][65]
+  float* sV = sK + tokens * ldk;                // [tokens][65]
+  float* sQ = sV + tokens * ldk;                // [warps][2][64]: q row, dO row
+  const int h = blockIdx.x, view = blockIdx.y, d = heads * DH, ld = 3 * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bf16* base = qkv + static_cast<size_t>(view) * tokens * ld + h * DH;
+  const bf16* gdo = dout + static_cast<size_t>(view) * tokens * d + h * DH;
+  for (int i = threadIdx.x; i < tokens * DH; i += blockDim.x) {
+    const int r = i / DH, c = i % DH;
+    sK[r * ldk + c] = __bfloat162float(base[static_cast<size_t>(r) * ld + d + c]);
+    sV[r * ldk + c] = __bfloat162float(base[static_cast<size_t>(r) * ld + 2 * d + c]);
+  }
+  __syncthreads();
+  float* q = sQ + warp * 2 * DH;
+  float* dorow = q + DH;
+  const float* L = lse + (static_cast<size_t>(view) * heads + h) * tokens;
+  for (int r = warp; r < tokens; r += nw) {
+    q[lane] = __bfloat162float(base[static_cast<size_t>(r) * ld + lane]);
+    q[lane + 32] = __bfloat162float(base[static_cast<size_t>(r) * ld + lane + 32]);
+    dorow[lane] = __bfloat162float(gdo[static_cast<size_t>(r) * d + lane]);
+    dorow[lane + 32] = __bfloat162float(gdo[static_cast<size_t>(r) * d + lane + 32]);
+    __syncwarp();
+    const float lr = L[r];
+    float acc = 0.f;
+    const int jend = causal ? r + 1 : tokens;
+    for (int j = lane; j < jend; j += 32) {
+      const float* kr = sK + j * ldk;
+      const float* vr = sV + j * ldk;
+      float s = 0.f, dp = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < DH; ++c) { s += q[c] * kr[c]; dp += dorow[c] * vr[c]; }
+      acc += __expf(s * scale - lr) * dp;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) delta[(static_cast<size_t>(view) * heads + h) * tokens + r] = acc;
+    __syncwarp();
+  }
+}
 
 // =============================================================================================== TMA-fed forward
 // Persistent forward kernel for the 64-view pass: one CTA per SM walks (view, head) units; Q/K/V of the NEXT unit are
@@ -2055,7 +2119,7 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
 }
 
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
-                          cudaStream_t st, int descending) {   // only the default kernel honours `descending`
+                          cudaStream_t st, int descending, int causal) {   // only the default kernel honours `descending`
   // TTL_ATTN: unset / "tc" = tcgen05 kernel where the geometry allows, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
   // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
@@ -2063,9 +2127,10 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   const bool want_pp = mode == nullptr || mode[0] == 'p';
   const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';
-  if (want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
-  if (want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
-  if (want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
+  // the causal form (77-token text tower) runs on the general kernel below
+  if (!causal && want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
+  if (!causal && want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
+  if (!causal && want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
   const int q_tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_fwd_smem(tokens);
   static size_t configured_dev[MAX_DEVICES] = {};
@@ -2075,7 +2140,7 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
     configured = smem;
   }
   launch_pdl(attention_fwd_kernel, dim3(heads, V), dim3(pick_warps(q_tiles) * 32), smem, st, qkv, out, lse, tokens, heads,
-             scale * LOG2E, q_tiles, nkp);
+             scale * LOG2E, q_tiles, nkp, causal);
 }
 
 void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
@@ -2143,10 +2208,10 @@ static bool launch_attention_bwd_tc(const bf16* qkv, const bf16* out, const bf16
 }
 
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
-                          int tokens, int heads, float scale, cudaStream_t st) {
+                          int tokens, int heads, float scale, cudaStream_t st, int causal, float* delta_ws) {
   // TTL_ATTN_BWD: unset / "tc" = tcgen05 kernel where the geometry allows (129..208 tokens), "mma" = the mma.sync kernel
   static const char* mode = std::getenv("TTL_ATTN_BWD");
-  if ((mode == nullptr || mode[0] == 't') && launch_attention_bwd_tc(qkv, out, dout, lse, dqkv, V, tokens, heads, scale, st)) return;
+  if (!causal && (mode == nullptr || mode[0] == 't') && launch_attention_bwd_tc(qkv, out, dout, lse, dqkv, V, tokens, heads, scale, st)) return;
   const int tiles = (tokens + 15) / 16, nkp = (tokens + 63) / 64 * 64;
   const size_t smem = attention_bwd_smem(tokens);
   static size_t configured_dev[MAX_DEVICES] = {};
@@ -2155,8 +2220,20 @@ void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, co
     cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
+  const float* delta = nullptr;
+  if (delta_ws != nullptr && tokens <= 128) {     // exact Delta (see attention_delta_kernel)
+    const size_t dsm = (2 * static_cast<size_t>(tokens) * (DH + 1) + 8 * 2 * DH) * sizeof(float);
+    static size_t dconf_dev[MAX_DEVICES] = {};
+    size_t& dconf = dconf_dev[current_device_slot()];
+    if (dsm > dconf) {
+      cudaFuncSetAttribute(attention_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dsm));
+      dconf = dsm;
+    }
+    launch_pdl(attention_delta_kernel, dim3(heads, V), dim3(256), dsm, st, qkv, dout, lse, delta_ws, tokens, heads, scale, causal);
+    delta = delta_ws;
+  }
   launch_pdl(attention_bwd_kernel, dim3(heads, V, 2), dim3(pick_warps(tiles) * 32), smem, st, qkv, out, dout, lse, dqkv, tokens,   // z: phase
-             heads, scale, tiles, nkp);
+             heads, scale, tiles, nkp, causal, delta);
 }
 
 }  // namespace ttl

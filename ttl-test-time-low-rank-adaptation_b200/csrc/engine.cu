@@ -163,6 +163,14 @@ struct ttl_ctx {
   float pix_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};   // ttl.py:226-227
   float pix_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
+  // text mode (`--lora_encoder text`, cfg.text_mode): this context is the CLIP TEXT tower with the adapter on its layers
+  // lo..hi.  "views" are the class prompts (tokens = context positions, causal attention, EOT pooling), the "classes" of the
+  // logits are the image views whose frozen features the caller supplies per test sample.
+  bool text_mode = false;
+  float *tok_emb = nullptr, *fhat = nullptr, *tn = nullptr, *attn_delta = nullptr;
+  int *tok_ids = nullptr, *eot = nullptr;
+  int n_prompts = 0;
+
   // optional DeYO branches (filter_ent / filter_plpd; deyo.cu): allocated on first use
   float *xprime = nullptr, *xscratch = nullptr, *XK2 = nullptr, *feats2 = nullptr, *logits2 = nullptr, *entropy2 = nullptr,
         *logits_s = nullptr, *entropy_s = nullptr, *plpd = nullptr;
@@ -250,6 +258,11 @@ bool has_lora(const ttl_ctx* c, int layer) { return layer >= c->lo && layer <= c
 
 // ---------------------------------------------------------------------------------------------- forward pieces
 int embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
+  if (c->text_mode) {   // token_embedding + position_embedding (HF CLIPTextEmbeddings); the text tower has no pre-LN
+    launch_text_embed(c->tok_ids, c->tok_emb, c->pos, x, V * c->tokens, c->tokens, c->d, c->cfg.vocab, st);
+    c->launches++;
+    return check_launch(c, "text embed");
+  }
   if (images != nullptr) {  // nullptr: graph capture, im2col is issued by the caller outside the graph
     launch_im2col(images, c->patches, V, c->cfg.image_size, c->cfg.patch, st);
   }
@@ -317,7 +330,7 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     RET_IF(gemm(c, g, st));
   }
   const int dir_attn = next_dir();
-  if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st, dir_attn);
+  if (!(skip & 2)) launch_attention_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st, dir_attn, c->text_mode ? 1 : 0);
   c->launches++;
   {
     GemmArgs g;
@@ -437,7 +450,7 @@ int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats
   NvtxRange nv("ttl:tail_infer(layers>=lo)+logits");
   const float* cur = x_in;
   const int last = c->L - 1;
-  const bool shortcut = c->cls_shortcut && last >= c->lo;
+  const bool shortcut = c->cls_shortcut && last >= c->lo && !c->text_mode;
   for (int l = c->lo; l < c->L; ++l) {
     if (shortcut && l == last) break;
     RET_IF(run_layer(c, l, cur, c->XB, c->XA, V, S, !c->b_zero, nullptr, st));
@@ -447,9 +460,10 @@ int forward_tail_infer(ttl_ctx* c, const float* x_in, int V, int S, float* feats
     RET_IF(run_last_layer_cls(c, last, cur, V, S, !c->b_zero, st));
     launch_pool_project(c->XCo, c->postg, c->postb, c->Wp, c->pooled, feats, V, 1, c->d, c->P, c->cfg.ln_eps, st);
   } else {
-    launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+    launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st,
+                        c->text_mode ? c->eot : nullptr);
   }
-  launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
+  if (logits != nullptr) launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
   c->launches += 4;
   return check_launch(c, "forward_tail_infer");
 }
@@ -463,7 +477,8 @@ int forward_tail_train(ttl_ctx* c, const float* x_in, int G, int S, cudaStream_t
     RET_IF(run_layer(c, l, cur, tp.x_mid, tp.x_out, G, S, !c->b_zero, &tp, st));
     cur = tp.x_out;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st,
+                      c->text_mode ? c->eot : nullptr);
   c->launches += 2;
   c->last_train_views = G;
   c->last_train_samples = S;
@@ -472,17 +487,24 @@ int forward_tail_train(ttl_ctx* c, const float* x_in, int G, int S, cudaStream_t
 }
 
 // dlogits_c [G,C] (G views of S samples, sample-major) -> LoRA gradients of every sample (overwrites c->lg)
+int backward_layers(ttl_ctx* c, int G, cudaStream_t st);
+
 int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   NvtxRange nv("ttl:backward(LoRA grads)");
   if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
+  const float* x_last = c->tape[c->n_train - 1].x_out;
+  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX,
+                  c->DXB, G, c->C, c->P, c->tokens, c->d, c->cfg.ln_eps, st);
+  c->launches += 4;
+  return backward_layers(c, G, st);
+}
+
+// c->DX / c->DXB hold d loss / d (last hidden state) of the G train-mode sequences: the train layers backwards -> LoRA gradients
+int backward_layers(ttl_ctx* c, int G, cudaStream_t st) {
   const int S = c->last_train_samples;
   const int Mg = G * c->tokens, Ms = Mg / S, d = c->d, F = c->F, r = c->r;
   const int kc = 64 * c->pack_samples;
   const int64_t lt = c->lora_total;
-  const float* x_last = c->tape[c->n_train - 1].x_out;
-  launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX,
-                  c->DXB, G, c->C, c->P, c->tokens, d, c->cfg.ln_eps, st);
-  c->launches += 4;
   float* dx = c->DX;
   float* dx2 = c->DX2;
   for (int l = c->L - 1; l >= c->lo; --l) {
@@ -512,7 +534,8 @@ int backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
       g.M = Mg; g.N = d; g.epi = EPI_BF16; g.out = c->DAO; g.ldo = d;
       RET_IF(gemm(c, g, st));
     }
-    launch_attention_bwd(tp.qkv, tp.ao, c->DAO, tp.lse, c->DQKV, G, c->tokens, c->H, 0.125f, st);
+    launch_attention_bwd(tp.qkv, tp.ao, c->DAO, tp.lse, c->DQKV, G, c->tokens, c->H, 0.125f, st, c->text_mode ? 1 : 0,
+                         c->text_mode ? c->attn_delta : nullptr);
     c->launches++;
     const bool lora = has_lora(c, l);
     if (lora) {
@@ -835,6 +858,62 @@ int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp
   return f32_tail_infer(c, c->XK, 1, c->pred_feats, c->pred, c->pred_entropy, st);   // view 0 with the adapted factors
 }
 
+// ================================================================================ `--lora_encoder text`
+// The adapter sits on q_proj / v_proj of layers lo..hi of the TEXT tower (ttl.py:145-149,190-191; clip/custom_clip.py:602-606).
+// The image features of the views are frozen (custom_clip.py:672-673); the class features are recomputed with gradient in every
+// forward (:677-678): layers below lo run once per class-name set (XK), layers lo.. run in train mode over all prompts per step.
+int text_features_now(ttl_ctx* c, bool train, cudaStream_t st) {   // current class features -> c->feats_c (raw), c->tn (normalised)
+  const int n = c->n_prompts;
+  if (train) RET_IF(forward_tail_train(c, c->XK, n, 1, st));
+  else RET_IF(forward_tail_infer(c, c->XK, n, 1, c->feats_c, nullptr, nullptr, st));
+  launch_l2norm_rows(c->feats_c, c->tn, n, c->P, st);
+  c->launches++;
+  return check_launch(c, "text features");
+}
+
+int text_adapt_body(ttl_ctx* c, const float* img_feats, int V, const ttl_hparams& hp, bool forced, cudaStream_t st) {
+  NvtxRange nv("ttl:adapt_predict(text-tower adapter)");
+  const int n = c->n_prompts, K = select_count(V, hp.selection_p);
+  RET_IF(lora_reset(c, 1, st));
+  launch_l2norm_rows(img_feats, c->fhat, V, c->P, st);
+  c->launches++;
+  const bool tpt = hp.head == TTL_HEAD_TPT;
+  const int nsteps = tpt ? hp.tta_steps : hp.tta_steps * hp.tta_steps;
+  const bool adapt = nsteps > 0 && (!tpt || K > 0);
+  if (!adapt) {
+    RET_IF(text_features_now(c, false, st));
+    launch_logits_entropy(img_feats, c->tn, c->logit_scale_exp, c->logits, c->entropy, V, n, c->P, st);
+    c->launches += 2;
+  }
+  for (int step = 0; step < nsteps && adapt; ++step) {
+    RET_IF(text_features_now(c, true, st));
+    float* lg = step == 0 ? c->logits : c->logits_c;
+    float* en = step == 0 ? c->entropy : c->entropy_c;
+    launch_logits_entropy(img_feats, c->tn, c->logit_scale_exp, lg, en, V, n, c->P, st);
+    c->launches += 2;
+    const int* idx = nullptr;
+    int rows = V;
+    if (tpt) {
+      if (step == 0) { launch_select(c->entropy, V, K, forced ? c->idx : nullptr, c->idx, st); c->launches++; }
+      launch_tpt_loss(lg, c->idx, K, n, c->loss, c->dlogits, st);      // selected_idx frozen after the first step (ttl.py:97-98)
+      idx = c->idx;
+      rows = K;
+    } else {
+      launch_deyo_loss(lg, V, n, hp.deyo_margin_e0, c->loss, c->dlogits, st);
+    }
+    c->launches++;
+    launch_text_head_bwd(c->dlogits, idx, rows, c->fhat, c->logit_scale_exp, c->feats_c, c->Wp, c->tape[c->n_train - 1].x_out, c->postg,
+                         c->eot, c->dfh, c->dpool, c->DX, c->DXB, n, c->P, c->tokens, c->d, c->cfg.ln_eps, st);
+    c->launches += 4;
+    RET_IF(backward_layers(c, n, st));
+    RET_IF(adamw(c, hp, 1, st));
+  }
+  RET_IF(text_features_now(c, false, st));                            // predict on view 0 with the adapted class features
+  launch_logits_entropy(img_feats, c->tn, c->logit_scale_exp, c->pred, c->pred_entropy, 1, n, c->P, st);
+  c->launches += 2;
+  return check_launch(c, "text_adapt_body");
+}
+
 // ---- optional branches of the weighted-entropy head (deyo.py:103-151): filter_ent, filter_plpd, reweight switches
 int ensure_deyo_general(ttl_ctx* c) {
   if (c->keep != nullptr) return TTL_OK;
@@ -933,6 +1012,7 @@ int copy_outputs(ttl_ctx* c, const ttl_outputs* o, int S, int V, const ttl_hpara
 
 int validate_run(ttl_ctx* c, int S, int V, const ttl_hparams* hp) {
   if (!c || !hp) return TTL_E_INVALID;
+  if (c->text_mode) { c->err = "text-mode context: use ttl_text_adapt_predict"; return TTL_E_STATE; }
   if (S <= 0 || S > c->Sm) { c->err = "n_samples out of range (ttl_config.max_samples)"; return TTL_E_SHAPE; }
   if (V <= 0 || V > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
@@ -1023,10 +1103,15 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     g_create_err = "device is not compute capability 10.x (sm_100a only; no fallback)";
     return TTL_E_ARCH;
   }
-  if (cfg->width % 128 != 0 || cfg->width > 1024 || cfg->width != cfg->heads * 64 || cfg->image_size % cfg->patch != 0 ||
+  const bool text_mode = cfg->text_mode != 0;
+  if (text_mode && (cfg->context <= 0 || cfg->context > 256 || cfg->vocab <= 0 || cfg->max_samples > 1 || cfg->precision != TTL_PRECISION_BF16)) {
+    g_create_err = "text mode: context in 1..256, vocab > 0, one sample per call, bf16 path";
+    return TTL_E_SHAPE;
+  }
+  if (cfg->width % 128 != 0 || cfg->width > 1024 || cfg->width != cfg->heads * 64 || (!text_mode && cfg->image_size % cfg->patch != 0) ||
       cfg->mlp_dim % 64 != 0 || (cfg->lora_rank != 16 && cfg->lora_rank != 32) || cfg->lora_layer_lo < 0 ||
       cfg->lora_layer_hi >= cfg->layers || cfg->lora_layer_lo > cfg->lora_layer_hi || cfg->max_views <= 0 ||
-      cfg->max_classes <= 0 || cfg->proj_dim <= 0 || (cfg->patch & 1) || cfg->max_samples < 0 || cfg->max_samples > 16) {
+      cfg->max_classes <= 0 || cfg->proj_dim <= 0 || (!text_mode && (cfg->patch & 1)) || cfg->max_samples < 0 || cfg->max_samples > 16) {
     g_create_err = "unsupported geometry (width%128, head_dim 64, rank 16/32, layer range, even patch, max_samples <= 16)";
     return TTL_E_SHAPE;
   }
@@ -1049,9 +1134,15 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
   c->d = cfg->width; c->F = cfg->mlp_dim; c->P = cfg->proj_dim; c->L = cfg->layers; c->H = cfg->heads;
   c->r = cfg->lora_rank; c->lo = cfg->lora_layer_lo; c->hi = cfg->lora_layer_hi;
   c->s = cfg->lora_alpha / cfg->lora_rank;
+  c->text_mode = text_mode;
+  if (text_mode) {     // sequences = prompts of `context` tokens; no patch embedding
+    c->T = cfg->context - 1; c->tokens = cfg->context; c->Kp = 64;
+    c->cfg.image_size = 16; c->cfg.patch = 16;       // sizes of the (unused) pixel staging buffers
+  } else {
   c->T = (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch);
   c->tokens = c->T + 1;
   c->Kp = (3 * cfg->patch * cfg->patch + 63) / 64 * 64;
+  }
   c->Vm = cfg->max_views; c->Sm = cfg->max_samples > 0 ? cfg->max_samples : 1;
   c->VVm = c->Vm * c->Sm; c->Mm = c->VVm * c->tokens; c->Cm = cfg->max_classes;
   c->n_train = c->L - c->lo; c->n_lora = c->hi - c->lo + 1;
@@ -1069,16 +1160,24 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     A(w.ln1g, d); A(w.ln1b, d); A(w.ln2g, d); A(w.ln2b, d);
     if (l >= c->lo) { A(w.wqkvT, 3 * d * d); A(w.woT, d * d); A(w.w1T, F * d); A(w.w2T, d * F); }
   }
-  A(c->patches, static_cast<size_t>(c->VVm) * c->T * c->Kp);
+  A(c->patches, text_mode ? 64 : static_cast<size_t>(c->VVm) * c->T * c->Kp);
+  if (text_mode) {
+    A(c->tok_emb, static_cast<size_t>(cfg->vocab) * d); A(c->tok_ids, static_cast<size_t>(c->VVm) * c->tokens); A(c->eot, c->VVm);
+    A(c->fhat, static_cast<size_t>(c->Cm) * c->P); A(c->tn, static_cast<size_t>(c->VVm) * c->P);
+    A(c->attn_delta, static_cast<size_t>(c->VVm) * c->H * c->tokens);
+  }
   A(c->Hb, static_cast<size_t>(M) * d); A(c->QKV, static_cast<size_t>(M) * 3 * d); A(c->AO, static_cast<size_t>(M) * d);
   A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64 * c->Sm);
   A(c->XK, static_cast<size_t>(M) * d); A(c->XA, static_cast<size_t>(M) * d); A(c->XB, static_cast<size_t>(M) * d);
   A(c->TIN, static_cast<size_t>(M) * d); A(c->PIN, static_cast<size_t>(c->Sm) * c->tokens * d);
   A(c->QC, static_cast<size_t>(c->VVm) * d); A(c->AOC, static_cast<size_t>(c->VVm) * d); A(c->HC, static_cast<size_t>(c->VVm) * d);
   A(c->GC, static_cast<size_t>(c->VVm) * F); A(c->XCm, static_cast<size_t>(c->VVm) * d); A(c->XCo, static_cast<size_t>(c->VVm) * d);
-  const size_t VV = c->VVm;
-  A(c->feats, VV * c->P); A(c->feats_c, VV * c->P); A(c->logits, VV * c->Cm); A(c->logits_c, VV * c->Cm);
-  A(c->entropy, VV); A(c->entropy_c, VV); A(c->loss, c->Sm + 4); A(c->dlogits, VV * c->Cm); A(c->pred, static_cast<size_t>(c->Sm) * c->Cm);
+  // head buffers.  Text mode: the roles of the two head dimensions swap between the class features ([prompts, P]) and the logits
+  // ([image views, prompts]), so both are bounded by the larger of the two limits.
+  const size_t VV = text_mode ? static_cast<size_t>(c->VVm > c->Cm ? c->VVm : c->Cm) : static_cast<size_t>(c->VVm);
+  const size_t CC = text_mode ? VV : static_cast<size_t>(c->Cm);
+  A(c->feats, VV * c->P); A(c->feats_c, VV * c->P); A(c->logits, VV * CC); A(c->logits_c, VV * CC);
+  A(c->entropy, VV); A(c->entropy_c, VV); A(c->loss, c->Sm + 4); A(c->dlogits, VV * CC); A(c->pred, static_cast<size_t>(c->Sm) * CC);
   A(c->pred_feats, static_cast<size_t>(c->Sm) * c->P); A(c->pred_entropy, c->Sm + 4); A(c->idx, VV);
   A(c->pooled, VV * d); A(c->dfh, VV * c->P); A(c->dpool, VV * d);
   c->tape.resize(c->n_train);
@@ -1118,7 +1217,7 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     const size_t kcm = 64 * static_cast<size_t>(c->Sm);
     A(c->pk[i].a_ext, kcm * d); A(c->pk[i].a_ext_t, d * kcm); A(c->pk[i].b_ext, 3 * d * kcm); A(c->pk[i].b_ext_t, kcm * 3 * d);
   }
-  c->stage_bytes = static_cast<size_t>(c->VVm) * 3 * cfg->image_size * cfg->image_size * sizeof(float);
+  c->stage_bytes = text_mode ? 1024 : static_cast<size_t>(c->VVm) * 3 * cfg->image_size * cfg->image_size * sizeof(float);
   A(c->stage[0], c->stage_bytes / sizeof(float)); A(c->stage[1], c->stage_bytes / sizeof(float));
 #undef A
   if (rc == TTL_OK) {
@@ -1197,6 +1296,10 @@ int ttl_set_weight(ttl_ctx* c, int32_t layer, int32_t kind, const float* host, i
       case TTL_W_POST_LN_G: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->postg, host, numel);
       case TTL_W_POST_LN_B: if (!need(d)) return TTL_E_SHAPE; return upload_f32(c, c->postb, host, numel);
       case TTL_W_VIS_PROJ: if (!need(static_cast<int64_t>(c->P) * d)) return TTL_E_SHAPE; return upload_f32(c, c->Wp, host, numel);
+      case TTL_W_TOKEN_EMB:
+        if (!c->text_mode) { c->err = "TTL_W_TOKEN_EMB belongs to a text-mode context"; return TTL_E_STATE; }
+        if (!need(static_cast<int64_t>(c->cfg.vocab) * d)) return TTL_E_SHAPE;
+        return upload_f32(c, c->tok_emb, host, numel);
       case TTL_W_PATCH_EMB: {
         const int K = 3 * c->cfg.patch * c->cfg.patch;
         if (!need(static_cast<int64_t>(d) * K)) return TTL_E_SHAPE;
@@ -1344,6 +1447,7 @@ int ttl_adamw_step(ttl_ctx* c, const ttl_hparams* hp, void* stream) {
 
 int ttl_forward(ttl_ctx* c, const float* images_dev, int32_t n_views, int32_t train, float* logits_dev, void* stream) {
   if (!c || !images_dev) return TTL_E_INVALID;
+  if (c->text_mode) { c->err = "text-mode context: use ttl_text_adapt_predict"; return TTL_E_STATE; }
   if (n_views <= 0 || n_views > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
   if (c->C <= 0) { c->err = "text features not set"; return TTL_E_STATE; }
   cudaSetDevice(c->cfg.device);
@@ -1458,6 +1562,82 @@ int ttl_deyo_last_plpd(ttl_ctx* c, float* plpd_host, int32_t* n_final_host, int3
   CK(cudaDeviceSynchronize());
   if (plpd_host && n_kept > 0) CK(cudaMemcpy(plpd_host, c->plpd, sizeof(float) * n_samples * n_kept, cudaMemcpyDeviceToHost));
   if (n_final_host) CK(cudaMemcpy(n_final_host, c->dg_nkept, sizeof(int) * n_samples, cudaMemcpyDeviceToHost));
+  return TTL_OK;
+}
+
+// ---- `--lora_encoder text`
+int ttl_image_features(ttl_ctx* c, const float* images_dev, int32_t n_views, float* feats_dev, void* stream) {
+  if (!c || !images_dev || !feats_dev) return TTL_E_INVALID;
+  if (c->text_mode || c->f32) { c->err = "ttl_image_features: image-tower context on the bf16 path"; return TTL_E_STATE; }
+  if (n_views <= 0 || n_views > c->Vm) { c->err = "n_views out of range"; return TTL_E_SHAPE; }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->pack_samples != 1) RET_IF(repack(c, 1, st));
+  RET_IF(forward_frozen(c, images_dev, n_views, st));
+  RET_IF(forward_tail_infer(c, c->XK, n_views, 1, c->feats, nullptr, nullptr, st));
+  CK(cudaMemcpyAsync(feats_dev, c->feats, sizeof(float) * n_views * c->P, cudaMemcpyDeviceToDevice, st));
+  return check_launch(c, "ttl_image_features");
+}
+
+int ttl_text_set_prompts(ttl_ctx* c, const int32_t* tokens_host, int32_t n_prompts, float logit_scale, void* stream) {
+  if (!c || !tokens_host) return TTL_E_INVALID;
+  if (!c->text_mode) { c->err = "ttl_text_set_prompts needs a text-mode context"; return TTL_E_STATE; }
+  if (n_prompts <= 0 || n_prompts > c->Vm) { c->err = "n_prompts out of range (ttl_config.max_views)"; return TTL_E_SHAPE; }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> eot(n_prompts);
+  for (int p = 0; p < n_prompts; ++p) {      // first argmax of the ids: the EOT token has the highest id (HF CLIPTextTransformer pooling)
+    const int32_t* row = tokens_host + static_cast<size_t>(p) * c->tokens;
+    int best = 0;
+    for (int j = 1; j < c->tokens; ++j) if (row[j] > row[best]) best = j;
+    eot[p] = best;
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemcpy(c->tok_ids, tokens_host, sizeof(int) * n_prompts * c->tokens, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->eot, eot.data(), sizeof(int) * n_prompts, cudaMemcpyHostToDevice));
+  c->n_prompts = n_prompts;
+  c->logit_scale_exp = std::exp(logit_scale);
+  c->C = n_prompts;
+  if (c->pack_samples != 1) RET_IF(repack(c, 1, st));
+  RET_IF(forward_frozen(c, nullptr, n_prompts, st));     // layers below the adapter: once per class-name set
+  return check_launch(c, "ttl_text_set_prompts");
+}
+
+int ttl_text_features(ttl_ctx* c, float* feats_host, void* stream) {
+  if (!c || !feats_host) return TTL_E_INVALID;
+  if (!c->text_mode || c->n_prompts <= 0) { c->err = "ttl_text_features: text-mode context with prompts set"; return TTL_E_STATE; }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET_IF(text_features_now(c, false, st));
+  CK(cudaMemcpyAsync(feats_host, c->tn, sizeof(float) * c->n_prompts * c->P, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TTL_OK;
+}
+
+int ttl_text_adapt_predict(ttl_ctx* c, const float* img_feats_dev, int32_t n_views, const ttl_hparams* hp,
+                           const int32_t* forced_idx_dev, const ttl_outputs* out_dev, void* stream) {
+  if (!c || !hp || !img_feats_dev) return TTL_E_INVALID;
+  if (!c->text_mode || c->n_prompts <= 0) { c->err = "ttl_text_adapt_predict: text-mode context with prompts set"; return TTL_E_STATE; }
+  if (n_views <= 0 || n_views > c->Cm) { c->err = "n_views out of range (ttl_config.max_classes bounds the image views in text mode)"; return TTL_E_SHAPE; }
+  if (hp->head != TTL_HEAD_TPT && hp->head != TTL_HEAD_DEYO) { c->err = "unknown head"; return TTL_E_INVALID; }
+  if (hp->tta_steps < 0 || hp->tta_steps > 64 || !(hp->selection_p >= 0.0 && hp->selection_p <= 1.0)) { c->err = "bad hparams"; return TTL_E_INVALID; }
+  cudaSetDevice(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = select_count(n_views, hp->selection_p);
+  const bool forced = forced_idx_dev != nullptr && hp->head == TTL_HEAD_TPT && K > 0;
+  if (forced) CK(cudaMemcpyAsync(c->idx, forced_idx_dev, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
+  const int64_t before = c->launches;
+  int r = text_adapt_body(c, img_feats_dev, n_views, *hp, forced, st);
+  c->last_launches = c->launches - before;
+  if (r != TTL_OK) return r;
+  if (out_dev) {
+    const int n = c->n_prompts;
+    if (out_dev->logits0) CK(cudaMemcpyAsync(out_dev->logits0, c->logits, sizeof(float) * n_views * n, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->entropy) CK(cudaMemcpyAsync(out_dev->entropy, c->entropy, sizeof(float) * n_views, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->idx && K > 0 && hp->head == TTL_HEAD_TPT) CK(cudaMemcpyAsync(out_dev->idx, c->idx, sizeof(int) * K, cudaMemcpyDeviceToDevice, st));
+    if (out_dev->loss) CK(cudaMemcpyAsync(out_dev->loss, c->loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out_dev->pred_logits) CK(cudaMemcpyAsync(out_dev->pred_logits, c->pred, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  }
   return TTL_OK;
 }
 

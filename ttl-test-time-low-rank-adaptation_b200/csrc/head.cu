@@ -37,12 +37,13 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // pooled[v,:] = LN(x[v*tokens + 0, :])   (HF post_layernorm on the CLS token); one CTA per view
 __global__ void __launch_bounds__(HT)
 cls_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float* __restrict__ pooled, int tokens, int d, float eps) {
+              float* __restrict__ pooled, int tokens, int d, float eps, const int* __restrict__ pool_row) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[32];
   const int v = blockIdx.x;
-  const float* xr = x + static_cast<size_t>(v) * tokens * d;
+  // pool_row (text tower): the pooled token of sequence v is row pool_row[v] (the EOT position) instead of row 0 (CLS)
+  const float* xr = x + (static_cast<size_t>(v) * tokens + (pool_row != nullptr ? pool_row[v] : 0)) * d;
   float s = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) s += xr[i];
   const float mean = block_sum(s, red) / d;
@@ -309,15 +310,45 @@ l2norm_bwd_kernel(const float* __restrict__ feats, float* __restrict__ dfh, int 
   for (int p = threadIdx.x; p < P; p += blockDim.x) dd[p] = (dd[p] - f[p] * inv * dt) * inv;
 }
 
+// y[r, :] = x[r, :] / |x[r, :]|
+__global__ void __launch_bounds__(HT)
+l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int P) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[32];
+  const float* xr = x + static_cast<size_t>(blockIdx.x) * P;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s += xr[p] * xr[p];
+  const float inv = rsqrtf(block_sum(s, red));
+  for (int p = threadIdx.x; p < P; p += blockDim.x) y[static_cast<size_t>(blockIdx.x) * P + p] = xr[p] * inv;
+}
+
+// `--lora_encoder text`: the class features carry the gradient.  d that[c, :] = scale * sum_k dlogits[k, c] * fhat[view(k), :],
+// view(k) = idx[k] (compact rows of the selected views) or k.  One CTA per class.
+__global__ void __launch_bounds__(HT)
+text_dfeat_kernel(const float* __restrict__ dlogits, const int* __restrict__ idx, const float* __restrict__ fhat, float scale,
+                  float* __restrict__ dth, int K, int C, int P) {
+  pdl_wait();
+  pdl_trigger();
+  const int c = blockIdx.x;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k)
+      acc += dlogits[static_cast<size_t>(k) * C + c] * fhat[static_cast<size_t>(idx != nullptr ? idx[k] : k) * P + p];
+    dth[static_cast<size_t>(c) * P + p] = acc * scale;
+  }
+}
+
 // LayerNorm backward on the CLS row of compact view g: dpool[g,:] -> dx[g*tokens + 0, :] (+ bf16 copy)
 __global__ void __launch_bounds__(HT)
 cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, const float* __restrict__ gamma,
-                  float* __restrict__ dx, bf16* __restrict__ dxb, int tokens, int d, float eps) {
+                  float* __restrict__ dx, bf16* __restrict__ dxb, int tokens, int d, float eps, const int* __restrict__ pool_row) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[32];
   const int g = blockIdx.x;
-  const float* xr = x + static_cast<size_t>(g) * tokens * d;
+  const size_t row = static_cast<size_t>(g) * tokens + (pool_row != nullptr ? pool_row[g] : 0);
+  const float* xr = x + row * d;
   const float* dp = dpool + static_cast<size_t>(g) * d;
   float sm = 0.f;
   for (int i = threadIdx.x; i < d; i += blockDim.x) sm += xr[i];
@@ -332,8 +363,8 @@ cls_ln_bwd_kernel(const float* __restrict__ dpool, const float* __restrict__ x, 
   }
   s1 = block_sum(s1, red) / d;
   s2 = block_sum(s2, red) / d;
-  float* dxr = dx + static_cast<size_t>(g) * tokens * d;
-  bf16* dbr = dxb + static_cast<size_t>(g) * tokens * d;
+  float* dxr = dx + row * d;
+  bf16* dbr = dxb + row * d;
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     const float gy = gamma[i] * dp[i], xh = (xr[i] - mean) * rstd;
     const float o = rstd * (gy - s1 - xh * s2);
@@ -355,9 +386,9 @@ static void small_gemm_nt_smem(size_t bytes) {
 }
 
 void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
-                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st) {
+                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st, const int* pool_row) {
   small_gemm_nt_smem(SG_TM * d * sizeof(float));
-  launch_pdl(cls_ln_kernel, dim3(V), dim3(HT), 0, st, x, gamma, beta, pooled, tokens, d, eps);
+  launch_pdl(cls_ln_kernel, dim3(V), dim3(HT), 0, st, x, gamma, beta, pooled, tokens, d, eps, pool_row);
   launch_pdl(small_gemm_nt_kernel, dim3(dim3((P + SG_NPC - 1) / SG_NPC, (V + SG_TM - 1) / SG_TM)), dim3(256), SG_TM * d * sizeof(float), st, pooled, Wp, feats, V, P, d);
 }
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
@@ -392,7 +423,22 @@ void launch_head_bwd(const float* dlogits, const float* text, float scale, const
   launch_pdl(l2norm_bwd_kernel, dim3(G), dim3(HT), 0, st, feats, dfh, P);
   launch_pdl(small_gemm_nn_kernel, dim3(dim3((d + 63) / 64, (G + 7) / 8)), dim3(256), (8 * P + 4 * 8 * 64) * sizeof(float), st, 
       dfh, Wp, dpool, G, d, P, 1.0f);
-  launch_pdl(cls_ln_bwd_kernel, dim3(G), dim3(HT), 0, st, dpool, x, gamma, dx, dx_bf16, tokens, d, eps);
+  launch_pdl(cls_ln_bwd_kernel, dim3(G), dim3(HT), 0, st, dpool, x, gamma, dx, dx_bf16, tokens, d, eps, static_cast<const int*>(nullptr));
+}
+void launch_l2norm_rows(const float* x, float* y, int rows, int P, cudaStream_t st) {
+  launch_pdl(l2norm_rows_kernel, dim3(rows), dim3(HT), 0, st, x, y, P);
+}
+void launch_text_head_bwd(const float* dlogits, const int* idx, int K, const float* fhat, float scale, const float* tfeats,
+                          const float* Wp, const float* x, const float* gamma, const int* eot, float* dfh, float* dpool, float* dx,
+                          bf16* dx_bf16, int C, int P, int tokens, int d, float eps, cudaStream_t st) {
+  cudaMemsetAsync(dx, 0, static_cast<size_t>(C) * tokens * d * sizeof(float), st);
+  cudaMemsetAsync(dx_bf16, 0, static_cast<size_t>(C) * tokens * d * sizeof(bf16), st);
+  // d that = scale * dlogits^T fhat ; d t (L2-norm backward) ; d pooled = d t @ text_projection ; final-LN backward on the EOT rows
+  launch_pdl(text_dfeat_kernel, dim3(C), dim3(HT), 0, st, dlogits, idx, fhat, scale, dfh, K, C, P);
+  launch_pdl(l2norm_bwd_kernel, dim3(C), dim3(HT), 0, st, tfeats, dfh, P);
+  launch_pdl(small_gemm_nn_kernel, dim3(dim3((d + 63) / 64, (C + 7) / 8)), dim3(256), (8 * P + 4 * 8 * 64) * sizeof(float), st,
+      static_cast<const float*>(dfh), Wp, dpool, C, d, P, 1.0f);
+  launch_pdl(cls_ln_bwd_kernel, dim3(C), dim3(HT), 0, st, static_cast<const float*>(dpool), x, gamma, dx, dx_bf16, tokens, d, eps, eot);
 }
 
 }  // namespace ttl

@@ -33,11 +33,14 @@ void launch_block_mask(bf16* x, int M, int ncols, int rows_per_sample, cudaStrea
 
 // ---- attention.cu   qkv bf16 [V*tokens, 3d] (q | k | v, heads concatenated, 64 per head)
 // out bf16 [V*tokens, d]; lse (nullable) fp32 [V, heads, tokens] natural-log softmax normaliser of scale*q.k
+// causal != 0: key j is visible to query i only for j <= i (text tower); served by the general mma.sync kernels
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
-                          cudaStream_t st, int descending = 0);
+                          cudaStream_t st, int descending = 0, int causal = 0);
 // dqkv bf16 [V*tokens, 3d]  from dout bf16 [V*tokens, d], qkv, out, lse
+// delta_ws (nullable; fp32 [V, heads, tokens], tokens <= 128): Delta = rowsum(P o dP) is computed exactly into it first instead of
+// being taken as rowsum(dO o O) from the bf16 O (text tower: strong cancellation in dP - Delta, see attention_delta_kernel)
 void launch_attention_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int V,
-                          int tokens, int heads, float scale, cudaStream_t st);
+                          int tokens, int heads, float scale, cudaStream_t st, int causal = 0, float* delta_ws = nullptr);
 // CLS-query attention of the last layer in inference: q_cls bf16 [V, d] (one query row per view), K/V from qkv rows;
 // out_cls bf16 [V, d]
 void launch_attention_cls(const bf16* q_cls, const bf16* qkv, bf16* out_cls, int V, int tokens, int heads, float scale,
@@ -47,8 +50,17 @@ size_t attention_bwd_smem(int tokens);
 
 // ---- head.cu
 // pooled = LN(x[v*tokens + 0, :]) ; feats[v,:] = Wp[P,d] @ pooled  (HF post_layernorm + visual_projection)
+// pool_row (nullable): row of each sequence that is pooled (text tower: the EOT position) instead of row 0
 void launch_pool_project(const float* x, const float* gamma, const float* beta, const float* Wp, float* pooled,
-                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st);
+                         float* feats, int V, int tokens, int d, int P, float eps, cudaStream_t st, const int* pool_row = nullptr);
+// y = x / |x| row-wise, [rows, P]
+void launch_l2norm_rows(const float* x, float* y, int rows, int P, cudaStream_t st);
+// `--lora_encoder text`: gradient of the loss w.r.t. the last text-tower hidden state from dlogits [K, C] (rows = the views
+// idx[k], or k when idx == nullptr), the L2-normalised image features fhat [V, P] and the raw class features tfeats [C, P]:
+// dx fp32 [C*tokens, d] (+ bf16 copy), non-zero on the EOT rows only
+void launch_text_head_bwd(const float* dlogits, const int* idx, int K, const float* fhat, float scale, const float* tfeats,
+                          const float* Wp, const float* x, const float* gamma, const int* eot, float* dfh, float* dpool, float* dx,
+                          bf16* dx_bf16, int C, int P, int tokens, int d, float eps, cudaStream_t st);
 // logits[v,c] = scale * <feats[v]/|feats[v]|, T[c]> ; entropy[v] = H(softmax(logits[v]))   (custom_clip.py:680-687, ttl.py:51)
 void launch_logits_entropy(const float* feats, const float* text, float scale, float* logits, float* entropy, int V,
                            int C, int P, cudaStream_t st);
@@ -128,6 +140,10 @@ void launch_im2col_f32(const float* images, float* patches, int V, int S, int p,
 // out[w, j] (or out[j, w] if transpose_out) = scale * sum_m wide[m, w] * narrow[m, j]
 void launch_reduce_tn_f32(const float* wide, int ldw, int nw, const float* narrow, int ldn, int nn, int M, float scale,
                           float* out, int transpose_out, cudaStream_t st);
+
+// ---- text.cu   x[m, :] = token_embedding[tokens[m], :] + position_embedding[m % ctx, :]
+void launch_text_embed(const int* tokens, const float* tok_emb, const float* pos_emb, float* x, int rows, int ctx, int d, int vocab,
+                       cudaStream_t st);
 
 // ---- deyo.cu   optional branches of the weighted-entropy head (deyo.py:103-151).  Kept entry b of sample s is view
 // s * V + idx[s * n1 + b] (idx == nullptr: b); x' fp32 [S * n1, 3, size, size]

@@ -262,6 +262,16 @@ int encode_chunk(ttl_text_ctx* c, int n, cudaStream_t st) {
 
 }  // namespace
 
+namespace ttl {
+void launch_text_embed(const int* tokens, const float* tok_emb, const float* pos_emb, float* x, int rows, int ctx, int d, int vocab,
+                       cudaStream_t st) {
+  const size_t total = static_cast<size_t>(rows) * (d / 4);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_pdl(text_embed_kernel, dim3(blocks), dim3(256), 0, st, tokens, tok_emb, pos_emb, x, rows, ctx, d / 4, vocab);
+}
+}  // namespace ttl
+
 extern "C" {
 
 const char* ttl_text_last_error(const ttl_text_ctx* c) { return c ? c->err.c_str() : g_text_err.c_str(); }

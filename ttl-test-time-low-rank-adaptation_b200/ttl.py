@@ -264,7 +264,8 @@ def test_time_adapt_eval(val_loader, model, model_state, optimizer, optim_state,
         if isinstance(payloads[0], tuple):      # uint8 image + view specs per sample: views are generated on the device
             pend = model.adapt_and_predict_images([im.numpy() for im, _ in payloads], [sp.numpy() for _, sp in payloads],
                                                   args, sync=False)
-        elif payloads[0].is_cuda or model.deyo_general(args):      # the optional DeYO branches build x' from device-resident views
+        elif payloads[0].is_cuda or model.deyo_general(args) or model.lora_encoder == "text":
+            # the optional DeYO branches build x' from device-resident views; the text route takes image features view by view
             pend = _Ready(model.adapt_and_predict_batch(torch.stack(payloads).to(model.device, non_blocking=True), args))
         else:                                   # fp32 views from the loader: stage in pinned memory, copy asynchronously
             shape = (S,) + tuple(payloads[0].shape)
@@ -359,8 +360,9 @@ def main_worker(gpu, args):
     torch.manual_seed(args.seed)
     if args.cocoop:
         raise NotImplementedError("--cocoop is outside the TTL path")
-    if args.lora_encoder != 'image':
-        raise NotImplementedError("the B200 path implements --lora_encoder image")
+    if args.lora_encoder == 'prompt':
+        raise NotImplementedError("--lora_encoder prompt does not run in the reference either (clip/custom_clip.py:680); "
+                                  "the B200 path implements image and text")
     from clip.custom_clip import get_coop
     rank, world = args.rank_id, args.world_size
     first = args.test_sets.split("/")[0]
@@ -371,6 +373,8 @@ def main_worker(gpu, args):
     # the GPU, bit-exactly as the reference's PIL/torchvision pipeline would (csrc/views.cu).  --views_on_host, --compat and
     # --precision fp32 take the reference's route: 64 fp32 views per sample from the DataLoader workers (ttl.py:232-241).
     args.views_on_device = not (args.views_on_host or args.compat or args.precision == "fp32")
+    if args.lora_encoder == 'text':
+        args.views_on_device = False      # the image tower only supplies frozen features here: it takes the fp32 views
     if args.deyo_selection and (args.filter_ent or args.filter_plpd or args.reweight_plpd or args.reweight_ent != 1):
         args.views_on_device = False      # filter_plpd destroys the structure of the fp32 views (deyo.py:116-136): they must exist
     extra["allow_synthetic"] = args.synthetic > 0 or args.random_init
@@ -397,13 +401,16 @@ def main_worker(gpu, args):
                      classnames=_classnames_for(first, args), max_views=args.batch_size,
                      max_samples=max(1, args.concurrent_samples), **extra)
     # requires-grad filter by parameter NAME, exactly the reference's rule (ttl.py:151-163)
+    enc_name = 'text_encoder' if args.lora_encoder == 'text' else 'image_encoder'      # ttl.py:145-149
     for name, param in model.named_parameters():
-        ok = ('image_encoder' in name and ("lora_A" in name or "lora_B" in name)
+        ok = (enc_name in name and ("lora_A" in name or "lora_B" in name)
               and any(f"layers.{i}." in name for i in range(args.layer_range[0], args.layer_range[1] + 1)))
         param.requires_grad_(ok)
     # optimizer groups walked like ttl.py:189-218
     groups = []
-    for i, layer in enumerate(model.image_encoder.vision_model.encoder.layers):
+    lora_layers = (model.text_encoder.text_model.encoder.layers if args.lora_encoder == 'text'
+                   else model.image_encoder.vision_model.encoder.layers)                 # ttl.py:190-193
+    for i, layer in enumerate(lora_layers):
         if args.layer_range[0] <= i <= args.layer_range[1]:
             groups.extend([{'params': layer.self_attn.q_proj.lora_A.parameters()},
                            {'params': layer.self_attn.q_proj.lora_B.parameters()},

@@ -21,7 +21,8 @@ class TtlConfig(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("proj_dim", C.c_int32), ("max_views", C.c_int32),
                 ("max_classes", C.c_int32), ("lora_rank", C.c_int32), ("lora_alpha", C.c_float),
                 ("lora_layer_lo", C.c_int32), ("lora_layer_hi", C.c_int32), ("ln_eps", C.c_float),
-                ("device", C.c_int32), ("max_samples", C.c_int32), ("precision", C.c_int32)]
+                ("device", C.c_int32), ("max_samples", C.c_int32), ("precision", C.c_int32), ("text_mode", C.c_int32),
+                ("context", C.c_int32), ("vocab", C.c_int32)]
 
 
 class TtlHparams(C.Structure):
@@ -57,7 +58,7 @@ class TtlOutputs(C.Structure):
 
 
 # weight kinds / enums (mirror include/ttl_b200.h)
-W_CLASS_EMB, W_PATCH_EMB, W_POS_EMB, W_PRE_LN_G, W_PRE_LN_B, W_POST_LN_G, W_POST_LN_B, W_VIS_PROJ = range(8)
+W_CLASS_EMB, W_PATCH_EMB, W_POS_EMB, W_PRE_LN_G, W_PRE_LN_B, W_POST_LN_G, W_POST_LN_B, W_VIS_PROJ, W_TOKEN_EMB = range(9)
 (W_LN1_G, W_LN1_B, W_Q_W, W_Q_B, W_K_W, W_K_B, W_V_W, W_V_B, W_O_W, W_O_B, W_LN2_G, W_LN2_B, W_FC1_W, W_FC1_B,
  W_FC2_W, W_FC2_B) = range(16, 32)
 LORA_A_Q, LORA_B_Q, LORA_A_V, LORA_B_V = range(4)
@@ -88,6 +89,10 @@ _SIGS = {
     "ttl_adapt_predict": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_host": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_batch": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
+    "ttl_image_features": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
+    "ttl_text_set_prompts": (C.c_int, [vp, vp, C.c_int32, C.c_float, vp]),
+    "ttl_text_features": (C.c_int, [vp, vp, vp]),
+    "ttl_text_adapt_predict": (C.c_int, [vp, vp, C.c_int32, C.POINTER(TtlHparams), vp, C.POINTER(TtlOutputs), vp]),
     "ttl_adapt_predict_batch_deyo": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.POINTER(TtlHparams), C.POINTER(TtlDeyoOptions),
                                                C.POINTER(TtlOutputs), vp]),
     "ttl_deyo_last_plpd": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32]),

@@ -64,24 +64,41 @@ class Pending:
         return self._outs
 
 
+# text towers per --arch (the adapter sits there with --lora_encoder text); `context` tokens per prompt
+TEXT_TOWER_GEOMETRY = {
+    "ViT-B/16": dict(width=512, layers=12, heads=8, mlp_dim=2048, proj_dim=512, context=77, vocab=49408),
+    "ViT-L/14": dict(width=768, layers=12, heads=12, mlp_dim=3072, proj_dim=768, context=77, vocab=49408),
+    "tiny": dict(width=128, layers=2, heads=2, mlp_dim=512, proj_dim=64, context=16, vocab=1000),
+}
+
+
 class Engine:
     def __init__(self, arch: str = "ViT-B/16", max_views: int = 64, max_classes: int = 1000, lora_rank: int = 16,
                  lora_alpha: float = 32.0, layer_range: Sequence[int] = (9, 11), device: int = 0,
-                 geometry: Optional[dict] = None, max_samples: int = 1, precision: str = "bf16"):
+                 geometry: Optional[dict] = None, max_samples: int = 1, precision: str = "bf16", text_mode: bool = False):
+        """text_mode=True: this engine is the CLIP TEXT tower carrying the adapter (`--lora_encoder text`): `max_views` bounds
+        the class prompts, `max_classes` the image views per test sample; see set_prompts / adapt_predict_text."""
         if not torch.cuda.is_available():
             raise RuntimeError("ttl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = L.load()
-        g = dict(geometry or ARCH_GEOMETRY[arch])
+        self.text_mode = bool(text_mode)
+        if self.text_mode:
+            g = dict(geometry or TEXT_TOWER_GEOMETRY[arch])
+            g.setdefault("image_size", 0)
+            g.setdefault("patch", 0)
+        else:
+            g = dict(geometry or ARCH_GEOMETRY[arch])
         self.arch, self.geom = arch, g
         self.device = torch.device("cuda", device)
         self.max_views, self.max_classes, self.max_samples = max_views, max_classes, max(1, int(max_samples))
         self.rank, self.alpha = lora_rank, lora_alpha
         self.layer_lo, self.layer_hi = int(layer_range[0]), int(layer_range[1])
-        self.tokens = (g["image_size"] // g["patch"]) ** 2 + 1
+        self.tokens = g["context"] if self.text_mode else (g["image_size"] // g["patch"]) ** 2 + 1
         self.n_classes = 0
         cfg = L.TtlConfig(g["image_size"], g["patch"], g["width"], g["layers"], g["heads"], g["mlp_dim"], g["proj_dim"],
                           max_views, max_classes, lora_rank, lora_alpha, self.layer_lo, self.layer_hi, 1e-5, device,
-                          self.max_samples, {"bf16": L.PRECISION_BF16, "fp32": L.PRECISION_FP32}[precision])
+                          self.max_samples, {"bf16": L.PRECISION_BF16, "fp32": L.PRECISION_FP32}[precision],
+                          1 if self.text_mode else 0, g.get("context", 0), g.get("vocab", 0))
         self.precision = precision
         ctx = C.c_void_p()
         L.check(self.lib.ttl_create(C.byref(ctx), C.byref(cfg)))
@@ -127,6 +144,84 @@ class Engine:
                                (L.W_FC1_W, "mlp.fc1.weight"), (L.W_FC1_B, "mlp.fc1.bias"),
                                (L.W_FC2_W, "mlp.fc2.weight"), (L.W_FC2_B, "mlp.fc2.bias")):
                 self._set(i, kind, sd[q + name])
+
+    # ------------------------------------------------------------------ `--lora_encoder text` (adapter on the text tower)
+    def load_text_weights(self, sd: Dict[str, "torch.Tensor"]) -> None:
+        """text_mode engine: HF names (`text_model.*`, `text_projection.weight`) as CLIPModel.from_pretrained yields them."""
+        p = "text_model."
+        self._set(-1, L.W_TOKEN_EMB, sd[p + "embeddings.token_embedding.weight"])
+        self._set(-1, L.W_POS_EMB, sd[p + "embeddings.position_embedding.weight"])
+        self._set(-1, L.W_POST_LN_G, sd[p + "final_layer_norm.weight"])
+        self._set(-1, L.W_POST_LN_B, sd[p + "final_layer_norm.bias"])
+        self._set(-1, L.W_VIS_PROJ, sd["text_projection.weight"])
+        for i in range(self.geom["layers"]):
+            q = f"{p}encoder.layers.{i}."
+            for kind, name in ((L.W_LN1_G, "layer_norm1.weight"), (L.W_LN1_B, "layer_norm1.bias"),
+                               (L.W_Q_W, "self_attn.q_proj.weight"), (L.W_Q_B, "self_attn.q_proj.bias"),
+                               (L.W_K_W, "self_attn.k_proj.weight"), (L.W_K_B, "self_attn.k_proj.bias"),
+                               (L.W_V_W, "self_attn.v_proj.weight"), (L.W_V_B, "self_attn.v_proj.bias"),
+                               (L.W_O_W, "self_attn.out_proj.weight"), (L.W_O_B, "self_attn.out_proj.bias"),
+                               (L.W_LN2_G, "layer_norm2.weight"), (L.W_LN2_B, "layer_norm2.bias"),
+                               (L.W_FC1_W, "mlp.fc1.weight"), (L.W_FC1_B, "mlp.fc1.bias"),
+                               (L.W_FC2_W, "mlp.fc2.weight"), (L.W_FC2_B, "mlp.fc2.bias")):
+                self._set(i, kind, sd[q + name])
+
+    def set_prompts(self, tokens, logit_scale: float) -> None:
+        """text_mode engine: tokenised class prompts int [C, context] (clip.tokenize layout); runs the layers below the adapter
+        once (reset_classnames, clip/custom_clip.py:343-372)."""
+        t = np.ascontiguousarray(tokens.cpu().numpy() if isinstance(tokens, torch.Tensor) else tokens, dtype=np.int32)
+        if t.ndim != 2 or t.shape[1] != self.tokens:
+            raise ValueError(f"tokens must be [n, {self.tokens}]")
+        self.n_classes = int(t.shape[0])
+        self._sync_in()
+        L.check(self.lib.ttl_text_set_prompts(self.ctx, t.ctypes.data_as(C.c_void_p), t.shape[0], float(logit_scale), self._st()),
+                self.ctx)
+        self._sync_out()
+
+    def text_features(self) -> torch.Tensor:
+        """text_mode engine: L2-normalised class features [C, P] with the current factors (host tensor)."""
+        out = np.empty((self.n_classes, self.geom["proj_dim"]), dtype=np.float32)
+        L.check(self.lib.ttl_text_features(self.ctx, out.ctypes.data_as(C.c_void_p), self._st()), self.ctx)
+        return torch.from_numpy(out)
+
+    def image_features(self, images: torch.Tensor) -> torch.Tensor:
+        """Image-tower engine: raw image features [n_views, P] of `images` [n_views,3,S,S] on the device (no adapter, no logits)."""
+        images = images.to(self.device, torch.float32).contiguous()
+        feats = torch.empty(images.shape[0], self.geom["proj_dim"], device=self.device, dtype=torch.float32)
+        self._sync_in()
+        L.check(self.lib.ttl_image_features(self.ctx, images.data_ptr(), images.shape[0], feats.data_ptr(), self._st()), self.ctx)
+        self._sync_out()
+        images.record_stream(self.stream)
+        return feats
+
+    def adapt_predict_text(self, img_feats: torch.Tensor, hp: Hparams, forced_idx: Optional[torch.Tensor] = None,
+                           want: Sequence[str] = ("pred_logits",)) -> Dict[str, torch.Tensor]:
+        """text_mode engine: one test sample with the adapter on the text tower (ttl.py:338-352 with lora_encoder == 'text'):
+        `img_feats` [V, P] = image_features() of the sample's views."""
+        img_feats = img_feats.to(self.device, torch.float32).contiguous()
+        V, n = int(img_feats.shape[0]), self.n_classes
+        K = int(V * hp.selection_p)
+        outs: Dict[str, torch.Tensor] = {}
+        o = L.TtlOutputs()
+        shapes = {"logits0": ((V, n), torch.float32), "entropy": ((V,), torch.float32), "idx": ((max(K, 1),), torch.int32),
+                  "loss": ((1,), torch.float32), "pred_logits": ((n,), torch.float32)}
+        for name in want:
+            shp, dt = shapes[name]
+            t = torch.empty(shp, dtype=dt, device=self.device)
+            outs[name] = t
+            setattr(o, name, t.data_ptr())
+        fidx = None if forced_idx is None else forced_idx.to(self.device, torch.int32).contiguous()
+        h = hp.to_c()
+        self._sync_in()
+        L.check(self.lib.ttl_text_adapt_predict(self.ctx, img_feats.data_ptr(), V, C.byref(h),
+                                                fidx.data_ptr() if fidx is not None else None, C.byref(o), self._st()), self.ctx)
+        self._sync_out()
+        img_feats.record_stream(self.stream)
+        if "idx" in outs:
+            outs["idx"] = outs["idx"][:K]
+        if "loss" in outs:
+            outs["loss"] = outs["loss"][0]
+        return outs
 
     def set_text_features(self, text, logit_scale: float) -> None:
         t = _f32(text)

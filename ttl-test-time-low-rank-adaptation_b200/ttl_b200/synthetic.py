@@ -67,3 +67,55 @@ def synthetic_text_features(n_classes: int, proj: int, seed: int = 11) -> torch.
     g = torch.Generator().manual_seed(seed)
     t = _randn(g, n_classes, proj)
     return t / t.norm(dim=-1, keepdim=True)
+
+
+def synthetic_text_weights(arch: str = "ViT-B/16", seed: int = 4321, affine_noise: float = 0.05) -> Dict[str, torch.Tensor]:
+    """Seeded random-init CLIP text tower with HF `_init_weights` standard deviations (HF names); for `--lora_encoder text`
+    runs without a checkpoint (--synthetic / --random_init)."""
+    from .engine import TEXT_TOWER_GEOMETRY
+    geo = TEXT_TOWER_GEOMETRY[arch]
+    d, L, F, P, ctx, vocab = geo["width"], geo["layers"], geo["mlp_dim"], geo["proj_dim"], geo["context"], geo["vocab"]
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, torch.Tensor] = {}
+    pre = "text_model."
+    w[pre + "embeddings.token_embedding.weight"] = _randn(g, vocab, d, std=0.02)
+    w[pre + "embeddings.position_embedding.weight"] = _randn(g, ctx, d, std=0.02)
+
+    def ln(name):
+        w[name + ".weight"] = 1.0 + _randn(g, d, std=affine_noise)
+        w[name + ".bias"] = _randn(g, d, std=affine_noise)
+
+    in_std, out_std, fc_std = d ** -0.5 * (2 * L) ** -0.5, d ** -0.5, (2 * d) ** -0.5
+    for i in range(L):
+        q = f"{pre}encoder.layers.{i}."
+        ln(q + "layer_norm1")
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            w[q + f"self_attn.{nm}.weight"] = _randn(g, d, d, std=in_std)
+            w[q + f"self_attn.{nm}.bias"] = _randn(g, d, std=affine_noise * 0.2)
+        w[q + "self_attn.out_proj.weight"] = _randn(g, d, d, std=out_std)
+        w[q + "self_attn.out_proj.bias"] = _randn(g, d, std=affine_noise * 0.2)
+        ln(q + "layer_norm2")
+        w[q + "mlp.fc1.weight"] = _randn(g, F, d, std=fc_std)
+        w[q + "mlp.fc1.bias"] = _randn(g, F, std=affine_noise * 0.2)
+        w[q + "mlp.fc2.weight"] = _randn(g, d, F, std=in_std)
+        w[q + "mlp.fc2.bias"] = _randn(g, d, std=affine_noise * 0.2)
+    ln(pre + "final_layer_norm")
+    w["text_projection.weight"] = _randn(g, P, d, std=d ** -0.5)
+    return w
+
+
+class HashTokenizer:
+    """Stand-in for the CLIP BPE table in random-init runs (the merge table is data of the reference, not shipped): stable ids
+    from the words of a prompt, clip.tokenize layout (SOT, ids, EOT = highest id, zero padding)."""
+
+    def __init__(self, vocab: int = 49408, context: int = 77):
+        self.vocab, self.context = vocab, context
+
+    def __call__(self, prompts):
+        import zlib
+        out = torch.zeros(len(prompts), self.context, dtype=torch.long)
+        for i, p in enumerate(prompts):
+            ids = [1 + zlib.crc32(wd.encode()) % (self.vocab - 3) for wd in p.replace(".", " .").split()][: self.context - 2]
+            row = [self.vocab - 2] + ids + [self.vocab - 1]
+            out[i, :len(row)] = torch.tensor(row)
+        return out
