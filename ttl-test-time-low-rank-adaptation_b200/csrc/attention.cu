@@ -1087,7 +1087,9 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issue
-    if (lane == 0) {
+    // elect.sync rather than `lane == 0`: ptxas then emits the tcgen05.mma of a block back to back instead of one
+    // ELECT / BRA.U.ANY retry loop per instruction (see attention_bwd_tc_kernel)
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, static_cast<uint32_t>(keys));
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
       const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);

@@ -3,7 +3,11 @@
 // and the fused AdamW step / adapter+optimiser reset (torch.optim.AdamW at ttl.py:218; LoRA_AB.reset at
 // clip/custom_clip.py:202-215 + optimizer.load_state_dict at ttl.py:344).
 #include "kernels.cuh"
+#include "gemm.cuh"
 #include "ptx.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
 
 namespace ttl {
 
@@ -141,6 +145,98 @@ skinny_partial_mma_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __
   }
 }
 
+// The weight-gradient reduction on the 5th-gen tensor cores: partial[seg, w, j] = sum_{m in segment} wide[m, w] * narrow[m, j] for a
+// 128-column block of `wide` (dY or X) and the 16 columns of `narrow` (X A^T or dY B), i.e. D[128 x 16] += W^T[128 x rows] N[rows x 16]
+// with the reduction dimension = rows.  Both operands are consumed as they sit in memory: row-major [rows][cols] is the MN-major
+// form of the transposed operand (TMA tiles of 128 rows, 128B swizzle for the 2 x 64-column atoms of `wide`, 32B swizzle for the
+// 16 columns of `narrow`); one tcgen05.mma 128 x 16 x 16 per 16 rows, fp32 accumulator in TMEM (32 columns).  A CTA streams one
+// segment of rows through a 4-stage TMA ring; the mma.sync version staged every tile through registers and ran at 39 % of the DRAM peak.
+constexpr int ST_STAGES = 4, ST_ROWS = 128;
+constexpr int ST_STAGE_BYTES = 2 * ST_ROWS * 128 + ST_ROWS * 32;      // wide: two [128][64] bf16 atoms; narrow: [128][16] bf16
+
+__global__ void __launch_bounds__(128)
+skinny_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN, int M, int nw, int seg_rows,
+                 float* __restrict__ ws) {
+  extern __shared__ uint8_t smem_st_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_st_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_STAGES * ST_STAGE_BYTES);
+  uint64_t* full = bars;                    // [ST_STAGES] tile landed
+  uint64_t* empty = bars + ST_STAGES;       // [ST_STAGES] the MMAs that read the tile have completed
+  uint64_t* done = bars + 2 * ST_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = blockIdx.x * 128, seg = blockIdx.y, grp = blockIdx.z;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmN);
+    for (int i = 0; i < ST_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 32);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_trigger();
+  const int row0 = seg * seg_rows;
+  const int rows = M - row0 < seg_rows ? M - row0 : seg_rows;            // rows of this segment (> 0 by construction of the grid)
+  const int nck = (rows + ST_ROWS - 1) / ST_ROWS;
+  if (warp == 0 && elect_one()) {
+    const uint32_t idesc = umma_idesc_bf16(128, 16, 1) | (1u << 15);      // A and B MN-major
+    auto load = [&](int i) {
+      const int st = i % ST_STAGES;
+      uint8_t* a = smem + st * ST_STAGE_BYTES;
+      mbar_expect_tx(&full[st], ST_STAGE_BYTES);
+      tma_load_3d(&tmW, &full[st], a, w0, row0 + i * ST_ROWS, grp);                        // rows beyond the group's M are zero-filled
+      tma_load_3d(&tmW, &full[st], a + ST_ROWS * 128, w0 + 64, row0 + i * ST_ROWS, grp);
+      tma_load_3d(&tmN, &full[st], a + 2 * ST_ROWS * 128, 0, row0 + i * ST_ROWS, grp);
+    };
+    for (int i = 0; i < nck && i < ST_STAGES; ++i) load(i);
+    for (int i = 0; i < nck; ++i) {
+      const int st = i % ST_STAGES;
+      const uint32_t ph = (i / ST_STAGES) & 1;
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint32_t a = smem_u32(smem + st * ST_STAGE_BYTES), b = a + 2 * ST_ROWS * 128;
+      // seg_rows is a multiple of the 128-row tile, so a tile never straddles two segments; rows beyond the group's M are zero
+#pragma unroll
+      for (int ks = 0; ks < ST_ROWS / 16; ++ks)
+        umma_bf16(tmem, umma_desc(a + ks * 2048, 1024, ST_ROWS * 128, 2), umma_desc(b + ks * 512, 256, 0, 6), idesc, (i | ks) != 0 ? 1u : 0u);
+      umma_commit(&empty[st]);
+      if (i + ST_STAGES < nck) {
+        mbar_wait(&empty[st], ph);
+        load(i + ST_STAGES);
+      }
+    }
+    umma_commit(done);
+  }
+  __syncwarp();
+  mbar_wait(done, 0);
+  tc_fence_after();
+  {
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16), r);
+    tmem_ld_wait();
+    float* o = ws + ((static_cast<size_t>(grp) * gridDim.y + seg) * nw + w0 + warp * 32 + lane) * 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(o)[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                                    __uint_as_float(r[4 * q + 3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 32);
+  }
+}
+
 __global__ void skinny_final_kernel(const float* __restrict__ ws, int chunks, int nw, int nn, float scale,
                                     float* __restrict__ out, int transpose_out, int64_t out_gstride) {
   pdl_wait();
@@ -203,9 +299,55 @@ void launch_lora_pack_layers(const float* params, int64_t layer_stride, int64_t 
   }
 }
 
+// tcgen05 / TMA route of launch_skinny_reduce (narrow width 16, nw a multiple of 128); false = not applicable, use the mma.sync kernels
+static bool launch_skinny_tc(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int M, float scale, float* out,
+                             int transpose_out, float* ws, int groups, int narrow_gstride, int64_t out_gstride, cudaStream_t st) {
+  if (nw % 128 != 0 || M < 4 * ST_ROWS || (reinterpret_cast<uintptr_t>(wide) & 15) || (reinterpret_cast<uintptr_t>(narrow) & 15) ||
+      (ldw % 8) || (ldn % 8) || (narrow_gstride % 8))
+    return false;
+  const int dv = current_device_slot();
+  static int num_sms_dev[MAX_DEVICES] = {};
+  static bool configured_dev[MAX_DEVICES] = {};
+  if (num_sms_dev[dv] == 0) cudaDeviceGetAttribute(&num_sms_dev[dv], cudaDevAttrMultiProcessorCount, dv);
+  const size_t smem = ST_STAGES * ST_STAGE_BYTES + 256 + 1024;
+  if (!configured_dev[dv]) {
+    if (cudaFuncSetAttribute(skinny_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured_dev[dv] = true;
+  }
+  // segments of rows per (column block, group): about two CTAs per SM in flight, at least 4 chunks of 128 rows each; the workspace
+  // the callers provide holds (ceil(M / 128) + groups) x nw x 32 floats per group set, far more than nseg x nw x 16 per group
+  const int col_blocks = nw / 128, nck_total = (M + ST_ROWS - 1) / ST_ROWS;
+  int nseg = (2 * num_sms_dev[dv] + col_blocks * groups - 1) / (col_blocks * groups);
+  if (nseg > nck_total / 4) nseg = nck_total / 4;
+  if (nseg < 1) nseg = 1;
+  const int seg_rows = (nck_total + nseg - 1) / nseg * ST_ROWS;
+  nseg = (M + seg_rows - 1) / seg_rows;
+  CUtensorMap tw, tn;
+  const uint64_t wd[3] = {static_cast<uint64_t>(nw), static_cast<uint64_t>(M), static_cast<uint64_t>(groups)};
+  const uint64_t wstr[2] = {static_cast<uint64_t>(ldw) * 2, static_cast<uint64_t>(M) * ldw * 2};
+  const uint32_t wbox[3] = {64, ST_ROWS, 1};
+  if (!encode_tiled_map(&tw, 0, wide, 3, wd, wstr, wbox, 128)) return false;
+  const uint64_t nd[3] = {16, static_cast<uint64_t>(M), static_cast<uint64_t>(groups)};
+  const uint64_t nstr[2] = {static_cast<uint64_t>(ldn) * 2, (static_cast<uint64_t>(M) * ldn + narrow_gstride) * 2};
+  const uint32_t nbox[3] = {16, ST_ROWS, 1};
+  if (!encode_tiled_map(&tn, 0, narrow, 3, nd, nstr, nbox, 32)) return false;
+  launch_pdl(skinny_tc_kernel, dim3(col_blocks, nseg, groups), dim3(128), smem, st, tw, tn, M, nw, seg_rows, ws);
+  launch_pdl(skinny_final_kernel, dim3(dim3((nw * 16 + 255) / 256, groups)), dim3(256), 0, st, static_cast<const float*>(ws), nseg, nw, 16, scale,
+             out, transpose_out, out_gstride);
+  return true;
+}
+
 void launch_skinny_reduce(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int nn, int M, float scale,
                           float* out, int transpose_out, float* ws, int groups, int narrow_gstride, int64_t out_gstride,
                           cudaStream_t st) {
+  // TTL_SKINNY: unset / "tc" = tcgen05 + TMA kernel where applicable, "mma" = mma.sync kernel, "scalar" = CUDA-core kernel
+  static const char* sk_mode = std::getenv("TTL_SKINNY");
+  if (nn == 16 && (sk_mode == nullptr || sk_mode[0] == 't') &&
+      launch_skinny_tc(wide, ldw, nw, narrow, ldn, M, scale, out, transpose_out, ws, groups, narrow_gstride, out_gstride, st))
+    return;
   const int chunks = (M + SR_MC - 1) / SR_MC;
   dim3 grid(nw / 64, chunks, groups);
   static const char* sk_env = std::getenv("TTL_SKINNY");      // "scalar": the CUDA-core kernel (A/B reference)
