@@ -35,7 +35,30 @@ for prec, S in (("bf16", 2), ("fp32", 1)):
         torch.manual_seed(0)
         specs = [ViewSpecSampler(V - 1)(im)[1] for im in imgs]
         print("images", eng.adapt_predict_images(imgs, specs, Hparams(selection_p=0.25))["pred_logits"].abs().mean().item())
+        # optional DeYO branches (deyo.cu): filter_ent + PLPD with the three structure-destroying transforms
+        x = torch.randn(S, V, 3, 224, 224, device="cuda")
+        for aug in ("occ", "patch", "pixel"):
+            o = eng.adapt_predict_batch_deyo(x, Hparams(head="deyo", selection_p=0.25), filter_ent=1, filter_plpd=1, plpd_threshold=-1.0,
+                                             aug_type=aug)
+            print("deyo", aug, o["pred_logits"].abs().mean().item(), eng.deyo_last_plpd()[1])
     eng.close()
+# adapter on the text tower (text-mode context: causal attention fwd/bwd, EOT pooling, exact-Delta kernel, swapped head)
+from ttl_b200.synthetic import synthetic_text_weights, HashTokenizer  # noqa: E402
+ev = Engine("ViT-B/16", max_views=V, max_classes=16)
+ev.load_weights(w)
+ev.set_lora_init(lora)
+et = Engine("ViT-B/16", max_views=16, max_classes=V, text_mode=True)
+et.load_text_weights(synthetic_text_weights("ViT-B/16"))
+g = torch.Generator().manual_seed(0)
+et.set_lora_init({i: [torch.randn(16, 512, generator=g) * 0.05, torch.zeros(512, 16), torch.randn(16, 512, generator=g) * 0.05,
+                      torch.zeros(512, 16)] for i in (9, 10, 11)})
+et.set_prompts(HashTokenizer()([f"a photo of a thing {i}." for i in range(12)]), math.log(100.0))
+feats = ev.image_features(torch.randn(V, 3, 224, 224, device="cuda"))
+for head in ("tpt", "deyo"):
+    o = et.adapt_predict_text(feats, Hparams(head=head, selection_p=0.25, tta_steps=2 if head == "tpt" else 1), want=("pred_logits", "loss"))
+    print("text-tower adapter", head, o["pred_logits"].abs().mean().item(), float(o["loss"]))
+ev.close()
+et.close()
 from ttl_b200.text import TextEncoder  # noqa: E402
 sys.path.insert(0, ROOT)
 from oracle import text_oracle as TO  # noqa: E402

@@ -1597,7 +1597,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* bar_sdp = bars + 2;     // S and dP of a sub-step complete in TMEM
   uint64_t* bar_pds = bars + 3;     // P and dS tiles of a sub-step written, its S / dP drained (8 softmax warps)
   uint64_t* bar_s2 = bars + 4;      // dQ / dV / dK MMAs of a sub-step complete: the P / dS tiles may be overwritten
-  uint64_t* bar_kv = bars + 5;      // every MMA up to and including the t = 1 sub-step of a key half has completed
+  uint64_t* bar_kv = bars + 5;      // every MMA of the unit has completed (one phase per unit)
   uint64_t* bar_drn = bars + 6;     // S / dP of a sub-step have been read out of TMEM (8 softmax warps): the next S / dP may be issued
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
@@ -1740,11 +1740,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
           }
           umma_commit(bar_s2);
-          if (t == 1) umma_commit(bar_kv);
+          if (sub == 3) umma_commit(bar_kv);
           BT_STAMP(3 + 2 * sub);
         }
+        mbar_wait(bar_kv, n_load & 1);      // every MMA of the unit has completed: the smem operands may be reloaded
         ++n_load;
-        mbar_wait(bar_kv, 1);       // second commit of the unit: every MMA has completed, the smem operands may be reloaded
         BT_STAMP(10);
       }
     }
@@ -1889,7 +1889,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (st) BT_STAMP(37 + 4 * sub);
       }
       // end of the unit: dV_1 / dK_1 (TMEM lane = key 128 + row) and dQ_0 / dQ_1 (TMEM lane = query of tile `half`)
-      mbar_wait(bar_kv, 1);
+      mbar_wait(bar_kv, (n_unit - 1) & 1);
       if (st) BT_STAMP(50);
       tc_fence_after();
       {   // dV_1 / dK_1 -> this warpgroup's staging tile, dQ_half -> its (dead) 64-key block of the dS tile; one hand-over for both

@@ -150,8 +150,8 @@ skinny_partial_mma_kernel(const bf16* __restrict__ wide, int ldw, const bf16* __
 // with the reduction dimension = rows.  Both operands are consumed as they sit in memory: row-major [rows][cols] is the MN-major
 // form of the transposed operand (TMA tiles of 128 rows, 128B swizzle for the 2 x 64-column atoms of `wide`, 32B swizzle for the
 // 16 columns of `narrow`); one tcgen05.mma 128 x 16 x 16 per 16 rows, fp32 accumulator in TMEM (32 columns).  A CTA streams one
-// segment of rows through a 4-stage TMA ring; the mma.sync version staged every tile through registers and ran at 39 % of the DRAM peak.
-constexpr int ST_STAGES = 4, ST_ROWS = 128;
+// segment of rows through a 3-stage TMA ring (two CTAs per SM); the mma.sync version staged every tile through registers and ran at 39 % of the DRAM peak.
+constexpr int ST_STAGES = 3, ST_ROWS = 128;      // 3 x 36 KB: two CTAs per SM
 constexpr int ST_STAGE_BYTES = 2 * ST_ROWS * 128 + ST_ROWS * 32;      // wide: two [128][64] bf16 atoms; narrow: [128][16] bf16
 
 __global__ void __launch_bounds__(128)
@@ -302,7 +302,7 @@ void launch_lora_pack_layers(const float* params, int64_t layer_stride, int64_t 
 // tcgen05 / TMA route of launch_skinny_reduce (narrow width 16, nw a multiple of 128); false = not applicable, use the mma.sync kernels
 static bool launch_skinny_tc(const bf16* wide, int ldw, int nw, const bf16* narrow, int ldn, int M, float scale, float* out,
                              int transpose_out, float* ws, int groups, int narrow_gstride, int64_t out_gstride, cudaStream_t st) {
-  if (nw % 128 != 0 || M < 4 * ST_ROWS || (reinterpret_cast<uintptr_t>(wide) & 15) || (reinterpret_cast<uintptr_t>(narrow) & 15) ||
+  if (nw % 128 != 0 || M < 2 * ST_ROWS || (reinterpret_cast<uintptr_t>(wide) & 15) || (reinterpret_cast<uintptr_t>(narrow) & 15) ||
       (ldw % 8) || (ldn % 8) || (narrow_gstride % 8))
     return false;
   const int dv = current_device_slot();
@@ -317,11 +317,12 @@ static bool launch_skinny_tc(const bf16* wide, int ldw, int nw, const bf16* narr
     }
     configured_dev[dv] = true;
   }
-  // segments of rows per (column block, group): about two CTAs per SM in flight, at least 4 chunks of 128 rows each; the workspace
-  // the callers provide holds (ceil(M / 128) + groups) x nw x 32 floats per group set, far more than nseg x nw x 16 per group
+  // segments of rows per (column block, group): ONE wave of at most two CTAs per SM (a second, partial wave cost 25 % at
+  // M = 113 472), at least two 128-row tiles per CTA; the workspace the callers provide holds (ceil(M / 128) + groups) x nw x 32
+  // floats per group set, far more than nseg x nw x 16 per group
   const int col_blocks = nw / 128, nck_total = (M + ST_ROWS - 1) / ST_ROWS;
-  int nseg = (2 * num_sms_dev[dv] + col_blocks * groups - 1) / (col_blocks * groups);
-  if (nseg > nck_total / 4) nseg = nck_total / 4;
+  int nseg = 2 * num_sms_dev[dv] / (col_blocks * groups);
+  if (nseg > nck_total / 2) nseg = nck_total / 2;
   if (nseg < 1) nseg = 1;
   const int seg_rows = (nck_total + nseg - 1) / nseg * ST_ROWS;
   nseg = (M + seg_rows - 1) / seg_rows;
