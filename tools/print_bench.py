@@ -4,7 +4,7 @@ import sys
 
 for path in sys.argv[1:]:
     try:
-        d = json.load(open(path))
+        d = json.loads([l for l in open(path).read().splitlines() if l.startswith('{')][-1])
     except Exception as e:
         print(path, "unreadable:", e)
         continue
