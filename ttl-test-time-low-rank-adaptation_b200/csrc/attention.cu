@@ -1452,6 +1452,313 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// =============================================================================================== tcgen05 forward, P kept in TMEM
+// attention_fwd_pp_kernel with (1) the probabilities handed to the tensor core through TMEM instead of shared memory (the TS form
+// of tcgen05.mma: A operand = 128 lanes x 8 columns of packed bf16 pairs per 16-key step) and (2) the two query tiles of a unit
+// DECOUPLED: each tile t is a stream of its own -- softmax warpgroup, MMA-issuing thread, Q double buffer, half of TMEM -- and the
+// streams only share the (double-buffered) K and V of a unit.  Stream 1 starts half a unit late, so one stream's MUFU-bound pass 2
+// runs while the other is in its pass 1 / O wait / epilogue instead of both fighting for the MUFU and then both leaving it idle.
+// Per tile t, TMEM columns [256 t, 256 t + 256):
+//   S_t  [0, keys)      fp32 scores, written by the S MMAs
+//   P_t  [0, keys / 2)  bf16 pairs, written IN PLACE by the softmax threads: pass 2 walks S in 32-column chunks and stores the 16
+//                       columns of packed P of chunk c at [poff + 16 c, poff + 16 c + 16), which only covers S columns the thread has
+//                       already loaded (23 + 16 c <= 32 c + 31)
+//   O_t  [192, 256)     fp32 accumulator of P V.  With keys = 208 it overlaps the 16-column tail of S, so pass 2 reads that tail
+//                       FIRST (its P pairs wait in 8 registers until chunk 0 has been loaded and go to columns [0, 8), poff = 8);
+//                       the first P V MMA is issued after all four warps of the tile delivered block 0, i.e. after every lane has
+//                       read its tail.
+// No swizzled shared-memory P stores, no proxy fences; the shared memory that P occupied holds the second K and Q buffers
+// (200 KB at 208 keys).  Exact two-pass softmax in fp32, 1 of 8 exponentials on the FMA pipe, as before; 129..208 tokens.
+//   warp 0 (one thread)   TMA producer: K + Q0 + Q1 of unit u into buffer u & 1 once both streams' S MMAs of unit u - 2 retired;
+//                         V likewise behind both streams' last P V MMA
+//   warp 1 / warp 10      MMA issue of stream 0 / 1 (one elected thread each; tcgen05.commit tracks the issuing thread's MMAs)
+//   warps 2-5 / 6-9       softmax + epilogue warpgroup of stream 0 / 1
+constexpr int PT_THREADS = 352;
+template <int MASK>     // which of every 8 exponentials run on the FMA pipe
+__global__ void __launch_bounds__(PT_THREADS, 1)
+attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
+                        int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev, int stagger) {
+  extern __shared__ uint8_t smem_pt_raw[];
+#define PT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && wg_tid == 0) dbg[(it * 2 + t) * 8 + (k)] = clock64(); } while (0)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_pt_raw) + 1023) & ~uintptr_t(1023));
+  const int KB = keys * 128;                       // bytes of K (or V): multiple of 1024 (keys % 16 == 0, keys >= 128)
+  uint8_t* sQ = smem;                              // [2 buffers][2 tiles] 16 KB each
+  uint8_t* sK = sQ + 4 * 16384;                    // [2 buffers]
+  uint8_t* sV = sK + 2 * KB;                       // [2 buffers]
+  uint8_t* sO = sV + 2 * KB;                       // [2 tiles] output stage, 16 KB each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * 16384);
+  uint64_t* bar_kq = bars;            // [2] K + Q0 + Q1 of a unit landed in buffer b
+  uint64_t* bar_kqfree = bars + 2;    // [2] both streams' S MMAs on buffer b retired (2 commits)
+  uint64_t* bar_v = bars + 4;         // [2] V buffer landed
+  uint64_t* bar_vfree = bars + 6;     // [2] both streams' P V MMAs on the V buffer retired (2 commits)
+  uint64_t* bar_s = bars + 8;         // [2] S_t complete in TMEM
+  uint64_t* bar_o = bars + 10;        // [2] O_t complete in TMEM (P_t dead)
+  uint64_t* bar_tfree = bars + 12;    // [2] O_t copied to registers: TMEM region t reusable
+  uint64_t* bar_p = bars + 14;        // [2][4] P block b (two 32-key chunks) of tile t stored in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * DH;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kq[i], 1);
+      mbar_init(&bar_kqfree[i], 2);
+      mbar_init(&bar_v[i], 1);
+      mbar_init(&bar_vfree[i], 2);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_tfree[i], 4);
+      for (int b = 0; b < 4; ++b) mbar_init(&bar_p[i * 4 + b], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_trigger();
+  const int n32 = keys / 32, rem16 = keys - n32 * 32;      // 32-key chunks + an optional 16-key tail
+  const int nblk = (n32 + 1) >> 1;                         // P blocks = pairs of chunks (the tail rides with block 0)
+  const uint32_t poff = rem16 ? 8u : 0u;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int u2 = rev ? units - 1 - unit : unit;            // descending walk (kernels.cuh)
+        const int view = u2 / heads, h = u2 - view * heads;
+        const int b = it & 1, use = it >> 1;
+        if (use >= 1) mbar_wait(&bar_kqfree[b], (use - 1) & 1);  // both S MMAs of unit it - 2 retired
+        mbar_expect_tx(&bar_kq[b], KB + 2 * 16384);
+        tma_load_3d(&tmKV, &bar_kq[b], sK + b * KB, d + h * DH, 0, view);
+        tma_load_3d(&tmQ, &bar_kq[b], sQ + b * 32768, h * DH, 0, view);
+        tma_load_3d(&tmQ, &bar_kq[b], sQ + b * 32768 + 16384, h * DH, 128, view);
+        if (use >= 1) mbar_wait(&bar_vfree[b], (use - 1) & 1);
+        mbar_expect_tx(&bar_v[b], KB);
+        tma_load_3d(&tmKV, &bar_v[b], sV + b * KB, 2 * d + h * DH, 0, view);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issue of stream t (one elected thread, counted loops:
+    // see attention_bwd_tc_kernel for the two ptxas pitfalls this avoids)
+    const int t = warp == 1 ? 0 : 1;
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, static_cast<uint32_t>(keys));
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+      const uint32_t v_lbo = static_cast<uint32_t>(KB);
+      const uint32_t tt = tmem + t * 256;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int b = it & 1, use = it >> 1;
+        const uint32_t qa = smem_u32(sQ + b * 32768 + t * 16384), ka = smem_u32(sK + b * KB);
+        mbar_wait(&bar_kq[b], use & 1);
+        if (it > 0) mbar_wait(&bar_tfree[t], ph ^ 1);             // the previous unit's O_t has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tt, umma_desc_k_sw128(qa + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s[t]);
+        umma_commit(&bar_kqfree[b]);
+        mbar_wait(&bar_v[b], use & 1);
+        const uint64_t vdesc = umma_desc(smem_u32(sV + b * KB), 1024, v_lbo, 2);     // + 128 per 16-key step (2048 B >> 4)
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk) {
+          const int ks0 = 4 * blk, ks1 = 4 * blk + 4 < 2 * n32 ? 4 * blk + 4 : 2 * n32;      // 16-key steps of this block
+          mbar_wait(&bar_p[t * 4 + blk], ph);
+          tc_fence_after();
+          if (blk == 0 && rem16) umma_bf16_ts(tt + 192, tt, vdesc + static_cast<uint64_t>(2 * n32) * 128, idesc_o, 0u);
+#pragma unroll 1
+          for (int ks = ks0; ks < ks1; ++ks)
+            umma_bf16_ts(tt + 192, tt + poff + 8 * ks, vdesc + static_cast<uint64_t>(ks) * 128, idesc_o,
+                         (ks != 0 || rem16) ? 1u : 0u);
+        }
+        umma_commit(&bar_o[t]);
+        umma_commit(&bar_vfree[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warpgroup of stream t
+    const int t = (warp - 2) >> 2;
+    const int quad = warp & 3, row = quad * 32 + lane;
+    const int wg_tid = threadIdx.x - 64 - t * 128;           // 0..127 inside the warpgroup
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + t * 256;
+    uint8_t* ostage = sO + t * 16384;
+    const int r0 = t * 128;
+    const bool active = r0 + quad * 32 < tokens;            // warp-uniform: at least one real query row
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int u2 = rev ? units - 1 - unit : unit;
+      const int view = u2 / heads, h = u2 - view * heads;
+      PT_STAMP(0);
+      mbar_wait(&bar_s[t], ph);
+      PT_STAMP(1);
+      tc_fence_after();
+      float m = -INFINITY, l = 0.f;
+      if (active) {
+        // pass 1: exact row maximum.  Columns >= tokens hold exact zeros (zero-filled K rows): harmless for softmax.
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(trow, ra);
+        for (int c = 0; c < n32; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n32) tmem_ld_32x32b_x32(trow + (c + 1) * 32, rb);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          if (c + 1 < n32) {
+            tmem_ld_wait();
+            if (c + 2 < n32) tmem_ld_32x32b_x32(trow + (c + 2) * 32, ra);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+          }
+        }
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        }
+      }
+      PT_STAMP(2);
+      if (wg_tid == 0) bulk_wait_read<0>();      // the previous unit's output store has finished reading the stage
+      named_bar_sync(1 + t, 128);
+      // the two streams take turns in pass 2: stream 1 runs its pass 2 of unit u after stream 0's, stream 0 its pass 2 of unit
+      // u + 1 after stream 1's of unit u (the last P block's barrier of the other tile is the token).  Left alone the streams
+      // fall into lockstep (measured: both in pass 2 together at 4.6 k cycles, the MUFU idle for the other 2.9 k of the unit).
+      if (stagger) {
+        if (t == 1) mbar_wait(&bar_p[nblk - 1], ph);
+        else if (it > 0) mbar_wait(&bar_p[4 + nblk - 1], ph ^ 1);
+      }
+      PT_STAMP(3);
+      if (active) {
+        // pass 2: p = 2^(s*scale - m*scale), row sum, packed bf16 P back into TMEM (layout above)
+        const float ms = m * scale_log2;
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t ptail[8];
+        if (rem16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(trow + n32 * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -ms));
+            float v1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -ms));
+            if (n32 * 32 + 2 * i >= tokens) v0 = 0.f;
+            if (n32 * 32 + 2 * i + 1 >= tokens) v1 = 0.f;
+            l0 += v0 + v1;
+            ptail[i] = pack_bf16(v0, v1);
+          }
+        }
+        for (int c = 0; c < n32; ++c) {
+          uint32_t r[32], pk[16];
+          tmem_ld_32x32b_x32(trow + c * 32, r);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= tokens) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x = fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms);
+                e[i] = ((MASK >> i) & 1) ? ex2_poly(x) : ex2_approx(x);
+              }
+              l0 += (e[0] + e[1]) + (e[2] + e[3]);
+              l1 += (e[4] + e[5]) + (e[6] + e[7]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pk[q4 * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
+                if (c * 32 + q4 * 8 + i >= tokens) v = 0.f;
+                e[i] = v;
+                l0 += v;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pk[q4 * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+            }
+          }
+          if (c == 0 && rem16) tmem_st_32x32b_x8(trow, ptail);
+          tmem_st_32x32b_x16(trow + poff + 16 * c, pk);
+          if ((c & 1) || c == n32 - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[t * 4 + (c >> 1)]);
+          }
+        }
+        l = l0 + l1;
+      } else {
+        tc_fence_before();
+        if (lane == 0)
+          for (int b = 0; b < nblk; ++b) mbar_arrive(&bar_p[t * 4 + b]);
+      }
+      PT_STAMP(4);
+      mbar_wait(&bar_o[t], ph);
+      PT_STAMP(5);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      if (active) {
+        tmem_ld_32x32b_x32(trow + 192, o0);
+        tmem_ld_32x32b_x32(trow + 224, o1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tfree[t]);
+      if (active) {
+        const float inv = 1.f / l;
+        const uint32_t obase = smem_u32(ostage) + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const uint32_t* r = q4 < 4 ? o0 + q4 * 8 : o1 + (q4 - 4) * 8;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (row & 7)) << 4)),
+                       "r"(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv)),
+                       "r"(pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv))
+                       : "memory");
+        }
+        if (lse != nullptr && r0 + row < tokens)
+          lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + row] = (m * scale_log2 + log2f(l)) * LN2;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(3 + t, 128);
+      if (wg_tid == 0 && r0 < tokens) {
+        tma_store_3d(&tmOut, ostage, h * DH, r0, view);
+        bulk_commit();
+      }
+      PT_STAMP(6);
+    }
+    if (wg_tid == 0) bulk_wait<0>();
+  }
+#undef PT_STAMP
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =============================================================================================== CLS-query attention
 // Last encoder layer in inference: only the CLS token of each view feeds post_layernorm / visual_projection
 // (HF CLIPVisionTransformer.forward: pooled_output = last_hidden_state[:, 0]), so only its query row is needed.
@@ -2077,6 +2384,63 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   return ok;
 }
 
+static bool launch_attention_fwd_pt(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                                    cudaStream_t st, int descending) {
+  const int keys = (tokens + 15) / 16 * 16;
+  if (tokens <= 128 || keys > 208) return false;      // exactly two query tiles; S_t [0, keys) and O_t [192, 256) share 256 columns
+  const int d = heads * DH;
+  const size_t smem = 4 * 16384 + static_cast<size_t>(4) * keys * 128 + 2 * 16384 + 256 + 1024;
+  CUtensorMap tq, tkv, to;
+  static const int variant = std::getenv("TTL_PT_VARIANT") ? std::atoi(std::getenv("TTL_PT_VARIANT")) : 0;
+  static const int stagger = std::getenv("TTL_PT_STAGGER") ? std::atoi(std::getenv("TTL_PT_STAGGER")) : 1;
+  auto kern = variant == 1 ? attention_fwd_pt_kernel<0x88> : variant == 2 ? attention_fwd_pt_kernel<0x00> : attention_fwd_pt_kernel<0x80>;
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+  const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
+  if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
+  const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+  const uint32_t obox[3] = {64, 128, 1};
+  if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
+  const int dv = current_device_slot();
+  static size_t configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  size_t& configured = configured_dev[dv];
+  int& num_sms = num_sms_dev[dv];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = smem;
+  }
+  const int units = V * heads;
+  const int grid = units < num_sms ? units : num_sms;
+  static long long* dbg = nullptr;
+  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
+  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
+  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
+  const bool ok = launch_pdl(kern, dim3(grid), dim3(PT_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units, keys,
+                             scale * LOG2E, want_dbg ? dbg : nullptr, descending, stagger) == cudaSuccess;
+  if (want_dbg) {
+    cudaStreamSynchronize(st);
+    static int printed = 0;
+    if (units >= 2000 && printed++ == 3) {
+      const char* nm[7] = {"loop top", "S ready", "pass1", "stage free", "pass2", "O ready", "stored"};
+      for (int it = 1; it < 8; ++it)
+        for (int t = 0; t < 2; ++t) {
+          const long long* q = dbg + (it * 2 + t) * 8;
+          std::fprintf(stderr, "pt unit %d tile %d:", it, t);
+          for (int k = 1; k < 7; ++k) std::fprintf(stderr, " %s +%lld", nm[k], q[k] - q[0]);
+          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 8)[0] - q[0], q[0] - (dbg + it * 2 * 8)[0]);
+        }
+    }
+  }
+  return ok;
+}
+
 static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                                      cudaStream_t st) {
   const int rows_pad = (tokens + 15) / 16 * 16, rows_alloc = (rows_pad + 31) / 32 * 32;
@@ -2126,10 +2490,12 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
   // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   static const char* mode = std::getenv("TTL_ATTN");
+  const bool want_pt = mode != nullptr && mode[0] == 'p' && mode[1] == 't';      // "pt": P kept in TMEM (TS-form P V MMAs)
   const bool want_pp = mode == nullptr || mode[0] == 'p';
   const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';
   // the causal form (77-token text tower) runs on the general kernel below
+  if (!causal && want_pt && launch_attention_fwd_pt(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
   if (!causal && want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
   if (!causal && want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
   if (!causal && want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
