@@ -6,7 +6,10 @@ import torch
 import gpu_util as gu
 
 lib = gu.lib()
-for (V, tokens, heads) in ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197, 12), (64, 257, 16)):
+FWD = ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197, 12), (64, 257, 16))
+if os.environ.get("ATTN_BENCH_FWD"):      # e.g. ATTN_BENCH_FWD=192,576: only these view counts at 197 tokens, no backward
+    FWD = tuple((int(v), 197, 12) for v in os.environ["ATTN_BENCH_FWD"].split(","))
+for (V, tokens, heads) in FWD:
     d = heads * 64
     ring = 4
     qkvs = [(torch.randn(V * tokens, 3 * d, device="cuda") * 1.5).bfloat16() for _ in range(ring)]
@@ -28,7 +31,7 @@ for (V, tokens, heads) in ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197,
     by = V * tokens * d * 2 * 4
     print(f"attention fwd V={V} tokens={tokens} heads={heads}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
 
-for (V, tokens, heads) in ((18, 197, 12), (6, 197, 12), (54, 197, 12), (64, 197, 12), (576, 197, 12)):
+for (V, tokens, heads) in (() if os.environ.get("ATTN_BENCH_FWD") else ((18, 197, 12), (6, 197, 12), (54, 197, 12), (64, 197, 12), (576, 197, 12))):
     d = heads * 64
     qkv = (torch.randn(V * tokens, 3 * d, device="cuda") * 1.5).bfloat16()
     out = torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16)

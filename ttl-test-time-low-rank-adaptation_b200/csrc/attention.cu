@@ -1456,37 +1456,41 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // attention_fwd_pp_kernel with (1) the probabilities handed to the tensor core through TMEM instead of shared memory (the TS form
 // of tcgen05.mma: A operand = 128 lanes x 8 columns of packed bf16 pairs per 16-key step) and (2) the two query tiles of a unit
 // DECOUPLED: each tile t is a stream of its own -- softmax warpgroup, MMA-issuing thread, Q double buffer, half of TMEM -- and the
-// streams only share the (double-buffered) K and V of a unit.  Stream 1 starts half a unit late, so one stream's MUFU-bound pass 2
-// runs while the other is in its pass 1 / O wait / epilogue instead of both fighting for the MUFU and then both leaving it idle.
+// streams only share the (double-buffered) K and V of a unit; every softmax WARP stores its own 32 output rows (own staging
+// slice, own TMA store), so no CTA- or warpgroup-wide barrier is left in the unit loop.  193..208 tokens (keys = 208).
 // Per tile t, TMEM columns [256 t, 256 t + 256):
-//   S_t  [0, keys)      fp32 scores, written by the S MMAs
-//   P_t  [0, keys / 2)  bf16 pairs, written IN PLACE by the softmax threads: pass 2 walks S in 32-column chunks and stores the 16
-//                       columns of packed P of chunk c at [poff + 16 c, poff + 16 c + 16), which only covers S columns the thread has
-//                       already loaded (23 + 16 c <= 32 c + 31)
-//   O_t  [192, 256)     fp32 accumulator of P V.  With keys = 208 it overlaps the 16-column tail of S, so pass 2 reads that tail
-//                       FIRST (its P pairs wait in 8 registers until chunk 0 has been loaded and go to columns [0, 8), poff = 8);
-//                       the first P V MMA is issued after all four warps of the tile delivered block 0, i.e. after every lane has
-//                       read its tail.
+//   S_t  [0, 208)       fp32 scores, written by the S MMAs
+//   P_t  [0, 104)       bf16 pairs, written IN PLACE by the softmax threads: pass 2 walks S in 16-key steps and stores the 8 columns
+//                       of packed P of step h at [8 + 8 h, 16 + 8 h), which only covers S columns the thread has already loaded;
+//                       the 16-key tail's P goes to [0, 8)
+//   O_t  [192, 256)     fp32 accumulator of P V.  It overlaps the 16-column tail of S, so pass 2 reads that tail FIRST; the first
+//                       P V MMA is issued after all four warps of the tile delivered block 0, i.e. after every lane has read its tail.
 // No swizzled shared-memory P stores, no proxy fences; the shared memory that P occupied holds the second K and Q buffers
-// (200 KB at 208 keys).  Exact two-pass softmax in fp32, 1 of 8 exponentials on the FMA pipe, as before; 129..208 tokens.
+// (200 KB).  Exact two-pass softmax in fp32; 1 of 8 exponentials on the FMA pipe (166.7 us at 576 views against 174.3 with 2 of 8
+// and 171.9 with none); scale and row sums as packed fp32 pairs.
 //   warp 0 (one thread)   TMA producer: K + Q0 + Q1 of unit u into buffer u & 1 once both streams' S MMAs of unit u - 2 retired;
 //                         V likewise behind both streams' last P V MMA
 //   warp 1 / warp 10      MMA issue of stream 0 / 1 (one elected thread each; tcgen05.commit tracks the issuing thread's MMAs)
-//   warps 2-5 / 6-9       softmax + epilogue warpgroup of stream 0 / 1
+//   warps 2-5 / 6-9       softmax + epilogue warps of stream 0 / 1
+// Measured on the way: a softmax warp that is alone on its scheduler runs pass 2 at about half the speed of two
+// (ptxas schedules for latency hiding by other warps: the static stall counts of the loop alone add up to more than the MUFU time),
+// so letting the streams take turns in pass 2 ("stagger") gains nothing; polling warps are not what slows it (suspend hint and
+// nanosleep back-off change nothing); neither do the tcgen05.ld / .st of the pass nor the P V MMAs.
 constexpr int PT_THREADS = 352;
-template <int MASK>     // which of every 8 exponentials run on the FMA pipe
+constexpr int PT_KEYS = 208, PT_KB = PT_KEYS * 128;      // bytes of K (or V) of a unit
+template <int MASK, bool DBG>     // MASK: which of every 8 exponentials run on the FMA pipe; DBG: clock64 stamps of CTA 0
 __global__ void __launch_bounds__(PT_THREADS, 1)
 attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const __grid_constant__ CUtensorMap tmOut, float* __restrict__ lse, int tokens, int heads,
-                        int units, int keys, float scale_log2, long long* __restrict__ dbg, int rev, int stagger) {
+                        int units, float scale_log2, long long* __restrict__ dbg, int rev) {
   extern __shared__ uint8_t smem_pt_raw[];
-#define PT_STAMP(k) do { if (dbg != nullptr && blockIdx.x == 0 && it < 12 && wg_tid == 0) dbg[(it * 2 + t) * 8 + (k)] = clock64(); } while (0)
+#define PT_STAMP(k) do { if (DBG && blockIdx.x == 0 && it < 12 && quad == 0 && lane == 0) dbg[(it * 2 + t) * 16 + (k)] = clock64(); } while (0)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_pt_raw) + 1023) & ~uintptr_t(1023));
-  const int KB = keys * 128;                       // bytes of K (or V): multiple of 1024 (keys % 16 == 0, keys >= 128)
+  constexpr int KB = PT_KB;
   uint8_t* sQ = smem;                              // [2 buffers][2 tiles] 16 KB each
   uint8_t* sK = sQ + 4 * 16384;                    // [2 buffers]
   uint8_t* sV = sK + 2 * KB;                       // [2 buffers]
-  uint8_t* sO = sV + 2 * KB;                       // [2 tiles] output stage, 16 KB each
+  uint8_t* sO = sV + 2 * KB;                       // [2 tiles][4 warps] output stage, 4 KB (32 rows) each
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * 16384);
   uint64_t* bar_kq = bars;            // [2] K + Q0 + Q1 of a unit landed in buffer b
   uint64_t* bar_kqfree = bars + 2;    // [2] both streams' S MMAs on buffer b retired (2 commits)
@@ -1495,7 +1499,7 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* bar_s = bars + 8;         // [2] S_t complete in TMEM
   uint64_t* bar_o = bars + 10;        // [2] O_t complete in TMEM (P_t dead)
   uint64_t* bar_tfree = bars + 12;    // [2] O_t copied to registers: TMEM region t reusable
-  uint64_t* bar_p = bars + 14;        // [2][4] P block b (two 32-key chunks) of tile t stored in TMEM
+  uint64_t* bar_p = bars + 14;        // [2][4] P block b (four 16-key steps; block 0 also the tail) of tile t stored in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1527,9 +1531,6 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   pdl_wait();
   pdl_trigger();
-  const int n32 = keys / 32, rem16 = keys - n32 * 32;      // 32-key chunks + an optional 16-key tail
-  const int nblk = (n32 + 1) >> 1;                         // P blocks = pairs of chunks (the tail rides with block 0)
-  const uint32_t poff = rem16 ? 8u : 0u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -1555,9 +1556,8 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // see attention_bwd_tc_kernel for the two ptxas pitfalls this avoids)
     const int t = warp == 1 ? 0 : 1;
     if (elect_one()) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, static_cast<uint32_t>(keys));
+      const uint32_t idesc_s = umma_idesc_bf16(128, PT_KEYS);
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
-      const uint32_t v_lbo = static_cast<uint32_t>(KB);
       const uint32_t tt = tmem + t * 256;
       int it = 0;
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
@@ -1573,17 +1573,15 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         umma_commit(&bar_s[t]);
         umma_commit(&bar_kqfree[b]);
         mbar_wait(&bar_v[b], use & 1);
-        const uint64_t vdesc = umma_desc(smem_u32(sV + b * KB), 1024, v_lbo, 2);     // + 128 per 16-key step (2048 B >> 4)
+        const uint64_t vdesc = umma_desc(smem_u32(sV + b * KB), 1024, KB, 2);     // + 128 per 16-key step (2048 B >> 4)
 #pragma unroll 1
-        for (int blk = 0; blk < nblk; ++blk) {
-          const int ks0 = 4 * blk, ks1 = 4 * blk + 4 < 2 * n32 ? 4 * blk + 4 : 2 * n32;      // 16-key steps of this block
+        for (int blk = 0; blk < 3; ++blk) {
           mbar_wait(&bar_p[t * 4 + blk], ph);
           tc_fence_after();
-          if (blk == 0 && rem16) umma_bf16_ts(tt + 192, tt, vdesc + static_cast<uint64_t>(2 * n32) * 128, idesc_o, 0u);
+          if (blk == 0) umma_bf16_ts(tt + 192, tt, vdesc + 12ull * 128, idesc_o, 0u);      // the tail first: O starts from it
 #pragma unroll 1
-          for (int ks = ks0; ks < ks1; ++ks)
-            umma_bf16_ts(tt + 192, tt + poff + 8 * ks, vdesc + static_cast<uint64_t>(ks) * 128, idesc_o,
-                         (ks != 0 || rem16) ? 1u : 0u);
+          for (int ks = 4 * blk; ks < 4 * blk + 4; ++ks)
+            umma_bf16_ts(tt + 192, tt + 8 + 8 * ks, vdesc + static_cast<uint64_t>(ks) * 128, idesc_o, 1u);
         }
         umma_commit(&bar_o[t]);
         umma_commit(&bar_vfree[b]);
@@ -1591,14 +1589,13 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue warpgroup of stream t
+    // ------------------------------------------------------------------ softmax + epilogue warps of stream t
     const int t = (warp - 2) >> 2;
     const int quad = warp & 3, row = quad * 32 + lane;
-    const int wg_tid = threadIdx.x - 64 - t * 128;           // 0..127 inside the warpgroup
     const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + t * 256;
-    uint8_t* ostage = sO + t * 16384;
-    const int r0 = t * 128;
-    const bool active = r0 + quad * 32 < tokens;            // warp-uniform: at least one real query row
+    uint8_t* ostage = sO + t * 16384 + quad * 4096;         // this warp's 32 rows x 128 B (1024-aligned: swizzle atoms intact)
+    const int r0 = t * 128 + quad * 32;                     // first query row of this warp
+    const bool active = r0 < tokens;                        // warp-uniform: at least one real query row
     int it = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -1611,105 +1608,98 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       float m = -INFINITY, l = 0.f;
       if (active) {
         // pass 1: exact row maximum.  Columns >= tokens hold exact zeros (zero-filled K rows): harmless for softmax.
-        uint32_t ra[32], rb[32];
+        uint32_t ra[32], rb[32], rt[16];
+        tmem_ld_32x32b_x16(trow + 192, rt);
         tmem_ld_32x32b_x32(trow, ra);
-        for (int c = 0; c < n32; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < n32) tmem_ld_32x32b_x32(trow + (c + 1) * 32, rb);
+        tmem_ld_32x32b_x32(trow + 32, rb);
+        tmem_ld_wait();
+        float m1 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
-          if (c + 1 < n32) {
-            tmem_ld_wait();
-            if (c + 2 < n32) tmem_ld_32x32b_x32(trow + (c + 2) * 32, ra);
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
-          }
+        for (int i = 0; i < 32; i += 2) {
+          m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          m1 = max3(m1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
         }
-        if (rem16) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(trow + n32 * 32, r);
-          tmem_ld_wait();
+        tmem_ld_32x32b_x32(trow + 64, ra);
+        tmem_ld_32x32b_x32(trow + 96, rb);
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        for (int i = 0; i < 16; i += 2) m = max3(m, __uint_as_float(rt[i]), __uint_as_float(rt[i + 1]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          m1 = max3(m1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
         }
+        tmem_ld_32x32b_x32(trow + 128, ra);
+        tmem_ld_32x32b_x32(trow + 160, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          m1 = max3(m1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+        }
+        m = fmaxf(m, m1);
       }
       PT_STAMP(2);
-      if (wg_tid == 0) bulk_wait_read<0>();      // the previous unit's output store has finished reading the stage
-      named_bar_sync(1 + t, 128);
-      // the two streams take turns in pass 2: stream 1 runs its pass 2 of unit u after stream 0's, stream 0 its pass 2 of unit
-      // u + 1 after stream 1's of unit u (the last P block's barrier of the other tile is the token).  Left alone the streams
-      // fall into lockstep (measured: both in pass 2 together at 4.6 k cycles, the MUFU idle for the other 2.9 k of the unit).
-      if (stagger) {
-        if (t == 1) mbar_wait(&bar_p[nblk - 1], ph);
-        else if (it > 0) mbar_wait(&bar_p[4 + nblk - 1], ph ^ 1);
-      }
-      PT_STAMP(3);
       if (active) {
-        // pass 2: p = 2^(s*scale - m*scale), row sum, packed bf16 P back into TMEM (layout above)
+        // pass 2: p = 2^(s*scale - m*scale), row sum, packed bf16 P back into TMEM (layout above).  16-key steps through two
+        // 16-register buffers: the load of step h + 1 flies while step h is evaluated.
         const float ms = m * scale_log2;
-        float l0 = 0.f, l1 = 0.f;
-        uint32_t ptail[8];
-        if (rem16) {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(trow + n32 * 32, r);
-          tmem_ld_wait();
+        const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nms2 = f32x2_pack(-ms, -ms);
+        uint64_t l2 = 0;
+        uint32_t ba[16], bb[16], pk[8];
+        auto eval16 = [&](const uint32_t (&r)[16]) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -ms));
-            float v1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -ms));
-            if (n32 * 32 + 2 * i >= tokens) v0 = 0.f;
-            if (n32 * 32 + 2 * i + 1 >= tokens) v1 = 0.f;
-            l0 += v0 + v1;
-            ptail[i] = pack_bf16(v0, v1);
+          for (int q = 0; q < 2; ++q) {
+            uint64_t e2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t x2 = f32x2_fma(f32x2_pack_bits(r[8 * q + 2 * i], r[8 * q + 2 * i + 1]), sc2, nms2);
+              const float e0 = ((MASK >> (2 * i)) & 1) ? ex2_poly(f32x2_lo(x2)) : ex2_approx(f32x2_lo(x2));
+              const float e1 = ((MASK >> (2 * i + 1)) & 1) ? ex2_poly(f32x2_hi(x2)) : ex2_approx(f32x2_hi(x2));
+              e2[i] = f32x2_pack(e0, e1);
+              pk[4 * q + i] = pack_bf16(e0, e1);
+            }
+            l2 = f32x2_add(l2, f32x2_add(f32x2_add(e2[0], e2[1]), f32x2_add(e2[2], e2[3])));
           }
+        };
+        tmem_ld_32x32b_x16(trow + 192, ba);
+        tmem_ld_32x32b_x16(trow, bb);
+        tmem_ld_wait();
+        float lt = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v0 = ex2_approx(fmaf(__uint_as_float(ba[2 * i]), scale_log2, -ms));
+          float v1 = ex2_approx(fmaf(__uint_as_float(ba[2 * i + 1]), scale_log2, -ms));
+          if (192 + 2 * i >= tokens) v0 = 0.f;
+          if (192 + 2 * i + 1 >= tokens) v1 = 0.f;
+          lt += v0 + v1;
+          pk[i] = pack_bf16(v0, v1);
         }
-        for (int c = 0; c < n32; ++c) {
-          uint32_t r[32], pk[16];
-          tmem_ld_32x32b_x32(trow + c * 32, r);
+        tmem_ld_32x32b_x16(trow + 16, ba);
+        tmem_st_32x32b_x8(trow, pk);               // S columns [0, 8) are in bb already
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {              // 16-key steps 2 i (in bb) and 2 i + 1 (in ba, in flight)
+          eval16(bb);
           tmem_ld_wait();
-          if (c * 32 + 32 <= tokens) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              float e[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms);
-                e[i] = ((MASK >> i) & 1) ? ex2_poly(x) : ex2_approx(x);
-              }
-              l0 += (e[0] + e[1]) + (e[2] + e[3]);
-              l1 += (e[4] + e[5]) + (e[6] + e[7]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pk[q4 * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-            }
-          } else {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              float e[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float v = ex2_approx(fmaf(__uint_as_float(r[q4 * 8 + i]), scale_log2, -ms));
-                if (c * 32 + q4 * 8 + i >= tokens) v = 0.f;
-                e[i] = v;
-                l0 += v;
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pk[q4 * 4 + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-            }
-          }
-          if (c == 0 && rem16) tmem_st_32x32b_x8(trow, ptail);
-          tmem_st_32x32b_x16(trow + poff + 16 * c, pk);
-          if ((c & 1) || c == n32 - 1) {
+          if (i < 5) tmem_ld_32x32b_x16(trow + 32 * i + 32, bb);
+          tmem_st_32x32b_x8(trow + 8 + 16 * i, pk);
+          eval16(ba);
+          tmem_ld_wait();
+          if (i < 5) tmem_ld_32x32b_x16(trow + 32 * i + 48, ba);
+          tmem_st_32x32b_x8(trow + 16 + 16 * i, pk);
+          if (i & 1) {                             // a P block of four steps is complete
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[t * 4 + (c >> 1)]);
+            if (lane == 0) mbar_arrive(&bar_p[t * 4 + (i >> 1)]);
+            PT_STAMP(8 + (i >> 1));
           }
         }
-        l = l0 + l1;
+        l = lt + f32x2_lo(l2) + f32x2_hi(l2);
       } else {
         tc_fence_before();
         if (lane == 0)
-          for (int b = 0; b < nblk; ++b) mbar_arrive(&bar_p[t * 4 + b]);
+          for (int b = 0; b < 3; ++b) mbar_arrive(&bar_p[t * 4 + b]);
       }
       PT_STAMP(4);
       mbar_wait(&bar_o[t], ph);
@@ -1719,6 +1709,7 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (active) {
         tmem_ld_32x32b_x32(trow + 192, o0);
         tmem_ld_32x32b_x32(trow + 224, o1);
+        if (lane == 0) bulk_wait_read<0>();      // this warp's previous output store has finished reading its stage
         tmem_ld_wait();
       }
       tc_fence_before();
@@ -1726,29 +1717,30 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (lane == 0) mbar_arrive(&bar_tfree[t]);
       if (active) {
         const float inv = 1.f / l;
-        const uint32_t obase = smem_u32(ostage) + row * 128;
+        const uint32_t obase = smem_u32(ostage) + lane * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const uint32_t* r = q4 < 4 ? o0 + q4 * 8 : o1 + (q4 - 4) * 8;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (row & 7)) << 4)),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (lane & 7)) << 4)),
                        "r"(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv)),
                        "r"(pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv)),
                        "r"(pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv)),
                        "r"(pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv))
                        : "memory");
         }
-        if (lse != nullptr && r0 + row < tokens)
-          lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + row] = (m * scale_log2 + log2f(l)) * LN2;
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(3 + t, 128);
-      if (wg_tid == 0 && r0 < tokens) {
-        tma_store_3d(&tmOut, ostage, h * DH, r0, view);
-        bulk_commit();
+        if (lse != nullptr && r0 + lane < tokens)
+          lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + lane] = (m * scale_log2 + log2f(l)) * LN2;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmOut, ostage, h * DH, r0, view);      // 32-row box; rows >= tokens are clipped
+          bulk_commit();
+        }
       }
       PT_STAMP(6);
     }
-    if (wg_tid == 0) bulk_wait<0>();
+    if (lane == 0) bulk_wait<0>();
+    (void)row;
   }
 #undef PT_STAMP
   tc_fence_before();
@@ -2360,8 +2352,8 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
   const int grid = units < num_sms ? units : num_sms;
   static long long* dbg = nullptr;
   static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
-  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
-  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
+  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 16 * sizeof(long long));
+  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 16 * sizeof(long long));
   const bool ok = (xkey >= 0 ? launch_pdl(attention_fwd_pp_kernel<true>, dim3(grid), dim3(PP_THREADS_XK), smem, st, tq, tkv, to, lse, tokens,
                                           heads, units, keys, scale * LOG2E, want_dbg ? dbg : nullptr, descending, ptile, vbufs, xkey, qkv, out)
                              : launch_pdl(attention_fwd_pp_kernel<false>, dim3(grid), dim3(PP_THREADS), smem, st, tq, tkv, to, lse, tokens,
@@ -2374,10 +2366,11 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
       const char* nm[7] = {"loop top", "S ready", "pass1", "stage free", "pass2", "O ready", "stored"};
       for (int it = 1; it < 8; ++it)
         for (int t = 0; t < 2; ++t) {
-          const long long* q = dbg + (it * 2 + t) * 8;
+          const long long* q = dbg + (it * 2 + t) * 16;
           std::fprintf(stderr, "unit %d tile %d:", it, t);
           for (int k = 1; k < 7; ++k) std::fprintf(stderr, " %s +%lld", nm[k], q[k] - q[0]);
-          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 8)[0] - q[0], q[0] - (dbg + it * 2 * 8)[0]);
+          std::fprintf(stderr, " | P blocks +%lld +%lld +%lld", q[8] - q[0], q[9] - q[0], q[10] - q[0]);
+          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 16)[0] - q[0], q[0] - (dbg + it * 2 * 16)[0]);
         }
     }
   }
@@ -2387,13 +2380,15 @@ static bool launch_attention_fwd_pp(const bf16* qkv, bf16* out, float* lse, int 
 static bool launch_attention_fwd_pt(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                                     cudaStream_t st, int descending) {
   const int keys = (tokens + 15) / 16 * 16;
-  if (tokens <= 128 || keys > 208) return false;      // exactly two query tiles; S_t [0, keys) and O_t [192, 256) share 256 columns
+  if (keys != PT_KEYS) return false;      // 193..208 tokens: two query tiles, twelve 16-key steps + a 16-key tail
   const int d = heads * DH;
-  const size_t smem = 4 * 16384 + static_cast<size_t>(4) * keys * 128 + 2 * 16384 + 256 + 1024;
+  const size_t smem = 4 * 16384 + static_cast<size_t>(4) * PT_KB + 2 * 16384 + 256 + 1024;
   CUtensorMap tq, tkv, to;
   static const int variant = std::getenv("TTL_PT_VARIANT") ? std::atoi(std::getenv("TTL_PT_VARIANT")) : 0;
-  static const int stagger = std::getenv("TTL_PT_STAGGER") ? std::atoi(std::getenv("TTL_PT_STAGGER")) : 1;
-  auto kern = variant == 1 ? attention_fwd_pt_kernel<0x88> : variant == 2 ? attention_fwd_pt_kernel<0x00> : attention_fwd_pt_kernel<0x80>;
+  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
+  auto kern = want_dbg ? attention_fwd_pt_kernel<0x80, true>
+                       : variant == 1 ? attention_fwd_pt_kernel<0x88, false>
+                                      : variant == 2 ? attention_fwd_pt_kernel<0x00, false> : attention_fwd_pt_kernel<0x80, false>;
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
   const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
   const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
@@ -2401,40 +2396,40 @@ static bool launch_attention_fwd_pt(const bf16* qkv, bf16* out, float* lse, int 
   if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
   const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
   const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
-  const uint32_t obox[3] = {64, 128, 1};
+  const uint32_t obox[3] = {64, 32, 1};      // one softmax warp's rows
   if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
   const int dv = current_device_slot();
-  static size_t configured_dev[MAX_DEVICES] = {};
+  static bool configured_dev[MAX_DEVICES] = {};
   static int num_sms_dev[MAX_DEVICES] = {};
-  size_t& configured = configured_dev[dv];
   int& num_sms = num_sms_dev[dv];
   if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
-  if (smem > configured) {
+  if (!configured_dev[dv]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    configured = smem;
+    configured_dev[dv] = true;
   }
   const int units = V * heads;
   const int grid = units < num_sms ? units : num_sms;
   static long long* dbg = nullptr;
-  static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
-  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 8 * sizeof(long long));
-  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 8 * sizeof(long long));
-  const bool ok = launch_pdl(kern, dim3(grid), dim3(PT_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units, keys,
-                             scale * LOG2E, want_dbg ? dbg : nullptr, descending, stagger) == cudaSuccess;
+  if (want_dbg && dbg == nullptr) cudaMallocManaged(&dbg, 12 * 2 * 16 * sizeof(long long));
+  if (want_dbg) std::memset(dbg, 0, 12 * 2 * 16 * sizeof(long long));
+  const bool ok = launch_pdl(kern, dim3(grid), dim3(PT_THREADS), smem, st, tq, tkv, to, lse, tokens, heads, units,
+                             scale * LOG2E, want_dbg ? dbg : nullptr, descending) == cudaSuccess;
   if (want_dbg) {
     cudaStreamSynchronize(st);
     static int printed = 0;
     if (units >= 2000 && printed++ == 3) {
-      const char* nm[7] = {"loop top", "S ready", "pass1", "stage free", "pass2", "O ready", "stored"};
-      for (int it = 1; it < 8; ++it)
+      const char* nm[7] = {"loop top", "S ready", "pass1", "", "pass2", "O ready", "stored"};
+      for (int it = 3; it < 6; ++it)
         for (int t = 0; t < 2; ++t) {
-          const long long* q = dbg + (it * 2 + t) * 8;
+          const long long* q = dbg + (it * 2 + t) * 16;
           std::fprintf(stderr, "pt unit %d tile %d:", it, t);
-          for (int k = 1; k < 7; ++k) std::fprintf(stderr, " %s +%lld", nm[k], q[k] - q[0]);
-          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 8)[0] - q[0], q[0] - (dbg + it * 2 * 8)[0]);
+          for (int k = 1; k < 7; ++k)
+            if (k != 3) std::fprintf(stderr, " %s +%lld", nm[k], q[k] - q[0]);
+          std::fprintf(stderr, " | P blocks +%lld +%lld +%lld", q[8] - q[0], q[9] - q[0], q[10] - q[0]);
+          std::fprintf(stderr, " | next top +%lld | since tile0 top %+lld\n", (dbg + ((it + 1) * 2 + t) * 16)[0] - q[0], q[0] - (dbg + it * 2 * 16)[0]);
         }
     }
   }
@@ -2490,7 +2485,7 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
   // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   static const char* mode = std::getenv("TTL_ATTN");
-  const bool want_pt = mode != nullptr && mode[0] == 'p' && mode[1] == 't';      // "pt": P kept in TMEM (TS-form P V MMAs)
+  const bool want_pt = mode == nullptr || (mode[0] == 'p' && mode[1] == 't');      // default for 193..208 tokens: P kept in TMEM
   const bool want_pp = mode == nullptr || mode[0] == 'p';
   const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';

@@ -86,13 +86,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The suspend-time hint lets the hardware park a waiting warp until the phase completes (or the hint expires) instead of
+// returning at once: a warp that polls takes issue slots from the working warps of its scheduler (measured in the
+// decoupled-stream attention forward: the softmax warp sharing a scheduler with a polling warp ran at half speed).
+#ifndef MBAR_SUSPEND_HINT_NS
+#define MBAR_SUSPEND_HINT_NS 1000000u
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
   return ok;
 }
 
@@ -107,6 +113,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// The same with the polling warp put to sleep between tries, for waits that are expected to be long while another warp of the
+// same scheduler is busy (a polling warp competes for the scheduler's issue slots).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t tries = 0;
+  do {
+    __nanosleep(ns);
+    if (++tries > 100000000u) {
+      printf("ttl: mbarrier wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  } while (!mbar_try_wait(bar, parity));
 }
 
 // ------------------------------------------------------------------ TMA
@@ -350,6 +370,33 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op; x 
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// Packed fp32 pairs (sm_100: one issue slot for two lanes of the FMA pipe); a pair lives in a 64-bit register, low word first.
+__device__ __forceinline__ uint64_t f32x2_pack_bits(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) { return f32x2_pack_bits(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ float f32x2_lo(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return __uint_as_float(lo);
+}
+__device__ __forceinline__ float f32x2_hi(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return __uint_as_float(hi);
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float y;
