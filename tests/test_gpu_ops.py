@@ -200,7 +200,8 @@ def _attn_ref(qkv, V, tokens, heads):
 # 129..208 tokens: tcgen05 backward (two query tiles x two key halves; 129 / 144 / 145 / 176 / 208 walk the 16..80-key second half
 # and the partial last query tile; 200 views x 12 heads = 2400 units > 148 CTAs wrap the mbarrier phases many times)
 @pytest.mark.parametrize("V,tokens,heads", [(3, 197, 12), (2, 257, 16), (4, 17, 2), (1, 64, 1), (64, 197, 12), (5, 50, 3),
-                                            (2, 129, 2), (2, 144, 3), (3, 145, 2), (7, 176, 4), (2, 208, 2), (200, 197, 12)])
+                                            (2, 129, 2), (2, 144, 3), (3, 145, 2), (7, 176, 4), (2, 208, 2), (200, 197, 12),
+                                            (3, 193, 2), (2, 200, 3)])      # 193..208: forward with P kept in TMEM (one row in the last active warp at 193)
 def test_attention_fwd_bwd(G, V, tokens, heads):
     gu, L = G
     d = heads * 64
@@ -223,6 +224,19 @@ def test_attention_fwd_bwd(G, V, tokens, heads):
     got = dqkv.float().view(V * tokens, 3, d)
     for i, nm in enumerate("qkv"):
         assert gu.rel_err(got[:, i], g[:, i]) < 1.5e-2, nm   # bf16 P/dS operands; fp32 accumulation
+
+
+@pytest.mark.parametrize("mode", ["pp", "tc", "mma"])
+def test_attention_forward_alternatives_still_agree(mode):
+    """TTL_ATTN selects the other forward kernels (read once per process, so each runs in a child): the two-tiles-in-flight
+    kernel with P in shared memory, the one-tile-per-item kernel and the mma.sync kernel must pass the same checks at 197 tokens."""
+    import os, subprocess, sys
+    env = dict(os.environ, TTL_ATTN=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "test_attention_fwd_bwd and (3-197-12 or 64-197-12) or test_attention_fwd_extreme_scores"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "3 passed" in r.stdout, r.stdout[-500:]
 
 
 def test_attention_fwd_extreme_scores(G):
