@@ -256,6 +256,116 @@ attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
   }
 }
 
+// The same backward as two launches for token counts whose four staged matrices exceed shared memory (257 tokens: 267 KB):
+// PHASE_DQ keeps K and V resident (Q_i, dO_i per warp), PHASE_DKV keeps Q and dO resident (K_j, V_j per warp).  Same arithmetic
+// and summation order as attention_f32_bwd_kernel.
+template <int PHASE_DKV>
+__global__ void __launch_bounds__(256)
+attention_f32_bwd_split_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
+                               const float* __restrict__ lse, float* __restrict__ dqkv, int tokens, int heads, float scale) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sm_att[];
+  float* sA = sm_att;                       // PHASE_DQ: K        PHASE_DKV: Q
+  float* sB = sA + tokens * LDF;            // PHASE_DQ: V        PHASE_DKV: dO
+  float* sD = sB + tokens * LDF;            // [tokens] D_i = dO_i . O_i
+  float* sL = sD + tokens;                  // [tokens] lse_i
+  float* sR = sL + tokens;                  // [warps][2][64] this warp's two rows (Q_i, dO_i  or  K_j, V_j)
+  float* sW = sR + 8 * 2 * DH;              // [warps][tokens] scratch (PHASE_DQ)
+  const int h = blockIdx.x, view = blockIdx.y, d = heads * DH, ld = 3 * d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const size_t vrow = static_cast<size_t>(view) * tokens;
+  const float* base = qkv + vrow * ld + h * DH;
+  for (int i = threadIdx.x; i < tokens * DH; i += blockDim.x) {
+    const int r = i / DH, c = i % DH;
+    if (PHASE_DKV) {
+      sA[r * LDF + c] = base[static_cast<size_t>(r) * ld + c];
+      sB[r * LDF + c] = dout[(vrow + r) * d + h * DH + c];
+    } else {
+      sA[r * LDF + c] = base[static_cast<size_t>(r) * ld + d + c];
+      sB[r * LDF + c] = base[static_cast<size_t>(r) * ld + 2 * d + c];
+    }
+  }
+  for (int r = warp; r < tokens; r += nw) {      // D_i and lse_i
+    const float* orow = out + (vrow + r) * d + h * DH;
+    const float* dor = dout + (vrow + r) * d + h * DH;
+    float t = dor[lane] * orow[lane] + dor[lane + 32] * orow[lane + 32];
+    t = warp_sum(t);
+    if (lane == 0) { sD[r] = t; sL[r] = lse[(static_cast<size_t>(view) * heads + h) * tokens + r]; }
+  }
+  __syncthreads();
+  float* r0 = sR + warp * 2 * DH;
+  float* r1 = r0 + DH;
+  if (!PHASE_DKV) {
+    float* w = sW + warp * tokens;
+    for (int i = warp; i < tokens; i += nw) {
+      r0[lane] = base[static_cast<size_t>(i) * ld + lane];
+      r0[lane + 32] = base[static_cast<size_t>(i) * ld + lane + 32];
+      r1[lane] = dout[(vrow + i) * d + h * DH + lane];
+      r1[lane + 32] = dout[(vrow + i) * d + h * DH + lane + 32];
+      __syncwarp();
+      for (int j = lane; j < tokens; j += 32) {
+        const float* kj = sA + j * LDF;
+        const float* vj = sB + j * LDF;
+        float s = 0.f, dp = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < DH; ++c) { s = fmaf(r0[c], kj[c], s); dp = fmaf(r1[c], vj[c], dp); }
+        const float pij = expf(s * scale - sL[i]);
+        w[j] = pij * (dp - sD[i]);
+      }
+      __syncwarp();
+      float a0 = 0.f, a1 = 0.f;
+      for (int j = 0; j < tokens; ++j) {
+        const float ds = w[j];
+        a0 = fmaf(ds, sA[j * LDF + lane], a0);
+        a1 = fmaf(ds, sA[j * LDF + lane + 32], a1);
+      }
+      float* o = dqkv + (vrow + i) * ld + h * DH;
+      o[lane] = a0 * scale;
+      o[lane + 32] = a1 * scale;
+      __syncwarp();
+    }
+  } else {
+    for (int j = warp; j < tokens; j += nw) {
+      r0[lane] = base[static_cast<size_t>(j) * ld + d + lane];
+      r0[lane + 32] = base[static_cast<size_t>(j) * ld + d + lane + 32];
+      r1[lane] = base[static_cast<size_t>(j) * ld + 2 * d + lane];
+      r1[lane + 32] = base[static_cast<size_t>(j) * ld + 2 * d + lane + 32];
+      __syncwarp();
+      float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+      for (int i0 = 0; i0 < tokens; i0 += 32) {
+        const int i = i0 + lane;
+        float pij = 0.f, ds = 0.f;
+        if (i < tokens) {
+          const float* qi = sA + i * LDF;
+          const float* doi = sB + i * LDF;
+          float s = 0.f, dp = 0.f;
+#pragma unroll 16
+          for (int c = 0; c < DH; ++c) { s = fmaf(qi[c], r0[c], s); dp = fmaf(doi[c], r1[c], dp); }
+          pij = expf(s * scale - sL[i]);
+          ds = pij * (dp - sD[i]);
+        }
+        const int n = min(32, tokens - i0);
+        for (int ii = 0; ii < n; ++ii) {
+          const float pb = __shfl_sync(0xffffffffu, pij, ii), db = __shfl_sync(0xffffffffu, ds, ii);
+          const float* qi = sA + (i0 + ii) * LDF;
+          const float* doi = sB + (i0 + ii) * LDF;
+          dv0 = fmaf(pb, doi[lane], dv0);
+          dv1 = fmaf(pb, doi[lane + 32], dv1);
+          dk0 = fmaf(db, qi[lane], dk0);
+          dk1 = fmaf(db, qi[lane + 32], dk1);
+        }
+      }
+      float* o = dqkv + (vrow + j) * ld + h * DH;
+      o[d + lane] = dk0 * scale;
+      o[d + lane + 32] = dk1 * scale;
+      o[2 * d + lane] = dv0;
+      o[2 * d + lane + 32] = dv1;
+      __syncwarp();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ row kernels, fp32 out
 __global__ void __launch_bounds__(256)
 layernorm_f32_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
@@ -328,7 +438,13 @@ cudaError_t launch_sgemm(const SgemmArgs& a, cudaStream_t st) {
 }
 
 size_t attention_f32_fwd_smem(int tokens) { return (2 * static_cast<size_t>(tokens) * LDF + 8 * DH + 8 * tokens) * sizeof(float); }
-size_t attention_f32_bwd_smem(int tokens) { return (4 * static_cast<size_t>(tokens) * LDF + 2 * tokens + 8 * tokens) * sizeof(float); }
+static size_t attention_f32_bwd_smem_whole(int tokens) { return (4 * static_cast<size_t>(tokens) * LDF + 2 * tokens + 8 * tokens) * sizeof(float); }
+static size_t attention_f32_bwd_smem_split(int tokens) { return (2 * static_cast<size_t>(tokens) * LDF + 2 * tokens + 16 * DH + 8 * tokens) * sizeof(float); }
+// shared memory the backward needs: the one-launch kernel where its four matrices fit, the two-launch form otherwise
+size_t attention_f32_bwd_smem(int tokens) {
+  const size_t whole = attention_f32_bwd_smem_whole(tokens);
+  return whole <= 227 * 1024 ? whole : attention_f32_bwd_smem_split(tokens);
+}
 
 void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st) {
   const size_t smem = attention_f32_fwd_smem(tokens);
@@ -343,7 +459,20 @@ void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, i
 
 void launch_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int V,
                               int tokens, int heads, float scale, cudaStream_t st) {
-  const size_t smem = attention_f32_bwd_smem(tokens);
+  if (attention_f32_bwd_smem_whole(tokens) > 227 * 1024) {      // e.g. 257 tokens (ViT-L/14): dQ and dK/dV as two launches
+    const size_t smem2 = attention_f32_bwd_smem_split(tokens);
+    static size_t configured2_dev[MAX_DEVICES] = {};
+    size_t& configured2 = configured2_dev[current_device_slot()];
+    if (smem2 > configured2) {
+      cudaFuncSetAttribute(attention_f32_bwd_split_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+      cudaFuncSetAttribute(attention_f32_bwd_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+      configured2 = smem2;
+    }
+    launch_pdl(attention_f32_bwd_split_kernel<0>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale);
+    launch_pdl(attention_f32_bwd_split_kernel<1>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale);
+    return;
+  }
+  const size_t smem = attention_f32_bwd_smem_whole(tokens);
   static size_t configured_dev[MAX_DEVICES] = {};
   size_t& configured = configured_dev[current_device_slot()];
   if (smem > configured) {
