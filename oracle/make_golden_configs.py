@@ -82,9 +82,20 @@ def reference_case(name: str, classes: str, head: str, steps: int, image_seed: i
             losses.append(float(v.detach()))
             return v
         ttl_ref.avg_entropy = rec_avg_entropy
+    # factors the LAST optimiser step starts from (multi-step cases): the gradient of that step can then be checked at the
+    # reference's own operating point (B != 0: LoRA branch in the forward, dA, U = dY B) instead of behind three sign-like Adam
+    # updates.  Captured by wrapping the optimiser's step at run time; nothing in the reference is edited.
+    pre_step = []
+    orig_step = opt.step
+
+    def rec_step(*a, **k):
+        pre_step.append([[p.detach().clone() for p in R.get_lora(model, spec.layers())[i]] for i in spec.layers()])
+        return orig_step(*a, **k)
+    opt.step = rec_step
     try:
         ttl_ref.test_time_tuning(model, imgs, opt, scaler, args)
     finally:
+        opt.step = orig_step
         if head == "tpt":
             ttl_ref.avg_entropy = orig
     with torch.no_grad():
@@ -100,8 +111,12 @@ def reference_case(name: str, classes: str, head: str, steps: int, image_seed: i
             p = lora_now[i][j]
             rec[f"lora_{i}_{nm}"] = p.detach().numpy().copy()
             rec[f"grad_{i}_{nm}"] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy().copy()
+    if head == "tpt" and steps > 1 and len(pre_step) == steps:
+        for li, i in enumerate(spec.layers()):
+            for j, nm in enumerate(NAMES):
+                rec[f"prelast_{i}_{nm}"] = pre_step[-1][li][j].numpy().copy()
     _save(name, rec)
-    print(f"  {name}: {time.time() - t0:.0f} s, losses {losses}", flush=True)
+    print(f"  {name}: {time.time() - t0:.0f} s, losses {losses}, optimiser steps seen {len(pre_step)}", flush=True)
 
 
 def oracle_l14_case(name: str = "oracle_l14_c10_tpt") -> None:

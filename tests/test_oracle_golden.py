@@ -67,6 +67,25 @@ def test_oracle_reproduces_reference_at_benched_configs(case, b16_weights, b16_v
             assert np.linalg.norm(got_g - ref_g) / denom < (2e-2 if multi else 1e-4) or np.abs(ref_g).max() == 0, (i, nm)
 
 
+def test_oracle_last_step_gradient_at_the_reference_operating_point(b16_weights, b16_views):
+    """4-step fixture: with the factors the reference had BEFORE its last optimiser step as the starting point (`prelast_*`,
+    captured by wrapping the reference optimiser's step, oracle/make_golden_configs.py) and its frozen selection, one oracle step
+    reproduces the reference's step-4 loss and gradients -- dA != 0 here -- at the single-step bar (the free-running comparison above
+    can only hold them to 2e-2 behind three sign-like Adam updates)."""
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt4.npz"))
+    arch, spec = O.ARCHS["ViT-B/16"], O.LoraSpec()
+    prelast = {i: [torch.from_numpy(g[f"prelast_{i}_{nm}"]) for nm in NAMES] for i in spec.layers()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    res = O.adapt_and_predict(arch, b16_weights, b16_views, torch.from_numpy(g["text_features"]), float(g["logit_scale"]), prelast,
+                              spec, head="tpt", tta_steps=1, forced_idx=torch.from_numpy(g["idx"]))
+    np.testing.assert_allclose(res.losses[-1], g["losses"][-1], rtol=2e-4, atol=2e-6)
+    for i in spec.layers():
+        for j, nm in enumerate(NAMES):
+            ref_g, got_g = g[f"grad_{i}_{nm}"], res.grads[i][j].numpy()
+            assert np.abs(ref_g).max() > 0, (i, nm)                      # dA and dB both live at this point
+            assert np.linalg.norm(got_g - ref_g) / np.linalg.norm(ref_g) < 1e-4, (i, nm)
+
+
 def test_golden_structural_facts():
     """at step 1 dA == 0 exactly and B == -lr*g/(|g|+eps); at step 2 dA != 0."""
     g = _load("tpt")
