@@ -189,3 +189,45 @@ def test_module_and_cli_with_the_adapter_on_the_text_tower(b16_weights, b16_view
                     '--lora_encoder', 'text'])
     assert set(res) == {'A'} and 0.0 <= res['A'][0] <= res['A'][1] <= 100.0
     assert ttl.test_time_adapt_eval.last_stats["fused"]
+
+
+@pytest.mark.parametrize("head", ["tpt", "deyo"])
+def test_text_tower_adapter_fp32_mode_vs_reference(b16_weights, b16_views, head):
+    """The same route in the fp32 validation mode (fp32 activations and contractions, causal fp32 attention forward / backward, the
+    shared head / AdamW / reset kernels) against the fixtures of the unmodified reference: 1e-4 on logits, loss and LoRA gradients,
+    selection free-running.  The bf16 bounds above (3-9e-2 on these prompts) are rounding of the bf16 tape against a nearly
+    cancelling sum; this test shows the arithmetic of the route itself is the reference's.  The frozen image features come from the
+    fp32 oracle (the image tower carries no adapter on this route)."""
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, f"ref_b16_c10_textlora_{head}.npz"))
+    tarch = TO.TEXT_ARCHS["ViT-B/16"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        feats = O.vision_forward(O.ARCHS["ViT-B/16"], b16_weights, b16_views, None, 0.0)
+    et = Engine("ViT-B/16", max_views=16, max_classes=64, layer_range=(9, 11), text_mode=True, precision="fp32")
+    try:
+        et.load_text_weights(TO.make_synthetic_text_weights(tarch, 4321))
+        et.set_lora_init(TO.text_lora_init(tarch, range(9, 12), seed=int(g["lora_seed"])))
+        et.set_prompts(g["tokens"], float(g["logit_scale"]))
+        out = et.adapt_predict_text(feats.cuda(), Hparams(head=head), want=("logits0", "entropy", "idx", "loss", "pred_logits"))
+        torch.cuda.synchronize()
+        e_log = _rel(out["logits0"].cpu().numpy(), g["logits0"])
+        assert e_log < 1e-4
+        assert float(np.abs(out["entropy"].cpu().numpy() - g["entropies"]).max()) < 1e-4
+        if head == "tpt":
+            assert sorted(out["idx"].cpu().tolist()) == g["idx_sorted"].tolist()
+        worst = 0.0
+        for i in (9, 10, 11):
+            for j, nm in enumerate(NAMES):
+                ref_g, got_g = g[f"grad_{i}_{nm}"], et.lora_get(i, j, L.LORA_GRAD)
+                if nm.startswith("A"):
+                    assert np.abs(got_g).max() == 0.0 and np.abs(ref_g).max() == 0.0
+                else:
+                    worst = max(worst, _rel(got_g, ref_g))
+        e_pred = _rel(out["pred_logits"].cpu().numpy(), g["pred_logits"][0])
+        print(f"[text-tower adapter, fp32 mode, {head}] logits {e_log:.2e}, worst dB {worst:.2e}, adapted prediction {e_pred:.2e}")
+        assert worst < 1e-4
+        assert e_pred < 1e-3 and int(out["pred_logits"].argmax()) == int(g["pred_logits"][0].argmax())
+    finally:
+        et.close()

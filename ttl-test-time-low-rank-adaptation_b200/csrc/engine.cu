@@ -604,7 +604,10 @@ const float* lora_ptr(const ttl_ctx* c, int layer, int which) {   // live fp32 f
   return c->lp + static_cast<int64_t>(layer - c->lo) * c->lora_per_layer + static_cast<int64_t>(which) * c->r * c->d;
 }
 
+int embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st);
+
 int f32_embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
+  if (c->text_mode) return embed(c, nullptr, V, x, st);      // token + position embedding: fp32 on both paths
   launch_im2col_f32(images, c->patches_f, V, c->cfg.image_size, c->cfg.patch, st);
   SgemmArgs a;
   a.A = c->patches_f; a.lda = c->Kp; a.B = c->wpatch_f; a.ldb = c->Kp; a.M = V * c->T; a.N = c->d; a.K = c->Kp;
@@ -638,7 +641,7 @@ int f32_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     RET_IF(sg(c, Tv, r, lora_ptr(c, layer, TTL_LORA_B_V), r, 0, M, d, r, c->s, nullptr, qkv + 2 * d, 3 * d, qkv + 2 * d, 3 * d, SE_LINEAR,
               nullptr, nullptr, st));
   }
-  launch_attention_f32_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st);
+  launch_attention_f32_fwd(qkv, ao, tp ? tp->lse : nullptr, V, c->tokens, c->H, 0.125f, st, c->text_mode ? 1 : 0);
   RET_IF(sg(c, ao, d, w.wo_f, d, 0, M, d, d, 1.f, w.bo, x_in, d, x_mid, d, SE_LINEAR, nullptr, nullptr, st));
   launch_layernorm_f32(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st);
   RET_IF(sg(c, h2, d, w.w1_f, d, 0, M, F, d, 1.f, w.b1, nullptr, 0, g, F, SE_GELU, tf ? tf->z : nullptr, nullptr, st));
@@ -659,8 +662,9 @@ int f32_tail_infer(ttl_ctx* c, const float* x_in, int V, float* feats, float* lo
     RET_IF(f32_layer(c, l, cur, c->XB, c->XA, V, !c->b_zero, nullptr, nullptr, st));
     cur = c->XA;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
-  launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, feats, V, c->tokens, c->d, c->P, c->cfg.ln_eps, st,
+                      c->text_mode ? c->eot : nullptr);
+  if (logits != nullptr) launch_logits_entropy(feats, c->text, c->logit_scale_exp, logits, entropy, V, c->C, c->P, st);
   c->launches += 4;
   return check_launch(c, "f32_tail_infer");
 }
@@ -672,7 +676,8 @@ int f32_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
     RET_IF(f32_layer(c, l, cur, tp.x_mid, tp.x_out, G, !c->b_zero, &tp, &c->tapef[l - c->lo], st));
     cur = tp.x_out;
   }
-  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st);
+  launch_pool_project(cur, c->postg, c->postb, c->Wp, c->pooled, c->feats_c, G, c->tokens, c->d, c->P, c->cfg.ln_eps, st,
+                      c->text_mode ? c->eot : nullptr);
   c->launches += 2;
   c->last_train_views = G;
   c->last_train_samples = 1;
@@ -680,13 +685,21 @@ int f32_tail_train(ttl_ctx* c, const float* x_in, int G, cudaStream_t st) {
   return check_launch(c, "f32_tail_train");
 }
 
+int f32_backward_layers(ttl_ctx* c, int G, cudaStream_t st);
+
 int f32_backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
   if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
-  const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
   const float* x_last = c->tape[c->n_train - 1].x_out;
   launch_head_bwd(dlogits_c, c->text, c->logit_scale_exp, c->feats_c, c->Wp, x_last, c->postg, c->dfh, c->dpool, c->DX, c->DXB, G,
-                  c->C, c->P, c->tokens, d, c->cfg.ln_eps, st);
+                  c->C, c->P, c->tokens, c->d, c->cfg.ln_eps, st);
   c->launches += 4;
+  return f32_backward_layers(c, G, st);
+}
+
+// c->DX = gradient of the last tape layer's output (written by the head backward of either route) -> LoRA gradients
+int f32_backward_layers(ttl_ctx* c, int G, cudaStream_t st) {
+  if (c->last_train_views != G || G <= 0) { c->err = "backward: no matching train forward"; return TTL_E_STATE; }
+  const int Mg = G * c->tokens, d = c->d, F = c->F, r = c->r;
   float* dx = c->DX;
   float* dx2 = c->DX2;
   for (int l = c->L - 1; l >= c->lo; --l) {
@@ -700,7 +713,7 @@ int f32_backward(ttl_ctx* c, const float* dlogits_c, int G, cudaStream_t st) {
     launch_layernorm_bwd(c->DH, tp.x_mid, w.ln2g, dx, dx2, c->DXB, Mg, d, c->cfg.ln_eps, st);
     // d attn_out = dx_mid Wo ; attention backward
     RET_IF(sg(c, dx2, d, w.wo_f, d, 1, Mg, d, d, 1.f, nullptr, nullptr, 0, c->DAOf, d, SE_LINEAR, nullptr, nullptr, st));
-    launch_attention_f32_bwd(tf.qkv, tf.ao, c->DAOf, tp.lse, c->DQKVf, G, c->tokens, c->H, 0.125f, st);
+    launch_attention_f32_bwd(tf.qkv, tf.ao, c->DAOf, tp.lse, c->DQKVf, G, c->tokens, c->H, 0.125f, st, c->text_mode ? 1 : 0);
     c->launches += 2;
     const bool lora = has_lora(c, l);
     if (lora) {
@@ -864,7 +877,10 @@ int adapt_body_f32(ttl_ctx* c, const float* images, int V, const ttl_hparams& hp
 // forward (:677-678): layers below lo run once per class-name set (XK), layers lo.. run in train mode over all prompts per step.
 int text_features_now(ttl_ctx* c, bool train, cudaStream_t st) {   // current class features -> c->feats_c (raw), c->tn (normalised)
   const int n = c->n_prompts;
-  if (train) RET_IF(forward_tail_train(c, c->XK, n, 1, st));
+  if (c->f32) {
+    if (train) RET_IF(f32_tail_train(c, c->XK, n, st));
+    else RET_IF(f32_tail_infer(c, c->XK, n, c->feats_c, nullptr, nullptr, st));
+  } else if (train) RET_IF(forward_tail_train(c, c->XK, n, 1, st));
   else RET_IF(forward_tail_infer(c, c->XK, n, 1, c->feats_c, nullptr, nullptr, st));
   launch_l2norm_rows(c->feats_c, c->tn, n, c->P, st);
   c->launches++;
@@ -905,7 +921,7 @@ int text_adapt_body(ttl_ctx* c, const float* img_feats, int V, const ttl_hparams
     launch_text_head_bwd(c->dlogits, idx, rows, c->fhat, c->logit_scale_exp, c->feats_c, c->Wp, c->tape[c->n_train - 1].x_out, c->postg,
                          c->eot, c->dfh, c->dpool, c->DX, c->DXB, n, c->P, c->tokens, c->d, c->cfg.ln_eps, st);
     c->launches += 4;
-    RET_IF(backward_layers(c, n, st));
+    RET_IF(c->f32 ? f32_backward_layers(c, n, st) : backward_layers(c, n, st));
     RET_IF(adamw(c, hp, 1, st));
   }
   RET_IF(text_features_now(c, false, st));                            // predict on view 0 with the adapted class features
@@ -1104,8 +1120,8 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     return TTL_E_ARCH;
   }
   const bool text_mode = cfg->text_mode != 0;
-  if (text_mode && (cfg->context <= 0 || cfg->context > 256 || cfg->vocab <= 0 || cfg->max_samples > 1 || cfg->precision != TTL_PRECISION_BF16)) {
-    g_create_err = "text mode: context in 1..256, vocab > 0, one sample per call, bf16 path";
+  if (text_mode && (cfg->context <= 0 || cfg->context > 256 || cfg->vocab <= 0 || cfg->max_samples > 1)) {
+    g_create_err = "text mode: context in 1..256, vocab > 0, one sample per call";
     return TTL_E_SHAPE;
   }
   if (cfg->width % 128 != 0 || cfg->width > 1024 || cfg->width != cfg->heads * 64 || (!text_mode && cfg->image_size % cfg->patch != 0) ||
@@ -1121,7 +1137,7 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     return TTL_E_SHAPE;
   }
   if (cfg->precision == TTL_PRECISION_FP32) {
-    const int tk = (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch) + 1;
+    const int tk = text_mode ? cfg->context : (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch) + 1;
     if (attention_f32_bwd_smem(tk) > 227 * 1024) {
       g_create_err = "the fp32 validation mode stages Q/K/V/dO of one (view, head) in shared memory: too many tokens";
       return TTL_E_SHAPE;
@@ -1599,7 +1615,8 @@ int ttl_text_set_prompts(ttl_ctx* c, const int32_t* tokens_host, int32_t n_promp
   c->logit_scale_exp = std::exp(logit_scale);
   c->C = n_prompts;
   if (c->pack_samples != 1) RET_IF(repack(c, 1, st));
-  RET_IF(forward_frozen(c, nullptr, n_prompts, st));     // layers below the adapter: once per class-name set
+  if (c->f32) RET_IF(f32_frozen(c, nullptr, n_prompts, st));
+  else RET_IF(forward_frozen(c, nullptr, n_prompts, st));     // layers below the adapter: once per class-name set
   return check_launch(c, "ttl_text_set_prompts");
 }
 

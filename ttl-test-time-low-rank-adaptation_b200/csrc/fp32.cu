@@ -100,7 +100,7 @@ constexpr int LDF = DH + 1;
 
 __global__ void __launch_bounds__(256)
 attention_f32_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ lse, int tokens, int heads,
-                         float scale) {
+                         float scale, int causal) {      // causal: query r sees keys 0..r (text tower)
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm_att[];
@@ -123,8 +123,9 @@ attention_f32_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
     q[lane] = base[static_cast<size_t>(r) * ld + lane];
     q[lane + 32] = base[static_cast<size_t>(r) * ld + lane + 32];
     __syncwarp();
+    const int nk = causal ? r + 1 : tokens;
     float mx = -INFINITY;
-    for (int j = lane; j < tokens; j += 32) {
+    for (int j = lane; j < nk; j += 32) {
       const float* kr = sK + j * LDF;
       float acc = 0.f;
 #pragma unroll 16
@@ -135,7 +136,7 @@ attention_f32_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < tokens; j += 32) {
+    for (int j = lane; j < nk; j += 32) {
       const float e = expf(p[j] - mx);
       p[j] = e;
       sum += e;
@@ -143,7 +144,7 @@ attention_f32_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
     sum = warp_sum(sum);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < tokens; ++j) {
+    for (int j = 0; j < nk; ++j) {
       const float pj = p[j];
       o0 = fmaf(pj, sV[j * LDF + lane], o0);
       o1 = fmaf(pj, sV[j * LDF + lane + 32], o1);
@@ -161,7 +162,7 @@ attention_f32_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
 // phase B (one warp per key row j): dV_j = sum_i p_ij dO_i, dK_j = scale sum_i dS_ij Q_i.  p recomputed from lse (exact).
 __global__ void __launch_bounds__(256)
 attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
-                         const float* __restrict__ lse, float* __restrict__ dqkv, int tokens, int heads, float scale) {
+                         const float* __restrict__ lse, float* __restrict__ dqkv, int tokens, int heads, float scale, int causal) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm_att[];
@@ -196,7 +197,8 @@ attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
   for (int i = warp; i < tokens; i += nw) {
     const float* qi = sQ + i * LDF;
     const float* doi = sDO + i * LDF;
-    for (int j = lane; j < tokens; j += 32) {
+    const int nk = causal ? i + 1 : tokens;
+    for (int j = lane; j < nk; j += 32) {
       const float* kj = sK + j * LDF;
       const float* vj = sV + j * LDF;
       float s = 0.f, dp = 0.f;
@@ -207,7 +209,7 @@ attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
     }
     __syncwarp();
     float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < tokens; ++j) {
+    for (int j = 0; j < nk; ++j) {
       const float ds = w[j];
       a0 = fmaf(ds, sK[j * LDF + lane], a0);
       a1 = fmaf(ds, sK[j * LDF + lane + 32], a1);
@@ -227,7 +229,7 @@ attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
     for (int i0 = 0; i0 < tokens; i0 += 32) {
       const int i = i0 + lane;
       float pij = 0.f, ds = 0.f;
-      if (i < tokens) {
+      if (i < tokens && (!causal || i >= j)) {
         const float* qi = sQ + i * LDF;
         const float* doi = sDO + i * LDF;
         float s = 0.f, dp = 0.f;
@@ -262,7 +264,8 @@ attention_f32_bwd_kernel(const float* __restrict__ qkv, const float* __restrict_
 template <int PHASE_DKV>
 __global__ void __launch_bounds__(256)
 attention_f32_bwd_split_kernel(const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout,
-                               const float* __restrict__ lse, float* __restrict__ dqkv, int tokens, int heads, float scale) {
+                               const float* __restrict__ lse, float* __restrict__ dqkv, int tokens, int heads, float scale,
+                               int causal) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm_att[];
@@ -304,7 +307,8 @@ attention_f32_bwd_split_kernel(const float* __restrict__ qkv, const float* __res
       r1[lane] = dout[(vrow + i) * d + h * DH + lane];
       r1[lane + 32] = dout[(vrow + i) * d + h * DH + lane + 32];
       __syncwarp();
-      for (int j = lane; j < tokens; j += 32) {
+      const int nk = causal ? i + 1 : tokens;
+      for (int j = lane; j < nk; j += 32) {
         const float* kj = sA + j * LDF;
         const float* vj = sB + j * LDF;
         float s = 0.f, dp = 0.f;
@@ -315,7 +319,7 @@ attention_f32_bwd_split_kernel(const float* __restrict__ qkv, const float* __res
       }
       __syncwarp();
       float a0 = 0.f, a1 = 0.f;
-      for (int j = 0; j < tokens; ++j) {
+      for (int j = 0; j < nk; ++j) {
         const float ds = w[j];
         a0 = fmaf(ds, sA[j * LDF + lane], a0);
         a1 = fmaf(ds, sA[j * LDF + lane + 32], a1);
@@ -336,7 +340,7 @@ attention_f32_bwd_split_kernel(const float* __restrict__ qkv, const float* __res
       for (int i0 = 0; i0 < tokens; i0 += 32) {
         const int i = i0 + lane;
         float pij = 0.f, ds = 0.f;
-        if (i < tokens) {
+        if (i < tokens && (!causal || i >= j)) {
           const float* qi = sA + i * LDF;
           const float* doi = sB + i * LDF;
           float s = 0.f, dp = 0.f;
@@ -446,7 +450,8 @@ size_t attention_f32_bwd_smem(int tokens) {
   return whole <= 227 * 1024 ? whole : attention_f32_bwd_smem_split(tokens);
 }
 
-void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st) {
+void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st,
+                              int causal) {
   const size_t smem = attention_f32_fwd_smem(tokens);
   static size_t configured_dev[MAX_DEVICES] = {};
   size_t& configured = configured_dev[current_device_slot()];
@@ -454,11 +459,11 @@ void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, i
     cudaFuncSetAttribute(attention_f32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  launch_pdl(attention_f32_fwd_kernel, dim3(heads, V), dim3(256), smem, st, qkv, out, lse, tokens, heads, scale);
+  launch_pdl(attention_f32_fwd_kernel, dim3(heads, V), dim3(256), smem, st, qkv, out, lse, tokens, heads, scale, causal);
 }
 
 void launch_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int V,
-                              int tokens, int heads, float scale, cudaStream_t st) {
+                              int tokens, int heads, float scale, cudaStream_t st, int causal) {
   if (attention_f32_bwd_smem_whole(tokens) > 227 * 1024) {      // e.g. 257 tokens (ViT-L/14): dQ and dK/dV as two launches
     const size_t smem2 = attention_f32_bwd_smem_split(tokens);
     static size_t configured2_dev[MAX_DEVICES] = {};
@@ -468,8 +473,8 @@ void launch_attention_f32_bwd(const float* qkv, const float* out, const float* d
       cudaFuncSetAttribute(attention_f32_bwd_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
       configured2 = smem2;
     }
-    launch_pdl(attention_f32_bwd_split_kernel<0>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale);
-    launch_pdl(attention_f32_bwd_split_kernel<1>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale);
+    launch_pdl(attention_f32_bwd_split_kernel<0>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale, causal);
+    launch_pdl(attention_f32_bwd_split_kernel<1>, dim3(heads, V), dim3(256), smem2, st, qkv, out, dout, lse, dqkv, tokens, heads, scale, causal);
     return;
   }
   const size_t smem = attention_f32_bwd_smem_whole(tokens);
@@ -479,7 +484,7 @@ void launch_attention_f32_bwd(const float* qkv, const float* out, const float* d
     cudaFuncSetAttribute(attention_f32_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = smem;
   }
-  launch_pdl(attention_f32_bwd_kernel, dim3(heads, V), dim3(256), smem, st, qkv, out, dout, lse, dqkv, tokens, heads, scale);
+  launch_pdl(attention_f32_bwd_kernel, dim3(heads, V), dim3(256), smem, st, qkv, out, dout, lse, dqkv, tokens, heads, scale, causal);
 }
 
 void launch_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, int rows, int d, float eps,

@@ -129,9 +129,10 @@ struct SgemmArgs {
 };
 cudaError_t launch_sgemm(const SgemmArgs& a, cudaStream_t st);
 // qkv fp32 [V*tokens, 3d] -> out fp32 [V*tokens, d], lse (nullable) [V, heads, tokens]
-void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st);
+void launch_attention_f32_fwd(const float* qkv, float* out, float* lse, int V, int tokens, int heads, float scale, cudaStream_t st,
+                              int causal = 0);
 void launch_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv, int V,
-                              int tokens, int heads, float scale, cudaStream_t st);
+                              int tokens, int heads, float scale, cudaStream_t st, int causal = 0);
 size_t attention_f32_fwd_smem(int tokens);
 size_t attention_f32_bwd_smem(int tokens);
 void launch_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, int rows, int d, float eps,
