@@ -1466,8 +1466,8 @@ attention_fwd_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 //   O_t  [192, 256)     fp32 accumulator of P V.  It overlaps the 16-column tail of S, so pass 2 reads that tail FIRST; the first
 //                       P V MMA is issued after all four warps of the tile delivered block 0, i.e. after every lane has read its tail.
 // No swizzled shared-memory P stores, no proxy fences; the shared memory that P occupied holds the second K and Q buffers
-// (200 KB).  Exact two-pass softmax in fp32; 1 of 8 exponentials on the FMA pipe (166.7 us at 576 views against 174.3 with 2 of 8
-// and 171.9 with none); scale and row sums as packed fp32 pairs.
+// (200 KB).  Exact two-pass softmax in fp32; 2 of 8 exponentials on the FMA pipe (163.3 us at 576 views against 166.4 with 1 of 8
+// and 168.9 with none); scale and row sums as packed fp32 pairs.
 //   warp 0 (one thread)   TMA producer: K + Q0 + Q1 of unit u into buffer u & 1 once both streams' S MMAs of unit u - 2 retired;
 //                         V likewise behind both streams' last P V MMA
 //   warp 1 / warp 10      MMA issue of stream 0 / 1 (one elected thread each; tcgen05.commit tracks the issuing thread's MMAs)
@@ -1567,6 +1567,9 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(&bar_kq[b], use & 1);
         if (it > 0) mbar_wait(&bar_tfree[t], ph ^ 1);             // the previous unit's O_t has left TMEM
         tc_fence_after();
+        // (S split into keys [0, 192) issued right behind the previous unit's last P V MMA and the 16-key tail behind bar_tfree:
+        //  S ready 200 cycles earlier, but the 384-cycle head then sits in front of the OTHER stream's last P V block in the one
+        //  tensor pipe: 171.0 against 166.7 us at 576 views)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tt, umma_desc_k_sw128(qa + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
@@ -1677,9 +1680,19 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         tmem_ld_32x32b_x16(trow + 16, ba);
         tmem_st_32x32b_x8(trow, pk);               // S columns [0, 8) are in bb already
+        auto deliver = [&](int blk) {              // P block blk (four steps) is in TMEM: tell the MMA thread
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[t * 4 + blk]);
+          PT_STAMP(8 + blk);
+        };
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {              // 16-key steps 2 i (in bb) and 2 i + 1 (in ba, in flight)
           eval16(bb);
+          // a block's delivery rides one evaluation behind its last store: tcgen05.wait::st then finds the stores retired
+          // (delivered right behind the store it cost ~150 cycles of the pass per block)
+          if (i == 2 || i == 4) deliver((i >> 1) - 1);
           tmem_ld_wait();
           if (i < 5) tmem_ld_32x32b_x16(trow + 32 * i + 32, bb);
           tmem_st_32x32b_x8(trow + 8 + 16 * i, pk);
@@ -1687,14 +1700,8 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_ld_wait();
           if (i < 5) tmem_ld_32x32b_x16(trow + 32 * i + 48, ba);
           tmem_st_32x32b_x8(trow + 16 + 16 * i, pk);
-          if (i & 1) {                             // a P block of four steps is complete
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_p[t * 4 + (i >> 1)]);
-            PT_STAMP(8 + (i >> 1));
-          }
         }
+        deliver(2);
         l = lt + f32x2_lo(l2) + f32x2_hi(l2);
       } else {
         tc_fence_before();
@@ -2386,9 +2393,9 @@ static bool launch_attention_fwd_pt(const bf16* qkv, bf16* out, float* lse, int 
   CUtensorMap tq, tkv, to;
   static const int variant = std::getenv("TTL_PT_VARIANT") ? std::atoi(std::getenv("TTL_PT_VARIANT")) : 0;
   static const bool want_dbg = std::getenv("TTL_ATTN_DBG") != nullptr;
-  auto kern = want_dbg ? attention_fwd_pt_kernel<0x80, true>
-                       : variant == 1 ? attention_fwd_pt_kernel<0x88, false>
-                                      : variant == 2 ? attention_fwd_pt_kernel<0x00, false> : attention_fwd_pt_kernel<0x80, false>;
+  auto kern = want_dbg ? attention_fwd_pt_kernel<0x88, true>
+                       : variant == 1 ? attention_fwd_pt_kernel<0x80, false>
+                                      : variant == 2 ? attention_fwd_pt_kernel<0x00, false> : attention_fwd_pt_kernel<0x88, false>;
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
   const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
   const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, static_cast<uint32_t>(keys), 1};
