@@ -131,10 +131,38 @@ def test_fp32_mode_compat_forward_backward(b16_fp32_engine, b16_views):
             assert _rel(eng.lora_get(i, j, L.LORA_GRAD), g[f"grad_{i}_{NAMES[j]}"]) < TOL
 
 
-def test_fp32_mode_rejects_what_it_does_not_cover():
-    from ttl_b200 import Engine
-    with pytest.raises(RuntimeError):
-        Engine("ViT-B/16", max_views=8, max_classes=16, max_samples=2, precision="fp32")      # one sample per call
+def test_fp32_mode_several_samples_per_call(b16_weights, b16_views):
+    """max_samples > 1 in the fp32 mode: a call with S samples is S consecutive single-sample passes over windows of the
+    sample-major state (own factors, gradients, AdamW moments, results).  Sample 1 of a two-sample call carries the reference
+    fixture's views: it must reproduce the fixture at 1e-4 like a single call, and sample 0 (other views) must equal its own
+    single-sample call bit for bit."""
+    from ttl_b200 import Engine, Hparams
+    from ttl_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "ref_b16_c10_tpt.npz"))
+    spec = O.LoraSpec()
+    other = O.make_synthetic_views(64, 224, seed=21)
+    eng = Engine("ViT-B/16", max_views=64, max_classes=16, max_samples=2, layer_range=(9, 11), precision="fp32")
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(O.lora_init(O.ARCHS["ViT-B/16"], spec, seed=0))
+        eng.set_text_features(g["text_features"], float(g["logit_scale"]))
+        x = torch.stack([other, b16_views]).cuda()
+        out = eng.adapt_predict_batch(x, Hparams(head="tpt"), want=("logits0", "idx", "loss", "pred_logits"))
+        torch.cuda.synchronize()
+        assert _rel(out["logits0"][1].cpu().numpy(), g["logits0"]) < TOL
+        assert sorted(out["idx"][1].cpu().tolist()) == g["idx_sorted"].tolist()
+        assert _rel(out["pred_logits"][1].cpu().numpy(), g["pred_logits"][0]) < TOL
+        for i in spec.layers():
+            for j in (1, 3):
+                assert _rel(eng.lora_get(i, j, L.LORA_GRAD, sample=1), g[f"grad_{i}_{NAMES[j]}"]) < TOL
+        grads0 = [eng.lora_get(i, j, L.LORA_GRAD, sample=0) for i in spec.layers() for j in (1, 3)]
+        pred0, loss0 = out["pred_logits"][0].cpu().clone(), float(out["loss"][0])
+        single = eng.adapt_predict_batch(other[None].cuda(), Hparams(head="tpt"), want=("loss", "pred_logits"))
+        assert torch.equal(single["pred_logits"][0].cpu(), pred0) and float(single["loss"][0]) == loss0
+        for a, b in zip(grads0, [eng.lora_get(i, j, L.LORA_GRAD, sample=0) for i in spec.layers() for j in (1, 3)]):
+            assert np.array_equal(a, b)
+    finally:
+        eng.close()
 
 
 def test_fp32_mode_vit_l14_64_views_vs_oracle():

@@ -1043,8 +1043,24 @@ int adapt_predict_impl(ttl_ctx* c, const float* images_dev, int S, int V, const 
   NvtxRange nv("ttl:adapt_predict");
   const int64_t before = c->launches;
   if (c->f32) {
-    if (S != 1 || images_dev == nullptr) { c->err = "fp32 validation mode: one sample per call, fp32 views as input"; return TTL_E_SHAPE; }
-    int r = adapt_body_f32(c, images_dev, V, *hp, forced, st);
+    if (images_dev == nullptr) { c->err = "fp32 validation mode: fp32 views as input"; return TTL_E_SHAPE; }
+    // S samples = S consecutive single-sample passes (the mode exists for checking, not for speed): the per-sample state and result
+    // arrays are sample-major, so sample s runs on a window of them.
+    const int K = select_count(V, hp->selection_p);
+    const size_t px = static_cast<size_t>(3) * c->cfg.image_size * c->cfg.image_size;
+    float *lp = c->lp, *lg = c->lg, *lm = c->lm, *lv = c->lv, *feats = c->feats, *logits = c->logits, *entropy = c->entropy;
+    float *loss = c->loss, *pred = c->pred, *pred_feats = c->pred_feats, *pred_entropy = c->pred_entropy;
+    int* idx = c->idx;
+    int r = TTL_OK;
+    for (int s = 0; s < S && r == TTL_OK; ++s) {
+      c->lp = lp + s * c->lora_total; c->lg = lg + s * c->lora_total; c->lm = lm + s * c->lora_total; c->lv = lv + s * c->lora_total;
+      c->feats = feats + static_cast<size_t>(s) * V * c->P; c->logits = logits + static_cast<size_t>(s) * V * c->C;
+      c->entropy = entropy + s * V; c->idx = idx + s * K; c->loss = loss + s; c->pred = pred + static_cast<size_t>(s) * c->C;
+      c->pred_feats = pred_feats + static_cast<size_t>(s) * c->P; c->pred_entropy = pred_entropy + s;
+      r = adapt_body_f32(c, images_dev + static_cast<size_t>(s) * V * px, V, *hp, forced, st);
+    }
+    c->lp = lp; c->lg = lg; c->lm = lm; c->lv = lv; c->feats = feats; c->logits = logits; c->entropy = entropy; c->idx = idx;
+    c->loss = loss; c->pred = pred; c->pred_feats = pred_feats; c->pred_entropy = pred_entropy;
     c->last_launches = c->launches - before;
     return r;
   }
@@ -1132,10 +1148,6 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     return TTL_E_SHAPE;
   }
   if (cfg->precision != TTL_PRECISION_BF16 && cfg->precision != TTL_PRECISION_FP32) { g_create_err = "unknown precision"; return TTL_E_INVALID; }
-  if (cfg->precision == TTL_PRECISION_FP32 && cfg->max_samples > 1) {
-    g_create_err = "the fp32 validation mode adapts one sample per call (max_samples <= 1)";
-    return TTL_E_SHAPE;
-  }
   if (cfg->precision == TTL_PRECISION_FP32) {
     const int tk = text_mode ? cfg->context : (cfg->image_size / cfg->patch) * (cfg->image_size / cfg->patch) + 1;
     if (attention_f32_bwd_smem(tk) > 227 * 1024) {

@@ -14,7 +14,7 @@ New flags (names chosen so that the launcher's `--data`/`--b` abbreviations stay
   --views_on_host the reference's input route: the DataLoader workers produce 64 fp32 views per sample (host -> device copy
                   of 38.5 MB per sample) instead of the default uint8 image + crop boxes
   --concurrent_samples S  adapt S test samples per library call (default 9; 1 = strictly one at a time)
-  --precision fp32  validation mode: every activation/contraction in fp32 (held to 1e-4 against the reference), one sample per call
+  --precision fp32  validation mode: every activation/contraction in fp32 (held to 1e-4 against the reference), samples one at a time
   --vision_checkpoint F  load image tower + text tower + logit_scale from one CLIP checkpoint file (HF or OpenAI format)
                   instead of the local HF cache
   --random_init   allow seeded random-init weights / random class features when no checkpoint exists (implied by --synthetic)
@@ -517,7 +517,7 @@ def build_parser():
                    help='(default on the fused path) generate the views on the GPU from the uint8 image, bit-exact with '
                         'PIL/torchvision; kept as an explicit flag for older command lines')
     p.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
-                   help='bf16 = tensor-core path (default); fp32 = validation mode (fp32 everywhere, one sample per call)')
+                   help='bf16 = tensor-core path (default); fp32 = validation mode (fp32 everywhere, samples one at a time)')
     p.add_argument('--vision_checkpoint', default=None, type=str,
                    help='CLIP checkpoint file for the image tower: HF model.safetensors / pytorch_model.bin or OpenAI ViT-*.pt')
     p.add_argument('--random_init', action='store_true', default=False,
