@@ -338,6 +338,36 @@ def test_zigzag_walk_is_bit_identical(b16_weights, monkeypatch):
         eng.close()
 
 
+def test_fused_layernorm_in_fc2_agrees(b16_weights, monkeypatch):
+    """TTL_FUSE_LN=1 (opt-in, a measured negative result: DESIGN 4.4): the fc2 GEMM of a frozen-pass layer walks its tiles in
+    256-row strips and also writes LayerNorm1 of the next layer (statistics kept by the epilogue threads, second sweep over the
+    rows it has just stored).  Same inputs, statistics merged in another order: the first-forward logits agree to fp32 noise
+    behind one bf16 rounding of the normalised rows, the selection is the same, 11 LayerNorm launches per forward fewer."""
+    from ttl_b200 import Engine, Hparams
+    arch = O.ARCHS["ViT-B/16"]
+    S, V = 2, 64
+    eng = Engine("ViT-B/16", max_views=V, max_classes=64, layer_range=(9, 11), max_samples=S)
+    try:
+        eng.load_weights(b16_weights)
+        eng.set_lora_init(O.lora_init(arch, O.LoraSpec(), seed=0))
+        eng.set_text_features(O.make_text_features(37, arch.proj), math.log(100.0))
+        eng.set_graphs(False)
+        imgs = torch.stack([O.make_synthetic_views(V, arch.image_size, seed=41 + i) for i in range(S)]).cuda()
+        res, launches = {}, {}
+        for f in ("0", "1"):
+            monkeypatch.setenv("TTL_FUSE_LN", f)
+            out = eng.adapt_predict_batch(imgs, Hparams(head="tpt"), want=("logits0", "pred_logits", "idx", "loss"))
+            res[f] = {k: v.float().cpu().numpy().copy() for k, v in out.items()}
+            launches[f] = eng.last_launch_count()
+        assert launches["0"] - launches["1"] == 11, launches
+        assert np.array_equal(res["0"]["idx"], res["1"]["idx"])
+        for k in ("logits0", "pred_logits"):
+            a, b = res["0"][k], res["1"][k]
+            assert np.linalg.norm(a - b) / np.linalg.norm(a) < 3e-3, k
+    finally:
+        eng.close()
+
+
 def test_edge_cases_few_views_few_classes():
     """Edge cases of ttl.py:50-54 on the tiny geometry: fewer than 10 views select nothing (int(8 * 0.1) == 0: the library leaves
     the adapter at its reset state instead of the reference's NaN loss), a ragged batch (fewer views than max_views), and

@@ -167,6 +167,9 @@ struct ttl_ctx {
   // lo..hi.  "views" are the class prompts (tokens = context positions, causal attention, EOT pooling), the "classes" of the
   // logits are the image views whose frozen features the caller supplies per test sample.
   bool text_mode = false;
+  // fused LayerNorm (TTL_FUSE_LN): the fc2 GEMM of an inference-mode layer also wrote LayerNorm1 of the NEXT layer over these rows
+  const float* h1_for = nullptr;
+  int h1_rows = 0;
   float *tok_emb = nullptr, *fhat = nullptr, *tn = nullptr, *attn_delta = nullptr;
   int *tok_ids = nullptr, *eot = nullptr;
   int n_prompts = 0;
@@ -302,9 +305,13 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   const bool zz_on = zz_env == nullptr || std::atoi(zz_env) != 0;
   const bool zz = zz_on && tp == nullptr && M >= 8192;
   auto next_dir = [&]() -> int { if (!zz) return 0; c->zz_dir ^= 1; return c->zz_dir; };
-  const int dir_ln1 = next_dir();
-  if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st, dir_ln1);
-  c->launches++;
+  const bool h1_ready = tp == nullptr && c->h1_for == x_in && c->h1_rows == M;      // written by the previous layer's fc2
+  c->h1_for = nullptr;
+  if (!h1_ready) {
+    const int dir_ln1 = next_dir();
+    if (!(skip & 1)) launch_layernorm(x_in, h1, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st, dir_ln1);
+    c->launches++;
+  }
   if (lora && (lora_on || tp)) {  // T = h1 [A_q;A_v]^T per sample (needed by dB even while B == 0)
     if (S != c->pack_samples) { c->err = "run_layer: adapter packs were built for another sample count"; return TTL_E_STATE; }
     GemmArgs g;
@@ -357,6 +364,16 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.b1 = opnd(w.w2, d, F, F);
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.b2; g.out = x_out; g.ldo = d; g.resid = x_mid; g.ldr = d;
     g.descending = next_dir();
+    // TTL_FUSE_LN=1: LayerNorm1 of the next layer rides in this GEMM (strip walk + L2-hot second sweep, gemm.cu): its K = 4 d
+    // main loop hides the sweep.  Inference-mode layers of the big first forward only.
+    const char* fuse_env = std::getenv("TTL_FUSE_LN");       // read per call: the tests toggle it
+    const bool fuse = fuse_env != nullptr && std::atoi(fuse_env) != 0;
+    if (fuse && tp == nullptr && layer + 1 < c->L && M >= 8192 && d % 256 == 0 && !(skip & 1)) {
+      const LayerW& wn = c->lw[layer + 1];
+      g.ln_gamma = wn.ln1g; g.ln_beta = wn.ln1b; g.ln_out = c->Hb; g.ld_ln = d; g.ln_eps = c->cfg.ln_eps;
+      c->h1_for = x_out;
+      c->h1_rows = M;
+    }
     RET_IF(gemm(c, g, st));
   }
   return check_launch(c, "run_layer");
@@ -380,8 +397,12 @@ int run_last_layer_cls(ttl_ctx* c, int layer, const float* x_in, int V, int S, b
   const int M = V * c->tokens, d = c->d, F = c->F, tk = c->tokens;
   const int kc = 64 * c->pack_samples;
   const bool lora = has_lora(c, layer) && lora_on;
-  launch_layernorm(x_in, c->Hb, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
-  c->launches++;
+  const bool h1_ready = c->h1_for == x_in && c->h1_rows == M;
+  c->h1_for = nullptr;
+  if (!h1_ready) {
+    launch_layernorm(x_in, c->Hb, w.ln1g, w.ln1b, M, d, c->cfg.ln_eps, st);
+    c->launches++;
+  }
   if (lora) {
     if (S != c->pack_samples) { c->err = "run_last_layer_cls: adapter packs were built for another sample count"; return TTL_E_STATE; }
     GemmArgs g;

@@ -332,6 +332,14 @@ struct Epi2Params {
   const __nv_bfloat16* aux;   // EPI_GELU_BWD: z [M, N] bf16, row pitch ldaux
   int ldaux;
   __nv_bfloat16* out2;        // EPI_GELU: optional copy of the pre-activation z = acc + bias (bf16, row pitch ldaux), for the backward
+  // EPI_RESID_F32 with a fused LayerNorm of the rows it writes (ln_out != nullptr): the tiles are walked in STRIPS (a cluster owns
+  // all N / BLOCK_N tiles of a 256-row block back to back), the epilogue threads keep running row statistics, and after the last
+  // tile of a strip every warp re-reads the fp32 rows it has just stored (L2-hot) and writes LayerNorm(row) as bf16 to ln_out.
+  const float* ln_gamma;
+  const float* ln_beta;
+  __nv_bfloat16* ln_out;
+  int ld_ln;
+  float ln_eps;
 };
 
 // CL = 2: one CTA pair per cluster (above).  CL = 4: two pairs stacked along M share every B tile: each CTA loads a QUARTER of
@@ -408,6 +416,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int num_kb = p.kb1 + p.kb2;
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+  const bool strips = EPI == EPI_RESID_F32 && CL == 2 && p.ln_out != nullptr;
+  // the k-th tile of this cluster: round-robin over all tiles, or (strips) all n tiles of every num_clusters-th row block
+  auto tile_at = [&](int k, int& m_pair, int& n_blk) -> bool {
+    if (strips) {
+      const int sk = k / n_tiles, strip = cluster_id + sk * num_clusters;
+      if (strip >= m_pairs) return false;
+      m_pair = p.rev ? m_pairs - 1 - strip : strip;
+      n_blk = k - sk * n_tiles;
+      return true;
+    }
+    const int tile = cluster_id + k * num_clusters;
+    if (tile >= num_tiles) return false;
+    const int t2 = p.rev ? num_tiles - 1 - tile : tile;
+    m_pair = t2 / n_tiles;
+    n_blk = t2 - m_pair * n_tiles;
+    return true;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer (one thread per CTA)
@@ -417,9 +442,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       const uint32_t full0 = mapa_u32(smem_u32(&full[0]), lead_rank);   // the pair LEADER's full barriers
       uint16_t bmask = 0;                                      // CL > 2: the CTAs of the same parity in every pair
       for (int q = 0; q < PAIRS; ++q) bmask |= static_cast<uint16_t>(1u << (rank + 2 * q));
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int t2 = p.rev ? num_tiles - 1 - tile : tile;
-        const int m_pair = t2 / n_tiles, n_blk = t2 - m_pair * n_tiles;
+      int m_pair = 0, n_blk = 0;
+      for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
         const int a_row = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128;
         const int b_row = n_blk * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2) + static_cast<int>(pair) * (BLOCK_N / CL);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -451,7 +475,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m_pair = 0, n_blk = 0;
+      for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
@@ -485,7 +510,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full0 = mapa_u32(smem_u32(&full[0]), lead_rank);
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m_pair = 0, n_blk = 0;
+      for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_expect_tx(&fullB[stage], C::B_BYTES);
           mbar_wait(&fullB[stage], phase);
@@ -506,9 +532,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int as = 0;
     uint32_t aphase = 0;
     uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int t2 = p.rev ? num_tiles - 1 - tile : tile;
-      const int m_pair = t2 / n_tiles, n_blk = t2 - m_pair * n_tiles;
+    float ln_mean = 0.f, ln_m2 = 0.f, ln_cnt = 0.f;      // strips: running statistics of this lane's row over this warp's columns
+    int m_pair = 0, n_blk = 0;
+    for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
       const int row0 = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128 + quad * 32;
       const int col_base = n_blk * BLOCK_N + half * (BLOCK_N / 2);
       const bool live = row0 < p.M;     // warp-uniform
@@ -560,6 +586,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             float4* slot = row + (i ^ (lane & 7));
             if (EPI == EPI_RESID_F32) v = add4(v, *slot);
             *slot = v;
+            if (EPI == EPI_RESID_F32) {      // keep the final values for the row statistics below
+              r[4 * i] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
+              r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
+            }
+          }
+          if (EPI == EPI_RESID_F32 && strips) {
+            // statistics of these 32 values (two-pass in registers), merged into the running ones (Chan et al.): no E[x^2] - mean^2
+            if (n_blk == 0 && c == 0) { ln_mean = 0.f; ln_m2 = 0.f; ln_cnt = 0.f; }
+            float sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sm += __uint_as_float(r[i]);
+            const float mc = sm * (1.f / 32.f);
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float t = __uint_as_float(r[i]) - mc; q = fmaf(t, t, q); }
+            const float tot = ln_cnt + 32.f, delta = mc - ln_mean;
+            ln_mean += delta * (32.f / tot);
+            ln_m2 += q + delta * delta * (ln_cnt * 32.f / tot);
+            ln_cnt = tot;
           }
         } else {
           uint4* row = reinterpret_cast<uint4*>(buf + lane * 64);
@@ -610,6 +655,57 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           }
         }
         ++g;
+      }
+      if (EPI == EPI_RESID_F32 && strips && n_blk == n_tiles - 1 && live && !(p.dbg & 1)) {
+        // ---- fused LayerNorm of the strip.  The other half of every row's columns belongs to warp ew ^ 4 (same TMEM quadrant):
+        // exchange the half-row statistics through this warp's (drained) first staging buffer.
+        if (lane == 0) bulk_wait<0>();              // every store of this warp has completed: the rows are in L2 / memory
+        __syncwarp();
+        reinterpret_cast<float2*>(ebuf)[lane] = make_float2(ln_mean, ln_m2);
+        named_bar_sync(1 + quad, 64);
+        const float2 oth = reinterpret_cast<const float2*>(sE + (ew ^ 4) * 2 * C::EBUF_BYTES)[lane];
+        named_bar_sync(1 + quad, 64);               // the partner has read before the loads below land in the buffer
+        const float delta = oth.x - ln_mean;
+        const float mean = ln_mean + 0.5f * delta;                                  // both halves hold N / 2 values
+        const float var = (ln_m2 + oth.y + delta * delta * (0.25f * p.N)) / static_cast<float>(p.N);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        const int Q = n_tiles * C::CHUNKS;
+        auto sweep_col = [&](int q) { return (q / C::CHUNKS) * BLOCK_N + half * (BLOCK_N / 2) + (q % C::CHUNKS) * 32; };
+        if (lane == 0) {
+          for (int q = 0; q < 2 && q < Q; ++q) {
+            const uint32_t b = (g + q) & 1;
+            mbar_expect_tx(&lb[b], C::EBUF_BYTES);
+            tma_load_2d(&tmOut, &lb[b], ebuf + b * C::EBUF_BYTES, sweep_col(q), row0);
+          }
+        }
+#pragma unroll 1
+        for (int q = 0; q < Q; ++q) {
+          const uint32_t b = g & 1;
+          const int col = sweep_col(q);
+          mbar_wait(&lb[b], (g >> 1) & 1);
+          const float4* row = reinterpret_cast<const float4*>(ebuf + b * C::EBUF_BYTES + lane * 128);
+          uint4 o4[4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = row[i ^ (lane & 7)];
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col) + i);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col) + i);
+            const uint32_t lo = pack_bf16(fmaf((v.x - mean) * rstd, gm.x, bt.x), fmaf((v.y - mean) * rstd, gm.y, bt.y));
+            const uint32_t hi = pack_bf16(fmaf((v.z - mean) * rstd, gm.z, bt.z), fmaf((v.w - mean) * rstd, gm.w, bt.w));
+            if (i & 1) { o4[i >> 1].z = lo; o4[i >> 1].w = hi; } else { o4[i >> 1].x = lo; o4[i >> 1].y = hi; }
+          }
+          if (row0 + lane < p.M) {
+            uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<size_t>(row0 + lane) * p.ld_ln + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = o4[i];
+          }
+          __syncwarp();
+          if (lane == 0 && q + 2 < Q) {             // this buffer is free again
+            mbar_expect_tx(&lb[b], C::EBUF_BYTES);
+            tma_load_2d(&tmOut, &lb[b], ebuf + b * C::EBUF_BYTES, sweep_col(q + 2), row0);
+          }
+          ++g;
+        }
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -699,6 +795,12 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   p.rev = g.descending;
   p.aux = g.aux; p.ldaux = g.ldo;
   p.out2 = EPI == EPI_GELU ? static_cast<__nv_bfloat16*>(g.out2) : nullptr;
+  p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_out = g.ln_out; p.ld_ln = g.ld_ln; p.ln_eps = g.ln_eps;
+  if (g.ln_out != nullptr && (EPI != EPI_RESID_F32 || CL != 2 || BLOCK_N != 256 || g.ln_gamma == nullptr || g.ln_beta == nullptr ||
+                              g.ld_ln % 8 != 0 || g.N % 256 != 0)) {
+    set_err("gemm2: fused LayerNorm needs the residual epilogue on CTA pairs, BLOCK_N = 256, gamma / beta, ld_ln % 8 == 0");
+    return cudaErrorInvalidValue;
+  }
   if (g.out2 != nullptr && EPI != EPI_GELU) { set_err("gemm2: out2 only with the QuickGELU epilogue"); return cudaErrorInvalidValue; }
   if (EPI == EPI_GELU_BWD && (g.aux == nullptr || g.ldo % 8 != 0)) { set_err("gemm2: EPI_GELU_BWD needs aux (z), ld % 8 == 0"); return cudaErrorInvalidValue; }
   auto kern = gemm2_kernel<BLOCK_N, EPI, CL>;
@@ -852,6 +954,13 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   }
   if (g.a1.rows < g.M || g.b1.rows < g.N) { set_err("gemm_launch: operand rows smaller than M/N"); return cudaErrorInvalidValue; }
   int bn = g.force_block_n;
+  if (g.ln_out != nullptr) {      // fused LayerNorm: CTA pairs, BLOCK_N = 256, strip walk (checked again in launch2_t)
+    if (g.epi != EPI_RESID_F32 || g.N % 256 != 0 || g.M < 1024 || g.resid == nullptr) {
+      set_err("gemm_launch: fused LayerNorm needs EPI_RESID_F32, N % 256 == 0, M >= 1024");
+      return cudaErrorInvalidValue;
+    }
+    return launch2_t<256, EPI_RESID_F32, 2>(g, stream, num_sms);
+  }
   {
     // force_block_n: 0 = heuristic; 64/128/256 = 1-CTA kernel; 1000 + {128,192,256} = CTA-pair kernel;
     // 2256 = 4-CTA cluster (two pairs, multicast B tiles), BLOCK_N = 256

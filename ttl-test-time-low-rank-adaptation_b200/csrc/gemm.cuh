@@ -42,6 +42,13 @@ struct GemmArgs {
   int force_block_n = 0;               // 0 = heuristic
   int max_clusters = 0;                // CTA-pair / cluster kernels: cap on the persistent grid (0 = every co-resident cluster)
   int descending = 0;                  // CTA-pair kernel: walk the row blocks from the last to the first (engine.cu zigzag)
+  // EPI_RESID_F32 on the CTA-pair kernel: also write LayerNorm(out row) * gamma + beta as bf16 [M, N] (row pitch ld_ln) -- the next
+  // block's LayerNorm fused into this GEMM (strip walk + L2-hot second sweep, gemm.cu)
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  __nv_bfloat16* ln_out = nullptr;
+  int ld_ln = 0;
+  float ln_eps = 1e-5f;
 };
 
 // Generic tiled tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point), shared with the
