@@ -1,13 +1,15 @@
+# Same-box A/B of the fused LayerNorm variants (TTL_FUSE_LN: 0 = off, 1 = fc2 -> LN1, 2 = out-proj -> LN2, 3 = both), alternating runs.
 export PYTHONPATH=.
-mkdir -p gpurun_out/s50
-TTL_FUSE_LN=1 timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_configs.py -m gpu -x -q 2>&1 | tail -5
+O=gpurun_out/s52; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_e2e.py -m gpu -x -q -k "fused_layernorm or zigzag" 2>&1 | tail -15
 FL="--steps 60 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline --no-torch-baseline --no-live-traffic"
 for rep in 1 2; do
-  for f in 0 1; do
-    TTL_FUSE_LN=$f timeout 300 python bench.py $FL > gpurun_out/s50/fuse${f}_$rep.json 2>>gpurun_out/s50/err.log
+  for f in 0 1 3 2; do
+    TTL_FUSE_LN=$f timeout 300 python bench.py $FL > $O/fuse${f}_$rep.json 2>>$O/err.log
   done
 done
-for f in gpurun_out/s50/*.json; do python -c "
+for f in $O/fuse*.json; do python -c "
 import json,sys
 d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', round(d['value'],1), round(d['windows']['median'],1), d['clocks']['sm_mhz'], d['gpu_launches'])"; done
-tail -3 gpurun_out/s50/err.log
+tail -3 $O/err.log
+( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 ) > $O/pytest_full.log 2>&1; tail -30 $O/pytest_full.log

@@ -167,9 +167,12 @@ struct ttl_ctx {
   // lo..hi.  "views" are the class prompts (tokens = context positions, causal attention, EOT pooling), the "classes" of the
   // logits are the image views whose frozen features the caller supplies per test sample.
   bool text_mode = false;
-  // fused LayerNorm (TTL_FUSE_LN): the fc2 GEMM of an inference-mode layer also wrote LayerNorm1 of the NEXT layer over these rows
+  // fused LayerNorm (TTL_FUSE_LN, bit 0): the fc2 GEMM of an inference-mode layer also wrote LayerNorm1 of the NEXT layer over
+  // these rows; bit 1: the out-proj GEMM writes LayerNorm2 of its own layer.  ln_stats / ln_cnt: see gemm.cuh
   const float* h1_for = nullptr;
   int h1_rows = 0;
+  float* ln_stats = nullptr;
+  int* ln_cnt = nullptr;
   float *tok_emb = nullptr, *fhat = nullptr, *tn = nullptr, *attn_delta = nullptr;
   int *tok_ids = nullptr, *eot = nullptr;
   int n_prompts = 0;
@@ -275,6 +278,7 @@ int embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st) {
   g.b1 = opnd(c->wpatch, c->d, c->Kp, c->Kp);
   g.M = V * c->T; g.N = c->d; g.epi = EPI_PATCH_F32; g.out = x; g.ldo = c->d; g.pos = c->pos; g.tokens_per_view = c->T;
   RET_IF(gemm(c, g, st));
+  c->h1_for = nullptr;
   launch_embed_preln(x, c->cls, c->pos, c->preg, c->preb, V, c->tokens, c->d, c->cfg.ln_eps, st);
   c->launches++;
   return check_launch(c, "embed");
@@ -305,6 +309,13 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
   const bool zz_on = zz_env == nullptr || std::atoi(zz_env) != 0;
   const bool zz = zz_on && tp == nullptr && M >= 8192;
   auto next_dir = [&]() -> int { if (!zz) return 0; c->zz_dir ^= 1; return c->zz_dir; };
+  // TTL_FUSE_LN (opt-in, bit 0: fc2 -> LayerNorm1 of the next layer, bit 1: out-proj -> LayerNorm2): the GEMM's epilogue warps keep
+  // row statistics and the last warp to finish a piece of 32 rows normalises them from L2 (gemm.cu).  Inference-mode layers of
+  // the big first forward only.
+  const char* fuse_env = std::getenv("TTL_FUSE_LN");       // read per call: the tests toggle it
+  const int fuse = fuse_env != nullptr ? std::atoi(fuse_env) : 0;
+  const bool fuse_ok = fuse != 0 && tp == nullptr && M >= 8192 && d % 256 == 0 && d <= 1024 && !(skip & 1) && !c->text_mode;
+  bool h2_ready = false;
   const bool h1_ready = tp == nullptr && c->h1_for == x_in && c->h1_rows == M;      // written by the previous layer's fc2
   c->h1_for = nullptr;
   if (!h1_ready) {
@@ -345,11 +356,18 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.b1 = opnd(w.wo, d, d, d);
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.bo; g.out = x_mid; g.ldo = d; g.resid = x_in; g.ldr = d;
     g.descending = next_dir();
+    if (fuse_ok && (fuse & 2)) {      // LayerNorm2 rides in the out-proj GEMM
+      g.ln_gamma = w.ln2g; g.ln_beta = w.ln2b; g.ln_out = h2; g.ld_ln = d; g.ln_eps = c->cfg.ln_eps;
+      g.ln_stats = c->ln_stats; g.ln_cnt = c->ln_cnt;
+      h2_ready = true;
+    }
     RET_IF(gemm(c, g, st));
   }
-  const int dir_ln2 = next_dir();
-  if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st, dir_ln2);
-  c->launches++;
+  if (!h2_ready) {
+    const int dir_ln2 = next_dir();
+    if (!(skip & 1)) launch_layernorm(x_mid, h2, w.ln2g, w.ln2b, M, d, c->cfg.ln_eps, st, dir_ln2);
+    c->launches++;
+  }
   {
     GemmArgs g;
     g.a1 = opnd(h2, M, d, d);
@@ -364,13 +382,10 @@ int run_layer(ttl_ctx* c, int layer, const float* x_in, float* x_mid, float* x_o
     g.b1 = opnd(w.w2, d, F, F);
     g.M = M; g.N = d; g.epi = EPI_RESID_F32; g.bias = w.b2; g.out = x_out; g.ldo = d; g.resid = x_mid; g.ldr = d;
     g.descending = next_dir();
-    // TTL_FUSE_LN=1: LayerNorm1 of the next layer rides in this GEMM (strip walk + L2-hot second sweep, gemm.cu): its K = 4 d
-    // main loop hides the sweep.  Inference-mode layers of the big first forward only.
-    const char* fuse_env = std::getenv("TTL_FUSE_LN");       // read per call: the tests toggle it
-    const bool fuse = fuse_env != nullptr && std::atoi(fuse_env) != 0;
-    if (fuse && tp == nullptr && layer + 1 < c->L && M >= 8192 && d % 256 == 0 && !(skip & 1)) {
+    if (fuse_ok && (fuse & 1) && layer + 1 < c->L) {      // LayerNorm1 of the next layer rides in the fc2 GEMM
       const LayerW& wn = c->lw[layer + 1];
       g.ln_gamma = wn.ln1g; g.ln_beta = wn.ln1b; g.ln_out = c->Hb; g.ld_ln = d; g.ln_eps = c->cfg.ln_eps;
+      g.ln_stats = c->ln_stats; g.ln_cnt = c->ln_cnt;
       c->h1_for = x_out;
       c->h1_rows = M;
     }
@@ -634,6 +649,7 @@ int f32_embed(ttl_ctx* c, const float* images, int V, float* x, cudaStream_t st)
   a.A = c->patches_f; a.lda = c->Kp; a.B = c->wpatch_f; a.ldb = c->Kp; a.M = V * c->T; a.N = c->d; a.K = c->Kp;
   a.out = x; a.ldo = c->d; a.epi = SE_PATCH; a.pos = c->pos; a.tpv = c->T;
   if (launch_sgemm(a, st) != cudaSuccess) { c->err = "sgemm (patch embedding) failed"; return TTL_E_CUDA; }
+  c->h1_for = nullptr;
   launch_embed_preln(x, c->cls, c->pos, c->preg, c->preb, V, c->tokens, c->d, c->cfg.ln_eps, st);
   c->launches += 3;
   return check_launch(c, "f32_embed");
@@ -1215,6 +1231,7 @@ int ttl_create(ttl_ctx** out, const ttl_config* cfg) {
     A(c->fhat, static_cast<size_t>(c->Cm) * c->P); A(c->tn, static_cast<size_t>(c->VVm) * c->P);
     A(c->attn_delta, static_cast<size_t>(c->VVm) * c->H * c->tokens);
   }
+  A(c->ln_stats, (static_cast<size_t>(M) + 32) * 2 * 8); A(c->ln_cnt, static_cast<size_t>(M) / 32 + 2);
   A(c->Hb, static_cast<size_t>(M) * d); A(c->QKV, static_cast<size_t>(M) * 3 * d); A(c->AO, static_cast<size_t>(M) * d);
   A(c->Gb, static_cast<size_t>(M) * F); A(c->Tm, static_cast<size_t>(M) * 64 * c->Sm);
   A(c->XK, static_cast<size_t>(M) * d); A(c->XA, static_cast<size_t>(M) * d); A(c->XB, static_cast<size_t>(M) * d);

@@ -332,14 +332,20 @@ struct Epi2Params {
   const __nv_bfloat16* aux;   // EPI_GELU_BWD: z [M, N] bf16, row pitch ldaux
   int ldaux;
   __nv_bfloat16* out2;        // EPI_GELU: optional copy of the pre-activation z = acc + bias (bf16, row pitch ldaux), for the backward
-  // EPI_RESID_F32 with a fused LayerNorm of the rows it writes (ln_out != nullptr): the tiles are walked in STRIPS (a cluster owns
-  // all N / BLOCK_N tiles of a 256-row block back to back), the epilogue threads keep running row statistics, and after the last
-  // tile of a strip every warp re-reads the fp32 rows it has just stored (L2-hot) and writes LayerNorm(row) as bf16 to ln_out.
+  // EPI_RESID_F32 with a fused LayerNorm of the rows it writes (ln_out != nullptr).  The 2 N / BLOCK_N epilogue warps (of up to
+  // N / BLOCK_N clusters) that own a piece of the same 32 rows each publish Welford statistics of their BLOCK_N / 2 columns and
+  // count an arrival; the warp that arrives LAST re-reads the 32 complete fp32 rows (just stored, L2-hot) and writes
+  // LayerNorm(row) as bf16 to ln_out.  The tile walk stays round-robin, so the clusters working on one row block still share its
+  // A tiles through L2 (the strip form, commit a995abe, walked n-inner and re-read A from HBM: 2.8 vs 1.1 GB per fc2 launch).
   const float* ln_gamma;
   const float* ln_beta;
   __nv_bfloat16* ln_out;
   int ld_ln;
   float ln_eps;
+  float2* ln_stats;           // [rows][2 N / BLOCK_N]
+  int* ln_cnt;                // [rows / 32], zero on entry and on exit
+  const float* ln_src;        // == the output matrix (generic-proxy view of what tmOut stores), row pitch ld_src
+  int ld_src;
 };
 
 // CL = 2: one CTA pair per cluster (above).  CL = 4: two pairs stacked along M share every B tile: each CTA loads a QUARTER of
@@ -416,16 +422,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int num_kb = p.kb1 + p.kb2;
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
-  const bool strips = EPI == EPI_RESID_F32 && CL == 2 && p.ln_out != nullptr;
-  // the k-th tile of this cluster: round-robin over all tiles, or (strips) all n tiles of every num_clusters-th row block
+  const bool fuse_ln = EPI == EPI_RESID_F32 && CL == 2 && p.ln_out != nullptr;
+  // the k-th tile of this cluster: round-robin over all tiles
   auto tile_at = [&](int k, int& m_pair, int& n_blk) -> bool {
-    if (strips) {
-      const int sk = k / n_tiles, strip = cluster_id + sk * num_clusters;
-      if (strip >= m_pairs) return false;
-      m_pair = p.rev ? m_pairs - 1 - strip : strip;
-      n_blk = k - sk * n_tiles;
-      return true;
-    }
     const int tile = cluster_id + k * num_clusters;
     if (tile >= num_tiles) return false;
     const int t2 = p.rev ? num_tiles - 1 - tile : tile;
@@ -532,7 +531,78 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int as = 0;
     uint32_t aphase = 0;
     uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
-    float ln_mean = 0.f, ln_m2 = 0.f, ln_cnt = 0.f;      // strips: running statistics of this lane's row over this warp's columns
+    float ln_mean = 0.f, ln_m2 = 0.f, ln_n = 0.f;      // fuse_ln: running statistics of this lane's row over this warp's columns of the tile
+    // fuse_ln: the statistics of a finished tile are published one tile later (after the next tile's residual prefetch has been
+    // issued), so the wait for this warp's output stores to COMPLETE is off the critical path
+    bool ln_pend = false;
+    int ln_prow0 = 0, ln_pslot = 0;
+    float ln_pmean = 0.f, ln_pm2 = 0.f;
+    const int ln_parts = 2 * n_tiles;
+    auto ln_finish = [&]() {
+      ln_pend = false;
+      // publish: this lane's row, this warp's column half of its tile
+      p.ln_stats[static_cast<size_t>(ln_prow0 + lane) * ln_parts + ln_pslot] = make_float2(ln_pmean, ln_pm2);
+      __threadfence();
+      int old = 0;
+      if (lane == 0) bulk_wait<0>();                // the stores of this warp's rows have completed (not just been read from smem)
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        old = atomicAdd(p.ln_cnt + (ln_prow0 >> 5), 1);
+      }
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old != ln_parts - 1) return;              // somebody else still owes a piece of these rows
+      __threadfence();
+      if (lane == 0) p.ln_cnt[ln_prow0 >> 5] = 0;   // ready for the next launch
+      // ---- this warp arrived last: LayerNorm of rows ln_prow0 .. +31 over all N columns, read back through L2
+      float mean = 0.f, m2 = 0.f;
+      {
+        const float2* sp = p.ln_stats + static_cast<size_t>(ln_prow0 + lane) * ln_parts;
+        float2 part[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[j] = j < ln_parts ? __ldcg(sp + j) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mean += part[j].x;
+        mean /= static_cast<float>(ln_parts);
+        const float cnt = static_cast<float>(BLOCK_N / 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < ln_parts) { const float dl = part[j].x - mean; m2 += part[j].y + cnt * dl * dl; }
+      }
+      const float rstd = rsqrtf(m2 / static_cast<float>(p.N) + p.ln_eps);
+      const int n4 = p.N >> 7;                      // float4 per lane and row
+#pragma unroll 1
+      for (int r = 0; r < 32; r += 2) {
+        if (ln_prow0 + r >= p.M) break;
+        const bool two = ln_prow0 + r + 1 < p.M;
+        const float mean0 = __shfl_sync(0xffffffffu, mean, r), rstd0 = __shfl_sync(0xffffffffu, rstd, r);
+        const float mean1 = __shfl_sync(0xffffffffu, mean, r + 1), rstd1 = __shfl_sync(0xffffffffu, rstd, r + 1);
+        const float4* src0 = reinterpret_cast<const float4*>(p.ln_src + static_cast<size_t>(ln_prow0 + r) * p.ld_src) + lane;
+        const float4* src1 = reinterpret_cast<const float4*>(p.ln_src + static_cast<size_t>(ln_prow0 + r + (two ? 1 : 0)) * p.ld_src) + lane;
+        uint2* dst0 = reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(ln_prow0 + r) * p.ld_ln) + lane;
+        uint2* dst1 = reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(ln_prow0 + r + 1) * p.ld_ln) + lane;
+        float4 v0[8], v1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < n4) { v0[i] = __ldcg(src0 + 32 * i); v1[i] = __ldcg(src1 + 32 * i); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < n4) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + lane + 32 * i);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + lane + 32 * i);
+            uint2 o;
+            o.x = pack_bf16(fmaf((v0[i].x - mean0) * rstd0, gm.x, bt.x), fmaf((v0[i].y - mean0) * rstd0, gm.y, bt.y));
+            o.y = pack_bf16(fmaf((v0[i].z - mean0) * rstd0, gm.z, bt.z), fmaf((v0[i].w - mean0) * rstd0, gm.w, bt.w));
+            dst0[32 * i] = o;
+            if (two) {
+              o.x = pack_bf16(fmaf((v1[i].x - mean1) * rstd1, gm.x, bt.x), fmaf((v1[i].y - mean1) * rstd1, gm.y, bt.y));
+              o.y = pack_bf16(fmaf((v1[i].z - mean1) * rstd1, gm.z, bt.z), fmaf((v1[i].w - mean1) * rstd1, gm.w, bt.w));
+              dst1[32 * i] = o;
+            }
+          }
+        }
+      }
+    };
     int m_pair = 0, n_blk = 0;
     for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
       const int row0 = (m_pair * PAIRS + static_cast<int>(pair)) * 256 + static_cast<int>(rank) * 128 + quad * 32;
@@ -547,6 +617,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           tma_load_2d(&tmRes, &lb[b], ebuf + b * C::EBUF_BYTES, col_base + c * 32, row0);
         }
       }
+      if (EPI == EPI_RESID_F32 && ln_pend) ln_finish();
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -591,9 +662,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
             }
           }
-          if (EPI == EPI_RESID_F32 && strips) {
+          if (EPI == EPI_RESID_F32 && fuse_ln) {
             // statistics of these 32 values (two-pass in registers), merged into the running ones (Chan et al.): no E[x^2] - mean^2
-            if (n_blk == 0 && c == 0) { ln_mean = 0.f; ln_m2 = 0.f; ln_cnt = 0.f; }
+            if (c == 0) { ln_mean = 0.f; ln_m2 = 0.f; ln_n = 0.f; }
             float sm = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sm += __uint_as_float(r[i]);
@@ -601,10 +672,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             float q = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float t = __uint_as_float(r[i]) - mc; q = fmaf(t, t, q); }
-            const float tot = ln_cnt + 32.f, delta = mc - ln_mean;
+            const float tot = ln_n + 32.f, delta = mc - ln_mean;
             ln_mean += delta * (32.f / tot);
-            ln_m2 += q + delta * delta * (ln_cnt * 32.f / tot);
-            ln_cnt = tot;
+            ln_m2 += q + delta * delta * (ln_n * 32.f / tot);
+            ln_n = tot;
           }
         } else {
           uint4* row = reinterpret_cast<uint4*>(buf + lane * 64);
@@ -656,60 +727,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         }
         ++g;
       }
-      if (EPI == EPI_RESID_F32 && strips && n_blk == n_tiles - 1 && live && !(p.dbg & 1)) {
-        // ---- fused LayerNorm of the strip.  The other half of every row's columns belongs to warp ew ^ 4 (same TMEM quadrant):
-        // exchange the half-row statistics through this warp's (drained) first staging buffer.
-        if (lane == 0) bulk_wait<0>();              // every store of this warp has completed: the rows are in L2 / memory
-        __syncwarp();
-        reinterpret_cast<float2*>(ebuf)[lane] = make_float2(ln_mean, ln_m2);
-        named_bar_sync(1 + quad, 64);
-        const float2 oth = reinterpret_cast<const float2*>(sE + (ew ^ 4) * 2 * C::EBUF_BYTES)[lane];
-        named_bar_sync(1 + quad, 64);               // the partner has read before the loads below land in the buffer
-        const float delta = oth.x - ln_mean;
-        const float mean = ln_mean + 0.5f * delta;                                  // both halves hold N / 2 values
-        const float var = (ln_m2 + oth.y + delta * delta * (0.25f * p.N)) / static_cast<float>(p.N);
-        const float rstd = rsqrtf(var + p.ln_eps);
-        const int Q = n_tiles * C::CHUNKS;
-        auto sweep_col = [&](int q) { return (q / C::CHUNKS) * BLOCK_N + half * (BLOCK_N / 2) + (q % C::CHUNKS) * 32; };
-        if (lane == 0) {
-          for (int q = 0; q < 2 && q < Q; ++q) {
-            const uint32_t b = (g + q) & 1;
-            mbar_expect_tx(&lb[b], C::EBUF_BYTES);
-            tma_load_2d(&tmOut, &lb[b], ebuf + b * C::EBUF_BYTES, sweep_col(q), row0);
-          }
-        }
-#pragma unroll 1
-        for (int q = 0; q < Q; ++q) {
-          const uint32_t b = g & 1;
-          const int col = sweep_col(q);
-          mbar_wait(&lb[b], (g >> 1) & 1);
-          const float4* row = reinterpret_cast<const float4*>(ebuf + b * C::EBUF_BYTES + lane * 128);
-          uint4 o4[4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v = row[i ^ (lane & 7)];
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col) + i);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col) + i);
-            const uint32_t lo = pack_bf16(fmaf((v.x - mean) * rstd, gm.x, bt.x), fmaf((v.y - mean) * rstd, gm.y, bt.y));
-            const uint32_t hi = pack_bf16(fmaf((v.z - mean) * rstd, gm.z, bt.z), fmaf((v.w - mean) * rstd, gm.w, bt.w));
-            if (i & 1) { o4[i >> 1].z = lo; o4[i >> 1].w = hi; } else { o4[i >> 1].x = lo; o4[i >> 1].y = hi; }
-          }
-          if (row0 + lane < p.M) {
-            uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<size_t>(row0 + lane) * p.ld_ln + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = o4[i];
-          }
-          __syncwarp();
-          if (lane == 0 && q + 2 < Q) {             // this buffer is free again
-            mbar_expect_tx(&lb[b], C::EBUF_BYTES);
-            tma_load_2d(&tmOut, &lb[b], ebuf + b * C::EBUF_BYTES, sweep_col(q + 2), row0);
-          }
-          ++g;
-        }
+      if (EPI == EPI_RESID_F32 && fuse_ln && live && !(p.dbg & 1)) {
+        ln_pend = true;
+        ln_prow0 = row0; ln_pslot = n_blk * 2 + half;
+        ln_pmean = ln_mean; ln_pm2 = ln_m2;
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (EPI == EPI_RESID_F32 && ln_pend) ln_finish();
     if (lane == 0) bulk_wait<0>();      // all output tiles written before the CTA retires
     __syncwarp();
   }
@@ -796,9 +822,12 @@ cudaError_t launch2_t(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   p.aux = g.aux; p.ldaux = g.ldo;
   p.out2 = EPI == EPI_GELU ? static_cast<__nv_bfloat16*>(g.out2) : nullptr;
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta; p.ln_out = g.ln_out; p.ld_ln = g.ld_ln; p.ln_eps = g.ln_eps;
+  p.ln_stats = reinterpret_cast<float2*>(g.ln_stats); p.ln_cnt = g.ln_cnt;
+  p.ln_src = static_cast<const float*>(g.out); p.ld_src = g.ldo;
   if (g.ln_out != nullptr && (EPI != EPI_RESID_F32 || CL != 2 || BLOCK_N != 256 || g.ln_gamma == nullptr || g.ln_beta == nullptr ||
-                              g.ld_ln % 8 != 0 || g.N % 256 != 0)) {
-    set_err("gemm2: fused LayerNorm needs the residual epilogue on CTA pairs, BLOCK_N = 256, gamma / beta, ld_ln % 8 == 0");
+                              g.ln_stats == nullptr || g.ln_cnt == nullptr || g.ld_ln % 4 != 0 || g.ldo % 4 != 0 ||
+                              g.N % 256 != 0 || g.N > 1024)) {
+    set_err("gemm2: fused LayerNorm needs the residual epilogue on CTA pairs, BLOCK_N = 256, N <= 1024, gamma / beta / stats / counters");
     return cudaErrorInvalidValue;
   }
   if (g.out2 != nullptr && EPI != EPI_GELU) { set_err("gemm2: out2 only with the QuickGELU epilogue"); return cudaErrorInvalidValue; }

@@ -43,12 +43,16 @@ struct GemmArgs {
   int max_clusters = 0;                // CTA-pair / cluster kernels: cap on the persistent grid (0 = every co-resident cluster)
   int descending = 0;                  // CTA-pair kernel: walk the row blocks from the last to the first (engine.cu zigzag)
   // EPI_RESID_F32 on the CTA-pair kernel: also write LayerNorm(out row) * gamma + beta as bf16 [M, N] (row pitch ld_ln) -- the next
-  // block's LayerNorm fused into this GEMM (strip walk + L2-hot second sweep, gemm.cu)
+  // LayerNorm fused into this GEMM.  Every epilogue warp publishes the statistics of its 32 rows x BLOCK_N / 2 columns to
+  // ln_stats ([M][2 N / BLOCK_N] float2) and counts an arrival in ln_cnt[row / 32]; the warp that arrives last normalises those
+  // 32 full rows from L2 and leaves the counter at zero for the next launch (gemm.cu).  ln_cnt must be zero on entry.
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   __nv_bfloat16* ln_out = nullptr;
   int ld_ln = 0;
   float ln_eps = 1e-5f;
+  float* ln_stats = nullptr;           // 2 * (M rounded up to 32) * (2 N / BLOCK_N) floats
+  int* ln_cnt = nullptr;               // (M + 31) / 32 counters
 };
 
 // Generic tiled tensor-map encoder (cuTensorMapEncodeTiled through the runtime's driver entry point), shared with the
