@@ -334,16 +334,18 @@ struct Epi2Params {
   __nv_bfloat16* out2;        // EPI_GELU: optional copy of the pre-activation z = acc + bias (bf16, row pitch ldaux), for the backward
   // EPI_RESID_F32 with a fused LayerNorm of the rows it writes (ln_out != nullptr).  The 2 N / BLOCK_N epilogue warps (of up to
   // N / BLOCK_N clusters) that own a piece of the same 32 rows each publish Welford statistics of their BLOCK_N / 2 columns and
-  // count an arrival; the warp that arrives LAST re-reads the 32 complete fp32 rows (just stored, L2-hot) and writes
-  // LayerNorm(row) as bf16 to ln_out.  The tile walk stays round-robin, so the clusters working on one row block still share its
-  // A tiles through L2 (the strip form, commit a995abe, walked n-inner and re-read A from HBM: 2.8 vs 1.1 GB per fc2 launch).
+  // count an arrival; one tile later every one of them re-reads ITS OWN 32 x BLOCK_N / 2 piece (fp32, L2-hot), by then with
+  // the statistics of the complete rows at hand, and writes LayerNorm(row) as bf16 to ln_out: the same extra work for every warp
+  // and tile.  (First form: the warp that arrived last swept all N columns of the 32 rows -- every tile then waited for its
+  // slowest warp: 338 vs 396 samples/s.)  The tile walk stays round-robin, so the clusters working on one row block still
+  // share its A tiles through L2 (the strip form, commit a995abe, walked n-inner and re-read A from HBM: 2.8 vs 1.1 GB per launch).
   const float* ln_gamma;
   const float* ln_beta;
   __nv_bfloat16* ln_out;
   int ld_ln;
   float ln_eps;
   float2* ln_stats;           // [rows][2 N / BLOCK_N]
-  int* ln_cnt;                // [rows / 32], zero on entry and on exit
+  int* ln_cnt;                // [rows / 32], zeroed by the launcher
   const float* ln_src;        // == the output matrix (generic-proxy view of what tmOut stores), row pitch ld_src
   int ld_src;
 };
@@ -422,7 +424,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int num_kb = p.kb1 + p.kb2;
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
   const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
-  const bool fuse_ln = EPI == EPI_RESID_F32 && CL == 2 && p.ln_out != nullptr;
+  const bool fuse_ln = EPI == EPI_RESID_F32 && CL == 2 && BLOCK_N == 256 && p.ln_out != nullptr;
   // the k-th tile of this cluster: round-robin over all tiles
   auto tile_at = [&](int k, int& m_pair, int& n_blk) -> bool {
     const int tile = cluster_id + k * num_clusters;
@@ -533,31 +535,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     uint32_t g = 0;                     // chunks this warp has pushed through its two smem buffers
     float ln_mean = 0.f, ln_m2 = 0.f, ln_n = 0.f;      // fuse_ln: running statistics of this lane's row over this warp's columns of the tile
     // fuse_ln: the statistics of a finished tile are published one tile later (after the next tile's residual prefetch has been
-    // issued), so the wait for this warp's output stores to COMPLETE is off the critical path
+    // issued: the wait for this warp's output stores to COMPLETE is off the critical path), and the warp normalises its own
+    // 32 x BLOCK_N / 2 piece one tile after that: the other warps that own columns of these rows have published theirs by then
+    // (they run the same tile round), and the rows -- stored with an evict_last L2 policy -- have not left L2 yet (normalising
+    // three tiles later re-read them from HBM: +372 MB per fc2 launch in ncu)
     bool ln_pend = false;
-    int ln_prow0 = 0, ln_pslot = 0;
+    int ln_prow0 = 0, ln_pcol = 0;
     float ln_pmean = 0.f, ln_pm2 = 0.f;
+    int lq_row0 = -1, lq_col0 = 0;                    // published, not yet normalised
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     const int ln_parts = 2 * n_tiles;
-    auto ln_finish = [&]() {
-      ln_pend = false;
-      // publish: this lane's row, this warp's column half of its tile
-      p.ln_stats[static_cast<size_t>(ln_prow0 + lane) * ln_parts + ln_pslot] = make_float2(ln_pmean, ln_pm2);
+    auto ln_publish = [&]() {
+      // this lane's row, this warp's column half of its tile
+      p.ln_stats[static_cast<size_t>(ln_prow0 + lane) * ln_parts + ln_pcol / (BLOCK_N / 2)] = make_float2(ln_pmean, ln_pm2);
       __threadfence();
-      int old = 0;
       if (lane == 0) bulk_wait<0>();                // the stores of this warp's rows have completed (not just been read from smem)
       __syncwarp();
       if (lane == 0) {
         __threadfence();
-        old = atomicAdd(p.ln_cnt + (ln_prow0 >> 5), 1);
+        atomicAdd(p.ln_cnt + (ln_prow0 >> 5), 1);
       }
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old != ln_parts - 1) return;              // somebody else still owes a piece of these rows
-      __threadfence();
-      if (lane == 0) p.ln_cnt[ln_prow0 >> 5] = 0;   // ready for the next launch
-      // ---- this warp arrived last: LayerNorm of rows ln_prow0 .. +31 over all N columns, read back through L2
+    };
+    auto ln_normalise = [&](int row0, int col0) {
+      // every owner of a piece of these 32 rows has published (normally long ago: no spinning)
+      if (lane == 0) {
+        const volatile int* cnt = p.ln_cnt + (row0 >> 5);
+        for (int spin = 0; *cnt < ln_parts && spin < (1 << 22); ++spin) __nanosleep(200);     // bounded: a miscount shows as wrong rows, not a hang
+        __threadfence();
+      }
+      __syncwarp();
       float mean = 0.f, m2 = 0.f;
       {
-        const float2* sp = p.ln_stats + static_cast<size_t>(ln_prow0 + lane) * ln_parts;
+        const float2* sp = p.ln_stats + static_cast<size_t>(row0 + lane) * ln_parts;
         float2 part[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) part[j] = j < ln_parts ? __ldcg(sp + j) : make_float2(0.f, 0.f);
@@ -570,38 +579,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           if (j < ln_parts) { const float dl = part[j].x - mean; m2 += part[j].y + cnt * dl * dl; }
       }
       const float rstd = rsqrtf(m2 / static_cast<float>(p.N) + p.ln_eps);
-      const int n4 = p.N >> 7;                      // float4 per lane and row
-#pragma unroll 1
-      for (int r = 0; r < 32; r += 2) {
-        if (ln_prow0 + r >= p.M) break;
-        const bool two = ln_prow0 + r + 1 < p.M;
-        const float mean0 = __shfl_sync(0xffffffffu, mean, r), rstd0 = __shfl_sync(0xffffffffu, rstd, r);
-        const float mean1 = __shfl_sync(0xffffffffu, mean, r + 1), rstd1 = __shfl_sync(0xffffffffu, rstd, r + 1);
-        const float4* src0 = reinterpret_cast<const float4*>(p.ln_src + static_cast<size_t>(ln_prow0 + r) * p.ld_src) + lane;
-        const float4* src1 = reinterpret_cast<const float4*>(p.ln_src + static_cast<size_t>(ln_prow0 + r + (two ? 1 : 0)) * p.ld_src) + lane;
-        uint2* dst0 = reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(ln_prow0 + r) * p.ld_ln) + lane;
-        uint2* dst1 = reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(ln_prow0 + r + 1) * p.ld_ln) + lane;
-        float4 v0[8], v1[8];
+      // lane <-> 4 columns of the piece (BLOCK_N / 2 == 128 columns), 16 rows in flight
+      static_assert(BLOCK_N != 256 || BLOCK_N / 2 == 128, "one float4 per lane and row");
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0) + lane);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0) + lane);
+      const float4* src = reinterpret_cast<const float4*>(p.ln_src + static_cast<size_t>(row0) * p.ld_src + col0) + lane;
+      uint2* dst = reinterpret_cast<uint2*>(p.ln_out + static_cast<size_t>(row0) * p.ld_ln + col0) + lane;
+      const int rows = p.M - row0 < 32 ? p.M - row0 : 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i < n4) { v0[i] = __ldcg(src0 + 32 * i); v1[i] = __ldcg(src1 + 32 * i); }
+      for (int rb = 0; rb < 32; rb += 16) {
+        float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < n4) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_gamma) + lane + 32 * i);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_beta) + lane + 32 * i);
+        for (int j = 0; j < 16; ++j)
+          if (rb + j < rows)
+            v[j] = ld_cg_hint_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + static_cast<size_t>(rb + j) * p.ld_src), pol_drop);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float mr = __shfl_sync(0xffffffffu, mean, rb + j), rs = __shfl_sync(0xffffffffu, rstd, rb + j);
+          if (rb + j < rows) {
             uint2 o;
-            o.x = pack_bf16(fmaf((v0[i].x - mean0) * rstd0, gm.x, bt.x), fmaf((v0[i].y - mean0) * rstd0, gm.y, bt.y));
-            o.y = pack_bf16(fmaf((v0[i].z - mean0) * rstd0, gm.z, bt.z), fmaf((v0[i].w - mean0) * rstd0, gm.w, bt.w));
-            dst0[32 * i] = o;
-            if (two) {
-              o.x = pack_bf16(fmaf((v1[i].x - mean1) * rstd1, gm.x, bt.x), fmaf((v1[i].y - mean1) * rstd1, gm.y, bt.y));
-              o.y = pack_bf16(fmaf((v1[i].z - mean1) * rstd1, gm.z, bt.z), fmaf((v1[i].w - mean1) * rstd1, gm.w, bt.w));
-              dst1[32 * i] = o;
-            }
+            o.x = pack_bf16(fmaf((v[j].x - mr) * rs, gm.x, bt.x), fmaf((v[j].y - mr) * rs, gm.y, bt.y));
+            o.y = pack_bf16(fmaf((v[j].z - mr) * rs, gm.z, bt.z), fmaf((v[j].w - mr) * rs, gm.w, bt.w));
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + static_cast<size_t>(rb + j) * p.ld_ln) = o;
           }
         }
       }
+    };
+    auto ln_step = [&]() {          // at the top of a tile: publish the tile just finished, normalise the one before it
+      ln_publish();
+      ln_pend = false;
+      if (lq_row0 >= 0) ln_normalise(lq_row0, lq_col0);
+      lq_row0 = ln_prow0; lq_col0 = ln_pcol;
     };
     int m_pair = 0, n_blk = 0;
     for (int tk = 0; tile_at(tk, m_pair, n_blk); ++tk) {
@@ -617,7 +625,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           tma_load_2d(&tmRes, &lb[b], ebuf + b * C::EBUF_BYTES, col_base + c * 32, row0);
         }
       }
-      if (EPI == EPI_RESID_F32 && ln_pend) ln_finish();
+      if (EPI == EPI_RESID_F32 && ln_pend) ln_step();
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -717,7 +725,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmOut, buf, col, row0);
+          if (EPI == EPI_RESID_F32 && fuse_ln) tma_store_2d_hint(&tmOut, buf, col, row0, pol_keep);   // re-read below: stay in L2
+          else tma_store_2d(&tmOut, buf, col, row0);
           bulk_commit();
           if (EPI == EPI_RESID_F32 && c + 2 < C::CHUNKS) {
             bulk_wait_read<0>();        // the store just issued must be done with the buffer before it is refilled
@@ -729,13 +738,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
       if (EPI == EPI_RESID_F32 && fuse_ln && live && !(p.dbg & 1)) {
         ln_pend = true;
-        ln_prow0 = row0; ln_pslot = n_blk * 2 + half;
+        ln_prow0 = row0; ln_pcol = col_base;
         ln_pmean = ln_mean; ln_pm2 = ln_m2;
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (EPI == EPI_RESID_F32 && ln_pend) ln_finish();
+    if (EPI == EPI_RESID_F32 && fuse_ln) {
+      if (ln_pend) ln_step();
+      if (lq_row0 >= 0) ln_normalise(lq_row0, lq_col0);
+    }
     if (lane == 0) bulk_wait<0>();      // all output tiles written before the CTA retires
     __syncwarp();
   }
@@ -988,6 +1000,9 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
       set_err("gemm_launch: fused LayerNorm needs EPI_RESID_F32, N % 256 == 0, M >= 1024");
       return cudaErrorInvalidValue;
     }
+    if (g.ln_cnt == nullptr) { set_err("gemm_launch: fused LayerNorm needs the arrival counters"); return cudaErrorInvalidValue; }
+    cudaError_t e = cudaMemsetAsync(g.ln_cnt, 0, static_cast<size_t>((g.M + 31) / 32) * sizeof(int), stream);
+    if (e != cudaSuccess) { set_err("gemm_launch: clearing the fused-LayerNorm counters failed"); return e; }
     return launch2_t<256, EPI_RESID_F32, 2>(g, stream, num_sms);
   }
   {

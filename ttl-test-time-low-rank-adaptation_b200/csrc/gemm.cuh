@@ -44,8 +44,8 @@ struct GemmArgs {
   int descending = 0;                  // CTA-pair kernel: walk the row blocks from the last to the first (engine.cu zigzag)
   // EPI_RESID_F32 on the CTA-pair kernel: also write LayerNorm(out row) * gamma + beta as bf16 [M, N] (row pitch ld_ln) -- the next
   // LayerNorm fused into this GEMM.  Every epilogue warp publishes the statistics of its 32 rows x BLOCK_N / 2 columns to
-  // ln_stats ([M][2 N / BLOCK_N] float2) and counts an arrival in ln_cnt[row / 32]; the warp that arrives last normalises those
-  // 32 full rows from L2 and leaves the counter at zero for the next launch (gemm.cu).  ln_cnt must be zero on entry.
+  // ln_stats ([M][2 N / BLOCK_N] float2) and counts an arrival in ln_cnt[row / 32] (cleared by the launcher); one tile later it
+  // normalises its own piece from L2 with the statistics of the complete rows (gemm.cu).
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   __nv_bfloat16* ln_out = nullptr;

@@ -339,6 +339,33 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
                : "memory");
 }
+// L2 eviction policies (createpolicy) and the hinted forms that take one: rows a kernel stores and re-reads a few microseconds
+// later are stored evict_last and read back evict_first (gemm.cu, fused LayerNorm)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, const void* smem_src, int32_t c_inner, int32_t c_outer,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer), "l"(policy)
+               : "memory");
+}
+// 16 bytes from L2 (not through L1: written by other SMs during this kernel) with an eviction policy
+__device__ __forceinline__ float4 ld_cg_hint_f4(const float4* ptr, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(policy)
+               : "memory");
+  return v;
+}
 // 3-D tiled TMA load / store (coordinates innermost first)
 __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
                                             int32_t c2) {
