@@ -995,7 +995,7 @@ cudaError_t gemm_launch(const GemmArgs& g, cudaStream_t stream, int num_sms) {
   }
   if (g.a1.rows < g.M || g.b1.rows < g.N) { set_err("gemm_launch: operand rows smaller than M/N"); return cudaErrorInvalidValue; }
   int bn = g.force_block_n;
-  if (g.ln_out != nullptr) {      // fused LayerNorm: CTA pairs, BLOCK_N = 256, strip walk (checked again in launch2_t)
+  if (g.ln_out != nullptr) {      // fused LayerNorm: CTA pairs, BLOCK_N = 256 (checked again in launch2_t)
     if (g.epi != EPI_RESID_F32 || g.N % 256 != 0 || g.M < 1024 || g.resid == nullptr) {
       set_err("gemm_launch: fused LayerNorm needs EPI_RESID_F32, N % 256 == 0, M >= 1024");
       return cudaErrorInvalidValue;
