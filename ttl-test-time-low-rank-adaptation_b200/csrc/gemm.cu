@@ -690,13 +690,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * i + j]);
-            if (p.bias != nullptr) {
+            if (p.bias != nullptr) {      // packed fp32 pairs: one issue slot per two bias adds
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 2 * i);
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 2 * i + 1);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              const uint64_t s0 = f32x2_add(f32x2_pack_bits(r[8 * i], r[8 * i + 1]), f32x2_pack(b0.x, b0.y));
+              const uint64_t s1 = f32x2_add(f32x2_pack_bits(r[8 * i + 2], r[8 * i + 3]), f32x2_pack(b0.z, b0.w));
+              const uint64_t s2 = f32x2_add(f32x2_pack_bits(r[8 * i + 4], r[8 * i + 5]), f32x2_pack(b1.x, b1.y));
+              const uint64_t s3 = f32x2_add(f32x2_pack_bits(r[8 * i + 6], r[8 * i + 7]), f32x2_pack(b1.z, b1.w));
+              v[0] = f32x2_lo(s0); v[1] = f32x2_hi(s0); v[2] = f32x2_lo(s1); v[3] = f32x2_hi(s1);
+              v[4] = f32x2_lo(s2); v[5] = f32x2_hi(s2); v[6] = f32x2_lo(s3); v[7] = f32x2_hi(s3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * i + j]);
             }
             if (EPI == EPI_GELU) {
               if (p.out2 != nullptr && row0 + lane < p.M) {      // pre-activation copy: 16 of this lane's 64 contiguous bytes
@@ -704,8 +709,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 zz.x = pack_bf16(v[0], v[1]); zz.y = pack_bf16(v[2], v[3]); zz.z = pack_bf16(v[4], v[5]); zz.w = pack_bf16(v[6], v[7]);
                 reinterpret_cast<uint4*>(p.out2 + static_cast<size_t>(row0 + lane) * p.ldaux + col)[i] = zz;
               }
+              {
+                // z * sigmoid(1.702 z) = z (0.5 + 0.5 tanh(0.851 z)): three roundings per element (0.851 z; 0.5 t + 0.5; z s), issued as
+                // packed fp32 pairs (bit-identical to the scalar form, half the issue slots; fc1 alone and the whole step are
+                // unchanged by it, 1248-1264 vs 1233-1256 TFLOP/s, gpurun s59: the epilogue is not what bounds this GEMM)
+                const uint64_t k2 = f32x2_pack(0.851f, 0.851f), h2 = f32x2_pack(0.5f, 0.5f);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = v[j] * (0.5f + 0.5f * tanh_approx(0.851f * v[j]));   // z * sigmoid(1.702 z)
+                for (int j = 0; j < 4; ++j) {
+                  const uint64_t z2 = f32x2_pack(v[2 * j], v[2 * j + 1]);
+                  const uint64_t a2 = f32x2_mul(z2, k2);
+                  const uint64_t s2 = f32x2_fma(f32x2_pack(tanh_approx(f32x2_lo(a2)), tanh_approx(f32x2_hi(a2))), h2, h2);
+                  const uint64_t g2 = f32x2_mul(z2, s2);
+                  v[2 * j] = f32x2_lo(g2); v[2 * j + 1] = f32x2_hi(g2);
+                }
+              }
             }
             if (EPI == EPI_GELU_BWD) {     // dz = dg * sigma(1.702 z) (1 + 1.702 z (1 - sigma(1.702 z)))
               const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zq[i]);
