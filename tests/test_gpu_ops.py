@@ -226,6 +226,31 @@ def test_attention_fwd_bwd(G, V, tokens, heads):
         assert gu.rel_err(got[:, i], g[:, i]) < 1.5e-2, nm   # bf16 P/dS operands; fp32 accumulation
 
 
+def test_attention_fwd_257_tokens_many_units_and_extreme_scores(G):
+    """257 tokens (ViT-L/14) on the P-in-TMEM kernel with the extra key / query row: 40 views x 16 heads = 640 units > 148 CTAs, so
+    every CTA wraps its double-buffered K / V and the mbarrier phases several times; a second input whose later keys -- key 256
+    included -- are scaled 40x exercises the exact-max softmax across the MMA keys and the folded-in key, and the CUDA-core row."""
+    gu, L = G
+    V, tokens, heads = 40, 257, 16
+    d = heads * 64
+    for extreme in (False, True):
+        qkv = torch.randn(V * tokens, 3 * d, device="cuda", generator=torch.Generator("cuda").manual_seed(5 + extreme)) * 1.5
+        if extreme:
+            qkv.view(V, tokens, 3, heads, 64)[:, 200:, 1] *= 40.0
+        qkv = qkv.bfloat16()
+        out = torch.empty(V * tokens, d, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(V, heads, tokens, device="cuda")
+        gu.ok(gu.lib().ttl_op_attention_fwd(gu.ptr(qkv), gu.ptr(out), gu.ptr(lse), V, tokens, heads, 0.125, gu.stream()))
+        torch.cuda.synchronize()
+        ref, lse_ref = _attn_ref(qkv.float(), V, tokens, heads)
+        assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+        assert gu.rel_err(out, ref) < 8e-3
+        o3, r3 = out.float().view(V, tokens, d), ref.view(V, tokens, d)
+        assert gu.rel_err(o3[:, 256], r3[:, 256]) < 8e-3                 # the CUDA-core query row
+        assert gu.rel_err(o3[:, 128:256], r3[:, 128:256]) < 8e-3         # the second query tile
+        assert float(((lse - lse_ref).abs() / lse_ref.abs().clamp_min(1.0)).max()) < 2e-3
+
+
 @pytest.mark.parametrize("mode", ["pp", "tc", "mma"])
 def test_attention_forward_alternatives_still_agree(mode):
     """TTL_ATTN selects the other forward kernels (read once per process, so each runs in a child): the two-tiles-in-flight

@@ -7,8 +7,9 @@ import gpu_util as gu
 
 lib = gu.lib()
 FWD = ((64, 197, 12), (192, 197, 12), (6, 197, 12), (1, 197, 12), (64, 257, 16))
-if os.environ.get("ATTN_BENCH_FWD"):      # e.g. ATTN_BENCH_FWD=192,576: only these view counts at 197 tokens, no backward
-    FWD = tuple((int(v), 197, 12) for v in os.environ["ATTN_BENCH_FWD"].split(","))
+if os.environ.get("ATTN_BENCH_FWD"):      # e.g. ATTN_BENCH_FWD=192,576: only these view counts (197 tokens x 12 heads unless ATTN_BENCH_TOKENS / _HEADS say otherwise), no backward
+    _tk, _hd = int(os.environ.get("ATTN_BENCH_TOKENS", "197")), int(os.environ.get("ATTN_BENCH_HEADS", "12"))      # 257 / 16: ViT-L/14
+    FWD = tuple((int(v), _tk, _hd) for v in os.environ["ATTN_BENCH_FWD"].split(","))
 for (V, tokens, heads) in FWD:
     d = heads * 64
     ring = 4

@@ -1758,6 +1758,475 @@ attention_fwd_pt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// =============================================================================================== tcgen05 forward, P kept in TMEM, 257 tokens
+// attention_fwd_pt_kernel for ViT-L/14's 257 tokens: 256 keys and 256 queries go through the MMAs (two full 128-row query tiles,
+// S_t = 128 x 256 fp32 fills the tile's 256 TMEM columns), key 256 is folded in by the softmax threads (score from global memory
+// while the S MMAs run, p_256 v_256 added to O in the epilogue) and query row 256 is computed by one extra warp on the CUDA cores
+// from the K / V tiles the unit has in shared memory anyway -- as in attention_fwd_pp_kernel<true>, which this kernel replaces.
+// Per tile t, TMEM columns [256 t, 256 t + 256):
+//   S_t   [0, 256)
+//   O_t   [192, 256)    overlaps the scores of keys 192..255: pass 2 evaluates those four 16-key steps FIRST and keeps their packed
+//                       probabilities in registers
+//   P_t   keys 128..255 at [128, 192) (step ks = 8..15 at column 64 + 8 ks): written while / after the steps 8..11 are evaluated,
+//                       i.e. only over S columns the thread has already loaded; block 0 (these eight steps) starts O
+//         keys 0..127   at [0, 64) (step ks at column 8 ks), in place behind the loads as in the 208-key kernel: blocks 1 and 2
+// The q / k / v rows of token 256 ride with the unit's K / V loads (three 128-byte TMA boxes per buffer, no swizzle), so no compute
+// warp touches global memory on its critical path (first version: __ldg of those rows in the softmax warps and the extra warp --
+// 609 us at 576 views x 16 heads, 264 us with both switched off, 573 us for attention_fwd_pp_kernel<true>).
+// Shared memory: Q 2 x 2 x 16 KB, K and V double-buffered (4 x 32 KB), per-warp output stages 32 KB: 224 KB (+ 1 KB: barriers and
+// the three rows).
+constexpr int PX_THREADS = PT_THREADS + 32;
+constexpr int PX_KB = 256 * 128;      // bytes of K (or V) of a unit
+template <int MASK>
+__global__ void __launch_bounds__(PX_THREADS, 1)
+attention_fwd_px_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse, int heads, int units, float scale_log2,
+                        int rev, const bf16* __restrict__ qkv, bf16* __restrict__ out, int dbg) {
+  extern __shared__ uint8_t smem_px_raw[];
+  constexpr int tokens = 257, XKEY = 256, KB = PX_KB;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_px_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // [2 buffers][2 tiles] 16 KB each
+  uint8_t* sK = sQ + 4 * 16384;                    // [2 buffers]
+  uint8_t* sV = sK + 2 * KB;                       // [2 buffers]
+  uint8_t* sO = sV + 2 * KB;                       // [2 tiles][4 warps] output stage, 4 KB (32 rows) each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * 16384);
+  uint64_t* bar_kq = bars;            // [2] K + Q0 + Q1 of a unit landed in buffer b
+  uint64_t* bar_kqfree = bars + 2;    // [2] both streams' S MMAs on buffer b retired (2 commits)
+  uint64_t* bar_v = bars + 4;         // [2] V buffer landed
+  uint64_t* bar_vfree = bars + 6;     // [2] both streams' P V MMAs on the V buffer retired (2 commits)
+  uint64_t* bar_s = bars + 8;         // [2] S_t complete in TMEM
+  uint64_t* bar_o = bars + 10;        // [2] O_t complete in TMEM (P_t dead)
+  uint64_t* bar_tfree = bars + 12;    // [2] O_t copied to registers: TMEM region t reusable
+  uint64_t* bar_p = bars + 14;        // [2][4] P block b of tile t stored in TMEM (three blocks used)
+  uint64_t* bar_xk = bars + 22;       // [2] the extra-query warp has read K buffer b, every softmax warp its q row and k_256 (9 arrivals)
+  uint64_t* bar_xv = bars + 24;       // [2] the extra-query warp has read V buffer b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint8_t* xrow = reinterpret_cast<uint8_t*>(bars + 32);     // [2 buffers][q_256 | k_256 | v_256] 128 B each, not swizzled
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * DH;
+  const size_t ld = static_cast<size_t>(3) * d;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmRow);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_kq[i], 1);
+      mbar_init(&bar_kqfree[i], 2);
+      mbar_init(&bar_v[i], 1);
+      mbar_init(&bar_vfree[i], 2);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_o[i], 1);
+      mbar_init(&bar_tfree[i], 4);
+      mbar_init(&bar_xk[i], 9);
+      mbar_init(&bar_xv[i], 1);
+      for (int b = 0; b < 4; ++b) mbar_init(&bar_p[i * 4 + b], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const int u2 = rev ? units - 1 - unit : unit;
+        const int view = u2 / heads, h = u2 - view * heads;
+        const int b = it & 1, use = it >> 1;
+        if (use >= 1) {
+          mbar_wait(&bar_kqfree[b], (use - 1) & 1);            // both S MMAs of unit it - 2 retired
+          mbar_wait(&bar_xk[b], (use - 1) & 1);                // ... and the extra-query warp is done with that K
+        }
+        mbar_expect_tx(&bar_kq[b], KB + 2 * 16384 + 256);
+        tma_load_3d(&tmRow, &bar_kq[b], xrow + b * 384, h * DH, XKEY, view);
+        tma_load_3d(&tmRow, &bar_kq[b], xrow + b * 384 + 128, d + h * DH, XKEY, view);
+        tma_load_3d(&tmKV, &bar_kq[b], sK + b * KB, d + h * DH, 0, view);
+        tma_load_3d(&tmQ, &bar_kq[b], sQ + b * 32768, h * DH, 0, view);
+        tma_load_3d(&tmQ, &bar_kq[b], sQ + b * 32768 + 16384, h * DH, 128, view);
+        if (use >= 1) {
+          mbar_wait(&bar_vfree[b], (use - 1) & 1);
+          mbar_wait(&bar_xv[b], (use - 1) & 1);
+        }
+        mbar_expect_tx(&bar_v[b], KB + 128);
+        tma_load_3d(&tmRow, &bar_v[b], xrow + b * 384 + 256, 2 * d + h * DH, XKEY, view);
+        tma_load_3d(&tmKV, &bar_v[b], sV + b * KB, 2 * d + h * DH, 0, view);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issue of stream t (one elected thread, counted loops)
+    const int t = warp == 1 ? 0 : 1;
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, 1);
+      const uint32_t tt = tmem + t * 256;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int b = it & 1, use = it >> 1;
+        const uint32_t qa = smem_u32(sQ + b * 32768 + t * 16384), ka = smem_u32(sK + b * KB);
+        mbar_wait(&bar_kq[b], use & 1);
+        if (it > 0) mbar_wait(&bar_tfree[t], ph ^ 1);             // the previous unit's O_t has left TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tt, umma_desc_k_sw128(qa + k * 32), umma_desc_k_sw128(ka + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s[t]);
+        umma_commit(&bar_kqfree[b]);
+        mbar_wait(&bar_v[b], use & 1);
+        const uint64_t vdesc = umma_desc(smem_u32(sV + b * KB), 1024, KB, 2);     // + 128 per 16-key step (2048 B >> 4)
+        mbar_wait(&bar_p[t * 4 + 0], ph);                         // block 0: keys 128..255, starts O
+        tc_fence_after();
+#pragma unroll 1
+        for (int ks = 8; ks < 16; ++ks)
+          umma_bf16_ts(tt + 192, tt + 64 + 8 * ks, vdesc + static_cast<uint64_t>(ks) * 128, idesc_o, ks != 8 ? 1u : 0u);
+#pragma unroll 1
+        for (int blk = 1; blk < 3; ++blk) {
+          mbar_wait(&bar_p[t * 4 + blk], ph);
+          tc_fence_after();
+#pragma unroll 1
+          for (int ks = 4 * blk - 4; ks < 4 * blk; ++ks)
+            umma_bf16_ts(tt + 192, tt + 8 * ks, vdesc + static_cast<uint64_t>(ks) * 128, idesc_o, 1u);
+        }
+        umma_commit(&bar_o[t]);
+        umma_commit(&bar_vfree[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ query row 256: one warp, mma.sync (m16n8k16) on the K / V
+    // tiles in shared memory (first version: CUDA cores, lane = key for the scores and lane = two output dimensions for P V, 2600
+    // instructions per unit on a scheduler it shares with two softmax warps -- 464 us at 576 views, 319 us with this warp idle)
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const int b = it & 1, use = it >> 1;
+      const int u2 = rev ? units - 1 - unit : unit;
+      const int view = u2 / heads, h = u2 - view * heads;
+      const uint8_t* xr = xrow + b * 384;
+      mbar_wait(&bar_kq[b], use & 1);            // K of the unit and the rows of token 256 have landed
+      if (dbg & 1) {      // development: no work, only the hand-overs
+        if (lane == 0) mbar_arrive(&bar_xk[b]);
+        mbar_wait(&bar_v[b], use & 1);
+        if (lane == 0) mbar_arrive(&bar_xv[b]);
+        continue;
+      }
+      // q_256 as row 0 of an m16 A tile (rows 1..15 zero): lanes 0..3 hold its words, S = q K^T and P V run on mma.sync over four
+      // 64-key chunks with an online softmax (exp2 domain); only the accumulators of row lane / 4 = 0 (c0, c1) mean anything
+      const uint32_t* qw = reinterpret_cast<const uint32_t*>(xr);
+      uint32_t aq[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        aq[ks][0] = lane < 4 ? qw[ks * 8 + lane] : 0u;
+        aq[ks][2] = lane < 4 ? qw[ks * 8 + 4 + lane] : 0u;
+        aq[ks][1] = 0u;
+        aq[ks][3] = 0u;
+      }
+      float sxx;
+      {
+        const float2 fq = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(xr)[lane]);
+        const float2 fk = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(xr + 128)[lane]);
+        sxx = warp_sum(fmaf(fq.x, fk.x, fq.y * fk.y));
+      }
+      const uint32_t sKa = smem_u32(sK + b * KB), sVa = smem_u32(sV + b * KB);
+      float o[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+      float mrow = -INFINITY, lrow = 0.f;
+#pragma unroll 1
+      for (int kc = 0; kc < 256; kc += 64) {
+        float sa[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sa[nt][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            uint32_t bf[4];
+            ldb_nk_sw(sKa, kc + np * 16, ks * 16, lane, bf);
+            mma_bf16_16816(sa[2 * np], aq[ks], bf[0], bf[1]);
+            mma_bf16_16816(sa[2 * np + 1], aq[ks], bf[2], bf[3]);
+          }
+        }
+        if (kc == 192) {                           // last read of K
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_xk[b]);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          sa[nt][0] *= scale_log2;
+          sa[nt][1] *= scale_log2;
+          mx = max3(mx, sa[nt][0], sa[nt][1]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(mrow, mx);
+        const float c = ex2_approx(mrow - mn);     // first chunk: 2^-inf = 0
+        mrow = mn;
+        lrow *= c;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          o[nt][0] *= c;
+          o[nt][1] *= c;
+          sa[nt][0] = ex2_approx(sa[nt][0] - mn);
+          sa[nt][1] = ex2_approx(sa[nt][1] - mn);
+          lrow += sa[nt][0] + sa[nt][1];
+        }
+        if (kc == 0) mbar_wait(&bar_v[b], use & 1);      // V of the unit
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t pf[4];
+          pf[0] = pack_bf16(sa[2 * kk][0], sa[2 * kk][1]);
+          pf[2] = pack_bf16(sa[2 * kk + 1][0], sa[2 * kk + 1][1]);
+          pf[1] = 0u;
+          pf[3] = 0u;
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            uint32_t bf[4];
+            ldb_kn_sw(sVa, kc + kk * 16, np * 16, lane, bf);
+            mma_bf16_16816(o[2 * np], pf, bf[0], bf[1]);
+            mma_bf16_16816(o[2 * np + 1], pf, bf[2], bf[3]);
+          }
+        }
+      }
+      // key 256, then the row sum across the four lanes of row 0
+      const float sx2 = sxx * scale_log2;
+      const float mn = fmaxf(mrow, sx2);
+      const float c = ex2_approx(mrow - mn), pxx = ex2_approx(sx2 - mn);
+      float l = lrow * c;
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      l += pxx;
+      const float inv = 1.f / l;
+      if (lane < 4) {
+        bf16* orow = out + (static_cast<size_t>(view) * tokens + XKEY) * d + h * DH;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float2 vx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + 256 + (nt * 8 + 2 * lane) * 2));
+          *reinterpret_cast<__nv_bfloat162*>(orow + nt * 8 + 2 * lane) =
+              __floats2bfloat162_rn(fmaf(pxx, vx.x, o[nt][0] * c) * inv, fmaf(pxx, vx.y, o[nt][1] * c) * inv);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_xv[b]);      // V (and v_256) may be overwritten
+      if (lane == 0 && lse != nullptr) lse[(static_cast<size_t>(view) * heads + h) * tokens + XKEY] = (mn + log2f(l)) * LN2;
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warps of stream t (every query row is real)
+    const int t = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + t * 256;
+    uint8_t* ostage = sO + t * 16384 + quad * 4096;         // this warp's 32 rows x 128 B (1024-aligned: swizzle atoms intact)
+    const int r0 = t * 128 + quad * 32;                     // first query row of this warp
+    int it = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int u2 = rev ? units - 1 - unit : unit;
+      const int view = u2 / heads, h = u2 - view * heads;
+      // key 256: its score q_i . k_256 while the S MMAs run, q row and k_256 from shared memory (the Q tile is swizzled)
+      const int b = it & 1, use = it >> 1;
+      float sx = 0.f;
+      mbar_wait(&bar_kq[b], use & 1);
+      if (!(dbg & 2)) {
+        const int row = quad * 32 + lane;
+        const uint32_t qa = smem_u32(sQ + b * 32768 + t * 16384) + row * 128;
+        const uint8_t* kr = xrow + b * 384 + 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 a;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                       : "r"(qa + ((static_cast<uint32_t>(c8) ^ (row & 7)) << 4)));
+          const uint4 kx = *reinterpret_cast<const uint4*>(kr + c8 * 16);
+          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+          const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fa = __bfloat1622float2(a2[j]), fb = __bfloat1622float2(k2[j]);
+            sx = fmaf(fa.x, fb.x, sx);
+            sx = fmaf(fa.y, fb.y, sx);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_xk[b]);    // this warp is done with the Q tile and k_256 of buffer b
+      mbar_wait(&bar_s[t], ph);
+      tc_fence_after();
+      float m = sx;
+      {
+        // pass 1: exact row maximum over the 256 scores in TMEM (two register buffers, loads one pair ahead)
+        uint32_t ra[32], rb[32];
+        float m1 = -INFINITY;
+        tmem_ld_32x32b_x32(trow, ra);
+        tmem_ld_32x32b_x32(trow + 32, rb);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m = max3(m, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+          if (c < 3) tmem_ld_32x32b_x32(trow + 64 * c + 64, ra);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) m1 = max3(m1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]));
+          if (c < 3) tmem_ld_32x32b_x32(trow + 64 * c + 96, rb);
+        }
+        m = fmaxf(m, m1);
+      }
+      float l;
+      uint4 vx[8];
+      const float ms = m * scale_log2;
+      const float px = ex2_approx(fmaf(sx, scale_log2, -ms));
+      {
+        // pass 2: p = 2^(s*scale - m*scale), row sum, packed bf16 P back into TMEM (layout above).  16-key steps through two
+        // 16-register buffers: the load of the next step flies while a step is evaluated.
+        const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nms2 = f32x2_pack(-ms, -ms);
+        uint64_t l2 = 0;
+        uint32_t ba[16], bb[16], pk[8], pa0[8], pa1[8], pa2[8], pa3[8];
+        auto eval16 = [&](const uint32_t (&r)[16], uint32_t (&o)[8]) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint64_t e2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t x2 = f32x2_fma(f32x2_pack_bits(r[8 * q + 2 * i], r[8 * q + 2 * i + 1]), sc2, nms2);
+              const float e0 = ((MASK >> (2 * i)) & 1) ? ex2_poly(f32x2_lo(x2)) : ex2_approx(f32x2_lo(x2));
+              const float e1 = ((MASK >> (2 * i + 1)) & 1) ? ex2_poly(f32x2_hi(x2)) : ex2_approx(f32x2_hi(x2));
+              e2[i] = f32x2_pack(e0, e1);
+              o[4 * q + i] = pack_bf16(e0, e1);
+            }
+            l2 = f32x2_add(l2, f32x2_add(f32x2_add(e2[0], e2[1]), f32x2_add(e2[2], e2[3])));
+          }
+        };
+        auto deliver = [&](int blk) {              // P block blk is in TMEM: tell the MMA thread
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_p[t * 4 + blk]);
+        };
+        // keys 192..255 (their S columns are O's home): evaluated first, kept in registers
+        tmem_ld_32x32b_x16(trow + 192, ba);
+        tmem_ld_32x32b_x16(trow + 208, bb);
+        tmem_ld_wait();
+        eval16(ba, pa0);
+        tmem_ld_32x32b_x16(trow + 224, ba);
+        eval16(bb, pa1);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 240, bb);
+        eval16(ba, pa2);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 128, ba);
+        eval16(bb, pa3);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 144, bb);
+        // keys 128..191: step ks = 8..11 -> columns [128 + 8 (ks - 8), + 8), inside S columns this thread has loaded
+        eval16(ba, pk);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 160, ba);
+        tmem_st_32x32b_x8(trow + 128, pk);
+        eval16(bb, pk);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 176, bb);
+        tmem_st_32x32b_x8(trow + 136, pk);
+        eval16(ba, pk);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow, ba);
+        tmem_st_32x32b_x8(trow + 144, pk);
+        eval16(bb, pk);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x16(trow + 16, bb);
+        tmem_st_32x32b_x8(trow + 152, pk);
+        tmem_st_32x32b_x8(trow + 160, pa0);        // keys 192..255 behind them: S columns 160..191 are in registers / done
+        tmem_st_32x32b_x8(trow + 168, pa1);
+        tmem_st_32x32b_x8(trow + 176, pa2);
+        tmem_st_32x32b_x8(trow + 184, pa3);
+        deliver(0);
+        // keys 0..127: step ks -> columns [8 ks, 8 ks + 8)
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {              // steps 2 i (in ba) and 2 i + 1 (in bb, landed by the wait below)
+          eval16(ba, pk);
+          tmem_ld_wait();
+          if (i < 3) tmem_ld_32x32b_x16(trow + 32 * i + 32, ba);
+          tmem_st_32x32b_x8(trow + 16 * i, pk);
+          eval16(bb, pk);
+          tmem_ld_wait();
+          if (i < 3) tmem_ld_32x32b_x16(trow + 32 * i + 48, bb);
+          tmem_st_32x32b_x8(trow + 16 * i + 8, pk);
+          if (i == 1) deliver(1);
+        }
+        // v_256 (lands with V) into registers BEFORE the last block is handed over: the buffer cannot be reloaded until then
+        mbar_wait(&bar_v[b], use & 1);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) vx[c8] = *reinterpret_cast<const uint4*>(xrow + b * 384 + 256 + c8 * 16);
+        deliver(2);
+        l = f32x2_lo(l2) + f32x2_hi(l2) + px;
+      }
+      mbar_wait(&bar_o[t], ph);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(trow + 192, o0);
+      tmem_ld_32x32b_x32(trow + 224, o1);
+      if (lane == 0) bulk_wait_read<0>();      // this warp's previous output store has finished reading its stage
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tfree[t]);
+      if (!(dbg & 2)) {                        // O_i += p_256 v_256
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vx[c8]);
+          uint32_t* o = c8 < 4 ? o0 + c8 * 8 : o1 + (c8 - 4) * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fv = __bfloat1622float2(v2[j]);
+            o[2 * j] = __float_as_uint(fmaf(px, fv.x, __uint_as_float(o[2 * j])));
+            o[2 * j + 1] = __float_as_uint(fmaf(px, fv.y, __uint_as_float(o[2 * j + 1])));
+          }
+        }
+      }
+      const float inv = 1.f / l;
+      const uint32_t obase = smem_u32(ostage) + lane * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const uint32_t* r = q4 < 4 ? o0 + q4 * 8 : o1 + (q4 - 4) * 8;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + ((static_cast<uint32_t>(q4) ^ (lane & 7)) << 4)),
+                     "r"(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv)),
+                     "r"(pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv)),
+                     "r"(pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv)),
+                     "r"(pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv))
+                     : "memory");
+      }
+      if (lse != nullptr) lse[(static_cast<size_t>(view) * heads + h) * tokens + r0 + lane] = (ms + log2f(l)) * LN2;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmOut, ostage, h * DH, r0, view);      // 32-row box, rows r0 .. r0 + 31 < 256
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =============================================================================================== CLS-query attention
 // Last encoder layer in inference: only the CLS token of each view feeds post_layernorm / visual_projection
 // (HF CLIPVisionTransformer.forward: pooled_output = last_hidden_state[:, 0]), so only its query row is needed.
@@ -2443,6 +2912,44 @@ static bool launch_attention_fwd_pt(const bf16* qkv, bf16* out, float* lse, int 
   return ok;
 }
 
+// 257 tokens (ViT-L/14): the P-in-TMEM kernel with 256 keys / queries through the MMAs, key 256 folded in by the softmax threads and
+// query row 256 on one extra warp (attention_fwd_px_kernel)
+static bool launch_attention_fwd_px(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
+                                    cudaStream_t st, int descending) {
+  if (tokens != 257) return false;
+  const int d = heads * DH;
+  const size_t smem = 4 * 16384 + static_cast<size_t>(4) * PX_KB + 2 * 16384 + 1024 + 1024;      // 226 KB
+  CUtensorMap tq, tkv, to, trow;
+  auto kern = attention_fwd_px_kernel<0x88>;
+  const uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3 * d) * 2, static_cast<uint64_t>(tokens) * 3 * d * 2};
+  const uint32_t boxq[3] = {64, 128, 1}, boxkv[3] = {64, 256, 1}, boxrow[3] = {64, 1, 1};
+  if (!encode_tiled_map(&tq, 0, qkv, 3, dims, strides, boxq, 128)) return false;
+  if (!encode_tiled_map(&tkv, 0, qkv, 3, dims, strides, boxkv, 128)) return false;
+  if (!encode_tiled_map(&trow, 0, qkv, 3, dims, strides, boxrow, 0)) return false;      // one token's 64 values of a head, not swizzled
+  const uint64_t odims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(tokens), static_cast<uint64_t>(V)};
+  const uint64_t ostrides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(tokens) * d * 2};
+  const uint32_t obox[3] = {64, 32, 1};      // one softmax warp's rows
+  if (!encode_tiled_map(&to, 0, out, 3, odims, ostrides, obox, 128)) return false;
+  const int dv = current_device_slot();
+  static bool configured_dev[MAX_DEVICES] = {};
+  static int num_sms_dev[MAX_DEVICES] = {};
+  int& num_sms = num_sms_dev[dv];
+  if (num_sms == 0) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dv);
+  if (!configured_dev[dv]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured_dev[dv] = true;
+  }
+  const int units = V * heads;
+  const int grid = units < num_sms ? units : num_sms;
+  static const int dbg = std::getenv("TTL_PX_DBG") ? std::atoi(std::getenv("TTL_PX_DBG")) : 0;      // development: 1 = idle extra warp, 2 = no key 256
+  return launch_pdl(kern, dim3(grid), dim3(PX_THREADS), smem, st, tq, tkv, to, trow, lse, heads, units, scale * LOG2E, descending,
+                    qkv, out, dbg) == cudaSuccess;
+}
+
 static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                                      cudaStream_t st) {
   const int rows_pad = (tokens + 15) / 16 * 16, rows_alloc = (rows_pad + 31) / 32 * 32;
@@ -2493,11 +3000,13 @@ void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tok
   // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   static const char* mode = std::getenv("TTL_ATTN");
   const bool want_pt = mode == nullptr || (mode[0] == 'p' && mode[1] == 't');      // default for 193..208 tokens: P kept in TMEM
+  const bool want_px = mode == nullptr || (mode[0] == 'p' && mode[1] == 'x');      // default for 257 tokens: the same with an extra key / query
   const bool want_pp = mode == nullptr || mode[0] == 'p';
   const bool want_tc = mode == nullptr || mode[0] == 't' || mode[0] == 'p';
   const bool want_tma = mode == nullptr || mode[0] != 'l';
   // the causal form (77-token text tower) runs on the general kernel below
   if (!causal && want_pt && launch_attention_fwd_pt(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
+  if (!causal && want_px && launch_attention_fwd_px(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
   if (!causal && want_pp && launch_attention_fwd_pp(qkv, out, lse, V, tokens, heads, scale, st, descending)) return;
   if (!causal && want_tc && launch_attention_fwd_tc(qkv, out, lse, V, tokens, heads, scale, st)) return;
   if (!causal && want_tma && launch_attention_fwd_tma(qkv, out, lse, V, tokens, heads, scale, st)) return;
