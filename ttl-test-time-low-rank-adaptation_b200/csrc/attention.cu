@@ -2995,9 +2995,9 @@ static bool launch_attention_fwd_tma(const bf16* qkv, bf16* out, float* lse, int
 
 void launch_attention_fwd(const bf16* qkv, bf16* out, float* lse, int V, int tokens, int heads, float scale,
                           cudaStream_t st, int descending, int causal) {   // only the default kernel honours `descending`
-  // TTL_ATTN: unset / "tc" = tcgen05 kernel where the geometry allows, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
-  // TTL_ATTN: unset / "pp" = tcgen05 kernel with both query tiles of a unit in flight (129..208 tokens), "tc" = tcgen05 kernel
-  // with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
+  // TTL_ATTN: unset = the fastest kernel the geometry allows: "pt" (193..208 tokens) / "px" (257 tokens) = tcgen05 with P kept in
+  // TMEM, "pp" = tcgen05 with both query tiles of a unit in flight and P through shared memory (129..208 and 257 tokens), "tc" =
+  // tcgen05 with one tile per work item and two CTAs per SM, "mma" = TMA-fed mma.sync kernel, "legacy" = first kernel
   static const char* mode = std::getenv("TTL_ATTN");
   const bool want_pt = mode == nullptr || (mode[0] == 'p' && mode[1] == 't');      // default for 193..208 tokens: P kept in TMEM
   const bool want_px = mode == nullptr || (mode[0] == 'p' && mode[1] == 'x');      // default for 257 tokens: the same with an extra key / query
